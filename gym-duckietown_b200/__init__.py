@@ -1,0 +1,20 @@
+"""dtsim-b200: batched Duckietown `Simulator.step()` hot path as sm_100a CUDA kernels.
+
+Public surface (mirrors gym_duckietown's):
+  Simulator, DuckietownEnv, MultiMapEnv      single-env gym.Env adapters (old 4-tuple API)
+  BatchedDuckietownEnv                       N envs per GPU, torch tensors in/out
+  load_map, list_maps                        MapFormat1 loader
+"""
+__version__ = "0.1.0"
+
+from .maps import InvalidMapException, list_maps, load_map  # noqa: F401
+
+
+def __getattr__(name):  # lazy: importing the package must not require torch/CUDA
+    if name in ("BatchedDuckietownEnv",):
+        from . import batched_env
+        return getattr(batched_env, name)
+    if name in ("Simulator", "DuckietownEnv", "MultiMapEnv", "NotInLane"):
+        from . import simulator
+        return getattr(simulator, name)
+    raise AttributeError(name)
