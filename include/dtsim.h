@@ -1,0 +1,176 @@
+/* dtsim.h — C ABI of libdtsim.so, the B200-native batched Duckietown step() hot path.
+ *
+ * The reference (duckietown/gym-duckietown @5c2a586) has no FFI for this path: Simulator.step()
+ * is Python all the way down to the OpenGL driver.  This header is the boundary we introduce
+ * beneath its gym.Env surface.  Every entry point names the reference code it
+ * replaces (paths relative to /root/reference/src/gym_duckietown).  Plain C, POD structs, raw
+ * pointers and sizes; no torch types.  All device work is stream-ordered on the cudaStream_t the
+ * caller passes (as a void*; NULL = legacy default stream); no entry point synchronises.
+ *
+ * Return value: 0 = ok, non-zero = error; dts_last_error() gives the message.
+ */
+#ifndef DTSIM_H
+#define DTSIM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTS_ABI_VERSION 1
+#define DTS_MAX_DELAY 8      /* command-delay line depth (steps) */
+#define DTS_MAX_OBJECTS 256  /* per map; visibility bitmask is 8 x u32 */
+
+typedef struct dts_sim dts_sim; /* opaque, one per GPU, not thread-safe */
+
+/* done_code values (simulator.py:1685-1705 DoneRewardInfo.done_code) */
+enum { DTS_IN_PROGRESS = 0, DTS_INVALID_POSE = 1, DTS_MAX_STEPS = 2 };
+/* action_mode */
+enum { DTS_ACTION_PWM = 0,      /* Simulator.step(action=[u_left,u_right])        simulator.py:1669 */
+       DTS_ACTION_VEL_STEER = 1 /* DuckietownEnv.step(action=[vel, steering])  envs/duckietown_env.py:36-59 */ };
+/* flags */
+enum { DTS_FLAG_AUTO_RESET = 1,   /* done envs are re-spawned on device inside dts_step */
+       DTS_FLAG_DOMAIN_RAND = 2,  /* simulator.py:213  (camera noise S:1768, DR sampling in device resets) */
+       DTS_FLAG_DISTORTION = 4,   /* simulator.py:223  fisheye gather fused into the render (distortion.py:118) */
+       DTS_FLAG_DYNAMICS_RAND = 8 /* simulator.py:224  per-env trim on the motor gains (S:746-748) */ };
+
+typedef struct {
+  int32_t abi_version;      /* DTS_ABI_VERSION */
+  int32_t num_envs;         /* N independent agents on this GPU */
+  int32_t device;           /* CUDA ordinal */
+  int32_t cam_width;        /* simulator.py:216 (default 640) */
+  int32_t cam_height;       /* simulator.py:217 (default 480) */
+  int32_t max_steps;        /* simulator.py:210 (1500) */
+  int32_t frame_skip;       /* simulator.py:215 (1) */
+  int32_t action_mode;
+  int32_t flags;
+  int32_t max_maps;         /* slots for dts_upload_map */
+  double frame_rate;        /* simulator.py:214 (30) */
+  double robot_speed;       /* simulator.py:218 (1.2): the constant used in the reward, S:1702 */
+  double accept_start_angle_deg; /* simulator.py:219 (60), device-side spawn only */
+  /* DuckietownEnv constructor (envs/duckietown_env.py:15-33) */
+  double gain, trim, radius, k, limit;
+  /* duckietown_world DB18 PWM dynamics — source absent, restated (DESIGN.md "dynamics"):
+   *   u' = u + dt(-u1 u - u2 w + u3 w^2 + uar*R + ual*L),  w' = w + dt(-w1 w - w2 u - w3 u w + war*R - wal*L)
+   *   q' = q * exp(dt * [u', 0, w']),  commands delayed by `delay` seconds.            call sites S:746-755, S:2083-2086 */
+  double dyn_u1, dyn_u2, dyn_u3, dyn_w1, dyn_w2, dyn_w3, dyn_uar, dyn_ual, dyn_war, dyn_wal;
+  double dyn_delay;         /* 0.15 (S:748-750) */
+  uint64_t seed;            /* device-side spawn/DR streams: stream k = hash(seed, global_env_id) */
+  int64_t env_id_offset;    /* global index of local env 0 (multi-GPU shards keep seeds GPU-count independent) */
+} dts_config;
+
+typedef struct { int32_t width, height; const uint8_t* rgba; /* [height][width][4], row 0 = t=0 */ } dts_texture;
+
+typedef struct {            /* one placed static prop: objects.py:33-66 (WorldObj), render O:123-148 */
+  float pos[3];
+  float scale;
+  float y_rot_deg;
+  int32_t mesh_id;
+  int32_t optional;         /* hidden w.p. 1/2 at reset under domain_rand (S:653-654) */
+} dts_object;
+
+typedef struct { int32_t tri_offset, tri_count; } dts_mesh;
+
+/* Everything the hot path reads about one map, prepared on the host (maps.py):
+ * tile grid S:788-860, curves S:1151-1335, static collidables S:1019-1038 / S:919-931,
+ * meshes objmesh.py:65-293, textures graphics.py:70-169. All pointers are HOST memory, copied. */
+typedef struct {
+  double tile_size;
+  int32_t grid_w, grid_h;
+  const int8_t* tile_kind;        /* [grid_h*grid_w], -1 = no tile */
+  const int8_t* tile_angle;       /* 0..3 (S,E,N,W) */
+  const uint8_t* tile_drivable;
+  const int16_t* tile_tex;        /* texture index per tile, -1 = none */
+  const int32_t* tile_curve_off;  /* first curve of the tile */
+  const int32_t* tile_curve_cnt;  /* 0, 2, 6 or 12 */
+  int32_t n_curves;
+  const double* curves;           /* [n_curves][4][3] */
+  int32_t n_coll;
+  const double* coll_corners;     /* [n_coll][2][4]  x row, z row */
+  const double* coll_norms;       /* [n_coll][2][2]  two SAT axes as rows */
+  const double* coll_centers;     /* [n_coll][3] */
+  const double* coll_radii;       /* [n_coll] safety radii */
+  int32_t n_objects;
+  const dts_object* objects;
+  int32_t n_meshes;
+  const dts_mesh* meshes;
+  int32_t n_tris;
+  const float* tri_pos;           /* [n_tris][3][3] */
+  const float* tri_nrm;           /* [n_tris][3][3] */
+  const float* tri_uv;            /* [n_tris][3][2] */
+  const float* tri_col;           /* [n_tris][3][3] */
+  const int16_t* tri_tex;         /* [n_tris] texture index, -1 = untextured */
+  int32_t n_textures;
+  const dts_texture* textures;
+} dts_map_blob;
+
+/* Per-episode inputs produced by Simulator.reset() (simulator.py:528-763), one
+ * entry per env of the batch (SoA, HOST pointers, length num_envs; entries of unmasked envs are
+ * ignored).  Any pointer may be NULL = keep the reference's non-randomized default. */
+typedef struct {
+  const int32_t* map_id;
+  const double* pos_x;  const double* pos_z;  const double* angle;   /* cur_pos / cur_angle S:740-741 */
+  const double* wheel_dist;      /* S:597 */
+  const double* trim;            /* S:747 (dynamics_rand) */
+  const float* cam_height;       /* S:602,612 */
+  const float* cam_angle_deg;    /* S:605,613 */
+  const float* cam_fov_y_deg;    /* S:608,614 */
+  const float* cam_noise;        /* [N][3] S:1768-1769 */
+  const float* horizon_color;    /* [N][3] S:551-562 */
+  const float* light_ambient;    /* [N][3] S:573-574 */
+  const float* light_diffuse;    /* [N][3] S:575-576 */
+  const float* light_pos;        /* [N][4] S:565-570, S:581 */
+  const int32_t* light_stale;    /* [N] 0: GL_POSITION captured under identity modelview (first reset);
+                                        1: under the previous frame's camera matrix (S:581) */
+  const float* ground_color;     /* [N][3] S:594 */
+  const uint32_t* obj_hidden;    /* [N][8] bit o set = object o invisible this episode (S:653-656) */
+} dts_episode_params;
+
+/* Device pointers to the library-owned SoA state (all length num_envs unless noted). */
+typedef struct {
+  double* pos_x; double* pos_z; double* angle;     /* cur_pos[0], cur_pos[2], cur_angle */
+  double* speed;                                   /* S:1568 */
+  double* reward;                                  /* f64 shadow of the f32 reward output */
+  double* lane_dist; double* lane_dot; double* lane_angle_rad;   /* LanePosition S:1409 (NaN if not in lane) */
+  double* prox_penalty;                            /* S:1430-1459 */
+  double* wheel_dist;
+  int32_t* step_count;
+  int32_t* tile_i; int32_t* tile_j;                /* get_grid_coords(cur_pos) S:1134 */
+  int32_t* map_id;
+  int32_t* episode;                                /* resets so far */
+  uint8_t* done_code;
+  uint8_t* in_lane;
+  uint8_t* collided;                               /* _collision() of the current pose S:1473 */
+} dts_state_view;
+
+/* Simulator.__init__ (simulator.py:207-384) minus map loading. */
+int dts_create(const dts_config* cfg, dts_sim** out);
+/* Simulator._load_map/_interpret_map/_load_objects (simulator.py:765-931) : device copy of one map. */
+int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* blob);
+/* Distortion.rmapx/rmapy (distortion.py:85-125): LUT of the fused fisheye gather, [H][W] each. */
+int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, int width, int height);
+/* Simulator.reset() (simulator.py:528-763) with host-drawn episode parameters.
+ * mask_dev: device u8[num_envs] (NULL = all). */
+int dts_reset(dts_sim* sim, const uint8_t* mask_dev, const dts_episode_params* params, void* stream);
+/* Same, but pose / DR are drawn on the device (counter-based RNG, not numpy's PCG64 stream). */
+int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream);
+/* Simulator.step() (simulator.py:1669-1683) for all envs: actions f32[N][2] -> obs u8[N][H][W][3]
+ * (NULL = skip rendering), reward f32[N], done u8[N]. All DEVICE pointers. */
+int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* reward_dev, uint8_t* done_dev,
+             void* stream);
+/* Simulator.render_obs() (simulator.py:1953-1972) of the current state. */
+int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream);
+int dts_get_state(dts_sim* sim, dts_state_view* out);
+/* End-of-rollout observation all-gather across GPU shards. `nccl_comm` is an ncclComm_t.
+ * send: u8[bytes_per_rank] on this GPU, recv: u8[world*bytes_per_rank]. */
+int dts_allgather_obs(dts_sim* sim, void* nccl_comm, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank,
+                      void* stream);
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+uint64_t dts_launch_count(dts_sim* sim);
+const char* dts_last_error(dts_sim* sim); /* sim may be NULL: error of the last failed dts_create */
+void dts_destroy(dts_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTSIM_H */

@@ -1,0 +1,230 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by executing the REFERENCE's own code (via oracle/refstub.py).
+
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py
+The fixtures it writes are committed; the GPU box has no /root/reference and only reads them.
+
+Files written
+  logic_<map>.npz      poses -> tile coords, drivable, valid_pose (sf 1.0 / 1.3), collision, proximity,
+                       lane pose, reward / done / done_code          (reference: simulator.py, collision.py, graphics.py)
+  action_map.npz       DuckietownEnv.step [vel, steer] -> wheel duty  (envs/duckietown_env.py:36-59)
+  reset_<map>.npz      Simulator.reset() outputs per seed, domain_rand off/on (simulator.py:528-763)
+  fisheye.npz          Distortion LUT digest, sub-sampled LUT, one remapped test image (distortion.py)
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import refstub  # noqa: E402
+from gym_duckietown_b200 import assets, maps  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+MAPS = ["small_loop", "loop_obstacles", "udem1"]
+
+
+def raw_map(name):
+    with open(os.path.join(ROOT, "gym-duckietown_b200", "maps", f"{name}.yaml")) as f:
+        return yaml.safe_load(f)
+
+
+def extents_for(raw):
+    objs = raw.get("objects") or []
+    descs = objs.values() if isinstance(objs, dict) else objs
+    ext = {}
+    for o in descs:
+        k = o["kind"]
+        m = assets.get_mesh(k)
+        ext["sign_generic" if k.startswith("sign") else k] = (m.min_coords, m.max_coords)
+    return ext
+
+
+def sample_poses(md: maps.MapData, n: int, rng) -> np.ndarray:
+    """Mixture: anywhere (incl. off-grid), on drivable tiles, hugging obstacles, exact tile edges."""
+    ts, W, H = md.tile_size, md.grid_w, md.grid_h
+    out = []
+    for k in range(n):
+        mode = k % 8
+        if mode == 0:
+            x, z = rng.uniform(-0.5, W + 0.5) * ts, rng.uniform(-0.5, H + 0.5) * ts
+        elif mode in (1, 2, 3, 4):
+            i, j = md.drivable_tiles[rng.integers(0, len(md.drivable_tiles))]
+            x, z = rng.uniform(i, i + 1) * ts, rng.uniform(j, j + 1) * ts
+        elif mode in (5, 6) and md.n_coll:
+            c = md.coll_centers[rng.integers(0, md.n_coll)]
+            r = rng.uniform(0, 0.35)
+            a = rng.uniform(0, 2 * np.pi)
+            x, z = c[0] + r * np.cos(a), c[2] + r * np.sin(a)
+        elif mode == 7:
+            i, j = md.drivable_tiles[rng.integers(0, len(md.drivable_tiles))]
+            x, z = i * ts, rng.uniform(j, j + 1) * ts  # exactly on a tile boundary in x
+            if k % 16 == 15:
+                x, z = rng.uniform(i, i + 1) * ts, (j + 1) * ts
+        else:
+            i, j = md.drivable_tiles[rng.integers(0, len(md.drivable_tiles))]
+            x, z = rng.uniform(i, i + 1) * ts, rng.uniform(j, j + 1) * ts
+        ang = rng.uniform(-np.pi, np.pi) if k % 5 else rng.choice([0.0, np.pi / 2, np.pi, -np.pi / 2, 2 * np.pi])
+        out.append((x, z, ang))
+    return np.array(out)
+
+
+def gen_logic(name: str, n=1536, seed=7):
+    raw = raw_map(name)
+    md = maps.load_map(name)
+    sim = refstub.build_reference_sim(raw, extents_for(raw))
+    S, C, G, O = refstub.modules()
+    from gym_duckietown.exceptions import NotInLane
+
+    rng = np.random.default_rng(seed)
+    poses = sample_poses(md, n, rng)
+    steps = rng.integers(0, 4, n)  # 0 -> step_count = max_steps (max-steps branch), else small
+    rec = {k: [] for k in ("ti", "tj", "drv", "valid10", "valid13", "coll1", "coll2", "prox", "inlane", "dist",
+                           "dot", "ang", "reward", "done", "code", "corners")}
+    for (x, z, a), st in zip(poses, steps):
+        pos = np.array([x, 0.0, z])
+        i, j = sim.get_grid_coords(pos)
+        rec["ti"].append(i); rec["tj"].append(j)
+        rec["drv"].append(sim._drivable_pos(pos))
+        rec["valid10"].append(sim._valid_pose(pos, a))
+        rec["valid13"].append(sim._valid_pose(pos, a, safety_factor=1.3))
+        corners = S.get_agent_corners(pos, a)
+        rec["corners"].append(corners)
+        rec["coll1"].append(sim._collision(corners))  # run_tests.py:50 usage (offset once)
+        rec["coll2"].append(sim._collision(S.get_agent_corners(S._actual_center(pos, a), a)))  # S:1502,1521
+        rec["prox"].append(sim.proximity_penalty2(pos, a))
+        try:
+            lp = sim.get_lane_pos2(pos, a)
+            rec["inlane"].append(True); rec["dist"].append(lp.dist); rec["dot"].append(lp.dot_dir)
+            rec["ang"].append(lp.angle_rad)
+        except NotInLane:
+            rec["inlane"].append(False); rec["dist"].append(np.nan); rec["dot"].append(np.nan)
+            rec["ang"].append(np.nan)
+        sim.cur_pos, sim.cur_angle = pos, a
+        sim.step_count = sim.max_steps if st == 0 else int(st)
+        d = sim._compute_done_reward()
+        rec["reward"].append(float(d.reward)); rec["done"].append(d.done)
+        rec["code"].append({"in-progress": 0, "invalid-pose": 1, "max-steps-reached": 2}[d.done_code])
+    arrs = {k: np.array(v) for k, v in rec.items()}
+    arrs["poses"] = poses
+    arrs["step_count"] = np.where(steps == 0, sim.max_steps, steps).astype(np.int32)
+    arrs["max_steps"] = np.int32(sim.max_steps)
+    # load-time arrays, to pin maps.py against the reference's own map interpretation
+    arrs["ref_curves"] = np.concatenate([t["curves"] for t in sim.drivable_tiles], 0)
+    arrs["ref_drivable_ij"] = np.array([t["coords"] for t in sim.drivable_tiles])
+    if md.n_coll:
+        arrs["ref_coll_corners"] = np.asarray(sim.collidable_corners)
+        arrs["ref_coll_norms"] = np.asarray(sim.collidable_norms)
+        arrs["ref_coll_centers"] = np.asarray(sim.collidable_centers)
+        arrs["ref_coll_radii"] = np.asarray(sim.collidable_safety_radii)
+    np.savez_compressed(os.path.join(OUT, f"logic_{name}.npz"), **arrs)
+    print(f"logic_{name}: {n} poses, done={arrs['done'].mean():.2f} inlane={arrs['inlane'].mean():.2f} "
+          f"coll={arrs['coll2'].mean():.3f}")
+
+
+def gen_action_map(n=512, seed=11):
+    refstub.install()
+    from gym_duckietown.envs import duckietown_env as E
+    import gym_duckietown.simulator as S
+
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    wd = rng.uniform(0.0918, 0.1122, n)
+    cfgs = [(1.0, 0.0, 0.0318, 27.0, 1.0), (0.8, 0.05, 0.03, 25.0, 0.9)]
+    got = np.zeros((len(cfgs), n, 2))
+    captured = {}
+
+    def fake_step(self, vels):
+        captured["v"] = np.array(vels, dtype=np.float64)
+        return None, 0.0, False, {}
+
+    orig = S.Simulator.step
+    S.Simulator.step = fake_step
+    try:
+        for c, (gain, trim, radius, k, limit) in enumerate(cfgs):
+            env = object.__new__(E.DuckietownEnv)
+            env.gain, env.trim, env.radius, env.k, env.limit = gain, trim, radius, k, limit
+            for q in range(n):
+                env.wheel_dist = np.array(wd[q])
+                env.step(acts[q])
+                got[c, q] = captured["v"]
+    finally:
+        S.Simulator.step = orig
+    np.savez_compressed(os.path.join(OUT, "action_map.npz"), actions=acts, wheel_dist=wd, cfgs=np.array(cfgs),
+                        vels=got)
+    print("action_map:", got.shape)
+
+
+RESET_KEYS = ["cur_pos", "cur_angle", "wheel_dist", "cam_height", "cam_angle", "cam_fov_y", "camera_noise",
+              "horizon_color", "ground_color", "light_pos", "trim", "obj_visible"]
+
+
+def gen_reset(name: str, seeds=range(24)):
+    raw = raw_map(name)
+    S, C, G, O = refstub.modules()
+    out = {}
+    for dr in (False, True):
+        rows = {k: [] for k in RESET_KEYS + ["ambient", "diffuse"]}
+        for seed in seeds:
+            sim = refstub.build_reference_sim(raw, extents_for(raw), domain_rand=dr, seed=int(seed))
+            captured = []
+            S.gl.glLightfv = lambda light, pname, arr: captured.append(arr)
+            # ctypes arrays are mocked: (gl.GLfloat * 4)(*vals) -> capture through a fake GLfloat
+            class _GLf:
+                def __mul__(self, n):
+                    return lambda *v: np.array(v, dtype=np.float32)
+            S.gl.GLfloat = _GLf()
+            for episode in range(2):  # two consecutive episodes from one stream
+                captured.clear()
+                sim.reset()
+                rows["cur_pos"].append(np.array(sim.cur_pos, float)); rows["cur_angle"].append(float(sim.cur_angle))
+                rows["wheel_dist"].append(float(sim.wheel_dist)); rows["cam_height"].append(float(sim.cam_height))
+                rows["cam_angle"].append(float(sim.cam_angle[0])); rows["cam_fov_y"].append(float(sim.cam_fov_y))
+                rows["camera_noise"].append(np.array(sim.randomization_settings["camera_noise"], float))
+                rows["horizon_color"].append(np.array(sim.horizon_color, float))
+                rows["ground_color"].append(np.array(sim.ground_color, float))
+                lp = np.zeros(4); lp[:len(captured[0])] = captured[0]
+                rows["light_pos"].append(lp)
+                rows["ambient"].append(np.array(captured[1], float)); rows["diffuse"].append(np.array(captured[2], float))
+                rows["trim"].append(float(sim.randomization_settings["trim"][0]))
+                rows["obj_visible"].append(np.array([o.visible for o in sim.objects], bool))
+        for k, v in rows.items():
+            out[f"{'dr' if dr else 'nodr'}_{k}"] = np.array(v)
+    out["seeds"] = np.array(list(seeds))
+    np.savez_compressed(os.path.join(OUT, f"reset_{name}.npz"), **out)
+    print(f"reset_{name}: seeds={len(out['seeds'])} x 2 episodes x (dr off/on)")
+
+
+def gen_fisheye():
+    refstub.install()
+    from gym_duckietown.distortion import Distortion
+
+    d = Distortion()
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    out = d.distort(img)
+    rx, ry = d.rmapx.astype(np.float32), d.rmapy.astype(np.float32)
+    np.savez_compressed(
+        os.path.join(OUT, "fisheye.npz"),
+        sha_rmapx=hashlib.sha256(rx.tobytes()).hexdigest(), sha_rmapy=hashlib.sha256(ry.tobytes()).hexdigest(),
+        rmapx_sub=rx[::8, ::8], rmapy_sub=ry[::8, ::8], img_seed=5,
+        out_sha=hashlib.sha256(out.tobytes()).hexdigest(), out_sub=out[::8, ::8],
+        new_camera_matrix=d.new_camera_matrix)
+    print("fisheye: holes-free LUT", np.isnan(rx).sum() == 0, "out mean", out.mean())
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for m in MAPS:
+        gen_logic(m)
+    gen_action_map()
+    for m in ("small_loop", "loop_obstacles", "udem1"):
+        gen_reset(m)
+    gen_fisheye()

@@ -1,0 +1,144 @@
+"""ctypes front-end of the CPU oracle (oracle/*.c).  TEST INFRASTRUCTURE — see oracle/README.md.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liborc.so")
+SOURCES = ["dt_oracle_logic.c", "dt_oracle_raster.c"]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    # -ffp-contract=off: no silent FMA contraction, so the float arithmetic is exactly what the
+    # source says (the raster oracle's fp32 spec relies on it); -mfma only makes fmaf() an instruction.
+    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+           "-mfma", "-mavx2", "-o", LIB] + srcs + ["-lm"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_proximity.restype = C.c_double
+    return _lib
+
+
+class OrcMap(C.Structure):
+    _fields_ = [("tile_size", C.c_double), ("grid_w", C.c_int32), ("grid_h", C.c_int32),
+                ("tile_kind", C.c_void_p), ("tile_drivable", C.c_void_p), ("tile_curve_off", C.c_void_p),
+                ("tile_curve_cnt", C.c_void_p), ("curves", C.c_void_p), ("n_coll", C.c_int32),
+                ("coll_corners", C.c_void_p), ("coll_norms", C.c_void_p), ("coll_centers", C.c_void_p),
+                ("coll_radii", C.c_void_p)]
+
+
+class OrcDynParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("u1", "u2", "u3", "w1", "w2", "w3", "uar", "ual", "war", "wal")] + \
+               [("delay_steps", C.c_int32)]
+
+
+class OrcDynState(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("theta", C.c_double), ("u", C.c_double),
+                ("w", C.c_double), ("fifo", (C.c_double * 2) * 8)]
+
+
+class OrcStepOut(C.Structure):
+    _fields_ = [("pos_x", C.c_double), ("pos_z", C.c_double), ("angle", C.c_double), ("speed", C.c_double),
+                ("reward", C.c_double), ("lane_dist", C.c_double), ("lane_dot", C.c_double),
+                ("lane_angle", C.c_double), ("prox", C.c_double), ("tile_i", C.c_int32), ("tile_j", C.c_int32),
+                ("step_count", C.c_int32), ("done", C.c_uint8), ("done_code", C.c_uint8), ("in_lane", C.c_uint8),
+                ("collided", C.c_uint8), ("drivable4", C.c_uint8)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleMap:
+    """Holds contiguous copies of a MapData's arrays and the orc_map struct pointing at them."""
+
+    def __init__(self, md):
+        self.md = md
+        self._keep = dict(
+            kind=np.ascontiguousarray(md.tile_kind, np.int8), drv=np.ascontiguousarray(md.tile_drivable, np.uint8),
+            coff=np.ascontiguousarray(md.tile_curve_off, np.int32), ccnt=np.ascontiguousarray(md.tile_curve_cnt, np.int32),
+            curves=np.ascontiguousarray(md.curves, np.float64),
+            cc=np.ascontiguousarray(md.coll_corners, np.float64), cn=np.ascontiguousarray(md.coll_norms, np.float64),
+            ce=np.ascontiguousarray(md.coll_centers, np.float64), cr=np.ascontiguousarray(md.coll_radii, np.float64))
+        k = self._keep
+        self.c = OrcMap(md.tile_size, md.grid_w, md.grid_h, _p(k["kind"]), _p(k["drv"]), _p(k["coff"]), _p(k["ccnt"]),
+                        _p(k["curves"]), md.n_coll, _p(k["cc"]), _p(k["cn"]), _p(k["ce"]), _p(k["cr"]))
+
+    def done_reward(self, px, pz, angle, step_count, max_steps=1500, robot_speed=1.2) -> OrcStepOut:
+        o = OrcStepOut()
+        lib().orc_done_reward(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle), C.c_int(step_count),
+                              C.c_int(max_steps), C.c_double(robot_speed), C.byref(o))
+        return o
+
+    def valid_pose(self, px, pz, angle, sf=1.0) -> bool:
+        return bool(lib().orc_valid_pose(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle),
+                                         C.c_double(sf), None, None))
+
+    def collision(self, px, pz, angle) -> bool:
+        return bool(lib().orc_collision(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle)))
+
+    def proximity(self, px, pz, angle) -> float:
+        return float(lib().orc_proximity(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle)))
+
+
+def action_map(vel, steer, wheel_dist, gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0):
+    out = (C.c_double * 2)()
+    lib().orc_action_map(*(C.c_double(float(v)) for v in (vel, steer, wheel_dist, gain, trim, radius, k, limit)), out)
+    return out[0], out[1]
+
+
+def default_dyn_params(dt=1.0 / 30, delay=0.15, trim=0.0) -> OrcDynParams:
+    """get_DB18_nominal / get_DB18_uncalibrated as restated in DESIGN.md (parity unpinned)."""
+    d = int(np.ceil(delay / dt - 1e-9)) if delay > 0 else 0
+    return OrcDynParams(5.0, 0.0, 0.0, 4.0, 0.0, 0.0, 1.5 * (1 + trim), 1.5 * (1 - trim), 15.0 * (1 + trim),
+                        15.0 * (1 - trim), d)
+
+
+class OracleEnv:
+    """One reference-style env stepped by the C oracle: the CPU side of every trajectory parity test."""
+
+    def __init__(self, omap: OracleMap, px, pz, angle, *, wheel_dist=0.102, action_mode=1, max_steps=1500,
+                 frame_skip=1, dt=1.0 / 30, robot_speed=1.2, env5=(1.0, 0.0, 0.0318, 27.0, 1.0), trim=0.0):
+        self.m = omap
+        self.dp = default_dyn_params(dt, 0.15, trim)
+        self.s = OrcDynState()
+        lib().orc_cartesian_from_weird(C.byref(omap.c), C.c_double(px), C.c_double(pz), C.c_double(angle), C.byref(self.s))
+        self.step_count = C.c_int(0)
+        self.px, self.pz = C.c_double(px), C.c_double(pz)
+        self.wheel_dist, self.action_mode, self.max_steps = wheel_dist, action_mode, max_steps
+        self.frame_skip, self.dt, self.robot_speed = frame_skip, dt, robot_speed
+        self.env5 = (C.c_double * 5)(*env5)
+
+    def step(self, action) -> OrcStepOut:
+        o = OrcStepOut()
+        a = (C.c_double * 2)(float(action[0]), float(action[1]))
+        lib().orc_step(C.byref(self.m.c), C.byref(self.dp), C.byref(self.s), C.byref(self.step_count),
+                       C.byref(self.px), C.byref(self.pz), a, C.c_int(self.action_mode), C.c_double(self.wheel_dist),
+                       self.env5, C.c_int(self.frame_skip), C.c_double(self.dt), C.c_int(self.max_steps),
+                       C.c_double(self.robot_speed), C.byref(o))
+        return o
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
