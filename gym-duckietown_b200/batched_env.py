@@ -1,0 +1,146 @@
+"""BatchedDuckietownEnv — N independent Duckietown agents per GPU behind the reference's reset/step API.
+
+`step(actions)` is `Simulator.step()` (simulator.py:1669-1683) for every env at once: the action and
+observation buffers are caller-visible torch CUDA tensors, the work runs on
+`torch.cuda.current_stream()` inside libdtsim.so, nothing synchronises.  Constructor keywords are the
+reference's (simulator.py:207-232, envs/duckietown_env.py:15) plus `num_envs`, `device`,
+`auto_reset`, `device_reset`.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .episode import EpisodeSampler
+from .maps import MapData, load_map
+
+
+class BatchedDuckietownEnv:
+    def __init__(self, num_envs: int, map_name: Union[str, Sequence[str]] = "udem1", *, device: int = 0,
+                 max_steps: int = 1500, domain_rand: bool = True, frame_rate: float = 30, frame_skip: int = 1,
+                 camera_width: int = 640, camera_height: int = 480, robot_speed: float = 1.2,
+                 accept_start_angle_deg: float = 60, user_tile_start=None, seed: Optional[int] = None,
+                 distortion: bool = False, dynamics_rand: bool = False, camera_rand: bool = False,
+                 color_ground=(0.15, 0.15, 0.15), color_sky=(0.45, 0.82, 1), num_tris_distractors: int = 12,
+                 gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
+                 action_mode: str = "vel_steer", auto_reset: bool = False, device_reset: bool = False,
+                 cycle_maps: bool = False, env_id_offset: int = 0):
+        if not torch.cuda.is_available():
+            raise L.DtsError("BatchedDuckietownEnv needs a CUDA device; there is no CPU implementation")
+        if camera_rand:
+            raise NotImplementedError("camera_rand needs carnivalmirror (distortion.py:58-83); out of scope")
+        names = [map_name] if isinstance(map_name, str) else list(map_name)
+        self.maps: List[MapData] = [load_map(n) for n in names]
+        self.num_envs, self.device_index = num_envs, device
+        self.device = torch.device("cuda", device)
+        self.camera_width, self.camera_height = camera_width, camera_height
+        self.max_steps, self.domain_rand, self.distortion = max_steps, domain_rand, distortion
+        self.frame_rate, self.delta_time, self.frame_skip = frame_rate, 1.0 / frame_rate, frame_skip
+        self.robot_speed = robot_speed
+        self.auto_reset, self.device_reset, self.cycle_maps = auto_reset, device_reset, cycle_maps
+        if auto_reset and not device_reset:
+            raise ValueError("auto_reset re-spawns on the device: pass device_reset=True")
+        flags = (L.FLAG_AUTO_RESET if auto_reset else 0) | (L.FLAG_DOMAIN_RAND if domain_rand else 0) | \
+                (L.FLAG_DISTORTION if distortion else 0) | (L.FLAG_DYNAMICS_RAND if dynamics_rand else 0)
+        self.cfg = L.default_config(
+            num_envs=num_envs, device=device, cam_width=camera_width, cam_height=camera_height, max_steps=max_steps,
+            frame_skip=int(frame_skip), action_mode=L.ACTION_VEL_STEER if action_mode == "vel_steer" else L.ACTION_PWM,
+            flags=flags, max_maps=len(self.maps), cycle_maps=len(self.maps) if cycle_maps else 0,
+            frame_rate=float(frame_rate), robot_speed=robot_speed, accept_start_angle_deg=float(accept_start_angle_deg),
+            gain=gain, trim=trim, radius=radius, k=k, limit=limit, seed=0 if seed is None else int(seed),
+            env_id_offset=env_id_offset)
+        self.sim = L.Sim(self.cfg)
+        for i, md in enumerate(self.maps):
+            self.sim.upload_map(i, md)
+        if distortion:
+            from .distortion import Distortion
+            self.camera_model = Distortion(camera_width, camera_height)
+            self.sim.set_fisheye_lut(self.camera_model.rmapx, self.camera_model.rmapy)
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((num_envs, camera_height, camera_width, 3), dtype=torch.uint8, device=self.device)
+            self.reward = torch.zeros(num_envs, dtype=torch.float32, device=self.device)
+            self._done_u8 = torch.zeros(num_envs, dtype=torch.uint8, device=self.device)
+            self.state: Dict[str, torch.Tensor] = {
+                k_: torch.as_tensor(v, device=self.device) for k_, v in self.sim.state_arrays().items()}
+        self.sampler = EpisodeSampler(
+            num_envs, domain_rand=domain_rand, dynamics_rand=dynamics_rand, accept_start_angle_deg=accept_start_angle_deg,
+            num_tris_distractors=num_tris_distractors, color_ground=color_ground, color_sky=color_sky,
+            user_tile_start=user_tile_start)
+        self.map_ids = np.zeros(num_envs, np.int32)
+        self._first_reset = True
+        self.seed(seed)
+
+    # ------------------------------------------------------------------ gym-like surface
+    def seed(self, seed=None):
+        """Env k gets seed+k (global index), like one reference env per seed (S:1043-1045)."""
+        off = self.cfg.env_id_offset
+        seeds = [None if seed is None else int(seed) + off + k for k in range(self.num_envs)]
+        self.sampler.seed(seeds)
+        return seeds
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask: Optional[torch.Tensor] = None, render: bool = True) -> torch.Tensor:
+        """Simulator.reset() (S:528-763) for the masked envs (all if None); returns the obs batch."""
+        mask_ptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mask_ptr = mask.data_ptr()
+        if self.device_reset:
+            self.sim.reset_random(mask_ptr, self._stream())
+        else:
+            envs = list(range(self.num_envs)) if mask is None else torch.nonzero(mask).flatten().tolist()
+            if envs:
+                if self.cycle_maps and not self._first_reset:  # MultiMapEnv.reset, envs/multimap_env.py:46
+                    self.map_ids[envs] = (self.map_ids[envs] + 1) % len(self.maps)
+                dense = self.sampler.sample(envs, [self.maps[self.map_ids[e]] for e in envs], self._query_for(envs))
+                params = {}
+                for key, val in dense.items():
+                    full = np.zeros((self.num_envs,) + val.shape[1:], val.dtype)
+                    full[envs] = val
+                    params[key] = full
+                params["map_id"] = self.map_ids.copy()
+                self.sim.reset(mask_ptr, params, self._stream())
+        self._first_reset = False
+        if render:
+            self.sim.render(self.obs.data_ptr(), self._stream())
+        return self.obs
+
+    def _query_for(self, envs):
+        def query(k, x, z, a, safety, hidden):
+            return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden)
+        return query
+
+    def step(self, actions: torch.Tensor, render: bool = True):
+        """actions f32[N,2] on this device: [vel, steering] (DuckietownEnv.step) or wheel duty
+        (Simulator.step) depending on action_mode.  Returns (obs u8[N,H,W,3], reward f32[N], done bool[N], info)."""
+        if actions.device != self.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
+            raise ValueError("actions must be a float32 CUDA tensor of shape [num_envs, 2] on the env's device")
+        actions = actions.contiguous()
+        self.sim.step(actions.data_ptr(), self.obs.data_ptr() if render else None, self.reward.data_ptr(),
+                      self._done_u8.data_ptr(), self._stream())
+        return self.obs, self.reward, self._done_u8.view(torch.bool), self.state
+
+    def render_obs(self) -> torch.Tensor:
+        self.sim.render(self.obs.data_ptr(), self._stream())
+        return self.obs
+
+    # convenience views --------------------------------------------------------------------------
+    @property
+    def cur_pos(self) -> torch.Tensor:
+        s = self.state
+        return torch.stack([s["pos_x"], torch.zeros_like(s["pos_x"]), s["pos_z"]], dim=1)
+
+    @property
+    def cur_angle(self) -> torch.Tensor:
+        return self.state["angle"]
+
+    def launch_count(self) -> int:
+        return self.sim.launch_count()
+
+    def close(self):
+        self.sim.close()

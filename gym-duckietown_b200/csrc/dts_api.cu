@@ -1,0 +1,425 @@
+// dts_api.cu — the C ABI of libdtsim.so (include/dtsim.h): handle management, host->device
+// staging of maps and episode parameters, and stream-ordered launches of the kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "dts_kernels.h"
+
+using namespace dts;
+
+namespace {
+thread_local std::string g_create_error;
+
+#define DTS_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return sim->fail("%s failed: %s", #expr, cudaGetErrorString(_e));     \
+  } while (0)
+}  // namespace
+
+struct dts_sim {
+  dts_config cfg;
+  StepCfg step_cfg;
+  DState S;
+  std::vector<void*> allocs;           // freed in dts_destroy
+  std::vector<std::vector<void*>> map_allocs;
+  std::vector<DMap> h_maps;
+  DMap* d_maps = nullptr;
+  // reset staging (device) sized num_envs
+  struct { int32_t* map_id; double *pos_x, *pos_z, *angle, *wheel_dist, *trim; float *f1[3]; float *f3[5];
+           float* light_pos; int32_t* light_stale; uint32_t* hidden; } stage{};
+  // render
+  void* render_scratch = nullptr;
+  int render_ctas = 0, max_prims = 0, max_pairs = 0;
+  float *lut_x = nullptr, *lut_y = nullptr;
+  int32_t* d_err = nullptr;
+  // query scratch
+  double* q_in = nullptr; double* q_outd = nullptr; int32_t* q_outi = nullptr; uint32_t* q_hidden = nullptr; int q_cap = 0;
+  // nccl (dlopen'ed)
+  void* nccl_lib = nullptr; void* nccl_comm = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+
+  int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return 1;
+  }
+  template <typename T> int dalloc(T** p, size_t count, std::vector<void*>* owner = nullptr) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu B) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaMemset(q, 0, count * sizeof(T) + 16);
+    (owner ? *owner : allocs).push_back(q);
+    *p = (T*)q;
+    return 0;
+  }
+  template <typename T> int upload(const T** dst, const T* src, size_t count, std::vector<void*>* owner) {
+    T* d = nullptr;
+    if (dalloc(&d, count ? count : 1, owner)) return 1;
+    if (count && src) {
+      cudaError_t e = cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return fail("cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+    }
+    *dst = d;
+    return 0;
+  }
+};
+
+extern "C" {
+
+const char* dts_last_error(dts_sim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int dts_create(const dts_config* cfg, dts_sim** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+  if (cfg->abi_version != DTS_ABI_VERSION) { g_create_error = "dts_config.abi_version mismatch"; return 1; }
+  if (cfg->num_envs <= 0 || cfg->cam_width <= 0 || cfg->cam_height <= 0 || cfg->max_maps <= 0) {
+    g_create_error = "num_envs, cam_width, cam_height and max_maps must be positive";
+    return 1;
+  }
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e); return 1; }
+  dts_sim* sim = new dts_sim();
+  sim->cfg = *cfg;
+  const int n = cfg->num_envs;
+  StepCfg& c = sim->step_cfg;
+  c.dt = 1.0 / cfg->frame_rate;                       // S:300
+  c.robot_speed = cfg->robot_speed;
+  c.accept_angle_deg = cfg->accept_start_angle_deg;
+  c.gain = cfg->gain; c.trim = cfg->trim; c.radius = cfg->radius; c.k = cfg->k; c.limit = cfg->limit;
+  c.dyn = DynParams{cfg->dyn_u1, cfg->dyn_u2, cfg->dyn_u3, cfg->dyn_w1, cfg->dyn_w2, cfg->dyn_w3,
+                    cfg->dyn_uar, cfg->dyn_ual, cfg->dyn_war, cfg->dyn_wal, 0};
+  // a command issued at t acts on integration intervals starting at or after t + delay
+  int d = 0;
+  while (d * c.dt < cfg->dyn_delay - 1e-12) d++;
+  if (d > DTS_MAX_DELAY) { g_create_error = "dyn_delay exceeds DTS_MAX_DELAY steps"; delete sim; return 1; }
+  c.dyn.delay_steps = d;
+  c.frame_skip = cfg->frame_skip; c.max_steps = cfg->max_steps; c.action_mode = cfg->action_mode; c.flags = cfg->flags;
+  c.seed = cfg->seed; c.env_id_offset = cfg->env_id_offset;
+  DState& S = sim->S;
+  S.n = n;
+  int bad = 0;
+  double** dbl[] = {&S.cx, &S.cy, &S.ctheta, &S.vu, &S.vw, &S.pos_x, &S.pos_z, &S.angle, &S.speed, &S.reward,
+                    &S.lane_dist, &S.lane_dot, &S.lane_angle, &S.prox, &S.wheel_dist, &S.trim};
+  for (auto p : dbl) bad |= sim->dalloc(p, n);
+  bad |= sim->dalloc(&S.fifo, (size_t)DTS_MAX_DELAY * 2 * n);
+  int32_t** i32[] = {&S.step_count, &S.tile_i, &S.tile_j, &S.map_id, &S.episode};
+  for (auto p : i32) bad |= sim->dalloc(p, n);
+  uint8_t** u8[] = {&S.done_code, &S.in_lane, &S.collided};
+  for (auto p : u8) bad |= sim->dalloc(p, n);
+  bad |= sim->dalloc(&S.rng, n);
+  bad |= sim->dalloc(&S.rep, n);
+  bad |= sim->dalloc(&sim->d_maps, cfg->max_maps);
+  bad |= sim->dalloc(&sim->d_err, 4);
+  auto& st = sim->stage;
+  bad |= sim->dalloc(&st.map_id, n);
+  double** sd[] = {&st.pos_x, &st.pos_z, &st.angle, &st.wheel_dist, &st.trim};
+  for (auto p : sd) bad |= sim->dalloc(p, n);
+  for (auto& p : st.f1) bad |= sim->dalloc(&p, n);
+  for (auto& p : st.f3) bad |= sim->dalloc(&p, 3 * (size_t)n);
+  bad |= sim->dalloc(&st.light_pos, 4 * (size_t)n);
+  bad |= sim->dalloc(&st.light_stale, n);
+  bad |= sim->dalloc(&st.hidden, 8 * (size_t)n);
+  if (bad) { g_create_error = sim->err; dts_destroy(sim); return 1; }
+  sim->h_maps.assign(cfg->max_maps, DMap{});
+  sim->map_allocs.resize(cfg->max_maps);
+  *out = sim;
+  return 0;
+}
+
+void dts_destroy(dts_sim* sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : sim->allocs) cudaFree(p);
+  for (auto& v : sim->map_allocs) for (void* p : v) cudaFree(p);
+  void* extra[] = {sim->render_scratch, sim->lut_x, sim->lut_y, sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
+  for (void* p : extra) if (p) cudaFree(p);
+  delete sim;
+}
+
+int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
+  if (!sim) return 1;
+  if (!b || map_id < 0 || map_id >= sim->cfg.max_maps) return sim->fail("bad map_id %d", map_id);
+  if (b->n_objects > DTS_MAX_OBJECTS) return sim->fail("map has %d objects, limit %d", b->n_objects, DTS_MAX_OBJECTS);
+  if (b->grid_w <= 0 || b->grid_h <= 0 || !(b->tile_size > 0)) return sim->fail("invalid tile grid");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  DTS_CUDA(cudaDeviceSynchronize());
+  auto& own = sim->map_allocs[map_id];
+  for (void* p : own) cudaFree(p);
+  own.clear();
+  DMap m{};
+  const size_t T = (size_t)b->grid_w * b->grid_h;
+  m.tile_size = b->tile_size; m.grid_w = b->grid_w; m.grid_h = b->grid_h; m.n_tiles = (int)T;
+  int bad = 0;
+  bad |= sim->upload(&m.tile_kind, b->tile_kind, T, &own);
+  bad |= sim->upload(&m.tile_angle, b->tile_angle, T, &own);
+  bad |= sim->upload(&m.tile_drivable, b->tile_drivable, T, &own);
+  bad |= sim->upload(&m.tile_tex, b->tile_tex, T, &own);
+  bad |= sim->upload(&m.tile_curve_off, b->tile_curve_off, T, &own);
+  bad |= sim->upload(&m.tile_curve_cnt, b->tile_curve_cnt, T, &own);
+  bad |= sim->upload(&m.curves, b->curves, (size_t)b->n_curves * 12, &own);
+  m.n_coll = b->n_coll;
+  bad |= sim->upload(&m.coll_corners, b->coll_corners, (size_t)b->n_coll * 8, &own);
+  bad |= sim->upload(&m.coll_norms, b->coll_norms, (size_t)b->n_coll * 4, &own);
+  bad |= sim->upload(&m.coll_centers, b->coll_centers, (size_t)b->n_coll * 3, &own);
+  bad |= sim->upload(&m.coll_radii, b->coll_radii, (size_t)b->n_coll, &own);
+  std::vector<int32_t> drv;
+  for (int j = 0; j < b->grid_h; j++)       // reference scan order S:810-860
+    for (int i = 0; i < b->grid_w; i++)
+      if (b->tile_kind[j * b->grid_w + i] >= 0 && b->tile_drivable[j * b->grid_w + i]) { drv.push_back(i); drv.push_back(j); }
+  m.n_drivable = (int)drv.size() / 2;
+  bad |= sim->upload(&m.drivable_ij, drv.data(), drv.size(), &own);
+  // objects: add spawn radius (S:1467) and a bounding sphere per placed mesh
+  std::vector<DObject> objs(b->n_objects);
+  for (int o = 0; o < b->n_objects; o++) {
+    const dts_object& s = b->objects[o];
+    if (s.mesh_id < 0 || s.mesh_id >= b->n_meshes) return sim->fail("object %d: bad mesh_id", o);
+    const dts_mesh& me = b->meshes[s.mesh_id];
+    DObject& d = objs[o];
+    memcpy(d.pos, s.pos, sizeof d.pos);
+    d.scale = s.scale; d.y_rot_deg = s.y_rot_deg; d.mesh_id = s.mesh_id; d.optional = s.optional;
+    d.tri_offset = me.tri_offset; d.tri_count = me.tri_count;
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int t = 0; t < me.tri_count * 3; t++)
+      for (int k = 0; k < 3; k++) {
+        const float v = b->tri_pos[((size_t)me.tri_offset * 3 + t) * 3 + k];
+        lo[k] = v < lo[k] ? v : lo[k];
+        hi[k] = v > hi[k] ? v : hi[k];
+      }
+    float mx = hi[0] > hi[1] ? hi[0] : hi[1];
+    mx = mx > hi[2] ? mx : hi[2];
+    d.spawn_rad = mx * 0.5f * s.scale + 0.25f;     // MIN_SPAWN_OBJ_DIST S:156
+    float r2 = 0.f;
+    for (int k = 0; k < 3; k++) { d.centre[k] = 0.5f * (lo[k] + hi[k]); const float h = 0.5f * (hi[k] - lo[k]); r2 += h * h; }
+    d.bound_rad = sqrtf(r2);
+  }
+  m.n_objects = b->n_objects;
+  bad |= sim->upload(&m.objects, objs.data(), objs.size(), &own);
+  m.n_tris = b->n_tris;
+  bad |= sim->upload(&m.tri_pos, b->tri_pos, (size_t)b->n_tris * 9, &own);
+  bad |= sim->upload(&m.tri_nrm, b->tri_nrm, (size_t)b->n_tris * 9, &own);
+  bad |= sim->upload(&m.tri_uv, b->tri_uv, (size_t)b->n_tris * 6, &own);
+  bad |= sim->upload(&m.tri_col, b->tri_col, (size_t)b->n_tris * 9, &own);
+  bad |= sim->upload(&m.tri_tex, b->tri_tex, (size_t)b->n_tris, &own);
+  std::vector<DTexture> tex(b->n_textures);
+  for (int t = 0; t < b->n_textures; t++) {
+    const dts_texture& s = b->textures[t];
+    if (s.width <= 0 || s.height <= 0 || (s.width & (s.width - 1)) || (s.height & (s.height - 1)))
+      return sim->fail("texture %d: %dx%d is not a power of two", t, s.width, s.height);
+    tex[t].w = s.width; tex[t].h = s.height;
+    bad |= sim->upload(&tex[t].rgba, s.rgba, (size_t)s.width * s.height * 4, &own);
+  }
+  m.n_textures = b->n_textures;
+  bad |= sim->upload(&m.textures, tex.data(), tex.size(), &own);
+  if (bad) return 1;
+  m.valid = 1;
+  sim->h_maps[map_id] = m;
+  DTS_CUDA(cudaMemcpy(sim->d_maps + map_id, &m, sizeof(DMap), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, int width, int height) {
+  if (!sim) return 1;
+  if (width != sim->cfg.cam_width || height != sim->cfg.cam_height)
+    return sim->fail("fisheye LUT is %dx%d but the camera is %dx%d", width, height, sim->cfg.cam_width, sim->cfg.cam_height);
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  const size_t n = (size_t)width * height;
+  if (!sim->lut_x) { DTS_CUDA(cudaMalloc(&sim->lut_x, n * 4)); DTS_CUDA(cudaMalloc(&sim->lut_y, n * 4)); }
+  DTS_CUDA(cudaMemcpy(sim->lut_x, rmapx, n * 4, cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(sim->lut_y, rmapy, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int check_maps(dts_sim* sim) {
+  if (!sim->h_maps[0].valid) return sim->fail("no map uploaded in slot 0");
+  const int cyc = sim->cfg.cycle_maps;
+  for (int k = 0; k < cyc; k++)
+    if (k >= sim->cfg.max_maps || !sim->h_maps[k].valid) return sim->fail("cycle_maps=%d but slot %d is empty", cyc, k);
+  return 0;
+}
+
+int dts_reset(dts_sim* sim, const uint8_t* mask_dev, const dts_episode_params* p, void* stream) {
+  if (!sim) return 1;
+  if (check_maps(sim)) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = sim->cfg.num_envs;
+  ResetStaging rs{};
+  auto& sg = sim->stage;
+  dts_episode_params z{};
+  if (!p) p = &z;
+  if (p->map_id) {
+    for (size_t e = 0; e < n; e++)
+      if (p->map_id[e] < 0 || p->map_id[e] >= sim->cfg.max_maps || !sim->h_maps[p->map_id[e]].valid)
+        return sim->fail("episode map_id[%zu]=%d has no uploaded map", e, p->map_id[e]);
+  }
+#define STAGE(field, dst, cnt)                                                                         \
+  if (p->field) { DTS_CUDA(cudaMemcpyAsync(dst, p->field, (cnt) * sizeof(*p->field), cudaMemcpyHostToDevice, st)); rs.field = dst; }
+  STAGE(map_id, sg.map_id, n)
+  STAGE(pos_x, sg.pos_x, n) STAGE(pos_z, sg.pos_z, n) STAGE(angle, sg.angle, n)
+  STAGE(wheel_dist, sg.wheel_dist, n) STAGE(trim, sg.trim, n)
+  STAGE(cam_height, sg.f1[0], n) STAGE(cam_angle_deg, sg.f1[1], n) STAGE(cam_fov_y_deg, sg.f1[2], n)
+  STAGE(cam_noise, sg.f3[0], 3 * n) STAGE(horizon_color, sg.f3[1], 3 * n) STAGE(light_ambient, sg.f3[2], 3 * n)
+  STAGE(light_diffuse, sg.f3[3], 3 * n) STAGE(ground_color, sg.f3[4], 3 * n)
+  STAGE(light_pos, sg.light_pos, 4 * n) STAGE(light_stale, sg.light_stale, n) STAGE(obj_hidden, sg.hidden, 8 * n)
+#undef STAGE
+  launch_reset_params(sim->S, sim->d_maps, sim->step_cfg, mask_dev, rs, st);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  // the staging buffers are pageable-host copies: make them safe to reuse before returning
+  DTS_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream) {
+  if (!sim) return 1;
+  if (check_maps(sim)) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  launch_reset_random(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, mask_dev, (cudaStream_t)stream);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_render(dts_sim* sim) {
+  if (sim->render_scratch) return 0;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sim->cfg.device);
+  int max_tris = 2;
+  for (const DMap& m : sim->h_maps) {
+    if (!m.valid) continue;
+    int t = 2;
+    for (int k = 0; k < m.n_tiles; k++) t += 98;  // upper bound (every cell has a tile)
+    // object triangles
+    std::vector<DObject> objs(m.n_objects);
+    if (m.n_objects) cudaMemcpy(objs.data(), m.objects, sizeof(DObject) * m.n_objects, cudaMemcpyDeviceToHost);
+    for (const DObject& o : objs) t += o.tri_count;
+    max_tris = t > max_tris ? t : max_tris;
+  }
+  sim->render_ctas = sms * 2 < sim->cfg.num_envs ? sms * 2 : sim->cfg.num_envs;
+  sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
+  const int bins = ((sim->cfg.cam_width + 15) / 16) * ((sim->cfg.cam_height + 15) / 16);
+  sim->max_pairs = sim->max_prims * 6 + bins * 8;
+  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs);
+  cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
+  if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
+  if (!sim) return 1;
+  if (!obs_dev) return sim->fail("obs_dev is NULL");
+  if (check_maps(sim)) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  if (ensure_render(sim)) return 1;
+  if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->lut_x) return sim->fail("distortion enabled but no fisheye LUT set");
+  RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs};
+  const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
+                              sim->max_pairs, sim->lut_x, sim->lut_y, sim->d_err, (cudaStream_t)stream);
+  sim->launches += k;
+  DTS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* reward_dev, uint8_t* done_dev,
+             void* stream) {
+  if (!sim) return 1;
+  if (!actions_dev) return sim->fail("actions_dev is NULL");
+  if (check_maps(sim)) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  launch_step_logic(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, actions_dev, reward_dev, done_dev,
+                    (cudaStream_t)stream);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  if (obs_dev) return dts_render(sim, obs_dev, stream);
+  return 0;
+}
+
+int dts_get_state(dts_sim* sim, dts_state_view* v) {
+  if (!sim || !v) return 1;
+  const DState& S = sim->S;
+  *v = dts_state_view{S.pos_x, S.pos_z, S.angle, S.speed, S.reward, S.lane_dist, S.lane_dot, S.lane_angle, S.prox,
+                      S.wheel_dist, S.step_count, S.tile_i, S.tile_j, S.map_id, S.episode, S.done_code, S.in_lane,
+                      S.collided};
+  return 0;
+}
+
+int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const uint32_t* hidden, double* out_f64,
+                    int32_t* out_i32) {
+  if (!sim) return 1;
+  if (map_id < 0 || map_id >= sim->cfg.max_maps || !sim->h_maps[map_id].valid) return sim->fail("bad map_id %d", map_id);
+  if (n <= 0) return 0;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  if (n > sim->q_cap) {
+    void* old[] = {sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
+    for (void* p : old) if (p) cudaFree(p);
+    sim->q_cap = n;
+    DTS_CUDA(cudaMalloc(&sim->q_in, (size_t)n * 32));
+    DTS_CUDA(cudaMalloc(&sim->q_outd, (size_t)n * 32));
+    DTS_CUDA(cudaMalloc(&sim->q_outi, (size_t)n * 32));
+    DTS_CUDA(cudaMalloc(&sim->q_hidden, (size_t)n * 32));
+  }
+  DTS_CUDA(cudaMemcpy(sim->q_in, query, (size_t)n * 32, cudaMemcpyHostToDevice));
+  if (hidden) DTS_CUDA(cudaMemcpy(sim->q_hidden, hidden, (size_t)n * 32, cudaMemcpyHostToDevice));
+  launch_query(sim->d_maps, map_id, n, sim->q_in, hidden ? sim->q_hidden : nullptr, sim->q_outd, sim->q_outi, 0);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  DTS_CUDA(cudaMemcpy(out_f64, sim->q_outd, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  DTS_CUDA(cudaMemcpy(out_i32, sim->q_outi, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+uint64_t dts_launch_count(dts_sim* sim) { return sim ? sim->launches : 0; }
+
+// ---- multi-GPU: one NCCL all-gather of the end-of-rollout observation batch ----------
+// libnccl is dlopen'ed (the torch-bundled copy); the communicator is created from a unique id that
+// the Python side broadcasts with torch.distributed.
+
+int dts_comm_load(dts_sim* sim, const char* libnccl_path) {
+  if (!sim) return 1;
+  if (sim->nccl_lib) return 0;
+  sim->nccl_lib = dlopen(libnccl_path, RTLD_NOW | RTLD_GLOBAL);
+  if (!sim->nccl_lib) return sim->fail("dlopen(%s) failed: %s", libnccl_path, dlerror());
+  return 0;
+}
+
+int dts_comm_unique_id(dts_sim* sim, uint8_t out[128]) {
+  if (!sim || !sim->nccl_lib) return sim ? sim->fail("dts_comm_load first") : 1;
+  auto f = (int (*)(void*))dlsym(sim->nccl_lib, "ncclGetUniqueId");
+  if (!f) return sim->fail("ncclGetUniqueId not found");
+  const int r = f(out);
+  return r ? sim->fail("ncclGetUniqueId -> %d", r) : 0;
+}
+
+struct nccl_uid { char b[128]; };
+
+int dts_comm_init(dts_sim* sim, const uint8_t id[128], int rank, int world) {
+  if (!sim || !sim->nccl_lib) return sim ? sim->fail("dts_comm_load first") : 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  auto f = (int (*)(void**, int, nccl_uid, int))dlsym(sim->nccl_lib, "ncclCommInitRank");
+  if (!f) return sim->fail("ncclCommInitRank not found");
+  nccl_uid u;
+  memcpy(u.b, id, 128);
+  const int r = f(&sim->nccl_comm, world, u, rank);
+  return r ? sim->fail("ncclCommInitRank -> %d", r) : 0;
+}
+
+int dts_allgather_obs(dts_sim* sim, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank, void* stream) {
+  if (!sim || !sim->nccl_comm) return sim ? sim->fail("dts_comm_init first") : 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  auto f = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(sim->nccl_lib, "ncclAllGather");
+  if (!f) return sim->fail("ncclAllGather not found");
+  const int r = f(send_dev, recv_dev, (size_t)bytes_per_rank, /*ncclUint8*/ 1, sim->nccl_comm, (cudaStream_t)stream);
+  return r ? sim->fail("ncclAllGather -> %d", r) : 0;
+}
+
+}  // extern "C"

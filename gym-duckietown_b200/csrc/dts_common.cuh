@@ -1,0 +1,97 @@
+// dts_common.cuh — device-side data layout shared by the dtsim kernels (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/dtsim.h"
+
+namespace dts {
+
+// ------------------------------------------------------------------ map data resident in HBM
+// One DMap per uploaded map; all pointers are device memory owned by the handle.  Read-only on
+// the hot path and shared by every env, so it lives in L2 after the first touch.
+struct DObject {
+  float pos[3];
+  float scale;
+  float y_rot_deg;
+  int32_t mesh_id;
+  int32_t optional;
+  float spawn_rad;   // max(max_coords)*0.5*scale + MIN_SPAWN_OBJ_DIST   (simulator.py:1467)
+  int32_t tri_offset, tri_count;
+  float bound_rad;   // object-space bounding radius (culling)
+  float centre[3];   // object-space bounding-sphere centre
+};
+
+struct DTexture { const uint8_t* rgba; int32_t w, h; };
+
+struct DMap {
+  double tile_size;
+  int32_t grid_w, grid_h;
+  int32_t n_tiles;              // grid_w * grid_h
+  const int8_t* tile_kind;
+  const int8_t* tile_angle;
+  const uint8_t* tile_drivable;
+  const int16_t* tile_tex;
+  const int32_t* tile_curve_off;
+  const int32_t* tile_curve_cnt;
+  const double* curves;         // [n][4][3]
+  int32_t n_coll;
+  const double* coll_corners;   // [K][2][4]
+  const double* coll_norms;     // [K][2][2]
+  const double* coll_centers;   // [K][3]
+  const double* coll_radii;     // [K]
+  int32_t n_drivable;
+  const int32_t* drivable_ij;   // [n_drivable][2] in reference scan order (S:806-860)
+  int32_t n_objects;
+  const DObject* objects;
+  int32_t n_tris;
+  const float* tri_pos;         // [T][3][3]
+  const float* tri_nrm;
+  const float* tri_uv;          // [T][3][2]
+  const float* tri_col;         // [T][3][3]
+  const int16_t* tri_tex;
+  int32_t n_textures;
+  const DTexture* textures;
+  int32_t valid;
+};
+
+// ------------------------------------------------------------------ per-env state, SoA in HBM
+// One thread per env in the logic kernels: consecutive threads touch consecutive doubles.
+struct DState {
+  int32_t n;
+  // dynamics (cartesian frame of duckietown_world: x right, y up; S:1629-1652)
+  double *cx, *cy, *ctheta, *vu, *vw;
+  double* fifo;          // [DTS_MAX_DELAY][2][n]  pending (left,right) duty, slot 0 = oldest
+  // simulator-frame pose and per-step outputs
+  double *pos_x, *pos_z, *angle, *speed, *reward, *lane_dist, *lane_dot, *lane_angle, *prox;
+  double *wheel_dist, *trim;
+  int32_t *step_count, *tile_i, *tile_j, *map_id, *episode;
+  uint8_t *done_code, *in_lane, *collided;
+  uint64_t* rng;         // counter of the device-side stream
+  struct RenderEp* rep;  // [n] per-episode render parameters (AoS: one CTA reads one record)
+};
+
+// Per-episode render inputs (simulator.py:546-614, 1768): 128 bytes, read by one CTA per frame.
+struct __align__(16) RenderEp {
+  float cam_height, cam_angle_deg, cam_fov_y_deg, pad0;
+  float cam_noise[3]; float pad1;
+  float horizon[3]; float pad2;
+  float ambient[3]; float pad3;       // GL_LIGHT0 ambient
+  float diffuse[3]; float pad4;       // GL_LIGHT0 diffuse
+  float light_eye[4];                 // GL_POSITION as stored by GL: already in eye space
+  float ground[3]; float pad5;
+  uint32_t hidden[8];                 // bit o = object o invisible
+};
+
+struct DynParams { double u1, u2, u3, w1, w2, w3, uar, ual, war, wal; int32_t delay_steps; };
+
+struct StepCfg {
+  double dt, robot_speed, accept_angle_deg;
+  double gain, trim, radius, k, limit;
+  DynParams dyn;
+  int32_t frame_skip, max_steps, action_mode, flags;
+  uint64_t seed;
+  int64_t env_id_offset;
+};
+
+}  // namespace dts

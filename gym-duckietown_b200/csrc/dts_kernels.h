@@ -1,0 +1,40 @@
+// dts_kernels.h — host-callable launchers of the dtsim kernels.
+#pragma once
+#include "dts_common.cuh"
+
+namespace dts {
+
+// Device copies of a dts_episode_params (NULL members keep defaults).
+struct ResetStaging {
+  const int32_t* map_id;
+  const double *pos_x, *pos_z, *angle, *wheel_dist, *trim;
+  const float *cam_height, *cam_angle_deg, *cam_fov_y_deg, *cam_noise, *horizon_color, *light_ambient,
+      *light_diffuse, *light_pos;
+  const int32_t* light_stale;
+  const float* ground_color;
+  const uint32_t* obj_hidden;
+};
+
+struct RenderCfg {
+  int32_t width, height;      // output obs size
+  int32_t flags;
+  int32_t n_envs;
+};
+
+void launch_step_logic(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const float* actions,
+                       float* reward, uint8_t* done, cudaStream_t st);
+void launch_reset_random(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const uint8_t* mask,
+                         cudaStream_t st);
+void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, const uint8_t* mask,
+                         const ResetStaging& p, cudaStream_t st);
+void launch_query(const DMap* maps, int map_id, int n, const double* q, const uint32_t* hidden, double* outd,
+                  int32_t* outi, cudaStream_t st);
+
+// render (dts_render.cu)
+struct RenderScratch;
+size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs);
+int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
+                  int max_prims, int max_pairs, const float* lut_x, const float* lut_y, int32_t* err_flag,
+                  cudaStream_t st);
+
+}  // namespace dts

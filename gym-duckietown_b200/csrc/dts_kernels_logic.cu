@@ -1,0 +1,268 @@
+// dts_kernels_logic.cu — one thread per env: Simulator.step() minus rendering, resets, pose queries.
+// HBM traffic per env-step: ~30 doubles read + ~20 written (SoA, coalesced); the map (grid, curves,
+// OBBs) is a few KB shared by all envs and stays in L1/L2.  Latency-bound, reported as us/launch.
+#include "dts_camera.cuh"
+#include "dts_kernels.h"
+#include "dts_logic.cuh"
+
+namespace dts {
+
+__device__ __forceinline__ void default_render_ep(RenderEp& r) {
+  r.cam_height = 0.108f; r.cam_angle_deg = 19.15f; r.cam_fov_y_deg = 75.0f; r.pad0 = 0;   // S:119-127
+  r.cam_noise[0] = r.cam_noise[1] = r.cam_noise[2] = 0.f; r.pad1 = 0;
+  r.horizon[0] = 0.45f; r.horizon[1] = 0.82f; r.horizon[2] = 1.0f; r.pad2 = 0;             // BLUE_SKY S:108
+  r.ambient[0] = r.ambient[1] = r.ambient[2] = 0.25f; r.pad3 = 0;                          // 0.5*DIM S:573
+  r.diffuse[0] = r.diffuse[1] = r.diffuse[2] = 0.35f; r.pad4 = 0;                          // 0.7*DIM S:575
+  r.light_eye[0] = 0.f; r.light_eye[1] = 3.f; r.light_eye[2] = 0.f; r.light_eye[3] = 1.f;  // S:570, identity modelview
+  r.ground[0] = r.ground[1] = r.ground[2] = 0.15f; r.pad5 = 0;                             // S:228
+  for (int k = 0; k < 8; k++) r.hidden[k] = 0u;
+}
+
+// Fill the per-step outputs for the env's current pose: get_agent_info fields + _compute_done_reward S:1685-1705.
+__device__ inline void evaluate_pose(const DState& S, const DMap& m, const StepCfg& c, int e, double px, double pz,
+                                     double ang, int step_count, float* reward, uint8_t* done) {
+  int ti, tj;
+  tile_at(m, px, pz, ti, tj);
+  const LanePose lp = lane_pose(m, px, pz, ang);
+  const double pen = proximity_penalty(m, px, pz, ang);
+  bool hit;
+  const bool ok = valid_pose(m, px, pz, ang, 1.0, &hit);
+  double rew;
+  uint8_t code;
+  if (!ok) { rew = kRewardInvalidPose; code = DTS_INVALID_POSE; }
+  else if (step_count >= c.max_steps) { rew = 0.0; code = DTS_MAX_STEPS; }
+  else {
+    code = DTS_IN_PROGRESS;
+    rew = lp.in_lane ? (+1.0 * c.robot_speed * lp.dot_dir + -10 * fabs(lp.dist) + +40 * pen) : 40 * pen;  // S:1654-1667
+  }
+  S.tile_i[e] = ti; S.tile_j[e] = tj;
+  S.lane_dist[e] = lp.dist; S.lane_dot[e] = lp.dot_dir; S.lane_angle[e] = lp.angle_rad; S.in_lane[e] = lp.in_lane;
+  S.prox[e] = pen; S.collided[e] = hit; S.reward[e] = rew; S.done_code[e] = code;
+  if (reward) reward[e] = (float)rew;
+  if (done) done[e] = code != DTS_IN_PROGRESS;
+}
+
+__device__ inline void set_pose(const DState& S, const DMap& m, int e, double px, double pz, double ang) {
+  S.pos_x[e] = px; S.pos_z[e] = pz; S.angle[e] = ang;
+  S.cx[e] = px; S.cy[e] = m.grid_h * m.tile_size - pz; S.ctheta[e] = ang;   // cartesian_from_weird S:1629-1638
+  S.vu[e] = 0.0; S.vw[e] = 0.0;                                           // init_vel = 0 S:743
+  for (int k = 0; k < DTS_MAX_DELAY; k++) { S.fifo[(k * 2 + 0) * S.n + e] = 0.0; S.fifo[(k * 2 + 1) * S.n + e] = 0.0; }
+  S.step_count[e] = 0; S.speed[e] = 0.0;                                  // S:535-539
+}
+
+// Device-side Simulator.reset() (S:528-763): DR sampling + spawn rejection loop.  Draw ORDER follows
+// the reference; the stream itself is counter-based, not numpy's PCG64 (DESIGN.md "resets").
+__device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, int e) {
+  Stream rs{mix64(c.seed ^ mix64((uint64_t)(c.env_id_offset + e))), S.rng[e]};
+  const bool dr = (c.flags & DTS_FLAG_DOMAIN_RAND) != 0;
+  RenderEp old = S.rep[e];
+  double Vprev[12];
+  camera_view(S.pos_x[e], S.pos_z[e], S.angle[e], old, dr, Vprev);
+  const bool first = S.episode[e] == 0;
+  int mid = S.map_id[e];
+  if (n_maps_cycle > 0 && !first) mid = (mid + 1) % n_maps_cycle;   // MultiMapEnv.reset envs/multimap_env.py:44-49
+  S.map_id[e] = mid;
+  const DMap& m = maps[mid];
+  RenderEp r;
+  default_render_ep(r);
+  // Randomizer.randomize: keys in sorted order (randomizer.py:33,46) — drawn even when DR is off
+  const double cam_angle = rs.uniform(0.8, 1.2), cam_fov = rs.uniform(0.8, 1.2), cam_h = rs.uniform(0.92, 1.08);
+  double noise[3];
+  for (int k = 0; k < 3; k++) noise[k] = rs.uniform(-0.005, 0.005);
+  const int horz = rs.integer(4);
+  float lpos[4] = {0.f, 3.f, 0.f, 1.f};
+  const double l0 = rs.uniform(-150, 150), l1 = rs.uniform(170, 220), l2 = rs.uniform(-150, 150);
+  const double trim = 0.02 * rs.normal();
+  double wheel = 0.102;
+  if (dr) {
+    const float base[4][3] = {{0.45f, 0.82f, 1.0f}, {0.64f, 0.71f, 0.28f}, {0.15f, 0.15f, 0.15f}, {0.9f, 0.9f, 0.9f}};
+    const double hs = horz < 2 ? 0.1 : 0.4;                                   // S:551-560
+    for (int k = 0; k < 3; k++) r.horizon[k] = (float)(base[horz][k] * rs.uniform(1 - hs, 1 + hs));
+    lpos[0] = (float)l0; lpos[1] = (float)l1; lpos[2] = (float)l2; lpos[3] = 0.f;  // 3 floats into a 4-array: w = 0
+    double p4[4];
+    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(0.7, 1.3);                 // _perturb(ambient, 0.3) S:574
+    for (int k = 0; k < 3; k++) r.ambient[k] = (float)(0.25 * p4[k]);
+    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(0.01, 1.99);               // _perturb(diffuse, 0.99) S:576
+    for (int k = 0; k < 3; k++) r.diffuse[k] = (float)(0.35 * p4[k]);
+    for (int k = 0; k < 3; k++) r.ground[k] = (float)(0.15 * rs.uniform(0.7, 1.3));  // S:594
+    wheel = 0.102 * rs.uniform(0.9, 1.1);                                     // S:597
+    r.cam_height = (float)(0.108 * cam_h);                                    // S:612-614
+    r.cam_angle_deg = (float)(19.15 * cam_angle);
+    r.cam_fov_y_deg = (float)(75.0 * cam_fov);
+    for (int k = 0; k < 3; k++) r.cam_noise[k] = (float)noise[k];
+    // distractor triangles (S:621-631) and tile colours (S:645) have no visible effect:
+    // their draws are skipped on this stream.
+    for (int o = 0; o < m.n_objects; o++)
+      if (m.objects[o].optional && rs.integer(2) != 0) r.hidden[o >> 5] |= 1u << (o & 31);   // S:653-654
+  }
+  if (first) { for (int k = 0; k < 4; k++) r.light_eye[k] = lpos[k]; }       // identity modelview at first reset
+  else light_to_eye(Vprev, lpos, r.light_eye);                               // stale modelview S:581
+  S.wheel_dist[e] = wheel;
+  S.trim[e] = (c.flags & DTS_FLAG_DYNAMICS_RAND) ? trim : 0.0;               // S:746-750
+  // start tile S:659-676, spawn loop S:692-736
+  const int t = m.n_drivable > 0 ? rs.integer(m.n_drivable) : 0;
+  const int ti = m.n_drivable > 0 ? m.drivable_ij[2 * t] : 0, tj = m.n_drivable > 0 ? m.drivable_ij[2 * t + 1] : 0;
+  double px = 1.0, pz = 1.0, ang = 1.0;                                      // fallback S:735-736
+  for (int attempt = 0; attempt < kMaxSpawnAttempts && m.n_drivable > 0; attempt++) {
+    const double x = rs.uniform(ti, ti + 1) * m.tile_size, z = rs.uniform(tj, tj + 1) * m.tile_size;
+    const double a = rs.uniform(0, 6.283185307179586);
+    bool bad = false;                                                       // _inconvenient_spawn S:1461-1471
+    for (int o = 0; o < m.n_objects && !bad; o++) {
+      if (r.hidden[o >> 5] >> (o & 31) & 1u) continue;
+      const DObject& ob = m.objects[o];
+      const double dx = ob.pos[0] - x, dy = ob.pos[1], dz = ob.pos[2] - z;
+      bad = sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad;
+    }
+    if (bad) continue;
+    if (!valid_pose(m, x, z, a, 1.3, nullptr)) continue;
+    const LanePose lp = lane_pose(m, x, z, a);
+    if (!lp.in_lane) continue;
+    const double deg = lp.angle_rad * 57.29577951308232;
+    if (!(-c.accept_angle_deg < deg && deg < c.accept_angle_deg)) continue;
+    px = x; pz = z; ang = a;
+    break;
+  }
+  set_pose(S, m, e, px, pz, ang);
+  S.rep[e] = r;
+  S.rng[e] = rs.ctr;
+  S.episode[e] += 1;
+}
+
+__global__ void __launch_bounds__(128) k_step_logic(DState S, const DMap* __restrict__ maps, StepCfg c,
+                                                    int n_maps_cycle, const float* __restrict__ actions,
+                                                    float* __restrict__ reward, uint8_t* __restrict__ done) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.n) return;
+  const DMap& m = maps[S.map_id[e]];
+  const float2 act = reinterpret_cast<const float2*>(actions)[e];
+  double ul = (double)act.x, ur = (double)act.y;
+  if (c.action_mode == DTS_ACTION_VEL_STEER) action_to_pwm((double)act.x, (double)act.y, S.wheel_dist[e], c, ul, ur);
+  ul = clampd(ul, -1.0, 1.0);   // np.clip S:1670
+  ur = clampd(ur, -1.0, 1.0);
+  double x = S.cx[e], y = S.cy[e], th = S.ctheta[e], u = S.vu[e], w = S.vw[e];
+  double px = S.pos_x[e], pz = S.pos_z[e], ang = S.angle[e], speed = 0.0;
+  int steps = S.step_count[e];
+  const double trim = S.trim[e];
+  const int D = c.dyn.delay_steps;
+  for (int f = 0; f < c.frame_skip; f++) {   // update_physics S:1551-1568
+    double l = ul, r = ur;
+    if (D > 0) {  // delay line: the command issued now acts D steps later
+      l = S.fifo[0 * S.n + e]; r = S.fifo[1 * S.n + e];
+      for (int k = 0; k + 1 < D; k++) {
+        S.fifo[(2 * k) * S.n + e] = S.fifo[(2 * k + 2) * S.n + e];
+        S.fifo[(2 * k + 1) * S.n + e] = S.fifo[(2 * k + 3) * S.n + e];
+      }
+      S.fifo[(2 * (D - 1)) * S.n + e] = ul; S.fifo[(2 * (D - 1) + 1) * S.n + e] = ur;
+    }
+    const double ppx = px, ppz = pz;
+    dynamics_step(x, y, th, u, w, l, r, c.dyn, trim, c.dt);
+    px = x; pz = m.grid_h * m.tile_size - y;          // weird_from_cartesian S:1640-1652
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    ang = atan2(sn, cs);
+    steps++;
+    speed = sqrt((px - ppx) * (px - ppx) + (pz - ppz) * (pz - ppz)) / c.dt;
+  }
+  S.cx[e] = x; S.cy[e] = y; S.ctheta[e] = th; S.vu[e] = u; S.vw[e] = w;
+  S.pos_x[e] = px; S.pos_z[e] = pz; S.angle[e] = ang; S.speed[e] = speed; S.step_count[e] = steps;
+  evaluate_pose(S, m, c, e, px, pz, ang, steps, reward, done);
+  if ((c.flags & DTS_FLAG_AUTO_RESET) && S.done_code[e] != DTS_IN_PROGRESS) respawn(S, maps, c, n_maps_cycle, e);
+}
+
+__global__ void __launch_bounds__(128) k_reset_random(DState S, const DMap* __restrict__ maps, StepCfg c,
+                                                      int n_maps_cycle, const uint8_t* __restrict__ mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.n || (mask && !mask[e])) return;
+  respawn(S, maps, c, n_maps_cycle, e);
+  const DMap& m = maps[S.map_id[e]];
+  evaluate_pose(S, m, c, e, S.pos_x[e], S.pos_z[e], S.angle[e], 0, nullptr, nullptr);
+}
+
+// dts_reset with host-drawn parameters (already copied to device staging arrays in `p`)
+__global__ void __launch_bounds__(128) k_reset_params(DState S, const DMap* __restrict__ maps, StepCfg c,
+                                                      const uint8_t* __restrict__ mask, ResetStaging p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.n || (mask && !mask[e])) return;
+  RenderEp old = S.rep[e];
+  double Vprev[12];
+  camera_view(S.pos_x[e], S.pos_z[e], S.angle[e], old, (c.flags & DTS_FLAG_DOMAIN_RAND) != 0, Vprev);
+  if (p.map_id) S.map_id[e] = p.map_id[e];
+  const DMap& m = maps[S.map_id[e]];
+  RenderEp r;
+  default_render_ep(r);
+  if (p.cam_height) r.cam_height = p.cam_height[e];
+  if (p.cam_angle_deg) r.cam_angle_deg = p.cam_angle_deg[e];
+  if (p.cam_fov_y_deg) r.cam_fov_y_deg = p.cam_fov_y_deg[e];
+  float lpos[4] = {0.f, 3.f, 0.f, 1.f};
+  for (int k = 0; k < 3; k++) {
+    if (p.cam_noise) r.cam_noise[k] = p.cam_noise[3 * e + k];
+    if (p.horizon_color) r.horizon[k] = p.horizon_color[3 * e + k];
+    if (p.light_ambient) r.ambient[k] = p.light_ambient[3 * e + k];
+    if (p.light_diffuse) r.diffuse[k] = p.light_diffuse[3 * e + k];
+    if (p.ground_color) r.ground[k] = p.ground_color[3 * e + k];
+  }
+  if (p.light_pos) for (int k = 0; k < 4; k++) lpos[k] = p.light_pos[4 * e + k];
+  if (p.light_stale && p.light_stale[e]) light_to_eye(Vprev, lpos, r.light_eye);
+  else for (int k = 0; k < 4; k++) r.light_eye[k] = lpos[k];
+  if (p.obj_hidden) for (int k = 0; k < 8; k++) r.hidden[k] = p.obj_hidden[8 * e + k];
+  S.wheel_dist[e] = p.wheel_dist ? p.wheel_dist[e] : 0.102;
+  S.trim[e] = p.trim ? p.trim[e] : 0.0;
+  const double px = p.pos_x ? p.pos_x[e] : 1.0, pz = p.pos_z ? p.pos_z[e] : 1.0, ang = p.angle ? p.angle[e] : 1.0;
+  set_pose(S, m, e, px, pz, ang);
+  S.rep[e] = r;
+  S.episode[e] += 1;
+  evaluate_pose(S, m, c, e, px, pz, ang, 0, nullptr, nullptr);
+}
+
+// Batched pose predicates for host callers: _valid_pose / _collision / get_lane_pos2 /
+// proximity_penalty2 / _inconvenient_spawn of arbitrary poses (used by the host-side reset).
+__global__ void __launch_bounds__(128) k_query(const DMap* __restrict__ maps, int map_id, int n,
+                                               const double* __restrict__ q /*[n][4] x z angle safety*/,
+                                               const uint32_t* __restrict__ hidden /*[n][8] or null*/,
+                                               double* __restrict__ outd /*[n][4] dist dot angle prox*/,
+                                               int32_t* __restrict__ outi /*[n][8]*/) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const DMap& m = maps[map_id];
+  const double x = q[4 * t], z = q[4 * t + 1], a = q[4 * t + 2], sf = q[4 * t + 3];
+  bool hit2;
+  const bool ok = valid_pose(m, x, z, a, sf, &hit2);
+  double sn, cs;
+  sincos(a, &sn, &cs);
+  const bool hit1 = agent_hits_static(m, x + kCentreOff * cs, z + kCentreOff * -sn, a);  // run_tests.py:50 usage
+  const LanePose lp = lane_pose(m, x, z, a);
+  bool bad = false;
+  for (int o = 0; o < m.n_objects && !bad; o++) {
+    if (hidden && (hidden[8 * t + (o >> 5)] >> (o & 31) & 1u)) continue;
+    const DObject& ob = m.objects[o];
+    const double dx = ob.pos[0] - x, dy = ob.pos[1], dz = ob.pos[2] - z;
+    bad = sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad;
+  }
+  int ti, tj;
+  const int idx = tile_at(m, x, z, ti, tj);
+  outd[4 * t] = lp.dist; outd[4 * t + 1] = lp.dot_dir; outd[4 * t + 2] = lp.angle_rad;
+  outd[4 * t + 3] = proximity_penalty(m, x, z, a);
+  outi[8 * t] = ok; outi[8 * t + 1] = hit1; outi[8 * t + 2] = hit2; outi[8 * t + 3] = lp.in_lane;
+  outi[8 * t + 4] = bad; outi[8 * t + 5] = ti; outi[8 * t + 6] = tj;
+  outi[8 * t + 7] = idx >= 0 && m.tile_drivable[idx];
+}
+
+// ------------------------------------------------------------------ launchers
+void launch_step_logic(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const float* actions,
+                       float* reward, uint8_t* done, cudaStream_t st) {
+  k_step_logic<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, c, n_maps_cycle, actions, reward, done);
+}
+void launch_reset_random(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const uint8_t* mask,
+                         cudaStream_t st) {
+  k_reset_random<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, c, n_maps_cycle, mask);
+}
+void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, const uint8_t* mask,
+                         const ResetStaging& p, cudaStream_t st) {
+  k_reset_params<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, c, mask, p);
+}
+void launch_query(const DMap* maps, int map_id, int n, const double* q, const uint32_t* hidden, double* outd,
+                  int32_t* outi, cudaStream_t st) {
+  k_query<<<(n + 127) / 128, 128, 0, st>>>(maps, map_id, n, q, hidden, outd, outi);
+}
+
+}  // namespace dts

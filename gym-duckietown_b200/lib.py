@@ -1,0 +1,293 @@
+"""ctypes binding of libdtsim.so (include/dtsim.h).  No fallback: if the CUDA library is missing or
+fails to load, importing the simulator classes raises — there is no CPU path in the product."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import assets
+from .maps import KIND_ID, TILE_KINDS, MapData
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdtsim.so")
+
+DTS_ABI_VERSION = 1
+ACTION_PWM, ACTION_VEL_STEER = 0, 1
+FLAG_AUTO_RESET, FLAG_DOMAIN_RAND, FLAG_DISTORTION, FLAG_DYNAMICS_RAND = 1, 2, 4, 8
+IN_PROGRESS, INVALID_POSE, MAX_STEPS = 0, 1, 2
+DONE_CODE_STR = {0: "in-progress", 1: "invalid-pose", 2: "max-steps-reached"}  # S:1685-1705
+
+
+class DtsError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("cam_width", C.c_int32),
+        ("cam_height", C.c_int32), ("max_steps", C.c_int32), ("frame_skip", C.c_int32), ("action_mode", C.c_int32),
+        ("flags", C.c_int32), ("max_maps", C.c_int32), ("cycle_maps", C.c_int32), ("reserved0", C.c_int32),
+        ("frame_rate", C.c_double), ("robot_speed", C.c_double), ("accept_start_angle_deg", C.c_double),
+        ("gain", C.c_double), ("trim", C.c_double), ("radius", C.c_double), ("k", C.c_double), ("limit", C.c_double),
+        ("dyn_u1", C.c_double), ("dyn_u2", C.c_double), ("dyn_u3", C.c_double), ("dyn_w1", C.c_double),
+        ("dyn_w2", C.c_double), ("dyn_w3", C.c_double), ("dyn_uar", C.c_double), ("dyn_ual", C.c_double),
+        ("dyn_war", C.c_double), ("dyn_wal", C.c_double), ("dyn_delay", C.c_double),
+        ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+    ]
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgba", C.c_void_p)]
+
+
+class Object(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("mesh_id", C.c_int32),
+                ("optional", C.c_int32)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("tri_offset", C.c_int32), ("tri_count", C.c_int32)]
+
+
+class MapBlob(C.Structure):
+    _fields_ = [
+        ("tile_size", C.c_double), ("grid_w", C.c_int32), ("grid_h", C.c_int32),
+        ("tile_kind", C.c_void_p), ("tile_angle", C.c_void_p), ("tile_drivable", C.c_void_p), ("tile_tex", C.c_void_p),
+        ("tile_curve_off", C.c_void_p), ("tile_curve_cnt", C.c_void_p), ("n_curves", C.c_int32), ("curves", C.c_void_p),
+        ("n_coll", C.c_int32), ("coll_corners", C.c_void_p), ("coll_norms", C.c_void_p), ("coll_centers", C.c_void_p),
+        ("coll_radii", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p), ("n_meshes", C.c_int32),
+        ("meshes", C.c_void_p), ("n_tris", C.c_int32), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p),
+        ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p), ("tri_tex", C.c_void_p), ("n_textures", C.c_int32),
+        ("textures", C.c_void_p),
+    ]
+
+
+_EP_FIELDS = ["map_id", "pos_x", "pos_z", "angle", "wheel_dist", "trim", "cam_height", "cam_angle_deg",
+              "cam_fov_y_deg", "cam_noise", "horizon_color", "light_ambient", "light_diffuse", "light_pos",
+              "light_stale", "ground_color", "obj_hidden"]
+_EP_DTYPES = {"map_id": np.int32, "pos_x": np.float64, "pos_z": np.float64, "angle": np.float64,
+              "wheel_dist": np.float64, "trim": np.float64, "cam_height": np.float32, "cam_angle_deg": np.float32,
+              "cam_fov_y_deg": np.float32, "cam_noise": np.float32, "horizon_color": np.float32,
+              "light_ambient": np.float32, "light_diffuse": np.float32, "light_pos": np.float32,
+              "light_stale": np.int32, "ground_color": np.float32, "obj_hidden": np.uint32}
+_EP_WIDTH = {"cam_noise": 3, "horizon_color": 3, "light_ambient": 3, "light_diffuse": 3, "light_pos": 4,
+             "ground_color": 3, "obj_hidden": 8}
+
+
+class EpisodeParams(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in _EP_FIELDS]
+
+
+_STATE_FIELDS = [("pos_x", np.float64), ("pos_z", np.float64), ("angle", np.float64), ("speed", np.float64),
+                 ("reward", np.float64), ("lane_dist", np.float64), ("lane_dot", np.float64),
+                 ("lane_angle_rad", np.float64), ("prox_penalty", np.float64), ("wheel_dist", np.float64),
+                 ("step_count", np.int32), ("tile_i", np.int32), ("tile_j", np.int32), ("map_id", np.int32),
+                 ("episode", np.int32), ("done_code", np.uint8), ("in_lane", np.uint8), ("collided", np.uint8)]
+
+
+class StateView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n, _ in _STATE_FIELDS]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libdtsim.so; build it first if the source tree is newer (nvcc needed). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _b
+        _b.build()
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # no fallback, by design
+        raise DtsError(f"cannot load {LIB_PATH}: {e}") from e
+    vp, i = C.c_void_p, C.c_int
+    lib.dts_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.dts_upload_map.argtypes = [vp, i, C.POINTER(MapBlob)]
+    lib.dts_set_fisheye_lut.argtypes = [vp, vp, vp, i, i]
+    lib.dts_reset.argtypes = [vp, vp, C.POINTER(EpisodeParams), vp]
+    lib.dts_reset_random.argtypes = [vp, vp, vp]
+    lib.dts_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.dts_render.argtypes = [vp, vp, vp]
+    lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
+    lib.dts_query_poses.argtypes = [vp, i, i, vp, vp, vp, vp]
+    lib.dts_comm_load.argtypes = [vp, C.c_char_p]
+    lib.dts_comm_unique_id.argtypes = [vp, vp]
+    lib.dts_comm_init.argtypes = [vp, vp, i, i]
+    lib.dts_allgather_obs.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.dts_launch_count.argtypes = [vp]
+    lib.dts_launch_count.restype = C.c_uint64
+    lib.dts_last_error.argtypes = [vp]
+    lib.dts_last_error.restype = C.c_char_p
+    lib.dts_destroy.argtypes = [vp]
+    lib.dts_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_reset_random", "dts_step",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_allgather_obs", "dts_launch_count", "dts_last_error", "dts_destroy"]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class MapBlobHolder:
+    """Flattens a MapData (tiles, curves, OBBs, placed meshes, textures) into a dts_map_blob and keeps
+    the numpy buffers alive for the duration of the upload."""
+
+    def __init__(self, md: MapData):
+        k = self.keep = {}
+        k["kind"] = np.ascontiguousarray(md.tile_kind, np.int8)
+        k["angle"] = np.ascontiguousarray(md.tile_angle, np.int8)
+        k["drv"] = np.ascontiguousarray(md.tile_drivable, np.uint8)
+        # textures: one per tile kind present, then the mesh textures
+        tex_imgs: List[np.ndarray] = []
+        kind_tex = {}
+        for kid in sorted(set(int(x) for x in md.tile_kind if x >= 0)):
+            kind_tex[kid] = len(tex_imgs)
+            tex_imgs.append(np.ascontiguousarray(assets.tile_texture(TILE_KINDS[kid])))
+        k["tex"] = np.array([kind_tex.get(int(x), -1) for x in md.tile_kind], np.int16)
+        k["coff"] = np.ascontiguousarray(md.tile_curve_off, np.int32)
+        k["ccnt"] = np.ascontiguousarray(md.tile_curve_cnt, np.int32)
+        k["curves"] = np.ascontiguousarray(md.curves, np.float64)
+        k["cc"] = np.ascontiguousarray(md.coll_corners, np.float64)
+        k["cn"] = np.ascontiguousarray(md.coll_norms, np.float64)
+        k["ce"] = np.ascontiguousarray(md.coll_centers, np.float64)
+        k["cr"] = np.ascontiguousarray(md.coll_radii, np.float64)
+        meshes = (Mesh * max(1, len(md.meshes)))()
+        pos, nrm, uv, col, ttex = [], [], [], [], []
+        off = 0
+        for mi, m in enumerate(md.meshes):
+            base = len(tex_imgs)
+            tex_imgs.extend(np.ascontiguousarray(t) for t in m.textures)
+            meshes[mi] = Mesh(off, len(m.tri_pos))
+            off += len(m.tri_pos)
+            pos.append(m.tri_pos); nrm.append(m.tri_nrm); uv.append(m.tri_uv); col.append(m.tri_col)
+            ttex.append(np.where(m.tri_tex >= 0, m.tri_tex + base, -1).astype(np.int16))
+        cat = lambda lst, shape, dt: (np.ascontiguousarray(np.concatenate(lst, 0), dt) if lst else np.zeros(shape, dt))
+        k["tpos"] = cat(pos, (0, 3, 3), np.float32); k["tnrm"] = cat(nrm, (0, 3, 3), np.float32)
+        k["tuv"] = cat(uv, (0, 3, 2), np.float32); k["tcol"] = cat(col, (0, 3, 3), np.float32)
+        k["ttex"] = cat(ttex, (0,), np.int16)
+        objs = (Object * max(1, len(md.objects)))()
+        for oi, o in enumerate(md.objects):
+            objs[oi] = Object((C.c_float * 3)(*[float(v) for v in o.pos]), float(o.scale),
+                              float(np.rad2deg(o.angle)), o.mesh_id, int(o.optional))  # y_rot O:57
+        texs = (Texture * max(1, len(tex_imgs)))()
+        for ti, im in enumerate(tex_imgs):
+            texs[ti] = Texture(im.shape[1], im.shape[0], im.ctypes.data)
+        k["tex_imgs"], k["meshes"], k["objs"], k["texs"] = tex_imgs, meshes, objs, texs
+        self.blob = MapBlob(
+            md.tile_size, md.grid_w, md.grid_h, _ptr(k["kind"]), _ptr(k["angle"]), _ptr(k["drv"]), _ptr(k["tex"]),
+            _ptr(k["coff"]), _ptr(k["ccnt"]), len(md.curves), _ptr(k["curves"]), md.n_coll, _ptr(k["cc"]),
+            _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(md.meshes),
+            C.cast(meshes, C.c_void_p), off, _ptr(k["tpos"]), _ptr(k["tnrm"]), _ptr(k["tuv"]), _ptr(k["tcol"]),
+            _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p))
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, n: int, dtype):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dtype).str, "data": (ptr, False),
+                                         "version": 2}
+
+
+class Sim:
+    """Thin OO veneer over the C handle; every method maps 1:1 to an entry point of dtsim.h."""
+
+    def __init__(self, cfg: Config):
+        self.lib = load()
+        self.h = C.c_void_p()
+        self.cfg = cfg
+        if self.lib.dts_create(C.byref(cfg), C.byref(self.h)):
+            raise DtsError("dts_create: " + self.lib.dts_last_error(None).decode())
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise DtsError(f"{what}: {self.lib.dts_last_error(self.h).decode()}")
+
+    def upload_map(self, map_id: int, md: MapData):
+        holder = MapBlobHolder(md)
+        self._check(self.lib.dts_upload_map(self.h, map_id, C.byref(holder.blob)), "dts_upload_map")
+
+    def set_fisheye_lut(self, rmapx: np.ndarray, rmapy: np.ndarray):
+        rx, ry = np.ascontiguousarray(rmapx, np.float32), np.ascontiguousarray(rmapy, np.float32)
+        self._check(self.lib.dts_set_fisheye_lut(self.h, _ptr(rx), _ptr(ry), rx.shape[1], rx.shape[0]),
+                    "dts_set_fisheye_lut")
+
+    def reset(self, mask_ptr: Optional[int], params: dict, stream: int = 0):
+        n = self.cfg.num_envs
+        keep, ep = [], EpisodeParams()
+        for f in _EP_FIELDS:
+            v = params.get(f)
+            if v is None:
+                continue
+            a = np.ascontiguousarray(v, _EP_DTYPES[f])
+            want = (n, _EP_WIDTH[f]) if f in _EP_WIDTH else (n,)
+            if a.shape != want:
+                raise ValueError(f"episode param {f}: shape {a.shape}, expected {want}")
+            keep.append(a)
+            setattr(ep, f, a.ctypes.data)
+        self._check(self.lib.dts_reset(self.h, mask_ptr, C.byref(ep), stream), "dts_reset")
+
+    def reset_random(self, mask_ptr: Optional[int], stream: int = 0):
+        self._check(self.lib.dts_reset_random(self.h, mask_ptr, stream), "dts_reset_random")
+
+    def step(self, actions_ptr: int, obs_ptr: Optional[int], reward_ptr: int, done_ptr: int, stream: int = 0):
+        self._check(self.lib.dts_step(self.h, actions_ptr, obs_ptr, reward_ptr, done_ptr, stream), "dts_step")
+
+    def render(self, obs_ptr: int, stream: int = 0):
+        self._check(self.lib.dts_render(self.h, obs_ptr, stream), "dts_render")
+
+    def state_arrays(self) -> dict:
+        v = StateView()
+        self._check(self.lib.dts_get_state(self.h, C.byref(v)), "dts_get_state")
+        return {n: _CudaArray(getattr(v, n), self.cfg.num_envs, dt) for n, dt in _STATE_FIELDS}
+
+    def query_poses(self, map_id: int, x, z, angle, safety=1.0, hidden=None):
+        q = np.empty((len(x), 4), np.float64)
+        q[:, 0], q[:, 1], q[:, 2], q[:, 3] = x, z, angle, safety
+        outd = np.empty((len(x), 4), np.float64)
+        outi = np.empty((len(x), 8), np.int32)
+        hid = None if hidden is None else np.ascontiguousarray(hidden, np.uint32)
+        self._check(self.lib.dts_query_poses(self.h, map_id, len(x), _ptr(q), _ptr(hid), _ptr(outd), _ptr(outi)),
+                    "dts_query_poses")
+        return outd, outi
+
+    def launch_count(self) -> int:
+        return int(self.lib.dts_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.dts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_config(**kw) -> Config:
+    """Reference defaults: Simulator.__init__ (S:207-232), DuckietownEnv.__init__ (E:15), DB18 nominal."""
+    c = Config(
+        abi_version=DTS_ABI_VERSION, num_envs=1, device=0, cam_width=640, cam_height=480, max_steps=1500, frame_skip=1,
+        action_mode=ACTION_VEL_STEER, flags=0, max_maps=1, cycle_maps=0, reserved0=0, frame_rate=30.0, robot_speed=1.2,
+        accept_start_angle_deg=60.0, gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
+        dyn_u1=5.0, dyn_u2=0.0, dyn_u3=0.0, dyn_w1=4.0, dyn_w2=0.0, dyn_w3=0.0, dyn_uar=1.5, dyn_ual=1.5,
+        dyn_war=15.0, dyn_wal=15.0, dyn_delay=0.15, seed=0, env_id_offset=0)
+    for k_, v in kw.items():
+        if not hasattr(c, k_):
+            raise TypeError(f"unknown config field {k_}")
+        setattr(c, k_, v)
+    return c

@@ -45,6 +45,9 @@ typedef struct {
   int32_t action_mode;
   int32_t flags;
   int32_t max_maps;         /* slots for dts_upload_map */
+  int32_t cycle_maps;       /* >0: every reset advances the env's map id modulo this count
+                               (MultiMapEnv.reset round-robin, envs/multimap_env.py:44-49) */
+  int32_t reserved0;
   double frame_rate;        /* simulator.py:214 (30) */
   double robot_speed;       /* simulator.py:218 (1.2): the constant used in the reward, S:1702 */
   double accept_start_angle_deg; /* simulator.py:219 (60), device-side spawn only */
@@ -161,10 +164,23 @@ int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* re
 /* Simulator.render_obs() (simulator.py:1953-1972) of the current state. */
 int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream);
 int dts_get_state(dts_sim* sim, dts_state_view* out);
-/* End-of-rollout observation all-gather across GPU shards. `nccl_comm` is an ncclComm_t.
+/* Batched pose predicates for host callers — the de-facto public helpers of Simulator:
+ * _valid_pose (S:1494), _collision(get_agent_corners()) (S:1473, run_tests.py:50), get_lane_pos2 (S:1371),
+ * proximity_penalty2 (S:1430), _inconvenient_spawn (S:1461), get_grid_coords (S:1134), _drivable_pos (S:1411).
+ * HOST pointers, synchronous. query[n][4] = x, z, angle, safety_factor; hidden[n][8] object-visibility
+ * bitmasks or NULL; out_f64[n][4] = lane dist, dot_dir, angle_rad (NaN when not in a lane), proximity;
+ * out_i32[n][8] = valid, collision (offset once), collision (as _valid_pose sees it), in_lane,
+ * inconvenient_spawn, tile_i, tile_j, drivable. */
+int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const uint32_t* hidden, double* out_f64,
+                    int32_t* out_i32);
+/* End-of-rollout observation all-gather across the GPU shards of one box; the step path
+ * itself has no collective.  libnccl is dlopen'ed from `libnccl_path` (the torch-bundled copy); rank 0
+ * creates a unique id, the caller broadcasts its 128 bytes (torch.distributed), every rank inits.
  * send: u8[bytes_per_rank] on this GPU, recv: u8[world*bytes_per_rank]. */
-int dts_allgather_obs(dts_sim* sim, void* nccl_comm, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank,
-                      void* stream);
+int dts_comm_load(dts_sim* sim, const char* libnccl_path);
+int dts_comm_unique_id(dts_sim* sim, uint8_t out[128]);
+int dts_comm_init(dts_sim* sim, const uint8_t id[128], int rank, int world);
+int dts_allgather_obs(dts_sim* sim, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank, void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t dts_launch_count(dts_sim* sim);
 const char* dts_last_error(dts_sim* sim); /* sim may be NULL: error of the last failed dts_create */

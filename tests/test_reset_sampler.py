@@ -1,0 +1,71 @@
+"""Host-side reset sampling (episode.py) against Simulator.reset() of the REFERENCE (golden vectors
+from oracle/make_golden.py).  The spawn predicates come from the C oracle here (CPU suite); the GPU
+suite repeats it through dts_query_poses."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from gym_duckietown_b200 import maps
+from gym_duckietown_b200.episode import EpisodeSampler
+
+MAPS = ["small_loop", "loop_obstacles", "udem1"]
+
+
+def oracle_query(md):
+    om = orc.OracleMap(md)
+
+    def query(k, x, z, a, safety, hidden):
+        n = len(x)
+        outd, outi = np.full((n, 4), np.nan), np.zeros((n, 8), np.int32)
+        for q in range(n):
+            o = om.done_reward(x[q], z[q], a[q], 0)
+            outd[q] = (o.lane_dist, o.lane_dot, o.lane_angle, o.prox)
+            outi[q, 0] = om.valid_pose(x[q], z[q], a[q], safety)
+            outi[q, 3] = o.in_lane
+            bad = False
+            for oi, ob in enumerate(md.objects):  # _inconvenient_spawn S:1461-1471
+                if hidden[q, oi >> 5] >> (oi & 31) & 1:
+                    continue
+                d = np.linalg.norm(ob.pos - np.array([x[q], 0, z[q]]))
+                bad |= bool(d < max(ob.max_coords) * 0.5 * ob.scale + 0.25)
+            outi[q, 4] = bad
+        return outd, outi
+    return query
+
+
+def check_against_golden(name, golden_dir, make_query):
+    g = np.load(os.path.join(golden_dir, f"reset_{name}.npz"))
+    md = maps.load_map(name)
+    for tag, dr in (("nodr", False), ("dr", True)):
+        s = EpisodeSampler(len(g["seeds"]), domain_rand=dr)
+        s.seed([int(v) for v in g["seeds"]])
+        envs = list(range(len(g["seeds"])))
+        for ep in range(2):
+            out = s.sample(envs, [md] * len(envs), make_query(md))
+            rows = np.arange(len(envs)) * 2 + ep
+            assert np.array_equal(out["pos_x"], g[f"{tag}_cur_pos"][rows, 0])
+            assert np.array_equal(out["pos_z"], g[f"{tag}_cur_pos"][rows, 2])
+            assert np.array_equal(out["angle"], g[f"{tag}_cur_angle"][rows])
+            assert np.array_equal(out["wheel_dist"], g[f"{tag}_wheel_dist"][rows])
+            assert np.array_equal(out["cam_height"], g[f"{tag}_cam_height"][rows])
+            assert np.array_equal(out["cam_angle_deg"], g[f"{tag}_cam_angle"][rows])
+            assert np.array_equal(out["cam_fov_y_deg"], g[f"{tag}_cam_fov_y"][rows])
+            assert np.array_equal(out["horizon_color"], g[f"{tag}_horizon_color"][rows])
+            assert np.array_equal(out["ground_color"], g[f"{tag}_ground_color"][rows])
+            # the reference hands these to GL as float32 (ctypes GLfloat arrays, S:581-583)
+            assert np.array_equal(out["light_pos"].astype(np.float32), g[f"{tag}_light_pos"][rows].astype(np.float32))
+            assert np.array_equal(out["light_ambient"].astype(np.float32), g[f"{tag}_ambient"][rows, :3].astype(np.float32))
+            assert np.array_equal(out["light_diffuse"].astype(np.float32), g[f"{tag}_diffuse"][rows, :3].astype(np.float32))
+            if dr:
+                assert np.array_equal(out["cam_noise"], g[f"{tag}_camera_noise"][rows])
+            vis = g[f"{tag}_obj_visible"][rows]
+            for q in range(len(envs)):
+                for oi in range(vis.shape[1]):
+                    assert bool(out["obj_hidden"][q, oi >> 5] >> (oi & 31) & 1) == (not vis[q, oi])
+
+
+@pytest.mark.parametrize("name", MAPS)
+def test_reset_draws_match_reference(name, golden_dir):
+    check_against_golden(name, golden_dir, oracle_query)
