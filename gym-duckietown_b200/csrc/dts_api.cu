@@ -85,6 +85,10 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
     g_create_error = "num_envs, cam_width, cam_height and max_maps must be positive";
     return 1;
   }
+  if (cfg->cam_width > 800 || cfg->cam_height > 800) {  // guard band of the rasteriser: 2.5*size*64 < 2^17
+    g_create_error = "camera larger than 800x800 is not supported by the rasteriser's fixed-point range";
+    return 1;
+  }
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e); return 1; }
   dts_sim* sim = new dts_sim();
@@ -309,7 +313,9 @@ static int ensure_render(dts_sim* sim) {
   sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
   const int bins = ((sim->cfg.cam_width + 15) / 16) * ((sim->cfg.cam_height + 15) / 16);
   sim->max_pairs = sim->max_prims * 6 + bins * 8;
-  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs);
+  if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
+  const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
+  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
   if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   return 0;

@@ -32,7 +32,7 @@ void launch_query(const DMap* maps, int map_id, int n, const double* q, const ui
 
 // render (dts_render.cu)
 struct RenderScratch;
-size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs);
+size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, size_t undistorted_frame_bytes);
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, const float* lut_x, const float* lut_y, int32_t* err_flag,
                   cudaStream_t st);

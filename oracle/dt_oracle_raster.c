@@ -1,0 +1,437 @@
+/* dt_oracle_raster.c — CPU ORACLE (test infrastructure, NOT product code): software restatement
+ * of what Simulator._render_img asks OpenGL to do (simulator.py:1707-1951, objects.py:123-148,
+ * objmesh.py:360-375, graphics.py:172-251) plus the fisheye gather (distortion.py:85-125).
+ *
+ * PARITY UNPINNED for pixels: the reference's pixels come out of an OpenGL driver that cannot run
+ * here (no pyglet/GL/display) and GL leaves rasterisation details implementation-defined.  This file
+ * therefore DEFINES pixel truth for the project by fixing one deterministic interpretation of the
+ * fixed-function pipeline (DESIGN.md "render spec"):
+ *   - matrices in float64, rounded once to float32; vertex / lighting / clip / raster math in
+ *     float32 with the exact operation order written below (built with -ffp-contract=off)
+ *   - per-vertex (Gouraud) lighting, one light, GL_COLOR_MATERIAL ambient+diffuse, global ambient 0.3
+ *   - clip against near/far and a 4x guard band, intersections computed from the inside vertex
+ *   - vertices snapped to 1/64 px, integer edge functions, shared-edge ownership rule
+ *   - 4x MSAA at (.375,.125)(.875,.375)(.125,.625)(.625,.875), colour shaded once per pixel centre,
+ *     depth per sample, float32 depth, GL_LESS, draw order = reference draw order
+ *   - bilinear RGBA8 textures, REPEAT wrap, GL_MODULATE
+ *   - resolve = mean of 4 samples, u8 = rint(255*c), image row 0 = top
+ * It is written for clarity (brute force over every triangle and every pixel of its bounding box),
+ * not speed; the CUDA rasteriser is structured differently (binning, lattice sharing) and must
+ * reproduce these numbers exactly.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { int32_t w, h; const uint8_t* rgba; } orr_texture;
+typedef struct { float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count; } orr_object;
+
+typedef struct {
+  double tile_size;
+  int32_t grid_w, grid_h;
+  const int8_t* tile_kind;
+  const int8_t* tile_angle;
+  const int16_t* tile_tex;
+  int32_t n_objects;
+  const orr_object* objects;
+  const float* tri_pos; /* [T][3][3] */
+  const float* tri_nrm;
+  const float* tri_uv;  /* [T][3][2] */
+  const float* tri_col;
+  const int16_t* tri_tex;
+  int32_t n_textures;
+  const orr_texture* textures;
+} orr_scene;
+
+typedef struct { /* mirrors the product's per-episode render record */
+  float cam_height, cam_angle_deg, cam_fov_y_deg;
+  float cam_noise[3], horizon[3], ambient[3], diffuse[3], light_eye[4], ground[3];
+  uint32_t hidden[8];
+} orr_episode;
+
+typedef struct { float cx, cy, cz, cw, r, g, b, u, v; } vtx; /* clip-space vertex with attributes */
+
+typedef struct {
+  int W, H;
+  float* col;   /* [H][W][4 samples][3] */
+  float* depth; /* [H][W][4] */
+} framebuf;
+
+static const int SX[4] = {24, 56, 8, 40}, SY[4] = {8, 24, 40, 56}; /* sample offsets in 1/64 px */
+#define GUARD 4.0f
+
+/* ---- camera (simulator.py:1758-1803), float64 ------------------------------------------------ */
+static void camera_view(double px, double pz, double angle, const orr_episode* ep, int domain_rand, double V[12]) {
+  double ex = px, ey = 0.0, ez = pz;
+  if (domain_rand) { ex += (double)ep->cam_noise[0]; ey += (double)ep->cam_noise[1]; ez += (double)ep->cam_noise[2]; }
+  ey += (double)ep->cam_height;
+  double fx = cos(angle), fy = 0.0, fz = -sin(angle);
+  double fn = sqrt(fx * fx + fy * fy + fz * fz);
+  fx /= fn; fy /= fn; fz /= fn;
+  double sx = fy * 0.0 - fz * 1.0, sy = fz * 0.0 - fx * 0.0, sz = fx * 1.0 - fy * 0.0;
+  double sn = sqrt(sx * sx + sy * sy + sz * sz);
+  sx /= sn; sy /= sn; sz /= sn;
+  double ux = sy * fz - sz * fy, uy = sz * fx - sx * fz, uz = sx * fy - sy * fx;
+  double L[12] = {sx, sy, sz, -(sx * ex + sy * ey + sz * ez), ux, uy, uz, -(ux * ex + uy * ey + uz * ez),
+                  -fx, -fy, -fz, (fx * ex + fy * ey + fz * ez)};
+  L[11] += 0.066;
+  double th = (double)ep->cam_angle_deg * 0.017453292519943295;
+  double c = cos(th), s = sin(th);
+  for (int k = 0; k < 4; k++) {
+    V[k] = L[k];
+    V[4 + k] = c * L[4 + k] - s * L[8 + k];
+    V[8 + k] = s * L[4 + k] + c * L[8 + k];
+  }
+}
+
+/* MV = V * T(t) * S(s) * Ry(c,s_) ; N = rot(V) * Ry / s   (both rounded to float32) */
+static void model_view(const double V[12], const double t[3], double sc, double c, double s, float MV[12], float N[9]) {
+  /* Ry = [[c,0,s],[0,1,0],[-s,0,c]] (glRotatef about +y) */
+  double R[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+  for (int r = 0; r < 3; r++) {
+    for (int k = 0; k < 3; k++) {
+      double a = V[4 * r + 0] * R[0 + k] + V[4 * r + 1] * R[3 + k] + V[4 * r + 2] * R[6 + k];
+      MV[4 * r + k] = (float)(a * sc);
+      N[3 * r + k] = (float)(a / sc);
+    }
+    MV[4 * r + 3] = (float)(V[4 * r + 0] * t[0] + V[4 * r + 1] * t[1] + V[4 * r + 2] * t[2] + V[4 * r + 3]);
+  }
+}
+
+typedef struct {
+  float MV[12], N[9];
+  float P00, P11, P22, P23;
+  const orr_episode* ep;
+} xform;
+
+/* object-space vertex -> lit clip-space vertex (fixed-function T&L, float32, no FMA) */
+static vtx shade_vertex(const xform* x, const float p[3], const float n[3], const float col[3], float u, float v) {
+  const float* M = x->MV;
+  float e[3], ne[3];
+  for (int r = 0; r < 3; r++) {
+    float t = M[4 * r] * p[0];
+    t = t + M[4 * r + 1] * p[1];
+    t = t + M[4 * r + 2] * p[2];
+    e[r] = t + M[4 * r + 3];
+    float q = x->N[3 * r] * n[0];
+    q = q + x->N[3 * r + 1] * n[1];
+    ne[r] = q + x->N[3 * r + 2] * n[2];
+  }
+  const float* lp = x->ep->light_eye;
+  float lx, ly, lz;
+  if (lp[3] == 0.0f) { lx = lp[0]; ly = lp[1]; lz = lp[2]; }
+  else { lx = lp[0] - e[0]; ly = lp[1] - e[1]; lz = lp[2] - e[2]; }
+  float len = lx * lx;
+  len = len + ly * ly;
+  len = len + lz * lz;
+  len = sqrtf(len);
+  float ndl = 0.0f;
+  if (len > 0.0f) {
+    lx = lx / len; ly = ly / len; lz = lz / len;
+    ndl = ne[0] * lx;
+    ndl = ndl + ne[1] * ly;
+    ndl = ndl + ne[2] * lz;
+    if (!(ndl > 0.0f)) ndl = 0.0f;
+  }
+  vtx o;
+  float lit[3];
+  for (int k = 0; k < 3; k++) {
+    float s = 0.3f + x->ep->ambient[k];
+    s = s + ndl * x->ep->diffuse[k];
+    float c = col[k] * s;
+    lit[k] = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+  }
+  o.r = lit[0]; o.g = lit[1]; o.b = lit[2];
+  o.u = u; o.v = v;
+  o.cx = x->P00 * e[0];
+  o.cy = x->P11 * e[1];
+  o.cz = x->P22 * e[2] + x->P23;
+  o.cw = -e[2];
+  return o;
+}
+
+static float plane_dist(const vtx* a, int pl) {
+  switch (pl) {
+    case 0: return a->cz + a->cw;          /* near:  z >= -w */
+    case 1: return a->cw - a->cz;          /* far:   z <=  w */
+    case 2: return a->cx + GUARD * a->cw;  /* x >= -G w */
+    case 3: return GUARD * a->cw - a->cx;
+    case 4: return a->cy + GUARD * a->cw;
+    default: return GUARD * a->cw - a->cy;
+  }
+}
+/* point on the edge from the INSIDE vertex `in` towards the OUTSIDE vertex `out` */
+static vtx clip_lerp(const vtx* in, const vtx* out, float din, float dout) {
+  float t = din / (din - dout);
+  vtx o;
+  const float* a = (const float*)in; const float* b = (const float*)out; float* c = (float*)&o;
+  for (int k = 0; k < 9; k++) { float d = b[k] - a[k]; c[k] = a[k] + t * d; }
+  return o;
+}
+static int clip_polygon(vtx* poly, int n) {
+  vtx tmp[12];
+  for (int pl = 0; pl < 6; pl++) {
+    int m = 0, any_out = 0;
+    float d[12];
+    for (int k = 0; k < n; k++) { d[k] = plane_dist(&poly[k], pl); if (!(d[k] >= 0.0f)) any_out = 1; }
+    if (!any_out) continue;
+    for (int k = 0; k < n; k++) {
+      int k2 = (k + 1) % n;
+      int in1 = d[k] >= 0.0f, in2 = d[k2] >= 0.0f;
+      if (in1) tmp[m++] = poly[k];
+      if (in1 && !in2) tmp[m++] = clip_lerp(&poly[k], &poly[k2], d[k], d[k2]);
+      else if (!in1 && in2) tmp[m++] = clip_lerp(&poly[k2], &poly[k], d[k2], d[k]);
+    }
+    n = m;
+    memcpy(poly, tmp, sizeof(vtx) * n);
+    if (n < 3) return 0;
+  }
+  return n;
+}
+
+static inline float tex_byte(const orr_texture* t, int i, int j, int c) { return (float)t->rgba[((size_t)j * t->w + i) * 4 + c]; }
+
+/* one screen-space triangle (already clipped); `id` only documents draw order (drawn in order, GL_LESS) */
+static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex) {
+  vtx* vs[3] = {&a, &b, &c};
+  int X[3], Y[3];
+  float zw[3], q[3];
+  const float Wf = (float)fb->W, Hf = (float)fb->H;
+  for (int k = 0; k < 3; k++) {
+    float iw = 1.0f / vs[k]->cw;
+    float nx = vs[k]->cx * iw, ny = vs[k]->cy * iw, nz = vs[k]->cz * iw;
+    float sx = (nx * 0.5f + 0.5f) * Wf;
+    float sy = (0.5f - ny * 0.5f) * Hf;
+    X[k] = (int)rintf(sx * 64.0f);
+    Y[k] = (int)rintf(sy * 64.0f);
+    zw[k] = nz * 0.5f + 0.5f;
+    q[k] = iw;
+  }
+  int64_t area2 = (int64_t)(X[1] - X[0]) * (Y[2] - Y[0]) - (int64_t)(X[2] - X[0]) * (Y[1] - Y[0]);
+  if (area2 == 0) return;
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (area2 < 0) { i1 = 2; i2 = 1; }
+  const int ix[3] = {i0, i1, i2};
+  int x0 = X[i0], y0 = Y[i0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
+  /* edges: e0 v1->v2, e1 v2->v0, e2 v0->v1 ; E(x,y) = (xb-xa)(y-ya) - (yb-ya)(x-xa) >= 0 inside */
+  const int ax[3] = {x1, x2, x0}, ay[3] = {y1, y2, y0}, bx[3] = {x2, x0, x1}, by[3] = {y2, y0, y1};
+  int bias[3];
+  for (int k = 0; k < 3; k++) {
+    int dx = bx[k] - ax[k], dy = by[k] - ay[k];
+    bias[k] = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;  /* non-owner edges exclude E == 0 */
+  }
+  /* attribute planes anchored at v0 (float32) */
+  const float dx1 = (float)(x1 - x0) * 0.015625f, dy1 = (float)(y1 - y0) * 0.015625f;
+  const float dx2 = (float)(x2 - x0) * 0.015625f, dy2 = (float)(y2 - y0) * 0.015625f;
+  const float areaf = dx1 * dy2 - dx2 * dy1;
+  const float ia = 1.0f / areaf;
+  float f0[7], fx[7], fy[7]; /* z, q, u*q, v*q, r*q, g*q, b*q */
+  for (int at = 0; at < 7; at++) {
+    float v[3];
+    for (int k = 0; k < 3; k++) {
+      const vtx* p = vs[ix[k]];
+      float qq = q[ix[k]];
+      switch (at) {
+        case 0: v[k] = zw[ix[k]]; break;
+        case 1: v[k] = qq; break;
+        case 2: v[k] = p->u * qq; break;
+        case 3: v[k] = p->v * qq; break;
+        case 4: v[k] = p->r * qq; break;
+        case 5: v[k] = p->g * qq; break;
+        default: v[k] = p->b * qq; break;
+      }
+    }
+    float d1 = v[1] - v[0], d2 = v[2] - v[0];
+    f0[at] = v[0];
+    fx[at] = (d1 * dy2 - d2 * dy1) * ia;
+    fy[at] = (d2 * dx1 - d1 * dx2) * ia;
+  }
+  int minx = x0 < x1 ? x0 : x1; minx = minx < x2 ? minx : x2;
+  int maxx = x0 > x1 ? x0 : x1; maxx = maxx > x2 ? maxx : x2;
+  int miny = y0 < y1 ? y0 : y1; miny = miny < y2 ? miny : y2;
+  int maxy = y0 > y1 ? y0 : y1; maxy = maxy > y2 ? maxy : y2;
+  int px0 = minx >> 6, px1 = maxx >> 6, py0 = miny >> 6, py1 = maxy >> 6;
+  if (px0 < 0) px0 = 0;
+  if (py0 < 0) py0 = 0;
+  if (px1 >= fb->W) px1 = fb->W - 1;
+  if (py1 >= fb->H) py1 = fb->H - 1;
+  for (int py = py0; py <= py1; py++)
+    for (int px = px0; px <= px1; px++) {
+      int mask = 0;
+      for (int s = 0; s < 4; s++) {
+        int sx = px * 64 + SX[s], sy = py * 64 + SY[s];
+        int inside = 1;
+        for (int k = 0; k < 3; k++) {
+          int64_t E = (int64_t)(bx[k] - ax[k]) * (sy - ay[k]) - (int64_t)(by[k] - ay[k]) * (sx - ax[k]);
+          if (E - bias[k] < 0) inside = 0;
+        }
+        if (inside) mask |= 1 << s;
+      }
+      if (!mask) continue;
+      /* shade once at the pixel centre */
+      const float cdx = (float)(px * 64 + 32 - x0) * 0.015625f, cdy = (float)(py * 64 + 32 - y0) * 0.015625f;
+      float at[7];
+      for (int k = 1; k < 7; k++) at[k] = fmaf(fy[k], cdy, fmaf(fx[k], cdx, f0[k]));
+      float qq = at[1];
+      if (!(qq > 1e-20f)) qq = 1e-20f;
+      const float rq = 1.0f / qq;
+      const float u = at[2] * rq, v = at[3] * rq;
+      float lit[3] = {at[4] * rq, at[5] * rq, at[6] * rq};
+      float colr[3];
+      if (tex) {
+        float tx = u * (float)tex->w - 0.5f, ty = v * (float)tex->h - 0.5f;
+        float txf = floorf(tx), tyf = floorf(ty);
+        float ffx = tx - txf, ffy = ty - tyf;
+        int ti0 = ((int)txf) & (tex->w - 1), ti1 = (ti0 + 1) & (tex->w - 1);
+        int tj0 = ((int)tyf) & (tex->h - 1), tj1 = (tj0 + 1) & (tex->h - 1);
+        for (int ch = 0; ch < 3; ch++) {
+          float t00 = tex_byte(tex, ti0, tj0, ch), t10 = tex_byte(tex, ti1, tj0, ch);
+          float t01 = tex_byte(tex, ti0, tj1, ch), t11 = tex_byte(tex, ti1, tj1, ch);
+          float ta = fmaf(ffx, t10 - t00, t00);
+          float tb = fmaf(ffx, t11 - t01, t01);
+          float tc = fmaf(ffy, tb - ta, ta);
+          colr[ch] = tc * (lit[ch] * 0.00392156862745098f);
+        }
+      } else { colr[0] = lit[0]; colr[1] = lit[1]; colr[2] = lit[2]; }
+      for (int s = 0; s < 4; s++) {
+        if (!(mask >> s & 1)) continue;
+        const float sdx = (float)(px * 64 + SX[s] - x0) * 0.015625f, sdy = (float)(py * 64 + SY[s] - y0) * 0.015625f;
+        const float z = fmaf(fy[0], sdy, fmaf(fx[0], sdx, f0[0]));
+        size_t si = ((size_t)py * fb->W + px) * 4 + s;
+        if (z < fb->depth[si]) {
+          fb->depth[si] = z;
+          fb->col[si * 3] = colr[0]; fb->col[si * 3 + 1] = colr[1]; fb->col[si * 3 + 2] = colr[2];
+        }
+      }
+    }
+}
+
+static void draw_triangle(framebuf* fb, const xform* x, const float* p, const float* n, const float* uv, const float* col,
+                          const orr_texture* tex) {
+  vtx poly[12];
+  for (int k = 0; k < 3; k++) poly[k] = shade_vertex(x, p + 3 * k, n + 3 * k, col + 3 * k, uv[2 * k], uv[2 * k + 1]);
+  /* trivial reject: all three outside one plane */
+  for (int pl = 0; pl < 6; pl++) {
+    int out = 0;
+    for (int k = 0; k < 3; k++) out += !(plane_dist(&poly[k], pl) >= 0.0f);
+    if (out == 3) return;
+  }
+  int m = clip_polygon(poly, 3);
+  for (int k = 1; k + 1 < m; k++) raster_triangle(fb, poly[0], poly[k], poly[k + 1], tex);
+}
+
+/* Render one env. out: u8 [H][W][3], row 0 = top.  lut_x/lut_y: NULL or fisheye LUT [H][W]. */
+void orr_render(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
+                int domain_rand, const float* lut_x, const float* lut_y, uint8_t* out) {
+  framebuf fb;
+  fb.W = W; fb.H = H;
+  fb.col = (float*)malloc(sizeof(float) * (size_t)W * H * 12);
+  fb.depth = (float*)malloc(sizeof(float) * (size_t)W * H * 4);
+  for (size_t k = 0; k < (size_t)W * H * 4; k++) {  /* glClear S:1753-1756 */
+    fb.depth[k] = 1.0f;
+    fb.col[3 * k] = ep->horizon[0]; fb.col[3 * k + 1] = ep->horizon[1]; fb.col[3 * k + 2] = ep->horizon[2];
+  }
+  double V[12];
+  camera_view(px, pz, angle, ep, domain_rand, V);
+  xform x;
+  x.ep = ep;
+  {  /* gluPerspective(fovy, W/H, 0.04, 100) S:1761 */
+    double f = 1.0 / tan((double)ep->cam_fov_y_deg * 0.017453292519943295 / 2.0), aspect = (double)W / (double)H;
+    double zn = 0.04, zf = 100.0;
+    x.P00 = (float)(f / aspect); x.P11 = (float)f;
+    x.P22 = (float)((zf + zn) / (zn - zf)); x.P23 = (float)(2.0 * zf * zn / (zn - zf));
+  }
+  const double zero3[3] = {0, 0, 0};
+  /* 1. ground quad S:1805-1812: glScalef(50,0.01,50) of (+-1,-0.8,+-1); colour ground_color; normal fixed to
+   *    unit +y in world space (the reference leaves it undefined) */
+  {
+    model_view(V, zero3, 1.0, 1.0, 0.0, x.MV, x.N);
+    const float gy = (float)(-0.8 * 0.01);
+    const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
+    const float nrm[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0}, uv[6] = {0, 0, 0, 0, 0, 0};
+    float col[9];
+    for (int k = 0; k < 3; k++) { col[k] = ep->ground[k]; col[3 + k] = ep->ground[k]; col[6 + k] = ep->ground[k]; }
+    const int tri[2][3] = {{0, 1, 2}, {0, 2, 3}};
+    for (int t = 0; t < 2; t++) {
+      float p[9];
+      for (int k = 0; k < 3; k++) memcpy(p + 3 * k, P[tri[t][k]], 12);
+      draw_triangle(&fb, &x, p, nrm, uv, col, NULL);
+    }
+  }
+  /* 2. road tiles S:1852-1884, vertex list S:386-507: i outer, j inner; 7x7 quads, (0,1,2)(0,2,3) split */
+  const double ts = sc->tile_size;
+  float lat[8];
+  for (int k = 0; k < 8; k++) lat[k] = (float)(-ts / 2 + ((double)k / 7.0) * ts);
+  for (int i = 0; i < sc->grid_w; i++)
+    for (int j = 0; j < sc->grid_h; j++) {
+      int idx = j * sc->grid_w + i;
+      if (sc->tile_kind[idx] < 0) continue;
+      /* glRotatef(angle*90+180, 0,1,0): multiples of 90 degrees -> exact cos/sin */
+      int quarter = (sc->tile_angle[idx] + 2) & 3;
+      const double cs[4] = {1, 0, -1, 0}, sn[4] = {0, 1, 0, -1};
+      const double t[3] = {(i + 0.5) * ts, 0.0, (j + 0.5) * ts};
+      model_view(V, t, 1.0, cs[quarter], sn[quarter], x.MV, x.N);
+      const orr_texture* tex = sc->tile_tex[idx] >= 0 ? &sc->textures[sc->tile_tex[idx]] : NULL;
+      const float white[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1}, up[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0};
+      for (int a = 0; a < 7; a++)
+        for (int b = 0; b < 7; b++) {
+          const int qa[4] = {a, a + 1, a + 1, a}, qb[4] = {b, b, b + 1, b + 1};
+          const int tri[2][3] = {{0, 1, 2}, {0, 2, 3}};
+          for (int tt = 0; tt < 2; tt++) {
+            float p[9], uv[6];
+            for (int k = 0; k < 3; k++) {
+              int u_ = qa[tri[tt][k]], v_ = qb[tri[tt][k]];
+              p[3 * k] = lat[u_]; p[3 * k + 1] = 0.0f; p[3 * k + 2] = lat[v_];
+              uv[2 * k] = (float)((double)u_ / 7.0);
+              uv[2 * k + 1] = (float)(1.0 - (double)v_ / 7.0);
+            }
+            draw_triangle(&fb, &x, p, up, uv, white, tex);
+          }
+        }
+    }
+  /* 3. objects S:1905-1907, O:123-148, M:360-375 */
+  for (int o = 0; o < sc->n_objects; o++) {
+    if (ep->hidden[o >> 5] >> (o & 31) & 1u) continue;
+    const orr_object* ob = &sc->objects[o];
+    const double t[3] = {ob->pos[0], ob->pos[1], ob->pos[2]};
+    const double th = (double)ob->y_rot_deg * 0.017453292519943295;
+    model_view(V, t, (double)ob->scale, cos(th), sin(th), x.MV, x.N);
+    for (int k = 0; k < ob->tri_count; k++) {
+      size_t ti = (size_t)ob->tri_offset + k;
+      const orr_texture* tex = sc->tri_tex[ti] >= 0 ? &sc->textures[sc->tri_tex[ti]] : NULL;
+      draw_triangle(&fb, &x, sc->tri_pos + ti * 9, sc->tri_nrm + ti * 9, sc->tri_uv + ti * 6, sc->tri_col + ti * 9, tex);
+    }
+  }
+  /* 4. resolve + readback S:1931-1949 (+ fused fisheye gather distortion.py:118) */
+  for (int y = 0; y < H; y++)
+    for (int xx = 0; xx < W; xx++) {
+      int sx = xx, sy = y, valid = 1;
+      if (lut_x) {
+        sx = (int)rintf(lut_x[(size_t)y * W + xx]);
+        sy = (int)rintf(lut_y[(size_t)y * W + xx]);
+        valid = sx >= 0 && sx < W && sy >= 0 && sy < H;  /* cv2.remap BORDER_CONSTANT -> 0 */
+      }
+      for (int ch = 0; ch < 3; ch++) {
+        uint8_t v = 0;
+        if (valid) {
+          const float* s = fb.col + ((size_t)sy * W + sx) * 12 + ch;
+          float c = ((s[0] + s[3]) + (s[6] + s[9])) * 0.25f;
+          c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+          v = (uint8_t)rintf(c * 255.0f);
+        }
+        out[((size_t)y * W + xx) * 3 + ch] = v;
+      }
+    }
+  free(fb.col);
+  free(fb.depth);
+}
+
+/* batch over envs (OpenMP): the cpu_baseline / --impl reference leg of bench.py */
+void orr_render_batch(const orr_scene* sc, int n, const double* px, const double* pz, const double* angle,
+                      const orr_episode* eps, int W, int H, int domain_rand, const float* lut_x, const float* lut_y,
+                      uint8_t* out, int threads) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int e = 0; e < n; e++)
+    orr_render(sc, px[e], pz[e], angle[e], &eps[e], W, H, domain_rand, lut_x, lut_y, out + (size_t)e * W * H * 3);
+}

@@ -142,3 +142,85 @@ class OracleEnv:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+
+
+# ----------------------------------------------------------------------------- raster oracle
+class OrrTexture(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("rgba", C.c_void_p)]
+
+
+class OrrObject(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("tri_offset", C.c_int32),
+                ("tri_count", C.c_int32)]
+
+
+class OrrScene(C.Structure):
+    _fields_ = [("tile_size", C.c_double), ("grid_w", C.c_int32), ("grid_h", C.c_int32), ("tile_kind", C.c_void_p),
+                ("tile_angle", C.c_void_p), ("tile_tex", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p),
+                ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p),
+                ("tri_tex", C.c_void_p), ("n_textures", C.c_int32), ("textures", C.c_void_p)]
+
+
+class OrrEpisode(C.Structure):
+    _fields_ = [("cam_height", C.c_float), ("cam_angle_deg", C.c_float), ("cam_fov_y_deg", C.c_float),
+                ("cam_noise", C.c_float * 3), ("horizon", C.c_float * 3), ("ambient", C.c_float * 3),
+                ("diffuse", C.c_float * 3), ("light_eye", C.c_float * 4), ("ground", C.c_float * 3),
+                ("hidden", C.c_uint32 * 8)]
+
+
+def default_episode(**kw) -> OrrEpisode:
+    """Non-randomized values of Simulator.reset() (S:546-614): what dts_reset uses for NULL params."""
+    ep = OrrEpisode(0.108, 19.15, 75.0, (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(0.45, 0.82, 1.0),
+                    (C.c_float * 3)(0.25, 0.25, 0.25), (C.c_float * 3)(0.35, 0.35, 0.35),
+                    (C.c_float * 4)(0, 3, 0, 1), (C.c_float * 3)(0.15, 0.15, 0.15), (C.c_uint32 * 8)())
+    for k, v in kw.items():
+        cur = getattr(ep, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(ep, k, v)
+    return ep
+
+
+class OracleScene:
+    """orr_scene for a MapData; array flattening shared with the product's blob builder (data only)."""
+
+    def __init__(self, md):
+        from gym_duckietown_b200.lib import MapBlobHolder
+        self.holder = h = MapBlobHolder(md)
+        k = h.keep
+        self.objs = (OrrObject * max(1, len(md.objects)))()
+        for i, o in enumerate(md.objects):
+            src = k["objs"][i]
+            me = k["meshes"][o.mesh_id]
+            self.objs[i] = OrrObject(src.pos, src.scale, src.y_rot_deg, me.tri_offset, me.tri_count)
+        self.texs = (OrrTexture * max(1, len(k["tex_imgs"])))()
+        for i, im in enumerate(k["tex_imgs"]):
+            self.texs[i] = OrrTexture(im.shape[1], im.shape[0], im.ctypes.data)
+        self.c = OrrScene(md.tile_size, md.grid_w, md.grid_h, _p(k["kind"]), _p(k["angle"]), _p(k["tex"]),
+                          len(md.objects), C.cast(self.objs, C.c_void_p), _p(k["tpos"]), _p(k["tnrm"]), _p(k["tuv"]),
+                          _p(k["tcol"]), _p(k["ttex"]), len(k["tex_imgs"]), C.cast(self.texs, C.c_void_p))
+
+    def render(self, px, pz, angle, ep: OrrEpisode = None, W=160, H=120, domain_rand=False, lut=None) -> np.ndarray:
+        ep = ep or default_episode()
+        out = np.zeros((H, W, 3), np.uint8)
+        lx = ly = None
+        if lut is not None:
+            lx, ly = np.ascontiguousarray(lut[0], np.float32), np.ascontiguousarray(lut[1], np.float32)
+        lib().orr_render(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle), C.byref(ep), W, H,
+                         int(domain_rand), _p(lx) if lx is not None else None, _p(ly) if ly is not None else None, _p(out))
+        return out
+
+    def render_batch(self, px, pz, angle, eps, W=160, H=120, domain_rand=False, lut=None, threads=1) -> np.ndarray:
+        n = len(px)
+        out = np.zeros((n, H, W, 3), np.uint8)
+        arr = (OrrEpisode * n)(*eps)
+        a = [np.ascontiguousarray(v, np.float64) for v in (px, pz, angle)]
+        lx = ly = None
+        if lut is not None:
+            lx, ly = np.ascontiguousarray(lut[0], np.float32), np.ascontiguousarray(lut[1], np.float32)
+        lib().orr_render_batch(C.byref(self.c), n, _p(a[0]), _p(a[1]), _p(a[2]), arr, W, H, int(domain_rand),
+                               _p(lx) if lx is not None else None, _p(ly) if ly is not None else None, _p(out),
+                               int(threads))
+        return out

