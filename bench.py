@@ -1,0 +1,271 @@
+#!/usr/bin/env python3
+"""bench.py — env-steps/s of the batched Simulator.step() hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E] [--map M]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch: `env.step(actions)` for all E envs of the
+rank (pose integration, lane/reward/collision, 160x120 render, device-side auto-reset).  Workload
+at every N: BASELINE.json configs[1] per GPU (Duckietown-small_loop stand-in, 4096 envs, 160x120,
+uniform random [vel, steer] actions, domain_rand off) -> weak scaling.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (obs+reward+done) at N envs, 1/2/4/8 B200 vs CPU ref"
+UNIT = "env-steps/s"
+
+
+def b_alg(w, h):
+    """Algorithmic bytes per env-step: obs store + bilinear RGBA8 texel reads + state."""
+    return w * h * (3 + 16) + 256
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_run(map_name, w, h, steps, warmup, sample_envs, threads):
+    """The CPU arm: oracle port of Simulator.step() (logic + software render), one env per OpenMP
+    task on all host cores.  Returns (env_steps_per_s, seconds, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+
+    md = maps.load_map(map_name)
+    rng = np.random.default_rng(1234)
+    tiles = [md.drivable_tiles[k % len(md.drivable_tiles)] for k in range(sample_envs)]
+    # spawn on lane centres of drivable tiles (valid poses), like a reset would
+    px = np.array([(i + 0.5) * md.tile_size for i, j in tiles]) + 0.0
+    pz = np.array([(j + 0.5) * md.tile_size for i, j in tiles]) + 0.0
+    om = orc.OracleMap(md)
+    ang = np.zeros(sample_envs)
+    for k in range(sample_envs):  # pick a heading that is a valid spawn
+        for a in np.linspace(-np.pi, np.pi, 16, endpoint=False):
+            o = om.done_reward(px[k], pz[k], a, 0)
+            if not o.done and o.in_lane and abs(o.lane_angle) < 0.5:
+                ang[k] = a
+                break
+    batch = orc.OracleBatch(md, px, pz, ang, W=w, H=h, threads=threads)
+    acts = rng.uniform(-1, 1, (warmup + steps, sample_envs, 2)).astype(np.float32)
+    for t in range(warmup):
+        batch.step(acts[t])
+    t0 = time.perf_counter()
+    for t in range(steps):
+        batch.step(acts[warmup + t])
+    dt = time.perf_counter() - t0
+    return sample_envs * steps / dt, dt, (f"{sample_envs} envs x {steps} steps of the same workload "
+                                          f"(oracle port: C logic + software rasteriser, {threads} OpenMP threads)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="dtsim", choices=["dtsim", "reference"])
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--map", default="small_loop")
+    ap.add_argument("--width", type=int, default=160)
+    ap.add_argument("--height", type=int, default=120)
+    ap.add_argument("--cpu-sample-envs", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    W, H, E = args.width, args.height, args.envs
+    cores = os.cpu_count() or 1
+    config = {"workload": f"Duckietown-{args.map}-v0 (stand-in map), {E} envs/GPU, {W}x{H} RGB, random [vel,steer] "
+                          f"actions, domain_rand=False, device-side auto-reset",
+              "envs_per_gpu": E, "width": W, "height": H, "map": args.map,
+              "l2": "obs batch written per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (E * W * H * 3 / 1e6)}
+
+    if args.impl == "reference":
+        # The reference's own Pyglet/OpenGL path cannot run in this image (no pyglet, GL, display,
+        # duckietown_world); the CPU arm is the oracle port of the same step on all host cores.
+        if rank != 0:
+            return
+        k = max(1, min(args.steps, 20))
+        w_ = max(1, min(args.warmup, 3))
+        val, secs, desc = cpu_reference_run(args.map, W, H, k, w_, args.cpu_sample_envs, cores)
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w_,
+                "ms_per_step": 1000 * secs / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 logic / f32 raster / u8 obs", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    env = BatchedDuckietownEnv(E, args.map, device=local_rank, camera_width=W, camera_height=H, domain_rand=False,
+                               seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E)
+    env.reset()
+    K, Wm = args.steps, max(3, args.warmup)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.rand((K + Wm, E, 2), device=dev, generator=gen) * 2 - 1   # Box(-1,1,(2,)).sample() distribution
+    gathered = None
+    if world > 1:
+        from gym_duckietown_b200.dist import ObsAllGather
+        ag = ObsAllGather(env, rank, world)
+        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: `value` -------------------------------------------------------------
+    for t in range(Wm):
+        env.step(actions[t])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rs = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    re_ = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = env.launch_count()
+    ev0.record()
+    for t in range(K):
+        env.step(actions[Wm + t], render=False)   # k_step_logic (+ device auto-reset)
+        rs[t].record()
+        env.render_obs()                          # k_render  — same two launches dts_step issues
+        re_[t].record()
+    if world > 1:
+        ag.all_gather(gathered)                   # the single end-of-rollout NCCL all-gather
+    ev1.record()
+    barrier()
+    launches = env.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    render_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(rs, re_)]))
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * E * K / (ms / 1000.0)
+
+    # ---- end-to-end arm: host buffers in/out through the public API -----------------------------------
+    Ke = max(5, min(K, 50))
+    h_act = torch.empty((Ke, E, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    h_obs = torch.empty(tuple(env.obs.shape), dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(E, dtype=torch.bool).pin_memory()
+    d_act = torch.empty((E, 2), dtype=torch.float32, device=dev)
+    for t in range(3):
+        d_act.copy_(h_act[t], non_blocking=True)
+        env.step(d_act)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(Ke):
+        d_act.copy_(h_act[t], non_blocking=True)
+        obs, rew, done, _ = env.step(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ems], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ems = float(tmax.item())
+    e2e = world * E * Ke / (ems / 1000.0)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    achieved = E * b_alg(W, H) / (render_ms / 1000.0) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "render_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("envs") == E and tj.get("width") == W and tj.get("map") == args.map:
+            traffic = tj.get("dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 logic / f32 raster / u8 obs", "data": "synthetic", "config": config,
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4, "d2h_bytes_per_step": E * (W * H * 3 + 4 + 1),
+                "steps": Ke},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": render_ms,
+                     "compulsory_frac": (E * (W * H * 3 + 256) / (render_ms / 1000.0) / 1e9) / peak},
+    }
+    if not args.no_cpu_baseline:
+        val, secs, desc = cpu_reference_run(args.map, W, H, 10, 2, args.cpu_sample_envs, cores)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

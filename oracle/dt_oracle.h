@@ -1,0 +1,79 @@
+/* dt_oracle.h — types and prototypes of the CPU oracle (TEST INFRASTRUCTURE, see the .c headers). */
+#ifndef DT_ORACLE_H
+#define DT_ORACLE_H
+#include <stdint.h>
+
+#define ORC_MAX_DELAY 8
+
+typedef struct {
+  double tile_size;
+  int32_t grid_w, grid_h;
+  const int8_t* tile_kind;
+  const uint8_t* tile_drivable;
+  const int32_t* tile_curve_off;
+  const int32_t* tile_curve_cnt;
+  const double* curves; /* [nc][4][3] */
+  int32_t n_coll;
+  const double* coll_corners; /* [K][2][4] */
+  const double* coll_norms;   /* [K][2][2] */
+  const double* coll_centers; /* [K][3] */
+  const double* coll_radii;   /* [K] */
+} orc_map;
+
+typedef struct {
+  double u1, u2, u3, w1, w2, w3, uar, ual, war, wal;
+  int32_t delay_steps; /* commands issued at step k act from step k+delay_steps on */
+} orc_dyn_params;
+
+typedef struct {
+  double x, y, theta; /* cartesian pose q (duckietown_world frame) */
+  double u, w;        /* longitudinal / angular velocity */
+  double fifo[ORC_MAX_DELAY][2]; /* pending (left,right) commands, [0] = oldest */
+} orc_dyn_state;
+
+typedef struct {
+  double pos_x, pos_z, angle, speed;
+  double reward;
+  double lane_dist, lane_dot, lane_angle;
+  double prox;
+  int32_t tile_i, tile_j, step_count;
+  uint8_t done, done_code, in_lane, collided, drivable4;
+} orc_step_out;
+
+typedef struct { int32_t w, h; const uint8_t* rgba; } orr_texture;
+typedef struct { float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count; } orr_object;
+
+typedef struct {
+  double tile_size;
+  int32_t grid_w, grid_h;
+  const int8_t* tile_kind;
+  const int8_t* tile_angle;
+  const int16_t* tile_tex;
+  int32_t n_objects;
+  const orr_object* objects;
+  const float* tri_pos; /* [T][3][3] */
+  const float* tri_nrm;
+  const float* tri_uv;  /* [T][3][2] */
+  const float* tri_col;
+  const int16_t* tri_tex;
+  int32_t n_textures;
+  const orr_texture* textures;
+} orr_scene;
+
+typedef struct { /* mirrors the product's per-episode render record */
+  float cam_height, cam_angle_deg, cam_fov_y_deg;
+  float cam_noise[3], horizon[3], ambient[3], diffuse[3], light_eye[4], ground[3];
+  uint32_t hidden[8];
+} orr_episode;
+
+void orc_action_map(double vel, double steer, double wheel_dist, double gain, double trim, double radius, double k,
+                    double limit, double out_lr[2]);
+void orc_dyn_step(orc_dyn_state* s, const orc_dyn_params* p, const double cmd_lr[2], double dt);
+void orc_weird_from_cartesian(const orc_map* m, const orc_dyn_state* s, double* px, double* pz, double* ang);
+void orc_cartesian_from_weird(const orc_map* m, double px, double pz, double ang, orc_dyn_state* s);
+void orc_step(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int* step_count, double* last_px,
+              double* last_pz, const double action[2], int action_mode, double wheel_dist, const double env5[5],
+              int frame_skip, double dt, int max_steps, double robot_speed, orc_step_out* o);
+void orr_render(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
+                int domain_rand, const float* lut_x, const float* lut_y, uint8_t* out);
+#endif

@@ -14,42 +14,8 @@
 #include <stdint.h>
 #include <string.h>
 
-#define ORC_MAX_DELAY 8
+#include "dt_oracle.h"
 
-typedef struct {
-  double tile_size;
-  int32_t grid_w, grid_h;
-  const int8_t* tile_kind;
-  const uint8_t* tile_drivable;
-  const int32_t* tile_curve_off;
-  const int32_t* tile_curve_cnt;
-  const double* curves; /* [nc][4][3] */
-  int32_t n_coll;
-  const double* coll_corners; /* [K][2][4] */
-  const double* coll_norms;   /* [K][2][2] */
-  const double* coll_centers; /* [K][3] */
-  const double* coll_radii;   /* [K] */
-} orc_map;
-
-typedef struct {
-  double u1, u2, u3, w1, w2, w3, uar, ual, war, wal;
-  int32_t delay_steps; /* commands issued at step k act from step k+delay_steps on */
-} orc_dyn_params;
-
-typedef struct {
-  double x, y, theta; /* cartesian pose q (duckietown_world frame) */
-  double u, w;        /* longitudinal / angular velocity */
-  double fifo[ORC_MAX_DELAY][2]; /* pending (left,right) commands, [0] = oldest */
-} orc_dyn_state;
-
-typedef struct {
-  double pos_x, pos_z, angle, speed;
-  double reward;
-  double lane_dist, lane_dot, lane_angle;
-  double prox;
-  int32_t tile_i, tile_j, step_count;
-  uint8_t done, done_code, in_lane, collided, drivable4;
-} orc_step_out;
 
 /* robot constants simulator.py:118-177 */
 static const double ROBOT_WIDTH = 0.13 + 0.02;

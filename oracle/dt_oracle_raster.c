@@ -24,31 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-typedef struct { int32_t w, h; const uint8_t* rgba; } orr_texture;
-typedef struct { float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count; } orr_object;
+#include "dt_oracle.h"
 
-typedef struct {
-  double tile_size;
-  int32_t grid_w, grid_h;
-  const int8_t* tile_kind;
-  const int8_t* tile_angle;
-  const int16_t* tile_tex;
-  int32_t n_objects;
-  const orr_object* objects;
-  const float* tri_pos; /* [T][3][3] */
-  const float* tri_nrm;
-  const float* tri_uv;  /* [T][3][2] */
-  const float* tri_col;
-  const int16_t* tri_tex;
-  int32_t n_textures;
-  const orr_texture* textures;
-} orr_scene;
-
-typedef struct { /* mirrors the product's per-episode render record */
-  float cam_height, cam_angle_deg, cam_fov_y_deg;
-  float cam_noise[3], horizon[3], ambient[3], diffuse[3], light_eye[4], ground[3];
-  uint32_t hidden[8];
-} orr_episode;
 
 typedef struct { float cx, cy, cz, cw, r, g, b, u, v; } vtx; /* clip-space vertex with attributes */
 

@@ -14,12 +14,13 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liborc.so")
-SOURCES = ["dt_oracle_logic.c", "dt_oracle_raster.c"]
+SOURCES = ["dt_oracle_logic.c", "dt_oracle_raster.c", "dt_oracle_batch.c"]
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+    deps = srcs + [os.path.join(HERE, "dt_oracle.h")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in deps):
         return LIB
     # -ffp-contract=off: no silent FMA contraction, so the float arithmetic is exactly what the
     # source says (the raster oracle's fp32 spec relies on it); -mfma only makes fmaf() an instruction.
@@ -224,3 +225,36 @@ class OracleScene:
                                _p(lx) if lx is not None else None, _p(ly) if ly is not None else None, _p(out),
                                int(threads))
         return out
+
+
+class OrcEnv(C.Structure):
+    _fields_ = [("s", OrcDynState), ("step_count", C.c_int32), ("px", C.c_double), ("pz", C.c_double),
+                ("px0", C.c_double), ("pz0", C.c_double), ("ang0", C.c_double)]
+
+
+class OracleBatch:
+    """n reference-style envs stepped + rendered on host cores (one env per OpenMP task)."""
+
+    def __init__(self, md, px, pz, angle, *, W=160, H=120, action_mode=1, max_steps=1500, threads=None):
+        self.om, self.sc = OracleMap(md), OracleScene(md)
+        self.n, self.W, self.H = len(px), W, H
+        self.envs = (OrcEnv * self.n)()
+        for k in range(self.n):
+            lib().orc_env_init(C.byref(self.om.c), C.byref(self.envs[k]), C.c_double(px[k]), C.c_double(pz[k]),
+                               C.c_double(angle[k]))
+        self.eps = (OrrEpisode * self.n)(*[default_episode() for _ in range(self.n)])
+        self.dp = default_dyn_params()
+        self.env5 = (C.c_double * 5)(1.0, 0.0, 0.0318, 27.0, 1.0)
+        self.action_mode, self.max_steps = action_mode, max_steps
+        self.threads = threads or os.cpu_count() or 1
+        self.obs = np.zeros((self.n, H, W, 3), np.uint8)
+        self.reward = np.zeros(self.n, np.float32)
+        self.done = np.zeros(self.n, np.uint8)
+
+    def step(self, actions: np.ndarray, render=True):
+        a = np.ascontiguousarray(actions, np.float32)
+        lib().orc_full_step_batch(C.byref(self.om.c), C.byref(self.sc.c), C.byref(self.dp), self.n, self.envs, _p(a),
+                                  self.action_mode, C.c_double(0.102), self.env5, 1, C.c_double(1.0 / 30),
+                                  self.max_steps, C.c_double(1.2), self.eps, self.W, self.H, int(render), _p(self.obs),
+                                  _p(self.reward), _p(self.done), self.threads)
+        return self.obs, self.reward, self.done
