@@ -18,3 +18,18 @@ def __getattr__(name):  # lazy: importing the package must not require torch/CUD
         from . import simulator
         return getattr(simulator, name)
     raise AttributeError(name)
+
+
+def _register_envs():
+    """One id per map like gym_duckietown/__init__.py:30-46, plus MultiMap-v0."""
+    from .gymshim import register
+    for _name in list_maps():
+        register(id=f"Duckietown-{_name}-v0", entry_point="gym_duckietown_b200.simulator:DuckietownEnv",
+                 reward_threshold=400.0, kwargs={"map_name": _name})
+    register(id="MultiMap-v0", entry_point="gym_duckietown_b200.simulator:MultiMapEnv", reward_threshold=400.0)
+
+
+try:
+    _register_envs()
+except Exception:  # duplicate registration on re-import under real gym
+    pass

@@ -301,10 +301,21 @@ static void draw_triangle(framebuf* fb, const xform* x, const float* p, const fl
 /* Render one env. out: u8 [H][W][3], row 0 = top.  lut_x/lut_y: NULL or fisheye LUT [H][W]. */
 void orr_render(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                 int domain_rand, const float* lut_x, const float* lut_y, uint8_t* out) {
+  /* per-thread sample buffers, kept across frames (a malloc/free of ~1 MB per frame turns into
+   * mmap/munmap + page faults and serialises the OpenMP batch) */
+  static _Thread_local float* tl_col = 0;
+  static _Thread_local float* tl_depth = 0;
+  static _Thread_local size_t tl_px = 0;
+  if (tl_px < (size_t)W * H) {
+    free(tl_col); free(tl_depth);
+    tl_px = (size_t)W * H;
+    tl_col = (float*)malloc(sizeof(float) * tl_px * 12);
+    tl_depth = (float*)malloc(sizeof(float) * tl_px * 4);
+  }
   framebuf fb;
   fb.W = W; fb.H = H;
-  fb.col = (float*)malloc(sizeof(float) * (size_t)W * H * 12);
-  fb.depth = (float*)malloc(sizeof(float) * (size_t)W * H * 4);
+  fb.col = tl_col;
+  fb.depth = tl_depth;
   for (size_t k = 0; k < (size_t)W * H * 4; k++) {  /* glClear S:1753-1756 */
     fb.depth[k] = 1.0f;
     fb.col[3 * k] = ep->horizon[0]; fb.col[3 * k + 1] = ep->horizon[1]; fb.col[3 * k + 2] = ep->horizon[2];
@@ -400,8 +411,6 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
         out[((size_t)y * W + xx) * 3 + ch] = v;
       }
     }
-  free(fb.col);
-  free(fb.depth);
 }
 
 /* batch over envs (OpenMP): the cpu_baseline / --impl reference leg of bench.py */
