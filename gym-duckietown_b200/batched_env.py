@@ -27,7 +27,7 @@ class BatchedDuckietownEnv:
                  color_ground=(0.15, 0.15, 0.15), color_sky=(0.45, 0.82, 1), num_tris_distractors: int = 12,
                  gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
                  action_mode: str = "vel_steer", auto_reset: bool = False, device_reset: bool = False,
-                 cycle_maps: bool = False, env_id_offset: int = 0):
+                 cycle_maps: bool = False, env_id_offset: int = 0, tessellate_tiles: bool = False):
         if not torch.cuda.is_available():
             raise L.DtsError("BatchedDuckietownEnv needs a CUDA device; there is no CPU implementation")
         if camera_rand:
@@ -44,7 +44,8 @@ class BatchedDuckietownEnv:
         if auto_reset and not device_reset:
             raise ValueError("auto_reset re-spawns on the device: pass device_reset=True")
         flags = (L.FLAG_AUTO_RESET if auto_reset else 0) | (L.FLAG_DOMAIN_RAND if domain_rand else 0) | \
-                (L.FLAG_DISTORTION if distortion else 0) | (L.FLAG_DYNAMICS_RAND if dynamics_rand else 0)
+                (L.FLAG_DISTORTION if distortion else 0) | (L.FLAG_DYNAMICS_RAND if dynamics_rand else 0) | \
+                (L.FLAG_TESSELLATE if tessellate_tiles else 0)
         self.cfg = L.default_config(
             num_envs=num_envs, device=device, cam_width=camera_width, cam_height=camera_height, max_steps=max_steps,
             frame_skip=int(frame_skip), action_mode=L.ACTION_VEL_STEER if action_mode == "vel_steer" else L.ACTION_PWM,

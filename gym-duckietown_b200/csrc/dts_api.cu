@@ -34,7 +34,7 @@ struct dts_sim {
            float* light_pos; int32_t* light_stale; uint32_t* hidden; } stage{};
   // render
   void* render_scratch = nullptr;
-  int render_ctas = 0, max_prims = 0, max_pairs = 0;
+  int render_ctas = 0, max_prims = 0, max_pairs = 0, max_lat = 0;
   float *lut_x = nullptr, *lut_y = nullptr;
   int32_t* d_err = nullptr;
   // query scratch
@@ -298,24 +298,24 @@ static int ensure_render(dts_sim* sim) {
   if (sim->render_scratch) return 0;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sim->cfg.device);
-  int max_tris = 2;
+  const bool tess = (sim->cfg.flags & DTS_FLAG_TESSELLATE) != 0;
+  int max_tris = 2, max_lat = 1;
   for (const DMap& m : sim->h_maps) {
     if (!m.valid) continue;
-    int t = 2;
-    for (int k = 0; k < m.n_tiles; k++) t += 98;  // upper bound (every cell has a tile)
-    // object triangles
+    int t = 2 + (tess ? 98 : 6) * m.n_tiles;   // a clipped tile quad fans into a few triangles
     std::vector<DObject> objs(m.n_objects);
     if (m.n_objects) cudaMemcpy(objs.data(), m.objects, sizeof(DObject) * m.n_objects, cudaMemcpyDeviceToHost);
     for (const DObject& o : objs) t += o.tri_count;
     max_tris = t > max_tris ? t : max_tris;
+    max_lat = m.n_tiles > max_lat ? m.n_tiles : max_lat;
   }
-  sim->render_ctas = sms * 2 < sim->cfg.num_envs ? sms * 2 : sim->cfg.num_envs;
+  sim->render_ctas = sms * 3 < sim->cfg.num_envs ? sms * 3 : sim->cfg.num_envs;
   sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
-  const int bins = ((sim->cfg.cam_width + 15) / 16) * ((sim->cfg.cam_height + 15) / 16);
-  sim->max_pairs = sim->max_prims * 6 + bins * 8;
   if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
+  sim->max_lat = max_lat;
+  sim->max_pairs = 640 * 24 + sim->max_prims * 4;   // per macro tile of <= 640 bins
   const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
-  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs, frame);
+  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
   if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   return 0;
@@ -328,9 +328,10 @@ int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   if (ensure_render(sim)) return 1;
   if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->lut_x) return sim->fail("distortion enabled but no fisheye LUT set");
-  RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs};
+  RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
+               (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0};
   const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
-                              sim->max_pairs, sim->lut_x, sim->lut_y, sim->d_err, (cudaStream_t)stream);
+                              sim->max_pairs, sim->max_lat, sim->lut_x, sim->lut_y, sim->d_err, (cudaStream_t)stream);
   sim->launches += k;
   DTS_CUDA(cudaGetLastError());
   return 0;

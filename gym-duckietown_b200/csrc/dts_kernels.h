@@ -19,6 +19,7 @@ struct RenderCfg {
   int32_t width, height;      // output obs size
   int32_t flags;
   int32_t n_envs;
+  int32_t tessellate;         // 1: literal 98 triangles per road tile (spec tile mode 0)
 };
 
 void launch_step_logic(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const float* actions,
@@ -32,9 +33,9 @@ void launch_query(const DMap* maps, int map_id, int n, const double* q, const ui
 
 // render (dts_render.cu)
 struct RenderScratch;
-size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, size_t undistorted_frame_bytes);
+size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_lat, size_t undistorted_frame_bytes);
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, const float* lut_x, const float* lut_y, int32_t* err_flag,
+                  int max_prims, int max_pairs, int max_lat, const float* lut_x, const float* lut_y, int32_t* err_flag,
                   cudaStream_t st);
 
 }  // namespace dts

@@ -2,20 +2,27 @@
 // simulator.py:1707-1951) on sm_100a.  No tensor cores: there is no dense contraction here.
 //
 // One persistent CTA (256 threads = 8 warps) renders one env at a time:
-//   G  geometry   warp-per-draw-item (ground / map tile / placed mesh): model-view in f64->f32,
-//                 per-vertex fixed-function lighting (tile lattice 8x8 shared through smem), frustum
-//                 cull, guard-band/near clip, snap to 1/64 px, triangle setup -> 128-byte PrimRec
-//                 appended to the CTA's slab in HBM/L2; per-16x16-bin counters in smem
-//   B  binning    exclusive scan of the bin counters, second pass scatters prim indices per bin
-//   R  raster     bin by bin: 64 PrimRecs at a time staged HBM->smem (edge functions re-based to the
-//                 bin so lanes work in int32), 8 warps each own an 8x4 pixel block, one pixel per
-//                 lane with its 4 MSAA samples (depth, colour, prim id) in registers
-//   O  output     box resolve -> u8, 16x16x3 tile staged in smem and stored as 16-byte rows
+//   G  geometry   warp per draw item (ground / map tile / placed mesh): model-view f64->f32,
+//                 fixed-function per-vertex lighting, frustum cull, near + guard-band clip, snap to
+//                 1/64 px, triangle setup -> 128-byte PrimRec appended to the CTA's slab (HBM/L2).
+//                 A road tile is ONE quad: its 8x8 lit lattice goes to a per-CTA table and the
+//                 Gouraud interpolant is evaluated per pixel (render spec, oracle tile mode 1);
+//                 RenderCfg.tessellate switches back to the literal 98 triangles (tile mode 0).
+//   B  binning    8x4-pixel bins (= one warp's pixel block): count, warp-scan, scatter; triangles
+//                 with large bounding boxes are binned warp-cooperatively with an exact edge test
+//   R  raster     warps pull bins from a shared counter — no CTA barrier inside the phase.  16 prims at a
+//                 time are staged lane-parallel (edge functions re-based to the bin so lanes work in
+//                 int32, exact trivial reject / trivial accept), ballot-compacted, then every lane owns
+//                 one pixel with its 4 MSAA samples (depth, colour, draw id) in registers; early-z
+//                 before shading; ground drawn last
+//   O  output     box resolve -> u8, rows packed with shuffles and stored as 32-bit words
 // Arithmetic follows the render spec in oracle/dt_oracle_raster.c / DESIGN.md bit for bit
 // (compiled with -fmad=false; fmaf() is spelled out where the spec has one).
 //
-// HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab write/read (~128 B x
-// visible triangles, L2-resident) + texels (shared by all envs, L2-resident).
+// HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / bin lists / lattice table
+// (tens of KB, L2-resident) + texels (shared by all envs, L2-resident).
+#include <cstddef>
+
 #include "dts_camera.cuh"
 #include "dts_kernels.h"
 
@@ -25,8 +32,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kBin = 16;          // bin edge in pixels
-constexpr int kChunk = 64;        // prims staged per pass
+constexpr int kBinW = 8, kBinH = 4;   // one warp's pixel block
+constexpr int kMtBinsX = 20, kMtBinsY = 32;  // macro tile = 160 x 128 px = 640 bins
+constexpr int kStage = 16;        // prims staged per pass and warp
+constexpr int kMaxLarge = 1024;
 constexpr float kGuard = 4.0f;
 constexpr int kSub = 64;          // sub-pixel units per pixel
 __constant__ int c_sx[4] = {24, 56, 8, 40};
@@ -34,27 +43,29 @@ __constant__ int c_sy[4] = {8, 24, 40, 56};
 
 struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 
-struct __align__(16) PrimRec {   // 128 B in the CTA's HBM slab
+struct __align__(16) PrimRec {   // 128 B in the CTA's slab
   int32_t X[3], Y[3];            // snapped vertices, orientation normalised (area > 0)
   float f0[7], fx[7], fy[7];     // planes anchored at vertex 0: z, q=1/w, u*q, v*q, r*q, g*q, b*q
   int32_t id_tex;                // draw id << 8 | (texture index + 1)
-  uint32_t bbox;                 // bin bbox: bx0 | by0<<8 | bx1<<16 | by1<<24
-  int32_t px0y0, px1y1;          // pixel bbox (x | y<<16)
+  int32_t pxmin, pxmax;          // pixel bbox (x | y<<16); 8-byte aligned, read as one int2 by the binner
+  int32_t lat;                   // lattice slot of an analytic road tile, -1 otherwise
   int32_t pad;
 };
+static_assert(offsetof(PrimRec, pxmin) % 8 == 0, "pxmin/pxmax are loaded as int2");
 static_assert(sizeof(PrimRec) == 128, "PrimRec must be 128 bytes");
 
-struct __align__(16) BinPrim {   // smem, per staged prim, values re-based to the current bin
+struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the current bin
   int32_t E0[3], A[3], B[3];     // E_k(x,y) = E0_k + A_k*x + B_k*y, x,y in 1/64 px from the bin corner
   int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
   float f0[7], fx[7], fy[7];
   int32_t id;                    // draw id
-  int32_t tex_w, tex_h;          // 0 = untextured
-  const uint8_t* tex;
-  int32_t px0, py0, px1, py1;    // pixel bbox relative to the bin
-  int32_t live;                  // 0 = trivially rejected for this bin
-  int32_t pad;
+  int32_t flags;                 // bit0: every sample of the bin is inside all three edges
+  const uint8_t* tex;            // nullptr = untextured
+  int32_t tex_wh;                // w | h<<16
+  int32_t lat;
+  int32_t pad[2];
 };
+static_assert(sizeof(BinPrim) == 160, "BinPrim layout");
 
 struct Xform { float MV[12], N[9]; };
 
@@ -62,10 +73,10 @@ struct Shared {
   RenderEp ep;
   double V[12];
   float P00, P11, P22, P23;
-  int n_prims, n_pairs, overflow;
-  Vtx lattice[kWarps][64];
-  BinPrim chunk[kChunk];
-  uint8_t tile[kBin][kBin * 3];
+  int n_prims, n_large, n_lat, overflow, next_bin, n_pairs;
+  Vtx corners[kWarps][4];
+  uint16_t large[kMaxLarge];
+  BinPrim stage[kWarps][kStage];
 };
 
 // MV = V * T(t) * S(sc) * Ry(c,s), N = rot(V) * Ry / sc — float64 then rounded (spec)
@@ -165,13 +176,12 @@ __device__ __forceinline__ int classify(const Vtx& a, const Vtx& b, const Vtx& c
 struct EmitCtx {
   Shared* sh;
   PrimRec* prims;
-  int* bin_count;
-  int max_prims, W, H, bins_x;
+  int max_prims, W, H;
 };
 
 // screen mapping + triangle setup (spec steps 5-7) and append to the slab
 __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                               int tex) {
+                                               int tex, int lat) {
   const Vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
   float zw[3], q[3];
@@ -191,10 +201,10 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
   if (area2 == 0) return;
   const int i1 = area2 < 0 ? 2 : 1, i2 = area2 < 0 ? 1 : 2;
   const int x0 = X[0], y0 = Y[0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
-  int minx = min(x0, min(x1, x2)), maxx = max(x0, max(x1, x2));
-  int miny = min(y0, min(y1, y2)), maxy = max(y0, max(y1, y2));
-  int px0 = max(minx >> 6, 0), px1 = min(maxx >> 6, ec.W - 1);
-  int py0 = max(miny >> 6, 0), py1 = min(maxy >> 6, ec.H - 1);
+  const int minx = min(x0, min(x1, x2)), maxx = max(x0, max(x1, x2));
+  const int miny = min(y0, min(y1, y2)), maxy = max(y0, max(y1, y2));
+  const int px0 = max(minx >> 6, 0), px1 = min(maxx >> 6, ec.W - 1);
+  const int py0 = max(miny >> 6, 0), py1 = min(maxy >> 6, ec.H - 1);
   if (px0 > px1 || py0 > py1) return;
   PrimRec r;
   r.X[0] = x0; r.X[1] = x1; r.X[2] = x2;
@@ -216,20 +226,16 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
     r.fy[at] = (d2 * dx1 - d1 * dx2) * ia;
   }
   r.id_tex = (id << 8) | (tex + 1);
-  const int bx0 = px0 / kBin, bx1 = px1 / kBin, by0 = py0 / kBin, by1 = py1 / kBin;
-  r.bbox = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bx1 << 16) | ((uint32_t)by1 << 24);
-  r.px0y0 = px0 | (py0 << 16);
-  r.px1y1 = px1 | (py1 << 16);
+  r.lat = lat;
+  r.pxmin = px0 | (py0 << 16);
+  r.pxmax = px1 | (py1 << 16);
   r.pad = 0;
   const int slot = atomicAdd(&ec.sh->n_prims, 1);
   if (slot >= ec.max_prims) { ec.sh->overflow = 1; return; }
-  // 128-byte record as 8 x 16-byte stores
   const int4* src = reinterpret_cast<const int4*>(&r);
   int4* dst = reinterpret_cast<int4*>(ec.prims + slot);
 #pragma unroll
   for (int k = 0; k < 8; k++) dst[k] = src[k];
-  for (int by = by0; by <= by1; by++)
-    for (int bx = bx0; bx <= bx1; bx++) atomicAdd(&ec.bin_count[by * ec.bins_x + bx], 1);
 }
 
 __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float din, float dout) {
@@ -245,24 +251,20 @@ __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float di
 
 // rare path: Sutherland-Hodgman against near, far and the guard band (spec step 4), then fan
 __device__ __noinline__ void clip_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                           int tex) {
+                                           int tex, int lat) {
   Vtx poly[12], tmp[12];
   float d[12];
   poly[0] = a; poly[1] = b; poly[2] = c;
   int n = 3;
+  for (int p2 = 0; p2 < 6; p2++) {   // the spec's trivial reject looks at the ORIGINAL triangle, guard planes
+    int cnt = 0;
+    for (int k = 0; k < 3; k++) cnt += !(plane_dist(poly[k], p2) >= 0.0f);
+    if (cnt == 3) return;
+  }
   for (int pl = 0; pl < 6; pl++) {
-    int any_out = 0, all_out = 1;
-    for (int k = 0; k < n; k++) { d[k] = plane_dist(poly[k], pl); const int o = !(d[k] >= 0.0f); any_out |= o; all_out &= o; }
-    if (pl == 0 && n == 3) {
-      // the oracle's trivial reject looks at all six planes of the ORIGINAL triangle before clipping
-      for (int p2 = 0; p2 < 6; p2++) {
-        int cnt = 0;
-        for (int k = 0; k < 3; k++) cnt += !(plane_dist(poly[k], p2) >= 0.0f);
-        if (cnt == 3) return;
-      }
-    }
+    int any_out = 0;
+    for (int k = 0; k < n; k++) { d[k] = plane_dist(poly[k], pl); any_out |= !(d[k] >= 0.0f); }
     if (!any_out) continue;
-    if (all_out) return;
     int m = 0;
     for (int k = 0; k < n; k++) {
       const int k2 = (k + 1 == n) ? 0 : k + 1;
@@ -275,49 +277,84 @@ __device__ __noinline__ void clip_and_emit(const EmitCtx& ec, const Vtx& a, cons
     for (int k = 0; k < n; k++) poly[k] = tmp[k];
     if (n < 3) return;
   }
-  for (int k = 1; k + 1 < n; k++) setup_and_emit(ec, poly[0], poly[k], poly[k + 1], id, tex);
+  for (int k = 1; k + 1 < n; k++) setup_and_emit(ec, poly[0], poly[k], poly[k + 1], id, tex, lat);
 }
 
 __device__ __forceinline__ void process_triangle(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                                 int tex) {
+                                                 int tex, int lat) {
   const int cls = classify(a, b, c);
   if (cls == 2) return;
-  if (cls == 0) setup_and_emit(ec, a, b, c, id, tex);
-  else clip_and_emit(ec, a, b, c, id, tex);
+  if (cls == 0) setup_and_emit(ec, a, b, c, id, tex, lat);
+  else clip_and_emit(ec, a, b, c, id, tex, lat);
+}
+
+// conservative triangle / bin overlap: false only if one edge has the whole bin on its outside
+__device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int ox, int oy) {
+  const int ax[3] = {X[1], X[2], X[0]}, ay[3] = {Y[1], Y[2], Y[0]}, bx[3] = {X[2], X[0], X[1]}, by[3] = {Y[2], Y[0], Y[1]};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int dx = bx[k] - ax[k], dy = by[k] - ay[k];
+    // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the bin's sample span [8, 7*64+56] x [8, 3*64+56]
+    const int xs = (-dy > 0) ? ox + 7 * kSub + 56 : ox + 8;
+    const int ys = (dx > 0) ? oy + 3 * kSub + 56 : oy + 8;
+    const long long e = (long long)dx * (ys - ay[k]) - (long long)dy * (xs - ax[k]);
+    if (e < 0) return false;
+  }
+  return true;
+}
+
+struct BinRange { int bx0, by0, bx1, by1; };
+
+__device__ __forceinline__ BinRange prim_bins(int pxmin, int pxmax, int mbx0, int mby0, int mbx1, int mby1) {
+  BinRange r;
+  r.bx0 = max((pxmin & 0xffff) / kBinW, mbx0); r.by0 = max((pxmin >> 16) / kBinH, mby0);
+  r.bx1 = min((pxmax & 0xffff) / kBinW, mbx1); r.by1 = min((pxmax >> 16) / kBinH, mby1);
+  return r;
 }
 
 }  // namespace
 
-size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, size_t undistorted_frame_bytes) {
-  const size_t slab = (size_t)max_prims * sizeof(PrimRec) + (((size_t)max_pairs * sizeof(uint16_t) + 255) & ~size_t(255));
-  return (size_t)n_ctas * (slab + undistorted_frame_bytes) + 256;
+__host__ __device__ size_t render_slab_bytes(int max_prims, int max_pairs, int max_lat) {
+  size_t b = (size_t)max_prims * sizeof(PrimRec);
+  b += (((size_t)max_pairs * sizeof(uint16_t)) + 255) & ~size_t(255);
+  b += (size_t)max_lat * 64 * sizeof(float4);
+  return (b + 255) & ~size_t(255);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_lat, size_t undistorted_frame_bytes) {
+  return (size_t)n_ctas * (render_slab_bytes(max_prims, max_pairs, max_lat) + undistorted_frame_bytes) + 256;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
 k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* __restrict__ obs,
-         uint8_t* __restrict__ scratch, int max_prims, int max_pairs, uint8_t* __restrict__ undist,
+         uint8_t* __restrict__ scratch, int max_prims, int max_pairs, int max_lat, uint8_t* __restrict__ undist,
          const float* __restrict__ lut_x, const float* __restrict__ lut_y, int32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int W = rc.width, H = rc.height;
-  const int bins_x = (W + kBin - 1) / kBin, bins_y = (H + kBin - 1) / kBin, n_bins = bins_x * bins_y;
+  const int bins_x = (W + kBinW - 1) / kBinW, bins_y = (H + kBinH - 1) / kBinH;
   int* bin_count = reinterpret_cast<int*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)));
-  int* bin_start = bin_count + n_bins;
-  const size_t slab = (size_t)max_prims * sizeof(PrimRec) + (((size_t)max_pairs * sizeof(uint16_t) + 255) & ~size_t(255));
-  PrimRec* prims = reinterpret_cast<PrimRec*>(scratch + (size_t)blockIdx.x * slab);
-  uint16_t* pairs = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(prims) + (size_t)max_prims * sizeof(PrimRec));
+  int* bin_start = bin_count + kMtBinsX * kMtBinsY;
+  const size_t slab = render_slab_bytes(max_prims, max_pairs, max_lat);
+  uint8_t* base = scratch + (size_t)blockIdx.x * slab;
+  PrimRec* prims = reinterpret_cast<PrimRec*>(base);
+  uint16_t* pairs = reinterpret_cast<uint16_t*>(base + (size_t)max_prims * sizeof(PrimRec));
+  float4* lat_tab = reinterpret_cast<float4*>(base + (size_t)max_prims * sizeof(PrimRec) +
+                                              ((((size_t)max_pairs * sizeof(uint16_t)) + 255) & ~size_t(255)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dr = (rc.flags & DTS_FLAG_DOMAIN_RAND) != 0;
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
   const size_t frame_bytes = (size_t)W * H * 3;
   uint8_t* my_undist = fisheye ? undist + (size_t)blockIdx.x * frame_bytes : nullptr;
+  const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside any bin (sub-pixels)
 
   for (int env = blockIdx.x; env < rc.n_envs; env += gridDim.x) {
     const DMap& m = maps[S.map_id[env]];
     uint8_t* out = fisheye ? my_undist : obs + (size_t)env * frame_bytes;
     // ---------------------------------------------------------------- per-frame setup
-    if (tid < (int)(sizeof(RenderEp) / 4)) reinterpret_cast<uint32_t*>(&sh.ep)[tid] = reinterpret_cast<const uint32_t*>(&S.rep[env])[tid];
-    for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
+    __syncthreads();
+    if (tid < (int)(sizeof(RenderEp) / 4))
+      reinterpret_cast<uint32_t*>(&sh.ep)[tid] = reinterpret_cast<const uint32_t*>(&S.rep[env])[tid];
     __syncthreads();
     if (tid == 0) {
       camera_view(S.pos_x[env], S.pos_z[env], S.angle[env], sh.ep, dr, sh.V);
@@ -325,13 +362,14 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
       const double zn = 0.04, zf = 100.0;                                     // gluPerspective S:1761
       sh.P00 = (float)(f / aspect); sh.P11 = (float)f;
       sh.P22 = (float)((zf + zn) / (zn - zf)); sh.P23 = (float)(2.0 * zf * zn / (zn - zf));
-      sh.n_prims = 0; sh.n_pairs = 0; sh.overflow = 0;
+      sh.n_prims = 0; sh.n_lat = 0; sh.overflow = 0;
     }
     __syncthreads();
     // ---------------------------------------------------------------- G: geometry, warp per draw item
-    EmitCtx ec{&sh, prims, bin_count, max_prims, W, H, bins_x};
+    EmitCtx ec{&sh, prims, max_prims, W, H};
     const int n_tiles = m.grid_w * m.grid_h;
     const int n_items = 1 + n_tiles + m.n_objects;
+    const int tris_per_tile = rc.tessellate ? 98 : 2;
     for (int item = warp; item < n_items; item += kWarps) {
       Xform x;
       if (item == 0) {
@@ -345,10 +383,10 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
           const Vtx a = shade_vertex(x, sh, P[0][0], P[0][1], P[0][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
           const Vtx b = shade_vertex(x, sh, P[i1][0], P[i1][1], P[i1][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
           const Vtx c = shade_vertex(x, sh, P[i2][0], P[i2][1], P[i2][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-          process_triangle(ec, a, b, c, lane, -1);
+          process_triangle(ec, a, b, c, lane, -1, -1);
         }
       } else if (item <= n_tiles) {
-        // road tile S:1852-1884: draw order i outer, j inner; the tile's 8x8 lattice is lit once (2 verts/lane)
+        // road tile S:1852-1884: draw order i outer, j inner
         const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
         const int idx = tj * m.grid_w + ti;
         if (m.tile_kind[idx] < 0) continue;
@@ -356,33 +394,63 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
         const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
         const double ts = m.tile_size;
         model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x);
+        const int tex = m.tile_tex[idx];
+        const int base_id = 2 + tris_per_tile * t;
+        // the tile's 8x8 lattice, two vertices per lane; also used to frustum-cull the whole tile
+        Vtx lv[2];
         int outside[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int vi = lane + 32 * h, a = vi >> 3, b = vi & 7;             // a: u index (x), b: v index (z)
           const float lx = (float)(-ts / 2 + ((double)a / 7.0) * ts), lz = (float)(-ts / 2 + ((double)b / 7.0) * ts);
-          const Vtx v = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)a / 7.0),
-                                     (float)(1.0 - (double)b / 7.0));
-          sh.lattice[warp][vi] = v;
+          lv[h] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)a / 7.0),
+                               (float)(1.0 - (double)b / 7.0));
+          const Vtx& v = lv[h];
           outside[0] += !(v.cz + v.cw >= 0.0f); outside[1] += !(v.cw - v.cz >= 0.0f);
           outside[2] += v.cx < -v.cw; outside[3] += v.cx > v.cw; outside[4] += v.cy < -v.cw; outside[5] += v.cy > v.cw;
         }
         bool culled = false;
 #pragma unroll
         for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
-        __syncwarp();
         if (culled) continue;
-        const int tex = m.tile_tex[idx];
-        const int base_id = 2 + 98 * t;
-        for (int k = lane; k < 98; k += 32) {                                // S:407-433 quad order, (0,1,2)(0,2,3) split
-          const int quad = k >> 1, half = k & 1, a = quad / 7, b = quad - 7 * a;
-          const Vtx& v0 = sh.lattice[warp][a * 8 + b];
-          const Vtx& v2 = sh.lattice[warp][(a + 1) * 8 + b + 1];
-          const Vtx& v1 = half == 0 ? sh.lattice[warp][(a + 1) * 8 + b] : v2;
-          const Vtx& v2b = half == 0 ? v2 : sh.lattice[warp][a * 8 + b + 1];
-          process_triangle(ec, v0, v1, v2b, base_id + k, tex);
+        if (!rc.tessellate) {
+          // analytic tile (spec tile mode 1): lattice colours -> table, one quad (0,1,2)(0,2,3) of the corners
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(&sh.n_lat, 1);
+          slot = __shfl_sync(0xffffffffu, slot, 0);
+          if (slot >= max_lat) { if (lane == 0) sh.overflow = 1; continue; }
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int vi = lane + 32 * h;
+            lat_tab[slot * 64 + vi] = make_float4(lv[h].r, lv[h].g, lv[h].b, 0.0f);
+            int corner = -1;
+            if (vi == 0) corner = 0; else if (vi == 56) corner = 1; else if (vi == 63) corner = 2; else if (vi == 7) corner = 3;
+            if (corner >= 0) { Vtx c = lv[h]; c.r = 0.f; c.g = 0.f; c.b = 0.f; sh.corners[warp][corner] = c; }
+          }
+          __syncwarp();
+          if (lane < 2) {
+            const Vtx& c0 = sh.corners[warp][0];
+            const Vtx& c1 = sh.corners[warp][lane == 0 ? 1 : 2];
+            const Vtx& c2 = sh.corners[warp][lane == 0 ? 2 : 3];
+            process_triangle(ec, c0, c1, c2, base_id + lane, tex, slot);
+          }
+          __syncwarp();
+        } else {
+          // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
+          for (int k = lane; k < 98; k += 32) {
+            const int quad = k >> 1, half = k & 1, a = quad / 7, b = quad - 7 * a;
+            Vtx v[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const int aa = j == 0 ? a : (j == 1 ? a + 1 : (half == 0 ? a + 1 : a));
+              const int bb = j == 0 ? b : (j == 1 ? (half == 0 ? b : b + 1) : b + 1);
+              const float lx = (float)(-ts / 2 + ((double)aa / 7.0) * ts), lz = (float)(-ts / 2 + ((double)bb / 7.0) * ts);
+              v[j] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)aa / 7.0),
+                                  (float)(1.0 - (double)bb / 7.0));
+            }
+            process_triangle(ec, v[0], v[1], v[2], base_id + k, tex, -1);
+          }
         }
-        __syncwarp();
       } else {
         // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
         const int o = item - 1 - n_tiles;
@@ -404,7 +472,7 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
           outside_ |= (-sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
           if (outside_) continue;
         }
-        int base_id = 2 + 98 * n_tiles;
+        int base_id = 2 + tris_per_tile * n_tiles;
         for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
         for (int k = lane; k < ob.tri_count; k += 32) {
           const size_t ti = (size_t)ob.tri_offset + k;
@@ -417,172 +485,257 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
           for (int j = 0; j < 3; j++)
             v[j] = shade_vertex(x, sh, p[3 * j], p[3 * j + 1], p[3 * j + 2], n[3 * j], n[3 * j + 1], n[3 * j + 2],
                                 c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
-          process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti]);
+          process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti], -1);
         }
       }
     }
     __syncthreads();
-    // ---------------------------------------------------------------- B: scan + scatter
     const int n_prims = min(sh.n_prims, max_prims);
-    if (warp == 0) {  // exclusive scan of bin_count by one warp
-      int carry = 0;
-      for (int base = 0; base < n_bins; base += 32) {
-        const int b = base + lane;
-        const int v = b < n_bins ? bin_count[b] : 0;
-        int inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
-        if (b < n_bins) bin_start[b] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-      }
-      if (lane == 0) { sh.n_pairs = carry; if (carry > max_pairs) sh.overflow = 1; }
-    }
-    __syncthreads();
-    const bool pairs_ok = sh.n_pairs <= max_pairs;
-    for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;   // reuse as fill cursors
-    __syncthreads();
-    if (pairs_ok) {
-      for (int p = tid; p < n_prims; p += kThreads) {
-        const uint32_t bb = prims[p].bbox;
-        const int bx0 = bb & 255, by0 = (bb >> 8) & 255, bx1 = (bb >> 16) & 255, by1 = bb >> 24;
-        for (int by = by0; by <= by1; by++)
-          for (int bx = bx0; bx <= bx1; bx++) {
-            const int b = by * bins_x + bx;
-            pairs[bin_start[b] + atomicAdd(&bin_count[b], 1)] = (uint16_t)p;
-          }
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && sh.overflow) atomicOr(err, 1);
-    // ---------------------------------------------------------------- R: raster, bin by bin
-    const int sbx = (warp & 1) * 8, sby = (warp >> 1) * 4;   // this warp's 8x4 block inside the bin
-    const int lx = sbx + (lane & 7), ly = sby + (lane >> 3); // this lane's pixel inside the bin
     const float clr[3] = {sh.ep.horizon[0], sh.ep.horizon[1], sh.ep.horizon[2]};
-    for (int bin = 0; bin < n_bins; bin++) {
-      const int bx = bin % bins_x, by = bin / bins_x;
-      const int count = pairs_ok ? bin_count[bin] : 0;
-      const int start = bin_start[bin];
-      float z[4], cr[4], cg[4], cb[4];
-      int wid[4];
-#pragma unroll
-      for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
-      for (int c0 = 0; c0 < count; c0 += kChunk) {
-        const int nch = min(kChunk, count - c0);
-        __syncthreads();   // previous chunk fully consumed
-        if (tid < nch) {
-          const PrimRec& r = prims[pairs[start + c0 + tid]];
-          BinPrim& bp = sh.chunk[tid];
-          const int ox = bx * kBin * kSub, oy = by * kBin * kSub;
-          const int X0 = r.X[0], X1 = r.X[1], X2 = r.X[2], Y0 = r.Y[0], Y1 = r.Y[1], Y2 = r.Y[2];
-          const int ax[3] = {X1, X2, X0}, ay[3] = {Y1, Y2, Y0}, bxv[3] = {X2, X0, X1}, byv[3] = {Y2, Y0, Y1};
-          int live = 1;
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const int dx = bxv[k] - ax[k], dy = byv[k] - ay[k];
-            const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
-            // E(x,y) = dx*(y-ay) - dy*(x-ax) - bias  at the bin corner, exact in 64 bits
-            long long e0 = (long long)dx * (oy - ay[k]) - (long long)dy * (ox - ax[k]) - bias;
-            // inside the bin |A*x+B*y| < 2^29: beyond +-2^30 the sign is decided for every sample
-            if (e0 < -(1LL << 30)) live = 0;
-            if (e0 > (1LL << 30)) e0 = (1LL << 30);
-            bp.E0[k] = (int)e0; bp.A[k] = -dy; bp.B[k] = dx;
+    // ---------------------------------------------------------------- macro tiles of <= 20 x 32 bins
+    for (int mby0 = 0; mby0 < bins_y; mby0 += kMtBinsY)
+      for (int mbx0 = 0; mbx0 < bins_x; mbx0 += kMtBinsX) {
+        const int mbx1 = min(mbx0 + kMtBinsX, bins_x) - 1, mby1 = min(mby0 + kMtBinsY, bins_y) - 1;
+        const int mw = mbx1 - mbx0 + 1, mh = mby1 - mby0 + 1, n_bins = mw * mh;
+        // ------------------------------------------------------------ B: count, scan, scatter
+        for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
+        if (tid == 0) { sh.n_large = 0; sh.next_bin = 0; }
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+          // small prims: one thread each
+          for (int p = tid; p < n_prims; p += kThreads) {
+            const int2 bb = *reinterpret_cast<const int2*>(&prims[p].pxmin);
+            const BinRange r = prim_bins(bb.x, bb.y, mbx0, mby0, mbx1, mby1);
+            if (r.bx0 > r.bx1 || r.by0 > r.by1) continue;
+            const int nb = (r.bx1 - r.bx0 + 1) * (r.by1 - r.by0 + 1);
+            if (nb > 4) {
+              if (pass == 0) { const int s = atomicAdd(&sh.n_large, 1); if (s < kMaxLarge) sh.large[s] = (uint16_t)p; else sh.overflow = 1; }
+              continue;
+            }
+            for (int by = r.by0; by <= r.by1; by++)
+              for (int bx = r.bx0; bx <= r.bx1; bx++) {
+                const int b = (by - mby0) * mw + (bx - mbx0);
+                const int pos = atomicAdd(&bin_count[b], 1);
+                if (pass == 1) pairs[bin_start[b] + pos] = (uint16_t)p;
+              }
           }
-          bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
+          __syncthreads();
+          // large prims: one warp each, lanes over the bins of the bounding box, exact edge test
+          const int n_large = min(sh.n_large, kMaxLarge);
+          for (int l = warp; l < n_large; l += kWarps) {
+            const int p = sh.large[l];
+            const PrimRec& pr = prims[p];
+            const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
+            const BinRange r = prim_bins(pr.pxmin, pr.pxmax, mbx0, mby0, mbx1, mby1);
+            const int bw = r.bx1 - r.bx0 + 1, nb = bw * (r.by1 - r.by0 + 1);
+            for (int q = lane; q < nb; q += 32) {
+              const int by = r.by0 + q / bw, bx = r.bx0 + q % bw;
+              if (!bin_overlaps(X, Y, bx * kBinW * kSub, by * kBinH * kSub)) continue;
+              const int b = (by - mby0) * mw + (bx - mbx0);
+              const int pos = atomicAdd(&bin_count[b], 1);
+              if (pass == 1) pairs[bin_start[b] + pos] = (uint16_t)p;
+            }
+          }
+          __syncthreads();
+          if (pass == 0) {
+            if (warp == 0) {  // exclusive scan of bin_count by one warp
+              int carry = 0;
+              for (int b0 = 0; b0 < n_bins; b0 += 32) {
+                const int b = b0 + lane;
+                const int v = b < n_bins ? bin_count[b] : 0;
+                int inc = v;
 #pragma unroll
-          for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
-          bp.id = r.id_tex >> 8;
-          const int tex = (r.id_tex & 255) - 1;
-          if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_w = t.w; bp.tex_h = t.h; }
-          else { bp.tex = nullptr; bp.tex_w = 0; bp.tex_h = 0; }
-          bp.px0 = (r.px0y0 & 0xffff) - bx * kBin; bp.py0 = (r.px0y0 >> 16) - by * kBin;
-          bp.px1 = (r.px1y1 & 0xffff) - bx * kBin; bp.py1 = (r.px1y1 >> 16) - by * kBin;
-          bp.live = live;
+                for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+                if (b < n_bins) bin_start[b] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+              }
+              if (lane == 0) { sh.n_pairs = carry; if (carry > max_pairs) sh.overflow = 1; }
+            }
+            __syncthreads();
+            if (sh.n_pairs > max_pairs) break;   // uniform: lists would not fit, render the clear colour
+            for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
+            __syncthreads();
+          }
+        }
+        const bool pairs_ok = sh.n_pairs <= max_pairs;
+        __syncthreads();
+        // ------------------------------------------------------------ R: raster, warps pull bins
+        for (;;) {
+          int bin = 0;
+          if (lane == 0) bin = atomicAdd(&sh.next_bin, 1);
+          bin = __shfl_sync(0xffffffffu, bin, 0);
+          if (bin >= n_bins) break;
+          const int bx = mbx0 + bin % mw, by = mby0 + bin / mw;
+          const int count = pairs_ok ? bin_count[bin] : 0;
+          const int start = bin_start[bin];
+          const int ox = bx * kBinW * kSub, oy = by * kBinH * kSub;   // bin corner, sub-pixels
+          float z[4], cr[4], cg[4], cb[4];
+          int wid[4];
+#pragma unroll
+          for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
+          BinPrim* stage = sh.stage[warp];
+          for (int c0 = 0; c0 < count; c0 += kStage) {
+            const int nch = min(kStage, count - c0);
+            __syncwarp();
+            bool live = false;
+            int my_id = 0x7fffffff;
+            if (lane < nch) {
+              // ---- stage one prim: re-base to this bin, exact reject, trivial accept
+              const PrimRec& r = prims[pairs[start + c0 + lane]];
+              BinPrim& bp = stage[lane];
+              const int X0 = r.X[0], X1 = r.X[1], X2 = r.X[2], Y0 = r.Y[0], Y1 = r.Y[1], Y2 = r.Y[2];
+              const int ax[3] = {X1, X2, X0}, ay[3] = {Y1, Y2, Y0}, bxv[3] = {X2, X0, X1}, byv[3] = {Y2, Y0, Y1};
+              live = true;
+              int inside = 1;
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                const int dx = bxv[k] - ax[k], dy = byv[k] - ay[k];
+                const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
+                // E(x,y) = dx*(y-ay) - dy*(x-ax) - bias at the bin corner, exact in 64 bits; inside the bin
+                // |A*x+B*y| < 2^29, so beyond +-2^30 the sign is the same for every sample
+                long long e0 = (long long)dx * (oy - ay[k]) - (long long)dy * (ox - ax[k]) - bias;
+                if (e0 < -(1LL << 30)) live = false;
+                if (e0 > (1LL << 30)) e0 = (1LL << 30);
+                const int A = -dy, B = dx, e = (int)e0;
+                // extremes over the bin's sample span x in [8, 504], y in [8, 248]
+                const int emax = e + (A > 0 ? A * 504 : A * 8) + (B > 0 ? B * 248 : B * 8);
+                const int emin = e + (A > 0 ? A * 8 : A * 504) + (B > 0 ? B * 8 : B * 248);
+                if (emax < 0) live = false;
+                if (emin < 0) inside = 0;
+                bp.E0[k] = e; bp.A[k] = A; bp.B[k] = B;
+              }
+              bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
+#pragma unroll
+              for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
+              my_id = r.id_tex >> 8;
+              bp.id = my_id;
+              bp.flags = inside;
+              const int tex = (r.id_tex & 255) - 1;
+              if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); }
+              else { bp.tex = nullptr; bp.tex_wh = 0; }
+              bp.lat = r.lat;
+            }
+            __syncwarp();
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
+            // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
+            for (int phase = 0; phase < 2; phase++) {
+              unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+              while (todo) {
+                const int k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const BinPrim& bp = stage[k];
+                int mask = 15;
+                if (!(bp.flags & 1)) {
+                  mask = 0;
+                  const int ec0 = bp.E0[0] + bp.A[0] * pxs + bp.B[0] * pys;
+                  const int ec1 = bp.E0[1] + bp.A[1] * pxs + bp.B[1] * pys;
+                  const int ec2 = bp.E0[2] + bp.A[2] * pxs + bp.B[2] * pys;
+#pragma unroll
+                  for (int s = 0; s < 4; s++) {
+                    const int e0 = ec0 + bp.A[0] * c_sx[s] + bp.B[0] * c_sy[s];
+                    const int e1 = ec1 + bp.A[1] * c_sx[s] + bp.B[1] * c_sy[s];
+                    const int e2 = ec2 + bp.A[2] * c_sx[s] + bp.B[2] * c_sy[s];
+                    if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                  }
+                  if (!mask) continue;
+                }
+                // ---- early z: depth of the covered samples, GL_LESS in draw order
+                const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
+                float zs[4];
+                int pass_mask = 0;
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                  // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
+                  // identical to the spec's (float)(X_sample - x0) / 64
+                  const float sdx = cdx + (float)(c_sx[s] - 32) * 0.015625f, sdy = cdy + (float)(c_sy[s] - 32) * 0.015625f;
+                  zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
+                  if ((mask >> s & 1) && (zs[s] < z[s] || (zs[s] == z[s] && bp.id < wid[s]))) pass_mask |= 1 << s;
+                }
+                if (!pass_mask) continue;
+                // ---- shade once at the pixel centre
+                float qq = fmaf(bp.fy[1], cdy, fmaf(bp.fx[1], cdx, bp.f0[1]));
+                if (!(qq > 1e-20f)) qq = 1e-20f;
+                const float rq = 1.0f / qq;
+                const float u = fmaf(bp.fy[2], cdy, fmaf(bp.fx[2], cdx, bp.f0[2])) * rq;
+                const float v = fmaf(bp.fy[3], cdy, fmaf(bp.fx[3], cdx, bp.f0[3])) * rq;
+                float c3[3];
+                if (bp.lat >= 0) {
+                  // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
+                  const float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
+                  int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
+                  ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
+                  ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
+                  const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
+                  const float4* L = lat_tab + bp.lat * 64 + ia * 8 + ib;
+                  const float4 c00 = L[0], c01 = L[1], c10 = L[8], c11 = L[9];
+                  if (fb <= fa) {
+                    c3[0] = fmaf(fb, c11.x - c10.x, fmaf(fa, c10.x - c00.x, c00.x));
+                    c3[1] = fmaf(fb, c11.y - c10.y, fmaf(fa, c10.y - c00.y, c00.y));
+                    c3[2] = fmaf(fb, c11.z - c10.z, fmaf(fa, c10.z - c00.z, c00.z));
+                  } else {
+                    c3[0] = fmaf(fa, c11.x - c01.x, fmaf(fb, c01.x - c00.x, c00.x));
+                    c3[1] = fmaf(fa, c11.y - c01.y, fmaf(fb, c01.y - c00.y, c00.y));
+                    c3[2] = fmaf(fa, c11.z - c01.z, fmaf(fb, c01.z - c00.z, c00.z));
+                  }
+                } else {
+                  c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
+                  c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
+                  c3[2] = fmaf(bp.fy[6], cdy, fmaf(bp.fx[6], cdx, bp.f0[6])) * rq;
+                }
+                if (bp.tex) {
+                  const int tw = bp.tex_wh & 0xffff, th = bp.tex_wh >> 16;
+                  const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
+                  const float txf = floorf(tx), tyf = floorf(ty);
+                  const float ffx = tx - txf, ffy = ty - tyf;
+                  const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
+                  const int tj0 = ((int)tyf) & (th - 1), tj1 = (tj0 + 1) & (th - 1);
+                  const uchar4* tp = reinterpret_cast<const uchar4*>(bp.tex);
+                  const uchar4 t00 = __ldg(tp + tj0 * tw + ti0), t10 = __ldg(tp + tj0 * tw + ti1);
+                  const uchar4 t01 = __ldg(tp + tj1 * tw + ti0), t11 = __ldg(tp + tj1 * tw + ti1);
+                  const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
+                  const float b0[3] = {(float)t01.x, (float)t01.y, (float)t01.z}, b1[3] = {(float)t11.x, (float)t11.y, (float)t11.z};
+#pragma unroll
+                  for (int ch = 0; ch < 3; ch++) {
+                    const float ta = fmaf(ffx, a1[ch] - a0[ch], a0[ch]);
+                    const float tb = fmaf(ffx, b1[ch] - b0[ch], b0[ch]);
+                    const float tc = fmaf(ffy, tb - ta, ta);
+                    c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
+                  }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                  if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2]; }
+              }
+            }
+          }
+          // ---------------------------------------------------------- O: resolve + store
+          float c;
+          c = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
+          const unsigned r8 = (unsigned)rintf(c * 255.0f);
+          c = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
+          const unsigned g8 = (unsigned)rintf(c * 255.0f);
+          c = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
+          const unsigned b8 = (unsigned)rintf(c * 255.0f);
+          const unsigned rgb = r8 | (g8 << 8) | (b8 << 16);
+          const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
+          if ((W & 3) == 0 && bx * kBinW + kBinW <= W) {
+            // a pixel row of the bin is 24 bytes = 6 aligned words; lane j<6 of the row builds word j
+            const int j = lane & 7, rowbase = lane & ~7;
+            const int p0 = (4 * j) / 3, sh8 = (4 * j - 3 * p0) * 8;
+            const unsigned lo = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0, 7));
+            const unsigned hi = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0 + 1, 7));
+            const unsigned long long both = (unsigned long long)lo | ((unsigned long long)hi << 24);
+            if (j < 6 && gy < H)
+              *reinterpret_cast<unsigned*>(out + ((size_t)gy * W + bx * kBinW) * 3 + 4 * j) = (unsigned)(both >> sh8);
+          } else if (gx < W && gy < H) {
+            uint8_t* d = out + ((size_t)gy * W + gx) * 3;
+            d[0] = (uint8_t)r8; d[1] = (uint8_t)g8; d[2] = (uint8_t)b8;
+          }
         }
         __syncthreads();
-        for (int k = 0; k < nch; k++) {
-          const BinPrim& bp = sh.chunk[k];
-          // warp-uniform reject: prim's pixel bbox vs this warp's 8x4 block
-          if (!bp.live || bp.px1 < sbx || bp.px0 > sbx + 7 || bp.py1 < sby || bp.py0 > sby + 3) continue;
-          const int pxs = lx * kSub, pys = ly * kSub;
-          int mask = 0;
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            const int xs = pxs + c_sx[s], ys = pys + c_sy[s];
-            const int e0 = bp.E0[0] + bp.A[0] * xs + bp.B[0] * ys;
-            const int e1 = bp.E0[1] + bp.A[1] * xs + bp.B[1] * ys;
-            const int e2 = bp.E0[2] + bp.A[2] * xs + bp.B[2] * ys;
-            if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
-          }
-          if (!mask) continue;
-          const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
-          float qq = fmaf(bp.fy[1], cdy, fmaf(bp.fx[1], cdx, bp.f0[1]));
-          if (!(qq > 1e-20f)) qq = 1e-20f;
-          const float rq = 1.0f / qq;
-          const float u = fmaf(bp.fy[2], cdy, fmaf(bp.fx[2], cdx, bp.f0[2])) * rq;
-          const float v = fmaf(bp.fy[3], cdy, fmaf(bp.fx[3], cdx, bp.f0[3])) * rq;
-          float c3[3];
-          c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
-          c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
-          c3[2] = fmaf(bp.fy[6], cdy, fmaf(bp.fx[6], cdx, bp.f0[6])) * rq;
-          if (bp.tex) {
-            const float tx = u * (float)bp.tex_w - 0.5f, ty = v * (float)bp.tex_h - 0.5f;
-            const float txf = floorf(tx), tyf = floorf(ty);
-            const float ffx = tx - txf, ffy = ty - tyf;
-            const int ti0 = ((int)txf) & (bp.tex_w - 1), ti1 = (ti0 + 1) & (bp.tex_w - 1);
-            const int tj0 = ((int)tyf) & (bp.tex_h - 1), tj1 = (tj0 + 1) & (bp.tex_h - 1);
-            const uchar4* tp = reinterpret_cast<const uchar4*>(bp.tex);
-            const uchar4 t00 = __ldg(tp + tj0 * bp.tex_w + ti0), t10 = __ldg(tp + tj0 * bp.tex_w + ti1);
-            const uchar4 t01 = __ldg(tp + tj1 * bp.tex_w + ti0), t11 = __ldg(tp + tj1 * bp.tex_w + ti1);
-            const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
-            const float b0[3] = {(float)t01.x, (float)t01.y, (float)t01.z}, b1[3] = {(float)t11.x, (float)t11.y, (float)t11.z};
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-              const float ta = fmaf(ffx, a1[ch] - a0[ch], a0[ch]);
-              const float tb = fmaf(ffx, b1[ch] - b0[ch], b0[ch]);
-              const float tc = fmaf(ffy, tb - ta, ta);
-              c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
-            }
-          }
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            if (!(mask >> s & 1)) continue;
-            const float sdx = (float)(pxs + c_sx[s] - bp.x0) * 0.015625f, sdy = (float)(pys + c_sy[s] - bp.y0) * 0.015625f;
-            const float zs = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
-            if (zs < z[s] || (zs == z[s] && bp.id < wid[s])) {   // GL_LESS in draw order
-              z[s] = zs; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2];
-            }
-          }
-        }
       }
-      // ------------------------------------------------------------ O: resolve + store
-      {
-        float c;
-        c = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-        sh.tile[ly][lx * 3 + 0] = (uint8_t)rintf(c * 255.0f);
-        c = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-        sh.tile[ly][lx * 3 + 1] = (uint8_t)rintf(c * 255.0f);
-        c = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-        sh.tile[ly][lx * 3 + 2] = (uint8_t)rintf(c * 255.0f);
-      }
-      __syncthreads();
-      {
-        const int gx0 = bx * kBin, gy0 = by * kBin;
-        const int cols = min(kBin, W - gx0), rows = min(kBin, H - gy0);
-        if (((W * 3) & 15) == 0 && cols == kBin) {
-          if (tid < rows * 3) {   // 3 x 16-byte stores per pixel row of the tile
-            const int row = tid / 3, part = tid - row * 3;
-            *reinterpret_cast<int4*>(out + ((size_t)(gy0 + row) * W + gx0) * 3 + part * 16) =
-                *reinterpret_cast<const int4*>(&sh.tile[row][part * 16]);
-          }
-        } else {
-          for (int t_ = tid; t_ < rows * cols * 3; t_ += kThreads) {
-            const int row = t_ / (cols * 3), col = t_ - row * cols * 3;
-            out[((size_t)(gy0 + row) * W + gx0) * 3 + col] = sh.tile[row][col];
-          }
-        }
-      }
-      __syncthreads();
-    }
+    if (tid == 0 && sh.overflow) atomicOr(err, 1);
     // ---------------------------------------------------------------- fisheye gather (distortion.py:118)
     if (fisheye) {
       __threadfence_block();
@@ -597,25 +750,22 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
         }
         dst[(size_t)p * 3] = r; dst[(size_t)p * 3 + 1] = g; dst[(size_t)p * 3 + 2] = b;
       }
-      __syncthreads();
     }
   }
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, const float* lut_x, const float* lut_y, int32_t* err_flag,
+                  int max_prims, int max_pairs, int max_lat, const float* lut_x, const float* lut_y, int32_t* err_flag,
                   cudaStream_t st) {
-  const int bins = ((rc.width + kBin - 1) / kBin) * ((rc.height + kBin - 1) / kBin);
-  const size_t smem = ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)bins * 2 * sizeof(int);
+  const size_t smem = ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)kMtBinsX * kMtBinsY * 2 * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
-  const size_t slab = (size_t)max_prims * sizeof(PrimRec) + (((size_t)max_pairs * sizeof(uint16_t) + 255) & ~size_t(255));
-  uint8_t* undist = reinterpret_cast<uint8_t*>(scratch) + (size_t)n_ctas * slab;
+  uint8_t* undist = reinterpret_cast<uint8_t*>(scratch) + (size_t)n_ctas * render_slab_bytes(max_prims, max_pairs, max_lat);
   k_render<<<n_ctas, kThreads, smem, st>>>(S, maps, rc, obs, reinterpret_cast<uint8_t*>(scratch), max_prims, max_pairs,
-                                           undist, lut_x, lut_y, err_flag);
+                                           max_lat, undist, lut_x, lut_y, err_flag);
   return 1;
 }
 

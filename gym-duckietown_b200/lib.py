@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libdtsim.so")
 
 DTS_ABI_VERSION = 1
 ACTION_PWM, ACTION_VEL_STEER = 0, 1
-FLAG_AUTO_RESET, FLAG_DOMAIN_RAND, FLAG_DISTORTION, FLAG_DYNAMICS_RAND = 1, 2, 4, 8
+FLAG_AUTO_RESET, FLAG_DOMAIN_RAND, FLAG_DISTORTION, FLAG_DYNAMICS_RAND, FLAG_TESSELLATE = 1, 2, 4, 8, 16
 IN_PROGRESS, INVALID_POSE, MAX_STEPS = 0, 1, 2
 DONE_CODE_STR = {0: "in-progress", 1: "invalid-pose", 2: "max-steps-reached"}  # S:1685-1705
 

@@ -32,7 +32,9 @@ enum { DTS_ACTION_PWM = 0,      /* Simulator.step(action=[u_left,u_right])      
 enum { DTS_FLAG_AUTO_RESET = 1,   /* done envs are re-spawned on device inside dts_step */
        DTS_FLAG_DOMAIN_RAND = 2,  /* simulator.py:213  (camera noise S:1768, DR sampling in device resets) */
        DTS_FLAG_DISTORTION = 4,   /* simulator.py:223  fisheye gather fused into the render (distortion.py:118) */
-       DTS_FLAG_DYNAMICS_RAND = 8 /* simulator.py:224  per-env trim on the motor gains (S:746-748) */ };
+       DTS_FLAG_DYNAMICS_RAND = 8,/* simulator.py:224  per-env trim on the motor gains (S:746-748) */
+       DTS_FLAG_TESSELLATE = 16   /* draw every road tile as the literal 7x7 quads of simulator.py:386-507
+                                     instead of one quad + analytic lattice lighting (DESIGN.md render spec) */ };
 
 typedef struct {
   int32_t abi_version;      /* DTS_ABI_VERSION */

@@ -15,6 +15,16 @@
  *     depth per sample, float32 depth, GL_LESS, draw order = reference draw order
  *   - bilinear RGBA8 textures, REPEAT wrap, GL_MODULATE
  *   - resolve = mean of 4 samples, u8 = rint(255*c), image row 0 = top
+ *   - road tiles, two interpretations selectable with orr_set_tile_mode():
+ *       0 "tessellated": the literal vertex list of simulator.py:386-507 — 7x7 quads = 98 triangles
+ *         per tile, Gouraud colours interpolated per small triangle;
+ *       1 "analytic" (DEFAULT, the parity spec): ONE quad (2 triangles) per tile for coverage, depth
+ *         and uv, and the colour is the same piecewise-linear Gouraud interpolant of the 8x8 lit
+ *         lattice evaluated at the pixel's (u,v).  Mathematically identical to mode 0 (perspective-
+ *         correct interpolation is linear in tile coordinates and continuous across the interior
+ *         edges); the two differ only by rounding and by <=1/64 px of edge placement on the tile
+ *         outline (tests/test_oracle_raster.py quantifies it).  The tessellation exists in the
+ *         reference only to approximate per-pixel lighting with fixed-function GL.
  * It is written for clarity (brute force over every triangle and every pixel of its bounding box),
  * not speed; the CUDA rasteriser is structured differently (binning, lattice sharing) and must
  * reproduce these numbers exactly.
@@ -36,6 +46,8 @@ typedef struct {
 } framebuf;
 
 static const int SX[4] = {24, 56, 8, 40}, SY[4] = {8, 24, 40, 56}; /* sample offsets in 1/64 px */
+static int g_tile_mode = 1;
+void orr_set_tile_mode(int mode) { g_tile_mode = mode; }
 #define GUARD 4.0f
 
 /* ---- camera (simulator.py:1758-1803), float64 ------------------------------------------------ */
@@ -170,7 +182,7 @@ static int clip_polygon(vtx* poly, int n) {
 static inline float tex_byte(const orr_texture* t, int i, int j, int c) { return (float)t->rgba[((size_t)j * t->w + i) * 4 + c]; }
 
 /* one screen-space triangle (already clipped); `id` only documents draw order (drawn in order, GL_LESS) */
-static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex) {
+static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat) {
   vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
   float zw[3], q[3];
@@ -255,6 +267,21 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
       const float rq = 1.0f / qq;
       const float u = at[2] * rq, v = at[3] * rq;
       float lit[3] = {at[4] * rq, at[5] * rq, at[6] * rq};
+      if (lat) { /* analytic tile: Gouraud interpolant of the lit 8x8 lattice at (u,v); lattice index a <-> u,
+                  * b <-> 1-v (S:394-401); cell split (0,1,2)(0,2,3) as drawn */
+        float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
+        int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
+        ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
+        ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
+        float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
+        const float* c00 = lat + (ia * 8 + ib) * 3;
+        const float* c10 = lat + ((ia + 1) * 8 + ib) * 3;
+        const float* c11 = lat + ((ia + 1) * 8 + ib + 1) * 3;
+        const float* c01 = lat + (ia * 8 + ib + 1) * 3;
+        for (int ch = 0; ch < 3; ch++)
+          lit[ch] = (fb <= fa) ? fmaf(fb, c11[ch] - c10[ch], fmaf(fa, c10[ch] - c00[ch], c00[ch]))
+                               : fmaf(fa, c11[ch] - c01[ch], fmaf(fb, c01[ch] - c00[ch], c00[ch]));
+      }
       float colr[3];
       if (tex) {
         float tx = u * (float)tex->w - 0.5f, ty = v * (float)tex->h - 0.5f;
@@ -284,10 +311,16 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
     }
 }
 
+static void draw_shaded(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat);
 static void draw_triangle(framebuf* fb, const xform* x, const float* p, const float* n, const float* uv, const float* col,
                           const orr_texture* tex) {
+  vtx v[3];
+  for (int k = 0; k < 3; k++) v[k] = shade_vertex(x, p + 3 * k, n + 3 * k, col + 3 * k, uv[2 * k], uv[2 * k + 1]);
+  draw_shaded(fb, v[0], v[1], v[2], tex, 0);
+}
+static void draw_shaded(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat) {
   vtx poly[12];
-  for (int k = 0; k < 3; k++) poly[k] = shade_vertex(x, p + 3 * k, n + 3 * k, col + 3 * k, uv[2 * k], uv[2 * k + 1]);
+  poly[0] = a; poly[1] = b; poly[2] = c;
   /* trivial reject: all three outside one plane */
   for (int pl = 0; pl < 6; pl++) {
     int out = 0;
@@ -295,7 +328,7 @@ static void draw_triangle(framebuf* fb, const xform* x, const float* p, const fl
     if (out == 3) return;
   }
   int m = clip_polygon(poly, 3);
-  for (int k = 1; k + 1 < m; k++) raster_triangle(fb, poly[0], poly[k], poly[k + 1], tex);
+  for (int k = 1; k + 1 < m; k++) raster_triangle(fb, poly[0], poly[k], poly[k + 1], tex, lat);
 }
 
 /* Render one env. out: u8 [H][W][3], row 0 = top.  lut_x/lut_y: NULL or fisheye LUT [H][W]. */
@@ -362,6 +395,23 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
       model_view(V, t, 1.0, cs[quarter], sn[quarter], x.MV, x.N);
       const orr_texture* tex = sc->tile_tex[idx] >= 0 ? &sc->textures[sc->tile_tex[idx]] : NULL;
       const float white[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1}, up[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0};
+      if (g_tile_mode == 1) {
+        /* analytic: light the 8x8 lattice once, draw the tile as one quad (0,1,2)(0,2,3) */
+        float lat_rgb[64 * 3];
+        vtx corner[4];
+        const int ca[4] = {0, 7, 7, 0}, cb[4] = {0, 0, 7, 7};
+        for (int a = 0; a < 8; a++)
+          for (int b = 0; b < 8; b++) {
+            const float p[3] = {lat[a], 0.0f, lat[b]};
+            vtx v = shade_vertex(&x, p, up, white, (float)((double)a / 7.0), (float)(1.0 - (double)b / 7.0));
+            lat_rgb[(a * 8 + b) * 3] = v.r; lat_rgb[(a * 8 + b) * 3 + 1] = v.g; lat_rgb[(a * 8 + b) * 3 + 2] = v.b;
+            for (int k = 0; k < 4; k++) if (a == ca[k] && b == cb[k]) corner[k] = v;
+          }
+        for (int k = 0; k < 4; k++) { corner[k].r = 0.0f; corner[k].g = 0.0f; corner[k].b = 0.0f; }
+        draw_shaded(&fb, corner[0], corner[1], corner[2], tex, lat_rgb);
+        draw_shaded(&fb, corner[0], corner[2], corner[3], tex, lat_rgb);
+        continue;
+      }
       for (int a = 0; a < 7; a++)
         for (int b = 0; b < 7; b++) {
           const int qa[4] = {a, a + 1, a + 1, a}, qb[4] = {b, b, b + 1, b + 1};
