@@ -16,7 +16,7 @@
 //                 one pixel with its 4 MSAA samples (depth, colour, draw id) in registers; early-z
 //                 before shading; ground drawn last
 //   O  output     box resolve -> u8, rows packed with shuffles and stored as 32-bit words
-// Arithmetic follows the render spec in oracle/dt_oracle_raster.c / DESIGN.md bit for bit
+// Arithmetic follows the render spec of DESIGN.md (the CPU checker implements the same spec) bit for bit
 // (compiled with -fmad=false; fmaf() is spelled out where the spec has one).
 //
 // HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / bin lists / lattice table
