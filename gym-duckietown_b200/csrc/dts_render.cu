@@ -38,8 +38,10 @@ constexpr int kStage = 16;        // prims staged per pass and warp
 constexpr int kMaxLarge = 1024;
 constexpr float kGuard = 4.0f;
 constexpr int kSub = 64;          // sub-pixel units per pixel
-__constant__ int c_sx[4] = {24, 56, 8, 40};
-__constant__ int c_sy[4] = {8, 24, 40, 56};
+// MSAA sample offsets in 1/64 px, (.375,.125)(.875,.375)(.125,.625)(.625,.875); constexpr so that the
+// unrolled sample loops fold them into immediates
+__host__ __device__ constexpr int sample_x(int s) { return s == 0 ? 24 : (s == 1 ? 56 : (s == 2 ? 8 : 40)); }
+__host__ __device__ constexpr int sample_y(int s) { return s == 0 ? 8 : (s == 1 ? 24 : (s == 2 ? 40 : 56)); }
 
 struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 
@@ -325,7 +327,10 @@ size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_la
   return (size_t)n_ctas * (render_slab_bytes(max_prims, max_pairs, max_lat) + undistorted_frame_bytes) + 256;
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+#ifndef DTS_RENDER_MIN_CTAS
+#define DTS_RENDER_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* __restrict__ obs,
          uint8_t* __restrict__ scratch, int max_prims, int max_pairs, int max_lat, uint8_t* __restrict__ undist,
          const float* __restrict__ lut_x, const float* __restrict__ lut_y, int32_t* __restrict__ err) {
@@ -560,12 +565,15 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
         const bool pairs_ok = sh.n_pairs <= max_pairs;
         __syncthreads();
         // ------------------------------------------------------------ R: raster, warps pull bins
-        for (;;) {
-          int bin = 0;
-          if (lane == 0) bin = atomicAdd(&sh.next_bin, 1);
-          bin = __shfl_sync(0xffffffffu, bin, 0);
-          if (bin >= n_bins) break;
-          const int bx = mbx0 + bin % mw, by = mby0 + bin / mw;
+        const unsigned inv_mw = (65536u + (unsigned)mw - 1u) / (unsigned)mw;   // bin / mw for bin < 3276
+        int bin = 0;
+        if (lane == 0) bin = atomicAdd(&sh.next_bin, 1);
+        bin = __shfl_sync(0xffffffffu, bin, 0);
+        while (bin < n_bins) {
+          int next_bin = 0;
+          if (lane == 0) next_bin = atomicAdd(&sh.next_bin, 1);   // consumed after this bin: latency hidden
+          const int brow = (int)(((unsigned)bin * inv_mw) >> 16);
+          const int bx = mbx0 + (bin - brow * mw), by = mby0 + brow;
           const int count = pairs_ok ? bin_count[bin] : 0;
           const int start = bin_start[bin];
           const int ox = bx * kBinW * kSub, oy = by * kBinH * kSub;   // bin corner, sub-pixels
@@ -633,9 +641,9 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
                   const int ec2 = bp.E0[2] + bp.A[2] * pxs + bp.B[2] * pys;
 #pragma unroll
                   for (int s = 0; s < 4; s++) {
-                    const int e0 = ec0 + bp.A[0] * c_sx[s] + bp.B[0] * c_sy[s];
-                    const int e1 = ec1 + bp.A[1] * c_sx[s] + bp.B[1] * c_sy[s];
-                    const int e2 = ec2 + bp.A[2] * c_sx[s] + bp.B[2] * c_sy[s];
+                    const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
+                    const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
+                    const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
                     if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
                   }
                   if (!mask) continue;
@@ -643,14 +651,21 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
                 // ---- early z: depth of the covered samples, GL_LESS in draw order
                 const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
                 float zs[4];
-                int pass_mask = 0;
+                int lt = 0, eq = 0;
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                   // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
                   // identical to the spec's (float)(X_sample - x0) / 64
-                  const float sdx = cdx + (float)(c_sx[s] - 32) * 0.015625f, sdy = cdy + (float)(c_sy[s] - 32) * 0.015625f;
+                  const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
                   zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
-                  if ((mask >> s & 1) && (zs[s] < z[s] || (zs[s] == z[s] && bp.id < wid[s]))) pass_mask |= 1 << s;
+                  lt |= (zs[s] < z[s]) << s;
+                  eq |= (zs[s] == z[s]) << s;
+                }
+                int pass_mask = mask & lt;
+                const int tie = mask & eq;
+                if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
+#pragma unroll
+                  for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
                 }
                 if (!pass_mask) continue;
                 // ---- shade once at the pixel centre
@@ -732,6 +747,7 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
             uint8_t* d = out + ((size_t)gy * W + gx) * 3;
             d[0] = (uint8_t)r8; d[1] = (uint8_t)g8; d[2] = (uint8_t)b8;
           }
+          bin = __shfl_sync(0xffffffffu, next_bin, 0);
         }
         __syncthreads();
       }
