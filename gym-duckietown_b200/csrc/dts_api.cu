@@ -309,7 +309,8 @@ static int ensure_render(dts_sim* sim) {
     max_tris = t > max_tris ? t : max_tris;
     max_lat = m.n_tiles > max_lat ? m.n_tiles : max_lat;
   }
-  sim->render_ctas = sms * 3 < sim->cfg.num_envs ? sms * 3 : sim->cfg.num_envs;
+  const int want = sms * render_ctas_per_sm();
+  sim->render_ctas = want < sim->cfg.num_envs ? want : sim->cfg.num_envs;
   sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
   if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
   sim->max_lat = max_lat;

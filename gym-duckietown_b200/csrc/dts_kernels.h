@@ -33,6 +33,7 @@ void launch_query(const DMap* maps, int map_id, int n, const double* q, const ui
 
 // render (dts_render.cu)
 struct RenderScratch;
+int render_ctas_per_sm();
 size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_lat, size_t undistorted_frame_bytes);
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, const float* lut_x, const float* lut_y, int32_t* err_flag,

@@ -30,7 +30,13 @@ namespace dts {
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef DTS_RENDER_THREADS
+#define DTS_RENDER_THREADS 256
+#endif
+#ifndef DTS_RENDER_MIN_CTAS
+#define DTS_RENDER_MIN_CTAS 3
+#endif
+constexpr int kThreads = DTS_RENDER_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kBinW = 8, kBinH = 4;   // one warp's pixel block
 constexpr int kMtBinsX = 20, kMtBinsY = 32;  // macro tile = 160 x 128 px = 640 bins
@@ -314,6 +320,86 @@ __device__ __forceinline__ BinRange prim_bins(int pxmin, int pxmax, int mbx0, in
   return r;
 }
 
+
+// Fragment colour of one staged prim at a pixel centre (spec steps 5-6 and 8): perspective-correct
+// u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles, bilinear REPEAT texel, MODULATE.
+__device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __restrict__ lat_tab, float cdx,
+                                            float cdy, float c3[3]) {
+  float qq = fmaf(bp.fy[1], cdy, fmaf(bp.fx[1], cdx, bp.f0[1]));
+  if (!(qq > 1e-20f)) qq = 1e-20f;
+  const float rq = 1.0f / qq;
+  const float u = fmaf(bp.fy[2], cdy, fmaf(bp.fx[2], cdx, bp.f0[2])) * rq;
+  const float v = fmaf(bp.fy[3], cdy, fmaf(bp.fx[3], cdx, bp.f0[3])) * rq;
+  if (bp.lat >= 0) {
+    // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
+    const float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
+    int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
+    ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
+    ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
+    const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
+    const float4* L = lat_tab + bp.lat * 64 + ia * 8 + ib;
+    const float4 c00 = L[0], c01 = L[1], c10 = L[8], c11 = L[9];
+    if (fb <= fa) {
+      c3[0] = fmaf(fb, c11.x - c10.x, fmaf(fa, c10.x - c00.x, c00.x));
+      c3[1] = fmaf(fb, c11.y - c10.y, fmaf(fa, c10.y - c00.y, c00.y));
+      c3[2] = fmaf(fb, c11.z - c10.z, fmaf(fa, c10.z - c00.z, c00.z));
+    } else {
+      c3[0] = fmaf(fa, c11.x - c01.x, fmaf(fb, c01.x - c00.x, c00.x));
+      c3[1] = fmaf(fa, c11.y - c01.y, fmaf(fb, c01.y - c00.y, c00.y));
+      c3[2] = fmaf(fa, c11.z - c01.z, fmaf(fb, c01.z - c00.z, c00.z));
+    }
+  } else {
+    c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
+    c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
+    c3[2] = fmaf(bp.fy[6], cdy, fmaf(bp.fx[6], cdx, bp.f0[6])) * rq;
+  }
+  if (bp.tex) {
+    const int tw = bp.tex_wh & 0xffff, th = bp.tex_wh >> 16;
+    const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
+    const float txf = floorf(tx), tyf = floorf(ty);
+    const float ffx = tx - txf, ffy = ty - tyf;
+    const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
+    const int tj0 = ((int)tyf) & (th - 1), tj1 = (tj0 + 1) & (th - 1);
+    const uchar4* tp = reinterpret_cast<const uchar4*>(bp.tex);
+    const uchar4 t00 = __ldg(tp + tj0 * tw + ti0), t10 = __ldg(tp + tj0 * tw + ti1);
+    const uchar4 t01 = __ldg(tp + tj1 * tw + ti0), t11 = __ldg(tp + tj1 * tw + ti1);
+    const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
+    const float b0[3] = {(float)t01.x, (float)t01.y, (float)t01.z}, b1[3] = {(float)t11.x, (float)t11.y, (float)t11.z};
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      const float ta = fmaf(ffx, a1[ch] - a0[ch], a0[ch]);
+      const float tb = fmaf(ffx, b1[ch] - b0[ch], b0[ch]);
+      const float tc = fmaf(ffy, tb - ta, ta);
+      c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
+    }
+  }
+}
+
+// u8 = rint(255 * clamp(c)) packed r | g<<8 | b<<16 (resolve of 4 equal samples is the value itself)
+__device__ __forceinline__ unsigned pack_rgb(float r, float g, float b) {
+  r = r < 0.f ? 0.f : (r > 1.f ? 1.f : r);
+  g = g < 0.f ? 0.f : (g > 1.f ? 1.f : g);
+  b = b < 0.f ? 0.f : (b > 1.f ? 1.f : b);
+  return (unsigned)rintf(r * 255.0f) | ((unsigned)rintf(g * 255.0f) << 8) | ((unsigned)rintf(b * 255.0f) << 16);
+}
+
+// one 8x4 bin of packed pixels -> global memory: rows of 24 bytes as 6 aligned words built with shuffles
+__device__ __forceinline__ void store_bin(uint8_t* __restrict__ out, unsigned rgb, int lane, int bx, int by, int W, int H) {
+  const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
+  if ((W & 3) == 0 && bx * kBinW + kBinW <= W) {
+    const int j = lane & 7, rowbase = lane & ~7;
+    const int p0 = (4 * j) / 3, sh8 = (4 * j - 3 * p0) * 8;
+    const unsigned lo = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0, 7));
+    const unsigned hi = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0 + 1, 7));
+    const unsigned long long both = (unsigned long long)lo | ((unsigned long long)hi << 24);
+    if (j < 6 && gy < H)
+      *reinterpret_cast<unsigned*>(out + ((size_t)gy * W + bx * kBinW) * 3 + 4 * j) = (unsigned)(both >> sh8);
+  } else if (gx < W && gy < H) {
+    uint8_t* d = out + ((size_t)gy * W + gx) * 3;
+    d[0] = (uint8_t)(rgb & 255); d[1] = (uint8_t)((rgb >> 8) & 255); d[2] = (uint8_t)(rgb >> 16);
+  }
+}
+
 }  // namespace
 
 __host__ __device__ size_t render_slab_bytes(int max_prims, int max_pairs, int max_lat) {
@@ -323,13 +409,12 @@ __host__ __device__ size_t render_slab_bytes(int max_prims, int max_pairs, int m
   return (b + 255) & ~size_t(255);
 }
 
+int render_ctas_per_sm() { return DTS_RENDER_MIN_CTAS; }
+
 size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_lat, size_t undistorted_frame_bytes) {
   return (size_t)n_ctas * (render_slab_bytes(max_prims, max_pairs, max_lat) + undistorted_frame_bytes) + 256;
 }
 
-#ifndef DTS_RENDER_MIN_CTAS
-#define DTS_RENDER_MIN_CTAS 3
-#endif
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* __restrict__ obs,
          uint8_t* __restrict__ scratch, int max_prims, int max_pairs, int max_lat, uint8_t* __restrict__ undist,
@@ -582,6 +667,7 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
 #pragma unroll
           for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
           BinPrim* stage = sh.stage[warp];
+          bool simple_done = false;
           for (int c0 = 0; c0 < count; c0 += kStage) {
             const int nch = min(kStage, count - c0);
             __syncwarp();
@@ -626,6 +712,23 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
             __syncwarp();
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
             const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
+            if (count <= kStage) {
+              // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
+              // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
+              // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
+              const unsigned full_mask = __ballot_sync(0xffffffffu, live && (stage[lane < nch ? lane : 0].flags & 1));
+              const unsigned others = live_mask & ~ground_mask;
+              const unsigned pick = others ? others : live_mask;
+              if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
+                const BinPrim& bp = stage[__ffs(pick) - 1];
+                const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
+                float c3[3];
+                shade_pixel(bp, lat_tab, cdx, cdy, c3);
+                store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
+                simple_done = true;
+                break;
+              }
+            }
             // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
             for (int phase = 0; phase < 2; phase++) {
               unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
@@ -668,56 +771,8 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
                   for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
                 }
                 if (!pass_mask) continue;
-                // ---- shade once at the pixel centre
-                float qq = fmaf(bp.fy[1], cdy, fmaf(bp.fx[1], cdx, bp.f0[1]));
-                if (!(qq > 1e-20f)) qq = 1e-20f;
-                const float rq = 1.0f / qq;
-                const float u = fmaf(bp.fy[2], cdy, fmaf(bp.fx[2], cdx, bp.f0[2])) * rq;
-                const float v = fmaf(bp.fy[3], cdy, fmaf(bp.fx[3], cdx, bp.f0[3])) * rq;
                 float c3[3];
-                if (bp.lat >= 0) {
-                  // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
-                  const float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
-                  int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
-                  ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
-                  ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
-                  const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
-                  const float4* L = lat_tab + bp.lat * 64 + ia * 8 + ib;
-                  const float4 c00 = L[0], c01 = L[1], c10 = L[8], c11 = L[9];
-                  if (fb <= fa) {
-                    c3[0] = fmaf(fb, c11.x - c10.x, fmaf(fa, c10.x - c00.x, c00.x));
-                    c3[1] = fmaf(fb, c11.y - c10.y, fmaf(fa, c10.y - c00.y, c00.y));
-                    c3[2] = fmaf(fb, c11.z - c10.z, fmaf(fa, c10.z - c00.z, c00.z));
-                  } else {
-                    c3[0] = fmaf(fa, c11.x - c01.x, fmaf(fb, c01.x - c00.x, c00.x));
-                    c3[1] = fmaf(fa, c11.y - c01.y, fmaf(fb, c01.y - c00.y, c00.y));
-                    c3[2] = fmaf(fa, c11.z - c01.z, fmaf(fb, c01.z - c00.z, c00.z));
-                  }
-                } else {
-                  c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
-                  c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
-                  c3[2] = fmaf(bp.fy[6], cdy, fmaf(bp.fx[6], cdx, bp.f0[6])) * rq;
-                }
-                if (bp.tex) {
-                  const int tw = bp.tex_wh & 0xffff, th = bp.tex_wh >> 16;
-                  const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
-                  const float txf = floorf(tx), tyf = floorf(ty);
-                  const float ffx = tx - txf, ffy = ty - tyf;
-                  const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
-                  const int tj0 = ((int)tyf) & (th - 1), tj1 = (tj0 + 1) & (th - 1);
-                  const uchar4* tp = reinterpret_cast<const uchar4*>(bp.tex);
-                  const uchar4 t00 = __ldg(tp + tj0 * tw + ti0), t10 = __ldg(tp + tj0 * tw + ti1);
-                  const uchar4 t01 = __ldg(tp + tj1 * tw + ti0), t11 = __ldg(tp + tj1 * tw + ti1);
-                  const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
-                  const float b0[3] = {(float)t01.x, (float)t01.y, (float)t01.z}, b1[3] = {(float)t11.x, (float)t11.y, (float)t11.z};
-#pragma unroll
-                  for (int ch = 0; ch < 3; ch++) {
-                    const float ta = fmaf(ffx, a1[ch] - a0[ch], a0[ch]);
-                    const float tb = fmaf(ffx, b1[ch] - b0[ch], b0[ch]);
-                    const float tc = fmaf(ffy, tb - ta, ta);
-                    c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
-                  }
-                }
+                shade_pixel(bp, lat_tab, cdx, cdy, c3);
 #pragma unroll
                 for (int s = 0; s < 4; s++)
                   if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2]; }
@@ -725,27 +780,11 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
             }
           }
           // ---------------------------------------------------------- O: resolve + store
-          float c;
-          c = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-          const unsigned r8 = (unsigned)rintf(c * 255.0f);
-          c = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-          const unsigned g8 = (unsigned)rintf(c * 255.0f);
-          c = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f; c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-          const unsigned b8 = (unsigned)rintf(c * 255.0f);
-          const unsigned rgb = r8 | (g8 << 8) | (b8 << 16);
-          const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
-          if ((W & 3) == 0 && bx * kBinW + kBinW <= W) {
-            // a pixel row of the bin is 24 bytes = 6 aligned words; lane j<6 of the row builds word j
-            const int j = lane & 7, rowbase = lane & ~7;
-            const int p0 = (4 * j) / 3, sh8 = (4 * j - 3 * p0) * 8;
-            const unsigned lo = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0, 7));
-            const unsigned hi = __shfl_sync(0xffffffffu, rgb, rowbase + min(p0 + 1, 7));
-            const unsigned long long both = (unsigned long long)lo | ((unsigned long long)hi << 24);
-            if (j < 6 && gy < H)
-              *reinterpret_cast<unsigned*>(out + ((size_t)gy * W + bx * kBinW) * 3 + 4 * j) = (unsigned)(both >> sh8);
-          } else if (gx < W && gy < H) {
-            uint8_t* d = out + ((size_t)gy * W + gx) * 3;
-            d[0] = (uint8_t)r8; d[1] = (uint8_t)g8; d[2] = (uint8_t)b8;
+          if (!simple_done) {
+            const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
+            const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
+            const float b_ = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f;
+            store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
           }
           bin = __shfl_sync(0xffffffffu, next_bin, 0);
         }
