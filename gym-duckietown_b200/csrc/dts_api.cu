@@ -122,7 +122,7 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   bad |= sim->dalloc(&S.rng, n);
   bad |= sim->dalloc(&S.rep, n);
   bad |= sim->dalloc(&sim->d_maps, cfg->max_maps);
-  bad |= sim->dalloc(&sim->d_err, 4);
+  bad |= sim->dalloc(&sim->d_err, 32);
   auto& st = sim->stage;
   bad |= sim->dalloc(&st.map_id, n);
   double** sd[] = {&st.pos_x, &st.pos_z, &st.angle, &st.wheel_dist, &st.trim};
@@ -387,6 +387,14 @@ int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const 
 }
 
 uint64_t dts_launch_count(dts_sim* sim) { return sim ? sim->launches : 0; }
+
+/* debug: copy the 32 int32 diagnostic counters (word 0 = overflow flag; 8.. = DTS_STATS counters) */
+int dts_debug_counters(dts_sim* sim, int32_t out[32]) {
+  if (!sim) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  DTS_CUDA(cudaMemcpy(out, sim->d_err, 32 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 // ---- multi-GPU: one NCCL all-gather of the end-of-rollout observation batch ----------
 // libnccl is dlopen'ed (the torch-bundled copy); the communicator is created from a unique id that

@@ -38,9 +38,11 @@ namespace {
 #endif
 constexpr int kThreads = DTS_RENDER_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kBinW = 8, kBinH = 4;   // one warp's pixel block
-constexpr int kMtBinsX = 20, kMtBinsY = 32;  // macro tile = 160 x 128 px = 640 bins
-constexpr int kStage = 16;        // prims staged per pass and warp
+constexpr int kBinW = 8, kBinH = 4;   // fine bin = one warp's pixel block (one pixel per lane)
+constexpr int kCFX = 4, kCFY = 2;     // coarse bin = 4 x 2 fine bins = 32 x 8 px: unit of binning and staging
+constexpr int kCoarseW = kBinW * kCFX, kCoarseH = kBinH * kCFY;
+constexpr int kMtBinsX = 20, kMtBinsY = 32;  // macro tile = 20 x 32 coarse bins = 640 x 256 px
+constexpr int kStage = 32;        // prims staged per pass and warp
 constexpr int kMaxLarge = 1024;
 constexpr float kGuard = 4.0f;
 constexpr int kSub = 64;          // sub-pixel units per pixel
@@ -67,7 +69,7 @@ struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the curre
   int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
   float f0[7], fx[7], fy[7];
   int32_t id;                    // draw id
-  int32_t flags;                 // bit0: every sample of the bin is inside all three edges
+  int32_t flags;                 // per fine bin f of the coarse bin: bit f = every sample inside, bit 8+f = may touch
   const uint8_t* tex;            // nullptr = untextured
   int32_t tex_wh;                // w | h<<16
   int32_t lat;
@@ -302,9 +304,9 @@ __device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const int dx = bx[k] - ax[k], dy = by[k] - ay[k];
-    // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the bin's sample span [8, 7*64+56] x [8, 3*64+56]
-    const int xs = (-dy > 0) ? ox + 7 * kSub + 56 : ox + 8;
-    const int ys = (dx > 0) ? oy + 3 * kSub + 56 : oy + 8;
+    // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the coarse bin's sample span
+    const int xs = (-dy > 0) ? ox + (kCoarseW - 1) * kSub + 56 : ox + 8;
+    const int ys = (dx > 0) ? oy + (kCoarseH - 1) * kSub + 56 : oy + 8;
     const long long e = (long long)dx * (ys - ay[k]) - (long long)dy * (xs - ax[k]);
     if (e < 0) return false;
   }
@@ -315,11 +317,50 @@ struct BinRange { int bx0, by0, bx1, by1; };
 
 __device__ __forceinline__ BinRange prim_bins(int pxmin, int pxmax, int mbx0, int mby0, int mbx1, int mby1) {
   BinRange r;
-  r.bx0 = max((pxmin & 0xffff) / kBinW, mbx0); r.by0 = max((pxmin >> 16) / kBinH, mby0);
-  r.bx1 = min((pxmax & 0xffff) / kBinW, mbx1); r.by1 = min((pxmax >> 16) / kBinH, mby1);
+  r.bx0 = max((pxmin & 0xffff) / kCoarseW, mbx0); r.by0 = max((pxmin >> 16) / kCoarseH, mby0);
+  r.bx1 = min((pxmax & 0xffff) / kCoarseW, mbx1); r.by1 = min((pxmax >> 16) / kCoarseH, mby1);
   return r;
 }
 
+
+// Stage one prim for a coarse bin whose corner is (ox, oy) sub-pixels: edge functions re-based to the
+// corner (exact in 64 bits, then int32: inside the coarse bin |A*x + B*y| < 2^30), per-fine-bin exact
+// reject / trivial-accept bits, planes and texture.  Returns the prim's draw id.
+__device__ __forceinline__ int stage_prim(const PrimRec& r, BinPrim& bp, int ox, int oy, const DMap& m) {
+  const int X0 = r.X[0], X1 = r.X[1], X2 = r.X[2], Y0 = r.Y[0], Y1 = r.Y[1], Y2 = r.Y[2];
+  const int ax[3] = {X1, X2, X0}, ay[3] = {Y1, Y2, Y0}, bxv[3] = {X2, X0, X1}, byv[3] = {Y2, Y0, Y1};
+  unsigned live = 0xffu, inside = 0xffu;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int dx = bxv[k] - ax[k], dy = byv[k] - ay[k];
+    const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
+    long long e0 = (long long)dx * (oy - ay[k]) - (long long)dy * (ox - ax[k]) - bias;
+    if (e0 < -(1LL << 30)) live = 0;          // negative for every sample of the coarse bin
+    if (e0 > (1LL << 30)) e0 = (1LL << 30);   // positive for every sample: keep the sign, stay in int32
+    const int A = -dy, B = dx, e = (int)e0;
+    bp.E0[k] = e; bp.A[k] = A; bp.B[k] = B;
+    // extremes of A*x + B*y over one fine bin's sample span x in [8, 504], y in [8, 248]
+    const int hi = (A > 0 ? A * 504 : A * 8) + (B > 0 ? B * 248 : B * 8);
+    const int lo = (A > 0 ? A * 8 : A * 504) + (B > 0 ? B * 8 : B * 248);
+#pragma unroll
+    for (int f = 0; f < 8; f++) {
+      const int ef = e + A * ((f & 3) * kBinW * kSub) + B * ((f >> 2) * kBinH * kSub);
+      if (ef + hi < 0) live &= ~(1u << f);
+      if (ef + lo < 0) inside &= ~(1u << f);
+    }
+  }
+  bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
+#pragma unroll
+  for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
+  const int id = r.id_tex >> 8;
+  bp.id = id;
+  bp.flags = (int)((inside & live) | (live << 8));
+  const int tex = (r.id_tex & 255) - 1;
+  if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); }
+  else { bp.tex = nullptr; bp.tex_wh = 0; }
+  bp.lat = r.lat;
+  return id;
+}
 
 // Fragment colour of one staged prim at a pixel centre (spec steps 5-6 and 8): perspective-correct
 // u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles, bilinear REPEAT texel, MODULATE.
@@ -422,7 +463,6 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int W = rc.width, H = rc.height;
-  const int bins_x = (W + kBinW - 1) / kBinW, bins_y = (H + kBinH - 1) / kBinH;
   int* bin_count = reinterpret_cast<int*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)));
   int* bin_start = bin_count + kMtBinsX * kMtBinsY;
   const size_t slab = render_slab_bytes(max_prims, max_pairs, max_lat);
@@ -581,13 +621,17 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
     }
     __syncthreads();
     const int n_prims = min(sh.n_prims, max_prims);
+#ifdef DTS_STATS
+    if (tid == 0) { atomicAdd(&err[18], n_prims); atomicAdd(&err[19], 1); }
+#endif
     const float clr[3] = {sh.ep.horizon[0], sh.ep.horizon[1], sh.ep.horizon[2]};
-    // ---------------------------------------------------------------- macro tiles of <= 20 x 32 bins
-    for (int mby0 = 0; mby0 < bins_y; mby0 += kMtBinsY)
-      for (int mbx0 = 0; mbx0 < bins_x; mbx0 += kMtBinsX) {
-        const int mbx1 = min(mbx0 + kMtBinsX, bins_x) - 1, mby1 = min(mby0 + kMtBinsY, bins_y) - 1;
+    // ---------------------------------------------------------------- macro tiles of <= 20 x 32 coarse bins
+    const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH;
+    for (int mby0 = 0; mby0 < cbins_y; mby0 += kMtBinsY)
+      for (int mbx0 = 0; mbx0 < cbins_x; mbx0 += kMtBinsX) {
+        const int mbx1 = min(mbx0 + kMtBinsX, cbins_x) - 1, mby1 = min(mby0 + kMtBinsY, cbins_y) - 1;
         const int mw = mbx1 - mbx0 + 1, mh = mby1 - mby0 + 1, n_bins = mw * mh;
-        // ------------------------------------------------------------ B: count, scan, scatter
+        // ------------------------------------------------------------ B: count, scan, scatter (coarse bins)
         for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
         if (tid == 0) { sh.n_large = 0; sh.next_bin = 0; }
         __syncthreads();
@@ -620,7 +664,7 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
             const int bw = r.bx1 - r.bx0 + 1, nb = bw * (r.by1 - r.by0 + 1);
             for (int q = lane; q < nb; q += 32) {
               const int by = r.by0 + q / bw, bx = r.bx0 + q % bw;
-              if (!bin_overlaps(X, Y, bx * kBinW * kSub, by * kBinH * kSub)) continue;
+              if (!bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
               const int b = (by - mby0) * mw + (bx - mbx0);
               const int pos = atomicAdd(&bin_count[b], 1);
               if (pass == 1) pairs[bin_start[b] + pos] = (uint16_t)p;
@@ -649,8 +693,10 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
         }
         const bool pairs_ok = sh.n_pairs <= max_pairs;
         __syncthreads();
-        // ------------------------------------------------------------ R: raster, warps pull bins
+        // ------------------------------------------------------------ R: raster, warps pull coarse bins
         const unsigned inv_mw = (65536u + (unsigned)mw - 1u) / (unsigned)mw;   // bin / mw for bin < 3276
+        const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
+        BinPrim* stage = sh.stage[warp];
         int bin = 0;
         if (lane == 0) bin = atomicAdd(&sh.next_bin, 1);
         bin = __shfl_sync(0xffffffffu, bin, 0);
@@ -658,133 +704,125 @@ k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* _
           int next_bin = 0;
           if (lane == 0) next_bin = atomicAdd(&sh.next_bin, 1);   // consumed after this bin: latency hidden
           const int brow = (int)(((unsigned)bin * inv_mw) >> 16);
-          const int bx = mbx0 + (bin - brow * mw), by = mby0 + brow;
+          const int cbx = mbx0 + (bin - brow * mw), cby = mby0 + brow;
           const int count = pairs_ok ? bin_count[bin] : 0;
           const int start = bin_start[bin];
-          const int ox = bx * kBinW * kSub, oy = by * kBinH * kSub;   // bin corner, sub-pixels
-          float z[4], cr[4], cg[4], cb[4];
-          int wid[4];
-#pragma unroll
-          for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
-          BinPrim* stage = sh.stage[warp];
-          bool simple_done = false;
-          for (int c0 = 0; c0 < count; c0 += kStage) {
-            const int nch = min(kStage, count - c0);
+          const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
+          const bool single = count <= kStage;
+#ifdef DTS_STATS
+          if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count); }
+#endif
+          int my_id = 0x7fffffff, my_flags = 0;
+          if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins
             __syncwarp();
-            bool live = false;
-            int my_id = 0x7fffffff;
-            if (lane < nch) {
-              // ---- stage one prim: re-base to this bin, exact reject, trivial accept
-              const PrimRec& r = prims[pairs[start + c0 + lane]];
-              BinPrim& bp = stage[lane];
-              const int X0 = r.X[0], X1 = r.X[1], X2 = r.X[2], Y0 = r.Y[0], Y1 = r.Y[1], Y2 = r.Y[2];
-              const int ax[3] = {X1, X2, X0}, ay[3] = {Y1, Y2, Y0}, bxv[3] = {X2, X0, X1}, byv[3] = {Y2, Y0, Y1};
-              live = true;
-              int inside = 1;
-#pragma unroll
-              for (int k = 0; k < 3; k++) {
-                const int dx = bxv[k] - ax[k], dy = byv[k] - ay[k];
-                const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
-                // E(x,y) = dx*(y-ay) - dy*(x-ax) - bias at the bin corner, exact in 64 bits; inside the bin
-                // |A*x+B*y| < 2^29, so beyond +-2^30 the sign is the same for every sample
-                long long e0 = (long long)dx * (oy - ay[k]) - (long long)dy * (ox - ax[k]) - bias;
-                if (e0 < -(1LL << 30)) live = false;
-                if (e0 > (1LL << 30)) e0 = (1LL << 30);
-                const int A = -dy, B = dx, e = (int)e0;
-                // extremes over the bin's sample span x in [8, 504], y in [8, 248]
-                const int emax = e + (A > 0 ? A * 504 : A * 8) + (B > 0 ? B * 248 : B * 8);
-                const int emin = e + (A > 0 ? A * 8 : A * 504) + (B > 0 ? B * 8 : B * 248);
-                if (emax < 0) live = false;
-                if (emin < 0) inside = 0;
-                bp.E0[k] = e; bp.A[k] = A; bp.B[k] = B;
-              }
-              bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
-#pragma unroll
-              for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
-              my_id = r.id_tex >> 8;
-              bp.id = my_id;
-              bp.flags = inside;
-              const int tex = (r.id_tex & 255) - 1;
-              if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); }
-              else { bp.tex = nullptr; bp.tex_wh = 0; }
-              bp.lat = r.lat;
-            }
+            if (lane < count) { my_id = stage_prim(prims[pairs[start + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
             __syncwarp();
-            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-            const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
-            if (count <= kStage) {
-              // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
-              // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
-              // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
-              const unsigned full_mask = __ballot_sync(0xffffffffu, live && (stage[lane < nch ? lane : 0].flags & 1));
-              const unsigned others = live_mask & ~ground_mask;
-              const unsigned pick = others ? others : live_mask;
-              if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
-                const BinPrim& bp = stage[__ffs(pick) - 1];
-                const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
-                float c3[3];
-                shade_pixel(bp, lat_tab, cdx, cdy, c3);
-                store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
-                simple_done = true;
-                break;
+          }
+#pragma unroll 1
+          for (int f = 0; f < kCFX * kCFY; f++) {
+            const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
+            if (bx * kBinW >= W || by * kBinH >= H) continue;
+            if (count == 0) { store_bin(out, clear_rgb, lane, bx, by, W, H); continue; }
+            const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
+            float z[4], cr[4], cg[4], cb[4];
+            int wid[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
+            bool simple_done = false;
+            for (int c0 = 0; c0 < count; c0 += kStage) {
+              const int nch = min(kStage, count - c0);
+              if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
+                __syncwarp();
+                my_id = 0x7fffffff; my_flags = 0;
+                if (lane < nch) { my_id = stage_prim(prims[pairs[start + c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
+                __syncwarp();
               }
-            }
-            // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
-            for (int phase = 0; phase < 2; phase++) {
-              unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
-              while (todo) {
-                const int k = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const BinPrim& bp = stage[k];
-                int mask = 15;
-                if (!(bp.flags & 1)) {
-                  mask = 0;
-                  const int ec0 = bp.E0[0] + bp.A[0] * pxs + bp.B[0] * pys;
-                  const int ec1 = bp.E0[1] + bp.A[1] * pxs + bp.B[1] * pys;
-                  const int ec2 = bp.E0[2] + bp.A[2] * pxs + bp.B[2] * pys;
+              const bool live = (my_flags >> (8 + f)) & 1;
+              const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+              const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
+#ifdef DTS_STATS
+              if (lane == 0) { atomicAdd(&err[11], __popc(live_mask)); atomicAdd(&err[12], __popc(ground_mask)); }
+#endif
+              if (single) {
+                // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
+                // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
+                // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
+                const unsigned full_mask = __ballot_sync(0xffffffffu, live && ((my_flags >> f) & 1));
+                const unsigned others = live_mask & ~ground_mask;
+                const unsigned pick = others ? others : live_mask;
+                if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
+                  const BinPrim& bp = stage[__ffs(pick) - 1];
+                  const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
+                  float c3[3];
+                  shade_pixel(bp, lat_tab, cdx, cdy, c3);
+                  store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
+                  simple_done = true;
+#ifdef DTS_STATS
+                  if (lane == 0) atomicAdd(&err[13], 1);
+#endif
+                  break;
+                }
+              }
+              // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
+              for (int phase = 0; phase < 2; phase++) {
+                unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+                while (todo) {
+                  const int k = __ffs(todo) - 1;
+                  todo &= todo - 1;
+                  const BinPrim& bp = stage[k];
+#ifdef DTS_STATS
+                  if (lane == 0) { atomicAdd(&err[16], 1); if ((bp.flags >> f) & 1) atomicAdd(&err[17], 1); }
+#endif
+                  int mask = 15;
+                  if (!((bp.flags >> f) & 1)) {
+                    mask = 0;
+                    const int ec0 = bp.E0[0] + bp.A[0] * pxc + bp.B[0] * pyc;
+                    const int ec1 = bp.E0[1] + bp.A[1] * pxc + bp.B[1] * pyc;
+                    const int ec2 = bp.E0[2] + bp.A[2] * pxc + bp.B[2] * pyc;
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                      const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
+                      const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
+                      const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
+                      if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                    }
+                    if (!mask) continue;
+                  }
+                  // ---- early z: depth of the covered samples, GL_LESS in draw order
+                  const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
+                  float zs[4];
+                  int lt = 0, eq = 0;
 #pragma unroll
                   for (int s = 0; s < 4; s++) {
-                    const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
-                    const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
-                    const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
-                    if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                    // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
+                    // identical to the spec's (float)(X_sample - x0) / 64
+                    const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
+                    zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
+                    lt |= (zs[s] < z[s]) << s;
+                    eq |= (zs[s] == z[s]) << s;
                   }
-                  if (!mask) continue;
-                }
-                // ---- early z: depth of the covered samples, GL_LESS in draw order
-                const float cdx = (float)(pxs + 32 - bp.x0) * 0.015625f, cdy = (float)(pys + 32 - bp.y0) * 0.015625f;
-                float zs[4];
-                int lt = 0, eq = 0;
+                  int pass_mask = mask & lt;
+                  const int tie = mask & eq;
+                  if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                  // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
-                  // identical to the spec's (float)(X_sample - x0) / 64
-                  const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
-                  zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
-                  lt |= (zs[s] < z[s]) << s;
-                  eq |= (zs[s] == z[s]) << s;
-                }
-                int pass_mask = mask & lt;
-                const int tie = mask & eq;
-                if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
+                    for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
+                  }
+                  if (!pass_mask) continue;
+                  float c3[3];
+                  shade_pixel(bp, lat_tab, cdx, cdy, c3);
 #pragma unroll
-                  for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
+                  for (int s = 0; s < 4; s++)
+                    if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2]; }
                 }
-                if (!pass_mask) continue;
-                float c3[3];
-                shade_pixel(bp, lat_tab, cdx, cdy, c3);
-#pragma unroll
-                for (int s = 0; s < 4; s++)
-                  if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2]; }
               }
             }
-          }
-          // ---------------------------------------------------------- O: resolve + store
-          if (!simple_done) {
-            const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
-            const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
-            const float b_ = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f;
-            store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
+            // -------------------------------------------------------- O: resolve + store
+            if (!simple_done) {
+              const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
+              const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
+              const float b_ = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f;
+              store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
+            }
           }
           bin = __shfl_sync(0xffffffffu, next_bin, 0);
         }

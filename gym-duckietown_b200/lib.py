@@ -122,6 +122,7 @@ def load() -> C.CDLL:
     lib.dts_comm_init.argtypes = [vp, vp, i, i]
     lib.dts_allgather_obs.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.dts_launch_count.argtypes = [vp]
+    lib.dts_debug_counters.argtypes = [vp, vp]
     lib.dts_launch_count.restype = C.c_uint64
     lib.dts_last_error.argtypes = [vp]
     lib.dts_last_error.restype = C.c_char_p
@@ -133,7 +134,7 @@ def load() -> C.CDLL:
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_reset_random", "dts_step",
            "dts_render", "dts_get_state", "dts_query_poses", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
-           "dts_allgather_obs", "dts_launch_count", "dts_last_error", "dts_destroy"]
+           "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_last_error", "dts_destroy"]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -265,6 +266,11 @@ class Sim:
 
     def launch_count(self) -> int:
         return int(self.lib.dts_launch_count(self.h))
+
+    def debug_counters(self) -> np.ndarray:
+        out = np.zeros(32, np.int32)
+        self._check(self.lib.dts_debug_counters(self.h, _ptr(out)), "dts_debug_counters")
+        return out
 
     def close(self):
         if self.h:

@@ -185,6 +185,8 @@ int dts_comm_init(dts_sim* sim, const uint8_t id[128], int rank, int world);
 int dts_allgather_obs(dts_sim* sim, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank, void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t dts_launch_count(dts_sim* sim);
+/* 32 diagnostic counters: [0] != 0 -> a render scratch buffer overflowed (frame incomplete). */
+int dts_debug_counters(dts_sim* sim, int32_t out[32]);
 const char* dts_last_error(dts_sim* sim); /* sim may be NULL: error of the last failed dts_create */
 void dts_destroy(dts_sim* sim);
 
