@@ -11,7 +11,7 @@ from .maps import InvalidMapException, list_maps, load_map  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must not require torch/CUDA
-    if name in ("BatchedDuckietownEnv",):
+    if name in ("BatchedDuckietownEnv", "HostPipeline"):
         from . import batched_env
         return getattr(batched_env, name)
     if name in ("Simulator", "DuckietownEnv", "MultiMapEnv", "NotInLane"):

@@ -116,15 +116,17 @@ class BatchedDuckietownEnv:
             return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden)
         return query
 
-    def step(self, actions: torch.Tensor, render: bool = True):
+    def step(self, actions: torch.Tensor, render: bool = True, out=None):
         """actions f32[N,2] on this device: [vel, steering] (DuckietownEnv.step) or wheel duty
-        (Simulator.step) depending on action_mode.  Returns (obs u8[N,H,W,3], reward f32[N], done bool[N], info)."""
+        (Simulator.step) depending on action_mode.  Returns (obs u8[N,H,W,3], reward f32[N], done bool[N], info).
+        `out=(obs, reward, done_u8)` writes into caller-provided CUDA tensors instead of the env's own."""
         if actions.device != self.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
             raise ValueError("actions must be a float32 CUDA tensor of shape [num_envs, 2] on the env's device")
         actions = actions.contiguous()
-        self.sim.step(actions.data_ptr(), self.obs.data_ptr() if render else None, self.reward.data_ptr(),
-                      self._done_u8.data_ptr(), self._stream())
-        return self.obs, self.reward, self._done_u8.view(torch.bool), self.state
+        obs, reward, done = (self.obs, self.reward, self._done_u8) if out is None else out
+        self.sim.step(actions.data_ptr(), obs.data_ptr() if render else None, reward.data_ptr(), done.data_ptr(),
+                      self._stream())
+        return obs, reward, done.view(torch.bool), self.state
 
     def render_obs(self) -> torch.Tensor:
         self.sim.render(self.obs.data_ptr(), self._stream())
@@ -145,3 +147,55 @@ class BatchedDuckietownEnv:
 
     def close(self):
         self.sim.close()
+
+
+class HostPipeline:
+    """Host-facing stepping with the copies taken off the critical path.
+
+    `submit(actions_host)` enqueues: pinned-host -> device copy of the actions, `dts_step`, and a
+    device -> pinned-host copy of obs / reward / done on a second stream; `result(ticket)` blocks until
+    that step's host buffers are complete.  With `depth` slots in flight the PCIe transfer of step k
+    overlaps the kernels of step k+1 (callers whose next action does not depend on the previous
+    observation — replay, open-loop or random-action rollouts as in the reference's benchmark.py — get the
+    full overlap; a closed-loop caller simply calls result() before the next submit())."""
+
+    def __init__(self, env: BatchedDuckietownEnv, depth: int = 2):
+        self.env, self.depth = env, depth
+        dev, n = env.device, env.num_envs
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                act=torch.empty((n, 2), dtype=torch.float32, device=dev),
+                obs=torch.empty_like(env.obs), rew=torch.empty_like(env.reward), done=torch.empty_like(env._done_u8),
+                h_obs=torch.empty(tuple(env.obs.shape), dtype=torch.uint8).pin_memory(),
+                h_rew=torch.empty(n, dtype=torch.float32).pin_memory(),
+                h_done=torch.empty(n, dtype=torch.uint8).pin_memory(),
+                computed=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False))
+        self.ticket = 0
+
+    def submit(self, actions_host: torch.Tensor) -> int:
+        """actions_host: float32 [N,2] CPU tensor (pinned for a truly asynchronous copy)."""
+        s = self.slots[self.ticket % self.depth]
+        cur = torch.cuda.current_stream(self.env.device)
+        if s["busy"]:
+            cur.wait_event(s["copied"])          # the slot's previous D2H must be done before we overwrite its buffers
+        s["act"].copy_(actions_host, non_blocking=True)
+        self.env.step(s["act"], out=(s["obs"], s["rew"], s["done"]))
+        s["computed"].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["computed"])
+            s["h_obs"].copy_(s["obs"], non_blocking=True)
+            s["h_rew"].copy_(s["rew"], non_blocking=True)
+            s["h_done"].copy_(s["done"], non_blocking=True)
+            s["copied"].record(self.copy_stream)
+        s["busy"] = True
+        self.ticket += 1
+        return self.ticket - 1
+
+    def result(self, ticket: int):
+        """(obs u8[N,H,W,3], reward f32[N], done bool[N]) pinned host tensors of that step; valid until the slot
+        is reused `depth` submits later."""
+        s = self.slots[ticket % self.depth]
+        s["copied"].synchronize()
+        return s["h_obs"], s["h_rew"], s["h_done"].view(torch.bool)

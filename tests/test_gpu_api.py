@@ -122,3 +122,26 @@ def test_multimap_cycle_and_stale_light_on_device(torch_cuda):
     assert ((ep - 1) % 2 == mid).all() and ep.max() > 2
     assert obs.float().std() > 5
     env.close()
+
+
+def test_host_pipeline_matches_sequential_stepping(torch_cuda):
+    """HostPipeline (double-buffered H2D / D2H) returns exactly what step-by-step device stepping returns."""
+    torch = torch_cuda
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv, HostPipeline
+    kw = dict(camera_width=84, camera_height=84, domain_rand=False, seed=11, auto_reset=True, device_reset=True)
+    a, b = BatchedDuckietownEnv(300, "loop_obstacles", **kw), BatchedDuckietownEnv(300, "loop_obstacles", **kw)
+    a.reset(); b.reset()
+    acts = torch.empty((12, 300, 2)).uniform_(-1, 1).pin_memory()
+    pipe = HostPipeline(b, depth=2)
+    tickets = []
+    for t in range(12):
+        tickets.append(pipe.submit(acts[t]))
+        if t >= 1:
+            ho, hr, hd = pipe.result(tickets[t - 1])
+            assert np.array_equal(ho.numpy(), ref[0]) and np.array_equal(hr.numpy(), ref[1]) and np.array_equal(hd.numpy(), ref[2])
+        o, r, d, _ = a.step(acts[t].to(a.device))
+        torch.cuda.synchronize()
+        ref = (o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy())
+    ho, hr, hd = pipe.result(tickets[-1])
+    assert np.array_equal(ho.numpy(), ref[0]) and np.array_equal(hd.numpy(), ref[2])
+    a.close(); b.close()
