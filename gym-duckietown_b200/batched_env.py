@@ -80,6 +80,8 @@ class BatchedDuckietownEnv:
         off = self.cfg.env_id_offset
         seeds = [None if seed is None else int(seed) + off + k for k in range(self.num_envs)]
         self.sampler.seed(seeds)
+        if self.device_reset:   # the device continues the very same numpy streams (np_random.cuh)
+            self.sim.seed_streams(self.sampler.rngs)
         return seeds
 
     def _stream(self) -> int:

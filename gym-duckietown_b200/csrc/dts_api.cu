@@ -42,6 +42,7 @@ struct dts_sim {
   // nccl (dlopen'ed)
   void* nccl_lib = nullptr; void* nccl_comm = nullptr;
   uint64_t launches = 0;
+  bool seeded = false;
   std::string err;
 
   int fail(const char* fmt, ...) {
@@ -119,7 +120,7 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   for (auto p : i32) bad |= sim->dalloc(p, n);
   uint8_t** u8[] = {&S.done_code, &S.in_lane, &S.collided};
   for (auto p : u8) bad |= sim->dalloc(p, n);
-  bad |= sim->dalloc(&S.rng, n);
+  bad |= sim->dalloc(&S.rng, 6 * (size_t)n);
   bad |= sim->dalloc(&S.rep, n);
   bad |= sim->dalloc(&sim->d_maps, cfg->max_maps);
   bad |= sim->dalloc(&sim->d_err, 32);
@@ -180,6 +181,8 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   for (int j = 0; j < b->grid_h; j++)       // reference scan order S:810-860
     for (int i = 0; i < b->grid_w; i++)
       if (b->tile_kind[j * b->grid_w + i] >= 0 && b->tile_drivable[j * b->grid_w + i]) { drv.push_back(i); drv.push_back(j); }
+  m.start_i = b->start_tile[0]; m.start_j = b->start_tile[1];
+  if (m.start_i < 0 || m.start_j < 0 || m.start_i >= b->grid_w || m.start_j >= b->grid_h) { m.start_i = -1; m.start_j = -1; }
   m.n_drivable = (int)drv.size() / 2;
   bad |= sim->upload(&m.drivable_ij, drv.data(), drv.size(), &own);
   // objects: add spawn radius (S:1467) and a bounding sphere per placed mesh
@@ -284,9 +287,26 @@ int dts_reset(dts_sim* sim, const uint8_t* mask_dev, const dts_episode_params* p
   return 0;
 }
 
+int dts_seed_streams(dts_sim* sim, const uint8_t* mask_host, const uint64_t* streams) {
+  if (!sim) return 1;
+  if (!streams) return sim->fail("streams is NULL");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  const size_t n = sim->cfg.num_envs;
+  std::vector<uint64_t> soa(6 * n);
+  DTS_CUDA(cudaMemcpy(soa.data(), sim->S.rng, 6 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  for (size_t e = 0; e < n; e++) {
+    if (mask_host && !mask_host[e]) continue;
+    for (int k = 0; k < 6; k++) soa[k * n + e] = streams[6 * e + k];
+  }
+  DTS_CUDA(cudaMemcpy(sim->S.rng, soa.data(), 6 * n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  sim->seeded = true;
+  return 0;
+}
+
 int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream) {
   if (!sim) return 1;
   if (check_maps(sim)) return 1;
+  if (!sim->seeded) return sim->fail("dts_seed_streams must be called before a device-side reset");
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   launch_reset_random(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, mask_dev, (cudaStream_t)stream);
   sim->launches++;
@@ -344,6 +364,8 @@ int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* re
   if (!actions_dev) return sim->fail("actions_dev is NULL");
   if (check_maps(sim)) return 1;
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  if ((sim->cfg.flags & DTS_FLAG_AUTO_RESET) && !sim->seeded)
+    return sim->fail("auto-reset needs seeded streams: call dts_seed_streams first");
   launch_step_logic(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, actions_dev, reward_dev, done_dev,
                     (cudaStream_t)stream);
   sim->launches++;
@@ -387,6 +409,14 @@ int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const 
 }
 
 uint64_t dts_launch_count(dts_sim* sim) { return sim ? sim->launches : 0; }
+
+int dts_debug_episode(dts_sim* sim, int env, void* out144) {
+  if (!sim) return 1;
+  if (env < 0 || env >= sim->cfg.num_envs) return sim->fail("env out of range");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  DTS_CUDA(cudaMemcpy(out144, sim->S.rep + env, sizeof(RenderEp), cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 /* debug: copy the 32 int32 diagnostic counters (word 0 = overflow flag; 8.. = DTS_STATS counters) */
 int dts_debug_counters(dts_sim* sim, int32_t out[32]) {

@@ -40,6 +40,7 @@ struct DMap {
   const double* coll_norms;     // [K][2][2]
   const double* coll_centers;   // [K][3]
   const double* coll_radii;     // [K]
+  int32_t start_i, start_j;     // map `start_tile` (S:867-871) or -1
   int32_t n_drivable;
   const int32_t* drivable_ij;   // [n_drivable][2] in reference scan order (S:806-860)
   int32_t n_objects;
@@ -67,7 +68,7 @@ struct DState {
   double *wheel_dist, *trim;
   int32_t *step_count, *tile_i, *tile_j, *map_id, *episode;
   uint8_t *done_code, *in_lane, *collided;
-  uint64_t* rng;         // counter of the device-side stream
+  uint64_t* rng;         // [6][n] numpy PCG64 stream per env: state hi, lo, inc hi, lo, has_uint32, cached uint32
   struct RenderEp* rep;  // [n] per-episode render parameters (AoS: one CTA reads one record)
 };
 

@@ -50,10 +50,15 @@ __device__ inline void set_pose(const DState& S, const DMap& m, int e, double px
   S.step_count[e] = 0; S.speed[e] = 0.0;                                  // S:535-539
 }
 
-// Device-side Simulator.reset() (S:528-763): DR sampling + spawn rejection loop.  Draw ORDER follows
-// the reference; the stream itself is counter-based, not numpy's PCG64 (DESIGN.md "resets").
+// Device-side Simulator.reset() (S:528-763): DR sampling + spawn rejection loop on the env's numpy-compatible
+// PCG64 stream, draw for draw in the reference's order (randomizer.py:46-89 sorted keys, then S:551-736).
 __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, int e) {
-  Stream rs{mix64(c.seed ^ mix64((uint64_t)(c.env_id_offset + e))), S.rng[e]};
+  const int n = S.n;
+  NpStream rs;
+  rs.state = ((unsigned __int128)S.rng[0 * n + e] << 64) | S.rng[1 * n + e];
+  rs.inc = ((unsigned __int128)S.rng[2 * n + e] << 64) | S.rng[3 * n + e];
+  rs.has32 = (uint32_t)S.rng[4 * n + e];
+  rs.cache32 = (uint32_t)S.rng[5 * n + e];
   const bool dr = (c.flags & DTS_FLAG_DOMAIN_RAND) != 0;
   RenderEp old = S.rep[e];
   double Vprev[12];
@@ -65,66 +70,78 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   const DMap& m = maps[mid];
   RenderEp r;
   default_render_ep(r);
-  // Randomizer.randomize: keys in sorted order (randomizer.py:33,46) — drawn even when DR is off
+  // Randomizer.randomize: keys in sorted order — drawn whether or not DR is on (randomizer.py:33,46-89, S:546)
   const double cam_angle = rs.uniform(0.8, 1.2), cam_fov = rs.uniform(0.8, 1.2), cam_h = rs.uniform(0.92, 1.08);
   double noise[3];
   for (int k = 0; k < 3; k++) noise[k] = rs.uniform(-0.005, 0.005);
-  const int horz = rs.integer(4);
+  const int horz = rs.integers(0, 4);
   float lpos[4] = {0.f, 3.f, 0.f, 1.f};
   const double l0 = rs.uniform(-150, 150), l1 = rs.uniform(170, 220), l2 = rs.uniform(-150, 150);
-  const double trim = 0.02 * rs.normal();
+  const double trim = rs.normal(0.0, 0.02);
   double wheel = 0.102;
   if (dr) {
-    const float base[4][3] = {{0.45f, 0.82f, 1.0f}, {0.64f, 0.71f, 0.28f}, {0.15f, 0.15f, 0.15f}, {0.9f, 0.9f, 0.9f}};
+    const double base[4][3] = {{0.45, 0.82, 1.0}, {0.64, 0.71, 0.28}, {0.15, 0.15, 0.15}, {0.9, 0.9, 0.9}};
     const double hs = horz < 2 ? 0.1 : 0.4;                                   // S:551-560
-    for (int k = 0; k < 3; k++) r.horizon[k] = (float)(base[horz][k] * rs.uniform(1 - hs, 1 + hs));
+    for (int k = 0; k < 3; k++) r.horizon[k] = (float)(base[horz][k] * rs.uniform(1.0 - hs, 1.0 + hs));
     lpos[0] = (float)l0; lpos[1] = (float)l1; lpos[2] = (float)l2; lpos[3] = 0.f;  // 3 floats into a 4-array: w = 0
     double p4[4];
-    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(0.7, 1.3);                 // _perturb(ambient, 0.3) S:574
+    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(1.0 - 0.3, 1.0 + 0.3);     // _perturb(ambient, 0.3) S:574
     for (int k = 0; k < 3; k++) r.ambient[k] = (float)(0.25 * p4[k]);
-    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(0.01, 1.99);               // _perturb(diffuse, 0.99) S:576
+    for (int k = 0; k < 4; k++) p4[k] = rs.uniform(1.0 - 0.99, 1.0 + 0.99);   // _perturb(diffuse, 0.99) S:576
     for (int k = 0; k < 3; k++) r.diffuse[k] = (float)(0.35 * p4[k]);
-    for (int k = 0; k < 3; k++) r.ground[k] = (float)(0.15 * rs.uniform(0.7, 1.3));  // S:594
-    wheel = 0.102 * rs.uniform(0.9, 1.1);                                     // S:597
+    for (int k = 0; k < 3; k++) r.ground[k] = (float)(0.15 * rs.uniform(1.0 - 0.3, 1.0 + 0.3));  // S:594
+    wheel = 0.102 * rs.uniform(1.0 - 0.1, 1.0 + 0.1);                         // S:597
     r.cam_height = (float)(0.108 * cam_h);                                    // S:612-614
     r.cam_angle_deg = (float)(19.15 * cam_angle);
     r.cam_fov_y_deg = (float)(75.0 * cam_fov);
     for (int k = 0; k < 3; k++) r.cam_noise[k] = (float)noise[k];
-    // distractor triangles (S:621-631) and tile colours (S:645) have no visible effect:
-    // their draws are skipped on this stream.
-    for (int o = 0; o < m.n_objects; o++)
-      if (m.objects[o].optional && rs.integer(2) != 0) r.hidden[o >> 5] |= 1u << (o & 31);   // S:653-654
+  }
+  // distractor triangles S:621-629: never visible (below the ground plane) but their draws are consumed
+  for (int t = 0; t < 36; t++) {
+    rs.next64(); rs.next64(); rs.next64();      // uniform(low=[-20,-0.6,-20], high=[20,-0.3,20], size=3)
+    rs.next64();                                // c = uniform(0, 0.9)
+    if (dr) { rs.next64(); rs.next64(); rs.next64(); }   // _perturb([c,c,c], 0.1)
+  }
+  if (dr) {
+    for (int t = 0; t < m.n_tiles; t++)         // tile["color"] = _perturb([1,1,1,1], 0.2) S:645 (no visible effect)
+      if (m.tile_kind[t] >= 0) { rs.next64(); rs.next64(); rs.next64(); rs.next64(); }
+    for (int o = 0; o < m.n_objects; o++) {     // S:648-656
+      rs.next64(); rs.next64(); rs.next64(); rs.next64();   // obj.color = _perturb([1,1,1,1], 0.3)
+      if (m.objects[o].optional && !(rs.integers(0, 2) == 0)) r.hidden[o >> 5] |= 1u << (o & 31);
+    }
   }
   if (first) { for (int k = 0; k < 4; k++) r.light_eye[k] = lpos[k]; }       // identity modelview at first reset
   else light_to_eye(Vprev, lpos, r.light_eye);                               // stale modelview S:581
   S.wheel_dist[e] = wheel;
   S.trim[e] = (c.flags & DTS_FLAG_DYNAMICS_RAND) ? trim : 0.0;               // S:746-750
   // start tile S:659-676, spawn loop S:692-736
-  const int t = m.n_drivable > 0 ? rs.integer(m.n_drivable) : 0;
-  const int ti = m.n_drivable > 0 ? m.drivable_ij[2 * t] : 0, tj = m.n_drivable > 0 ? m.drivable_ij[2 * t + 1] : 0;
+  int ti = 0, tj = 0;
+  if (m.start_i >= 0) { ti = m.start_i; tj = m.start_j; }
+  else if (m.n_drivable > 0) { const int t = rs.integers(0, m.n_drivable); ti = m.drivable_ij[2 * t]; tj = m.drivable_ij[2 * t + 1]; }
   double px = 1.0, pz = 1.0, ang = 1.0;                                      // fallback S:735-736
   for (int attempt = 0; attempt < kMaxSpawnAttempts && m.n_drivable > 0; attempt++) {
-    const double x = rs.uniform(ti, ti + 1) * m.tile_size, z = rs.uniform(tj, tj + 1) * m.tile_size;
-    const double a = rs.uniform(0, 6.283185307179586);
+    const double x = rs.uniform((double)ti, (double)(ti + 1)) * m.tile_size, z = rs.uniform((double)tj, (double)(tj + 1)) * m.tile_size;
+    const double a = rs.uniform(0.0, 2 * 3.141592653589793);
     bool bad = false;                                                       // _inconvenient_spawn S:1461-1471
     for (int o = 0; o < m.n_objects && !bad; o++) {
       if (r.hidden[o >> 5] >> (o & 31) & 1u) continue;
       const DObject& ob = m.objects[o];
-      const double dx = ob.pos[0] - x, dy = ob.pos[1], dz = ob.pos[2] - z;
+      const double dx = (double)ob.pos[0] - x, dy = (double)ob.pos[1], dz = (double)ob.pos[2] - z;
       bad = sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad;
     }
     if (bad) continue;
     if (!valid_pose(m, x, z, a, 1.3, nullptr)) continue;
     const LanePose lp = lane_pose(m, x, z, a);
     if (!lp.in_lane) continue;
-    const double deg = lp.angle_rad * 57.29577951308232;
+    const double deg = lp.angle_rad * 57.29577951308232;                    // np.rad2deg S:1406
     if (!(-c.accept_angle_deg < deg && deg < c.accept_angle_deg)) continue;
     px = x; pz = z; ang = a;
     break;
   }
   set_pose(S, m, e, px, pz, ang);
   S.rep[e] = r;
-  S.rng[e] = rs.ctr;
+  S.rng[0 * n + e] = (uint64_t)(rs.state >> 64); S.rng[1 * n + e] = (uint64_t)rs.state;
+  S.rng[4 * n + e] = rs.has32; S.rng[5 * n + e] = rs.cache32;
   S.episode[e] += 1;
 }
 

@@ -4,6 +4,7 @@
 // Citations: S = simulator.py, C = collision.py, G = graphics.py, E = envs/duckietown_env.py.
 #pragma once
 #include "dts_common.cuh"
+#include "np_random.cuh"
 
 namespace dts {
 
@@ -223,25 +224,5 @@ __device__ __forceinline__ void dynamics_step(double& x, double& y, double& th, 
   u = u1;
   w = w1;
 }
-
-// ------------------------------------------------------------------ device-side random streams
-// Counter-based: value k of env e = splitmix64(seed, e, k).  NOT numpy's PCG64 stream; used only
-// by dts_reset_random / auto-reset (DESIGN.md "resets").
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ULL;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-  return z ^ (z >> 31);
-}
-struct Stream {
-  uint64_t key, ctr;
-  __device__ double uniform() { return (double)(mix64(key + mix64(ctr++)) >> 11) * (1.0 / 9007199254740992.0); }
-  __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * uniform(); }
-  __device__ int integer(int n) { return (int)(uniform() * n); }
-  __device__ double normal() {
-    const double u1 = 1.0 - uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-  }
-};
 
 }  // namespace dts

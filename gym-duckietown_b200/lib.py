@@ -61,7 +61,7 @@ class MapBlob(C.Structure):
         ("coll_radii", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p), ("n_meshes", C.c_int32),
         ("meshes", C.c_void_p), ("n_tris", C.c_int32), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p),
         ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p), ("tri_tex", C.c_void_p), ("n_textures", C.c_int32),
-        ("textures", C.c_void_p),
+        ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2),
     ]
 
 
@@ -113,6 +113,7 @@ def load() -> C.CDLL:
     lib.dts_set_fisheye_lut.argtypes = [vp, vp, vp, i, i]
     lib.dts_reset.argtypes = [vp, vp, C.POINTER(EpisodeParams), vp]
     lib.dts_reset_random.argtypes = [vp, vp, vp]
+    lib.dts_seed_streams.argtypes = [vp, vp, vp]
     lib.dts_step.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dts_render.argtypes = [vp, vp, vp]
     lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
@@ -123,6 +124,7 @@ def load() -> C.CDLL:
     lib.dts_allgather_obs.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.dts_launch_count.argtypes = [vp]
     lib.dts_debug_counters.argtypes = [vp, vp]
+    lib.dts_debug_episode.argtypes = [vp, i, vp]
     lib.dts_launch_count.restype = C.c_uint64
     lib.dts_last_error.argtypes = [vp]
     lib.dts_last_error.restype = C.c_char_p
@@ -132,9 +134,9 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_reset_random", "dts_step",
+EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
            "dts_render", "dts_get_state", "dts_query_poses", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
-           "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_last_error", "dts_destroy"]
+           "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_last_error", "dts_destroy"]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -191,7 +193,8 @@ class MapBlobHolder:
             _ptr(k["coff"]), _ptr(k["ccnt"]), len(md.curves), _ptr(k["curves"]), md.n_coll, _ptr(k["cc"]),
             _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(md.meshes),
             C.cast(meshes, C.c_void_p), off, _ptr(k["tpos"]), _ptr(k["tnrm"]), _ptr(k["tuv"]), _ptr(k["tcol"]),
-            _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p))
+            _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p),
+            (C.c_int32 * 2)(*(md.start_tile if md.start_tile is not None else (-1, -1))))
 
 
 class _CudaArray:
@@ -240,6 +243,20 @@ class Sim:
             setattr(ep, f, a.ctypes.data)
         self._check(self.lib.dts_reset(self.h, mask_ptr, C.byref(ep), stream), "dts_reset")
 
+    def seed_streams(self, generators, mask: Optional[np.ndarray] = None):
+        """Upload one numpy PCG64 stream per env (list of numpy.random.Generator) for device-side resets."""
+        n = self.cfg.num_envs
+        arr = np.zeros((n, 6), np.uint64)
+        m64 = (1 << 64) - 1
+        for e, g in enumerate(generators):
+            st = g.bit_generator.state
+            if st["bit_generator"] != "PCG64":
+                raise ValueError("device streams are PCG64")
+            s, inc = st["state"]["state"], st["state"]["inc"]
+            arr[e] = (s >> 64, s & m64, inc >> 64, inc & m64, st["has_uint32"], st["uinteger"])
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._check(self.lib.dts_seed_streams(self.h, _ptr(mk), _ptr(arr)), "dts_seed_streams")
+
     def reset_random(self, mask_ptr: Optional[int], stream: int = 0):
         self._check(self.lib.dts_reset_random(self.h, mask_ptr, stream), "dts_reset_random")
 
@@ -266,6 +283,13 @@ class Sim:
 
     def launch_count(self) -> int:
         return int(self.lib.dts_launch_count(self.h))
+
+    def debug_episode(self, env: int) -> dict:
+        raw = np.zeros(36, np.float32)
+        self._check(self.lib.dts_debug_episode(self.h, env, _ptr(raw)), "dts_debug_episode")
+        return dict(cam_height=raw[0], cam_angle_deg=raw[1], cam_fov_y_deg=raw[2], cam_noise=raw[4:7], horizon=raw[8:11],
+                    ambient=raw[12:15], diffuse=raw[16:19], light_eye=raw[20:24], ground=raw[24:27],
+                    hidden=raw[28:36].view(np.uint32))
 
     def debug_counters(self) -> np.ndarray:
         out = np.zeros(32, np.int32)

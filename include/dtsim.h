@@ -107,6 +107,7 @@ typedef struct {
   const int16_t* tri_tex;         /* [n_tris] texture index, -1 = untextured */
   int32_t n_textures;
   const dts_texture* textures;
+  int32_t start_tile[2];          /* map `start_tile` (simulator.py:867-871) or {-1,-1}: device resets spawn there */
 } dts_map_blob;
 
 /* Per-episode inputs produced by Simulator.reset() (simulator.py:528-763), one
@@ -157,7 +158,12 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
 /* Simulator.reset() (simulator.py:528-763) with host-drawn episode parameters.
  * mask_dev: device u8[num_envs] (NULL = all). */
 int dts_reset(dts_sim* sim, const uint8_t* mask_dev, const dts_episode_params* params, void* stream);
-/* Same, but pose / DR are drawn on the device (counter-based RNG, not numpy's PCG64 stream). */
+/* Simulator.seed() (simulator.py:1043-1045): one numpy PCG64 stream per env for the DEVICE-side resets.
+ * streams[N][6] (HOST) = state_hi, state_lo, inc_hi, inc_lo, has_uint32, uinteger of
+ * numpy.random.Generator(PCG64(SeedSequence(seed))).bit_generator.state; mask_host u8[N] or NULL = all. */
+int dts_seed_streams(dts_sim* sim, const uint8_t* mask_host, const uint64_t* streams);
+/* Simulator.reset() with pose / DR drawn ON THE DEVICE from the env's numpy-compatible stream, draw for draw
+ * in the reference's order (np_random.cuh): same seeds -> same episodes as the reference. */
 int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream);
 /* Simulator.step() (simulator.py:1669-1683) for all envs: actions f32[N][2] -> obs u8[N][H][W][3]
  * (NULL = skip rendering), reward f32[N], done u8[N]. All DEVICE pointers. */
@@ -185,6 +191,9 @@ int dts_comm_init(dts_sim* sim, const uint8_t id[128], int rank, int world);
 int dts_allgather_obs(dts_sim* sim, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank, void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t dts_launch_count(dts_sim* sim);
+/* debug: the env's per-episode render record as 36 x 32-bit words (cam_height, cam_angle_deg, cam_fov_y_deg, -,
+ * cam_noise[3], -, horizon[3], -, ambient[3], -, diffuse[3], -, light_eye[4], ground[3], -, hidden u32[8]). */
+int dts_debug_episode(dts_sim* sim, int env, void* out144);
 /* 32 diagnostic counters: [0] != 0 -> a render scratch buffer overflowed (frame incomplete). */
 int dts_debug_counters(dts_sim* sim, int32_t out[32]);
 const char* dts_last_error(dts_sim* sim); /* sim may be NULL: error of the last failed dts_create */

@@ -148,3 +148,94 @@ def test_device_reset_spawns_valid_poses(torch_cuda):
     outd, outi = env.sim.query_poses(0, s["pos_x"], s["pos_z"], s["angle"], 1.0)
     assert outi[:, 0].all()  # nobody is left sitting in an invalid pose
     env.close()
+
+
+@pytest.mark.parametrize("name", MAPS)
+@pytest.mark.parametrize("dr", [False, True])
+def test_device_reset_reproduces_reference_reset_draw_for_draw(name, dr, golden_dir, torch_cuda):
+    """dts_reset_random runs Simulator.reset() ON THE DEVICE from the env's numpy-compatible PCG64 stream:
+    pose and every DR value equal what the REFERENCE's reset() produced for the same seeds (golden vectors from
+    oracle/make_golden.py), first and second episode."""
+    torch = torch_cuda
+    g = np.load(os.path.join(golden_dir, f"reset_{name}.npz"))
+    tag = "dr" if dr else "nodr"
+    n = len(g["seeds"])
+    env = make_env(name, n, domain_rand=dr, seed=int(g["seeds"][0]), device_reset=True)   # env k gets seed0 + k
+    assert list(g["seeds"]) == list(range(int(g["seeds"][0]), int(g["seeds"][0]) + n))
+    for ep in range(2):
+        env.reset(render=False)
+        torch.cuda.synchronize()
+        st = {k: v.cpu().numpy() for k, v in env.state.items()}
+        rows = np.arange(n) * 2 + ep
+        assert np.array_equal(st["pos_x"], g[f"{tag}_cur_pos"][rows, 0])
+        assert np.array_equal(st["pos_z"], g[f"{tag}_cur_pos"][rows, 2])
+        assert np.array_equal(st["angle"], g[f"{tag}_cur_angle"][rows])
+        assert np.array_equal(st["wheel_dist"], g[f"{tag}_wheel_dist"][rows])
+        for k in range(n):
+            r = env.sim.debug_episode(k)
+            row = rows[k]
+            assert r["cam_height"] == np.float32(g[f"{tag}_cam_height"][row])
+            assert r["cam_angle_deg"] == np.float32(g[f"{tag}_cam_angle"][row])
+            assert r["cam_fov_y_deg"] == np.float32(g[f"{tag}_cam_fov_y"][row])
+            assert np.array_equal(r["horizon"], g[f"{tag}_horizon_color"][row].astype(np.float32))
+            assert np.array_equal(r["ground"], g[f"{tag}_ground_color"][row].astype(np.float32))
+            assert np.array_equal(r["ambient"], g[f"{tag}_ambient"][row, :3].astype(np.float32))
+            assert np.array_equal(r["diffuse"], g[f"{tag}_diffuse"][row, :3].astype(np.float32))
+            if dr:
+                assert np.array_equal(r["cam_noise"], g[f"{tag}_camera_noise"][row].astype(np.float32))
+            if ep == 0:  # first reset: GL_POSITION captured under the identity modelview
+                assert np.array_equal(r["light_eye"], g[f"{tag}_light_pos"][row].astype(np.float32))
+            vis = g[f"{tag}_obj_visible"][row]
+            for oi in range(len(vis)):
+                assert bool(r["hidden"][oi >> 5] >> (oi & 31) & 1) == (not vis[oi])
+    env.close()
+
+
+def test_auto_reset_rollout_equals_reference_style_loop(torch_cuda):
+    """Device auto-reset (step + respawn in one kernel, numpy-compatible streams) against the reference-style
+    host loop `obs, r, done, _ = env.step(a); if done: env.reset()` built from the CPU oracle (step) and the host
+    reset sampler (reference draw order, numpy Generator): same seeds, same actions -> same episodes."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    from gym_duckietown_b200.episode import EpisodeSampler
+    from test_reset_sampler import oracle_query
+
+    name, N, T = "loop_obstacles", 32, 400
+    md = maps.load_map(name)
+    env = make_env(name, N, seed=500, device_reset=True, auto_reset=True, max_steps=60)
+    env.reset(render=False)
+    torch.cuda.synchronize()
+    host = EpisodeSampler(N, domain_rand=False)
+    host.seed([500 + k for k in range(N)])
+    q = oracle_query(md)
+    first = host.sample(list(range(N)), [md] * N, q)
+    om = orc.OracleMap(md)
+    cpu = [orc.OracleEnv(om, first["pos_x"][k], first["pos_z"][k], first["angle"][k], wheel_dist=first["wheel_dist"][k],
+                         max_steps=60) for k in range(N)]
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    assert np.array_equal(st["pos_x"], first["pos_x"]) and np.array_equal(st["angle"], first["angle"])
+    acts = np.random.default_rng(3).uniform(-1, 1, (T, N, 2)).astype(np.float32)
+    acts[:, :, 0] = np.abs(acts[:, :, 0])          # drive forward: episodes end quickly (off-road, duckies, max_steps)
+    resets = 0
+    for t in range(T):
+        _, rew, done, info = env.step(torch.from_numpy(acts[t]).to(env.device), render=False)
+        torch.cuda.synchronize()
+        s = {k: v.cpu().numpy() for k, v in info.items()}
+        d, r64 = done.cpu().numpy(), s["reward"]
+        for k in range(N):
+            o = cpu[k].step(acts[t, k])
+            assert bool(d[k]) == bool(o.done) and s["done_code"][k] == o.done_code, (t, k)
+            assert abs(r64[k] - o.reward) <= 1e-5 * max(1.0, abs(o.reward)), (t, k)
+            if o.done:   # reference-style: the caller resets; the device already did
+                nxt = host.sample([k], [md], q)
+                cpu[k] = orc.OracleEnv(om, nxt["pos_x"][0], nxt["pos_z"][0], nxt["angle"][0],
+                                       wheel_dist=nxt["wheel_dist"][0], max_steps=60)
+                assert s["pos_x"][k] == nxt["pos_x"][0] and s["pos_z"][k] == nxt["pos_z"][0] and s["angle"][k] == nxt["angle"][0], (t, k)
+                assert s["step_count"][k] == 0
+                resets += 1
+            else:
+                assert abs(s["pos_x"][k] - o.pos_x) <= 1e-5 and abs(s["pos_z"][k] - o.pos_z) <= 1e-5, (t, k)
+                assert s["step_count"][k] == o.step_count
+    assert resets > 3 * N      # every env went through several episodes
+    env.close()
