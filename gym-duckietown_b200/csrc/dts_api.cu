@@ -34,7 +34,7 @@ struct dts_sim {
            float* light_pos; int32_t* light_stale; uint32_t* hidden; } stage{};
   // render
   void* render_scratch = nullptr;
-  int render_ctas = 0, max_prims = 0, max_pairs = 0, max_lat = 0;
+  int render_ctas = 0, max_prims = 0, bin_cap = 0, max_lat = 0, items_max = 0;
   float *lut_x = nullptr, *lut_y = nullptr;
   int32_t* d_err = nullptr;
   // query scratch
@@ -319,7 +319,7 @@ static int ensure_render(dts_sim* sim) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sim->cfg.device);
   const bool tess = (sim->cfg.flags & DTS_FLAG_TESSELLATE) != 0;
-  int max_tris = 2, max_lat = 1;
+  int max_tris = 2, max_lat = 1, items_max = 1;
   for (const DMap& m : sim->h_maps) {
     if (!m.valid) continue;
     int t = 2 + (tess ? 98 : 6) * m.n_tiles;   // a clipped tile quad fans into a few triangles
@@ -328,15 +328,18 @@ static int ensure_render(dts_sim* sim) {
     for (const DObject& o : objs) t += o.tri_count;
     max_tris = t > max_tris ? t : max_tris;
     max_lat = m.n_tiles > max_lat ? m.n_tiles : max_lat;
+    const int items = 1 + m.n_tiles + m.n_objects;
+    items_max = items > items_max ? items : items_max;
   }
-  const int want = sms * render_ctas_per_sm();
-  sim->render_ctas = want < sim->cfg.num_envs ? want : sim->cfg.num_envs;
+  sim->render_ctas = sms * render_ctas_per_sm();
   sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
   if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
   sim->max_lat = max_lat;
-  sim->max_pairs = 640 * 24 + sim->max_prims * 4;   // per macro tile of <= 640 bins
+  sim->items_max = items_max;
+  sim->bin_cap = tess ? 512 : 96;    // entries per 32x8-px coarse bin; longer lists fall back to scanning all prims
+  const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
   const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
-  const size_t bytes = render_scratch_bytes(sim->render_ctas, sim->max_prims, sim->max_pairs, sim->max_lat, frame);
+  const size_t bytes = render_scratch_bytes(sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
   if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   return 0;
@@ -352,7 +355,8 @@ int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
   RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
                (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0};
   const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
-                              sim->max_pairs, sim->max_lat, sim->lut_x, sim->lut_y, sim->d_err, (cudaStream_t)stream);
+                              sim->bin_cap, sim->max_lat, sim->items_max, sim->lut_x, sim->lut_y, sim->d_err,
+                              (cudaStream_t)stream);
   sim->launches += k;
   DTS_CUDA(cudaGetLastError());
   return 0;

@@ -1,26 +1,27 @@
 // dts_render.cu — batched software rasteriser for the agent camera (Simulator._render_img,
 // simulator.py:1707-1951) on sm_100a.  No tensor cores: there is no dense contraction here.
 //
-// One persistent CTA (256 threads = 8 warps) renders one env at a time:
-//   G  geometry   warp per draw item (ground / map tile / placed mesh): model-view f64->f32,
-//                 fixed-function per-vertex lighting, frustum cull, near + guard-band clip, snap to
-//                 1/64 px, triangle setup -> 128-byte PrimRec appended to the CTA's slab (HBM/L2).
-//                 A road tile is ONE quad: its 8x8 lit lattice goes to a per-CTA table and the
-//                 Gouraud interpolant is evaluated per pixel (render spec, oracle tile mode 1);
-//                 RenderCfg.tessellate switches back to the literal 98 triangles (tile mode 0).
-//   B  binning    8x4-pixel bins (= one warp's pixel block): count, warp-scan, scatter; triangles
-//                 with large bounding boxes are binned warp-cooperatively with an exact edge test
-//   R  raster     warps pull bins from a shared counter — no CTA barrier inside the phase.  16 prims at a
-//                 time are staged lane-parallel (edge functions re-based to the bin so lanes work in
-//                 int32, exact trivial reject / trivial accept), ballot-compacted, then every lane owns
-//                 one pixel with its 4 MSAA samples (depth, colour, draw id) in registers; early-z
-//                 before shading; ground drawn last
-//   O  output     box resolve -> u8, rows packed with shuffles and stored as 32-bit words
+// Three stream-ordered kernels per frame batch, no CTA-wide barrier anywhere:
+//   k_frame_setup  thread per env: camera matrices (f64), gluPerspective, counters -> FrameCtx[env]
+//   k_geometry     warp per (env, draw item) over the whole GPU: ground / map tile / placed mesh.  Model-view
+//                  f64->f32, fixed-function per-vertex lighting, frustum cull, near + guard-band clip, snap to
+//                  1/64 px, triangle setup -> 128-byte PrimRec appended to the env's slab; the prim is binned
+//                  right away into 32x8-px coarse bins (small ones by the emitting lane, large ones by the whole
+//                  warp with an exact edge test) through per-bin atomic cursors.  A road tile is ONE quad: its
+//                  8x8 lit lattice goes to the env's table and the Gouraud interpolant is evaluated per pixel
+//                  (render spec tile mode 1); RenderCfg.tessellate switches to the literal 98 triangles (mode 0).
+//   k_raster       persistent warps pull rows of coarse bins (any env) from one global counter.  A coarse bin's
+//                  list is staged lane-parallel once (edge functions re-based so lanes work in int32, exact
+//                  reject / trivial-accept bits for each of its 8 fine 8x4 bins), then every lane owns one pixel
+//                  of a fine bin with its 4 MSAA samples (depth, colour, draw id) in registers; simple bins (one
+//                  fully covering prim) skip the depth machinery; early-z before shading; ground drawn last;
+//                  box resolve -> u8, rows packed with shuffles and stored as 32-bit words
+//   k_fisheye      (distortion only) out[y,x] = undistorted[rint(rmapy), rint(rmapx)]      distortion.py:118
 // Arithmetic follows the render spec of DESIGN.md (the CPU checker implements the same spec) bit for bit
 // (compiled with -fmad=false; fmaf() is spelled out where the spec has one).
 //
 // HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / bin lists / lattice table
-// (tens of KB, L2-resident) + texels (shared by all envs, L2-resident).
+// (tens of KB per env, written by k_geometry and read once by k_raster) + texels (shared, L2-resident).
 #include <cstddef>
 
 #include "dts_camera.cuh"
@@ -41,9 +42,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kBinW = 8, kBinH = 4;   // fine bin = one warp's pixel block (one pixel per lane)
 constexpr int kCFX = 4, kCFY = 2;     // coarse bin = 4 x 2 fine bins = 32 x 8 px: unit of binning and staging
 constexpr int kCoarseW = kBinW * kCFX, kCoarseH = kBinH * kCFY;
-constexpr int kMtBinsX = 20, kMtBinsY = 32;  // macro tile = 20 x 32 coarse bins = 640 x 256 px
 constexpr int kStage = 32;        // prims staged per pass and warp
-constexpr int kMaxLarge = 1024;
 constexpr float kGuard = 4.0f;
 constexpr int kSub = 64;          // sub-pixel units per pixel
 // MSAA sample offsets in 1/64 px, (.375,.125)(.875,.375)(.125,.625)(.625,.875); constexpr so that the
@@ -79,15 +78,22 @@ static_assert(sizeof(BinPrim) == 160, "BinPrim layout");
 
 struct Xform { float MV[12], N[9]; };
 
-struct Shared {
+struct __align__(16) FrameCtx {   // per env, global memory
+  double V[12];                  // agent camera modelview (S:1780-1803)
+  float P00, P11, P22, P23;      // gluPerspective (S:1761)
+  int32_t n_prims, n_lat, overflow, pad;
+};
+
+constexpr int kMaxLargeWarp = 32;
+struct __align__(16) GeoWarp {    // per warp of k_geometry, shared memory
   RenderEp ep;
   double V[12];
   float P00, P11, P22, P23;
-  int n_prims, n_large, n_lat, overflow, next_bin, n_pairs;
-  Vtx corners[kWarps][4];
-  uint16_t large[kMaxLarge];
-  BinPrim stage[kWarps][kStage];
+  Vtx corners[4];
+  int n_large;
+  uint16_t large[kMaxLargeWarp];
 };
+using Shared = GeoWarp;           // shade_vertex reads ep and P from it
 
 // MV = V * T(t) * S(sc) * Ry(c,s), N = rot(V) * Ry / sc — float64 then rounded (spec)
 __device__ __forceinline__ void model_view(const double* V, double tx, double ty, double tz, double sc, double c,
@@ -183,11 +189,22 @@ __device__ __forceinline__ int classify(const Vtx& a, const Vtx& b, const Vtx& c
   return need ? 1 : 0;
 }
 
+__device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int ox, int oy);
+
 struct EmitCtx {
-  Shared* sh;
-  PrimRec* prims;
-  int max_prims, W, H;
+  GeoWarp* gw;
+  FrameCtx* ctx;
+  PrimRec* prims;          // this env's slab
+  int* bin_count;          // [cbins] this env's cursors
+  uint16_t* lists;         // [cbins][cap]
+  int cap, max_prims, W, H, cbins_x;
 };
+
+__device__ __forceinline__ void bin_append(const EmitCtx& ec, int b, int slot) {
+  // a list longer than `cap` is not an error: k_raster then scans all of the env's prims for that bin
+  const int pos = atomicAdd(&ec.bin_count[b], 1);
+  if (pos < ec.cap) ec.lists[(size_t)b * ec.cap + pos] = (uint16_t)slot;
+}
 
 // screen mapping + triangle setup (spec steps 5-7) and append to the slab
 __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
@@ -240,12 +257,46 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
   r.pxmin = px0 | (py0 << 16);
   r.pxmax = px1 | (py1 << 16);
   r.pad = 0;
-  const int slot = atomicAdd(&ec.sh->n_prims, 1);
-  if (slot >= ec.max_prims) { ec.sh->overflow = 1; return; }
+  const int slot = atomicAdd(&ec.ctx->n_prims, 1);
+  if (slot >= ec.max_prims) { ec.ctx->overflow = 1; return; }
   const int4* src = reinterpret_cast<const int4*>(&r);
   int4* dst = reinterpret_cast<int4*>(ec.prims + slot);
 #pragma unroll
   for (int k = 0; k < 8; k++) dst[k] = src[k];
+  // bin it: few coarse bins -> this lane appends; a large bounding box -> the whole warp does it afterwards
+  const int bx0 = px0 / kCoarseW, bx1 = px1 / kCoarseW, by0 = py0 / kCoarseH, by1 = py1 / kCoarseH;
+  if ((bx1 - bx0 + 1) * (by1 - by0 + 1) <= 4) {
+    for (int by = by0; by <= by1; by++)
+      for (int bx = bx0; bx <= bx1; bx++) bin_append(ec, by * ec.cbins_x + bx, slot);
+  } else {
+    const int l = atomicAdd(&ec.gw->n_large, 1);
+    if (l < kMaxLargeWarp) ec.gw->large[l] = (uint16_t)slot;
+    else {   // more large prims than the warp list holds: fall back to the bounding box
+      for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) bin_append(ec, by * ec.cbins_x + bx, slot);
+    }
+  }
+}
+
+// after an item's triangles are emitted: all lanes bin the warp's large prims with the exact edge test
+__device__ __forceinline__ void bin_large(const EmitCtx& ec, int lane) {
+  __syncwarp();
+  const int nl = min(ec.gw->n_large, kMaxLargeWarp);
+  for (int l = 0; l < nl; l++) {
+    const int slot = ec.gw->large[l];
+    const PrimRec& pr = ec.prims[slot];
+    const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
+    const int bx0 = (pr.pxmin & 0xffff) / kCoarseW, by0 = (pr.pxmin >> 16) / kCoarseH;
+    const int bx1 = (pr.pxmax & 0xffff) / kCoarseW, by1 = (pr.pxmax >> 16) / kCoarseH;
+    const int bw = bx1 - bx0 + 1, nb = bw * (by1 - by0 + 1);
+    for (int q = lane; q < nb; q += 32) {
+      const int by = by0 + q / bw, bx = bx0 + q % bw;
+      if (bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) bin_append(ec, by * ec.cbins_x + bx, slot);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) ec.gw->n_large = 0;
+  __syncwarp();
 }
 
 __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float din, float dout) {
@@ -443,423 +494,405 @@ __device__ __forceinline__ void store_bin(uint8_t* __restrict__ out, unsigned rg
 
 }  // namespace
 
-__host__ __device__ size_t render_slab_bytes(int max_prims, int max_pairs, int max_lat) {
-  size_t b = (size_t)max_prims * sizeof(PrimRec);
-  b += (((size_t)max_pairs * sizeof(uint16_t)) + 255) & ~size_t(255);
-  b += (size_t)max_lat * 64 * sizeof(float4);
-  return (b + 255) & ~size_t(255);
-}
 
 int render_ctas_per_sm() { return DTS_RENDER_MIN_CTAS; }
 
-size_t render_scratch_bytes(int n_ctas, int max_prims, int max_pairs, int max_lat, size_t undistorted_frame_bytes) {
-  return (size_t)n_ctas * (render_slab_bytes(max_prims, max_pairs, max_lat) + undistorted_frame_bytes) + 256;
+// ------------------------------------------------------------------------------------------------ frame memory
+struct FrameMem {
+  FrameCtx* ctx;        // [N]
+  PrimRec* prims;       // [N][max_prims]
+  uint16_t* lists;      // [N][cbins][cap]
+  int* bin_count;       // [N][cbins]
+  float4* lat;          // [N][max_lat][64]
+  uint8_t* undist;      // [N][H][W][3] (distortion only)
+  int* work;            // [4] global work counters
+};
+
+__host__ __device__ inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+__host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int cap, int max_lat, size_t undist_frame) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
+  FrameMem f;
+  f.work = reinterpret_cast<int*>(p); p += 256;
+  f.ctx = reinterpret_cast<FrameCtx*>(p); p += align256((size_t)n * sizeof(FrameCtx));
+  f.bin_count = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
+  f.prims = reinterpret_cast<PrimRec*>(p); p += align256((size_t)n * max_prims * sizeof(PrimRec));
+  f.lists = reinterpret_cast<uint16_t*>(p); p += align256((size_t)n * cbins * cap * sizeof(uint16_t));
+  f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
+  f.undist = undist_frame ? p : nullptr;
+  return f;
 }
 
-__global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
-k_render(const DState S, const DMap* __restrict__ maps, RenderCfg rc, uint8_t* __restrict__ obs,
-         uint8_t* __restrict__ scratch, int max_prims, int max_pairs, int max_lat, uint8_t* __restrict__ undist,
-         const float* __restrict__ lut_x, const float* __restrict__ lut_y, int32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
-  const int W = rc.width, H = rc.height;
-  int* bin_count = reinterpret_cast<int*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)));
-  int* bin_start = bin_count + kMtBinsX * kMtBinsY;
-  const size_t slab = render_slab_bytes(max_prims, max_pairs, max_lat);
-  uint8_t* base = scratch + (size_t)blockIdx.x * slab;
-  PrimRec* prims = reinterpret_cast<PrimRec*>(base);
-  uint16_t* pairs = reinterpret_cast<uint16_t*>(base + (size_t)max_prims * sizeof(PrimRec));
-  float4* lat_tab = reinterpret_cast<float4*>(base + (size_t)max_prims * sizeof(PrimRec) +
-                                              ((((size_t)max_pairs * sizeof(uint16_t)) + 255) & ~size_t(255)));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool dr = (rc.flags & DTS_FLAG_DOMAIN_RAND) != 0;
-  const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
-  const size_t frame_bytes = (size_t)W * H * 3;
-  uint8_t* my_undist = fisheye ? undist + (size_t)blockIdx.x * frame_bytes : nullptr;
-  const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside any bin (sub-pixels)
+size_t render_scratch_bytes(int n, int max_prims, int cbins, int cap, int max_lat, size_t undist_frame) {
+  return 256 + align256((size_t)n * sizeof(FrameCtx)) + align256((size_t)n * cbins * sizeof(int)) +
+         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * cbins * cap * sizeof(uint16_t)) +
+         align256((size_t)n * max_lat * 64 * sizeof(float4)) + (size_t)n * undist_frame + 256;
+}
 
-  for (int env = blockIdx.x; env < rc.n_envs; env += gridDim.x) {
-    const DMap& m = maps[S.map_id[env]];
-    uint8_t* out = fisheye ? my_undist : obs + (size_t)env * frame_bytes;
-    // ---------------------------------------------------------------- per-frame setup
-    __syncthreads();
-    if (tid < (int)(sizeof(RenderEp) / 4))
-      reinterpret_cast<uint32_t*>(&sh.ep)[tid] = reinterpret_cast<const uint32_t*>(&S.rep[env])[tid];
-    __syncthreads();
-    if (tid == 0) {
-      camera_view(S.pos_x[env], S.pos_z[env], S.angle[env], sh.ep, dr, sh.V);
-      const double f = 1.0 / tan((double)sh.ep.cam_fov_y_deg * kDeg2Rad / 2.0), aspect = (double)W / (double)H;
-      const double zn = 0.04, zf = 100.0;                                     // gluPerspective S:1761
-      sh.P00 = (float)(f / aspect); sh.P11 = (float)f;
-      sh.P22 = (float)((zf + zn) / (zn - zf)); sh.P23 = (float)(2.0 * zf * zn / (zn - zf));
-      sh.n_prims = 0; sh.n_lat = 0; sh.overflow = 0;
+// ------------------------------------------------------------------------------------------------ k_frame_setup
+__global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg rc, FrameMem fm) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= rc.n_envs) return;
+  FrameCtx& c = fm.ctx[env];
+  const RenderEp ep = S.rep[env];
+  double V[12];
+  camera_view(S.pos_x[env], S.pos_z[env], S.angle[env], ep, (rc.flags & DTS_FLAG_DOMAIN_RAND) != 0, V);
+#pragma unroll
+  for (int k = 0; k < 12; k++) c.V[k] = V[k];
+  const double f = 1.0 / tan((double)ep.cam_fov_y_deg * kDeg2Rad / 2.0), aspect = (double)rc.width / (double)rc.height;
+  const double zn = 0.04, zf = 100.0;                                     // gluPerspective S:1761
+  c.P00 = (float)(f / aspect); c.P11 = (float)f;
+  c.P22 = (float)((zf + zn) / (zn - zf)); c.P23 = (float)(2.0 * zf * zn / (zn - zf));
+  c.n_prims = 0; c.n_lat = 0; c.overflow = 0; c.pad = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ k_geometry
+__global__ void __launch_bounds__(kThreads)
+k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
+           int cap, int max_lat, int32_t* __restrict__ err) {
+  __shared__ GeoWarp gws[kWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long gw_id = (long long)blockIdx.x * kWarps + wib;
+  const int env = (int)(gw_id / items_max), item = (int)(gw_id % items_max);
+  if (env >= rc.n_envs) return;
+  const DMap& m = maps[S.map_id[env]];
+  const int n_tiles = m.grid_w * m.grid_h;
+  if (item >= 1 + n_tiles + m.n_objects) return;
+  const int W = rc.width, H = rc.height;
+  const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
+  GeoWarp& sh = gws[wib];
+  FrameCtx& ctx = fm.ctx[env];
+  for (int k = lane; k < (int)(sizeof(RenderEp) / 4); k += 32)
+    reinterpret_cast<uint32_t*>(&sh.ep)[k] = reinterpret_cast<const uint32_t*>(&S.rep[env])[k];
+  if (lane < 12) sh.V[lane] = ctx.V[lane];
+  if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; sh.n_large = 0; }
+  __syncwarp();
+  EmitCtx ec{&sh, &ctx, fm.prims + (size_t)env * max_prims, fm.bin_count + (size_t)env * cbins,
+             fm.lists + (size_t)env * cbins * cap, cap, max_prims, W, H, cbins_x};
+  float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
+  const int tris_per_tile = rc.tessellate ? 98 : 2;
+  Xform x;
+  if (item == 0) {
+    // ground quad S:1805-1812: glScalef(50,0.01,50) applied to (+-1,-0.8,+-1), world-space +y normal
+    if (lane < 2) {
+      model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x);
+      const float gy = (float)(-0.8 * 0.01);
+      const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
+      const int i1 = lane == 0 ? 1 : 2, i2 = lane == 0 ? 2 : 3;
+      const float* g = sh.ep.ground;
+      const Vtx a = shade_vertex(x, sh, P[0][0], P[0][1], P[0][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
+      const Vtx b = shade_vertex(x, sh, P[i1][0], P[i1][1], P[i1][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
+      const Vtx c = shade_vertex(x, sh, P[i2][0], P[i2][1], P[i2][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
+      process_triangle(ec, a, b, c, lane, -1, -1);
     }
-    __syncthreads();
-    // ---------------------------------------------------------------- G: geometry, warp per draw item
-    EmitCtx ec{&sh, prims, max_prims, W, H};
-    const int n_tiles = m.grid_w * m.grid_h;
-    const int n_items = 1 + n_tiles + m.n_objects;
-    const int tris_per_tile = rc.tessellate ? 98 : 2;
-    for (int item = warp; item < n_items; item += kWarps) {
-      Xform x;
-      if (item == 0) {
-        // ground quad S:1805-1812: glScalef(50,0.01,50) applied to (+-1,-0.8,+-1), world-space +y normal
-        if (lane < 2) {
-          model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x);
-          const float gy = (float)(-0.8 * 0.01);
-          const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
-          const int i1 = lane == 0 ? 1 : 2, i2 = lane == 0 ? 2 : 3;
-          const float* g = sh.ep.ground;
-          const Vtx a = shade_vertex(x, sh, P[0][0], P[0][1], P[0][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-          const Vtx b = shade_vertex(x, sh, P[i1][0], P[i1][1], P[i1][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-          const Vtx c = shade_vertex(x, sh, P[i2][0], P[i2][1], P[i2][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-          process_triangle(ec, a, b, c, lane, -1, -1);
-        }
-      } else if (item <= n_tiles) {
-        // road tile S:1852-1884: draw order i outer, j inner
-        const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
-        const int idx = tj * m.grid_w + ti;
-        if (m.tile_kind[idx] < 0) continue;
-        const int quarter = (m.tile_angle[idx] + 2) & 3;                     // glRotatef(angle*90+180) S:1873
-        const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
-        const double ts = m.tile_size;
-        model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x);
-        const int tex = m.tile_tex[idx];
-        const int base_id = 2 + tris_per_tile * t;
-        // the tile's 8x8 lattice, two vertices per lane; also used to frustum-cull the whole tile
-        Vtx lv[2];
-        int outside[6] = {0, 0, 0, 0, 0, 0};
+    bin_large(ec, lane);
+  } else if (item <= n_tiles) {
+    // road tile S:1852-1884: draw order i outer, j inner
+    const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
+    const int idx = tj * m.grid_w + ti;
+    if (m.tile_kind[idx] < 0) return;
+    const int quarter = (m.tile_angle[idx] + 2) & 3;                     // glRotatef(angle*90+180) S:1873
+    const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
+    const double ts = m.tile_size;
+    model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x);
+    const int tex = m.tile_tex[idx];
+    const int base_id = 2 + tris_per_tile * t;
+    // the tile's 8x8 lattice, two vertices per lane; also used to frustum-cull the whole tile
+    Vtx lv[2];
+    int outside[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int vi = lane + 32 * h, a = vi >> 3, b = vi & 7;             // a: u index (x), b: v index (z)
-          const float lx = (float)(-ts / 2 + ((double)a / 7.0) * ts), lz = (float)(-ts / 2 + ((double)b / 7.0) * ts);
-          lv[h] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)a / 7.0),
-                               (float)(1.0 - (double)b / 7.0));
-          const Vtx& v = lv[h];
-          outside[0] += !(v.cz + v.cw >= 0.0f); outside[1] += !(v.cw - v.cz >= 0.0f);
-          outside[2] += v.cx < -v.cw; outside[3] += v.cx > v.cw; outside[4] += v.cy < -v.cw; outside[5] += v.cy > v.cw;
-        }
-        bool culled = false;
+    for (int h = 0; h < 2; h++) {
+      const int vi = lane + 32 * h, a = vi >> 3, b = vi & 7;             // a: u index (x), b: v index (z)
+      const float lx = (float)(-ts / 2 + ((double)a / 7.0) * ts), lz = (float)(-ts / 2 + ((double)b / 7.0) * ts);
+      lv[h] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)a / 7.0),
+                           (float)(1.0 - (double)b / 7.0));
+      const Vtx& v = lv[h];
+      outside[0] += !(v.cz + v.cw >= 0.0f); outside[1] += !(v.cw - v.cz >= 0.0f);
+      outside[2] += v.cx < -v.cw; outside[3] += v.cx > v.cw; outside[4] += v.cy < -v.cw; outside[5] += v.cy > v.cw;
+    }
+    bool culled = false;
 #pragma unroll
-        for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
-        if (culled) continue;
-        if (!rc.tessellate) {
-          // analytic tile (spec tile mode 1): lattice colours -> table, one quad (0,1,2)(0,2,3) of the corners
-          int slot = 0;
-          if (lane == 0) slot = atomicAdd(&sh.n_lat, 1);
-          slot = __shfl_sync(0xffffffffu, slot, 0);
-          if (slot >= max_lat) { if (lane == 0) sh.overflow = 1; continue; }
+    for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
+    if (culled) return;
+    if (!rc.tessellate) {
+      // analytic tile (spec tile mode 1): lattice colours -> table, one quad (0,1,2)(0,2,3) of the corners
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&ctx.n_lat, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot >= max_lat) { if (lane == 0) ctx.overflow = 1; return; }
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int vi = lane + 32 * h;
-            lat_tab[slot * 64 + vi] = make_float4(lv[h].r, lv[h].g, lv[h].b, 0.0f);
-            int corner = -1;
-            if (vi == 0) corner = 0; else if (vi == 56) corner = 1; else if (vi == 63) corner = 2; else if (vi == 7) corner = 3;
-            if (corner >= 0) { Vtx c = lv[h]; c.r = 0.f; c.g = 0.f; c.b = 0.f; sh.corners[warp][corner] = c; }
-          }
-          __syncwarp();
-          if (lane < 2) {
-            const Vtx& c0 = sh.corners[warp][0];
-            const Vtx& c1 = sh.corners[warp][lane == 0 ? 1 : 2];
-            const Vtx& c2 = sh.corners[warp][lane == 0 ? 2 : 3];
-            process_triangle(ec, c0, c1, c2, base_id + lane, tex, slot);
-          }
-          __syncwarp();
-        } else {
-          // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
-          for (int k = lane; k < 98; k += 32) {
-            const int quad = k >> 1, half = k & 1, a = quad / 7, b = quad - 7 * a;
-            Vtx v[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-              const int aa = j == 0 ? a : (j == 1 ? a + 1 : (half == 0 ? a + 1 : a));
-              const int bb = j == 0 ? b : (j == 1 ? (half == 0 ? b : b + 1) : b + 1);
-              const float lx = (float)(-ts / 2 + ((double)aa / 7.0) * ts), lz = (float)(-ts / 2 + ((double)bb / 7.0) * ts);
-              v[j] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)aa / 7.0),
-                                  (float)(1.0 - (double)bb / 7.0));
-            }
-            process_triangle(ec, v[0], v[1], v[2], base_id + k, tex, -1);
-          }
-        }
-      } else {
-        // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
-        const int o = item - 1 - n_tiles;
-        if (sh.ep.hidden[o >> 5] >> (o & 31) & 1u) continue;
-        const DObject& ob = m.objects[o];
-        double sn, cs;
-        sincos((double)ob.y_rot_deg * kDeg2Rad, &sn, &cs);
-        model_view(sh.V, (double)ob.pos[0], (double)ob.pos[1], (double)ob.pos[2], (double)ob.scale, cs, sn, x);
-        {  // conservative bounding-sphere cull in eye space against the four side planes and near
-          const float cx_ = x.MV[0] * ob.centre[0] + x.MV[1] * ob.centre[1] + x.MV[2] * ob.centre[2] + x.MV[3];
-          const float cy_ = x.MV[4] * ob.centre[0] + x.MV[5] * ob.centre[1] + x.MV[6] * ob.centre[2] + x.MV[7];
-          const float cz_ = x.MV[8] * ob.centre[0] + x.MV[9] * ob.centre[1] + x.MV[10] * ob.centre[2] + x.MV[11];
-          const float rad = ob.bound_rad * ob.scale * 1.001f + 1e-4f;
-          const float hx = rsqrtf(sh.P00 * sh.P00 + 1.0f), hy = rsqrtf(sh.P11 * sh.P11 + 1.0f);
-          bool outside_ = cz_ - rad > -0.04f;                                  // entirely behind the near plane
-          outside_ |= (sh.P00 * cx_ + cz_) * hx > rad * 1.01f;                 // right plane: P00*x <= -z
-          outside_ |= (-sh.P00 * cx_ + cz_) * hx > rad * 1.01f;
-          outside_ |= (sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
-          outside_ |= (-sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
-          if (outside_) continue;
-        }
-        int base_id = 2 + tris_per_tile * n_tiles;
-        for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
-        for (int k = lane; k < ob.tri_count; k += 32) {
-          const size_t ti = (size_t)ob.tri_offset + k;
-          const float* p = m.tri_pos + ti * 9;
-          const float* n = m.tri_nrm + ti * 9;
-          const float* uv = m.tri_uv + ti * 6;
-          const float* c = m.tri_col + ti * 9;
+      for (int h = 0; h < 2; h++) {
+        const int vi = lane + 32 * h;
+        lat_tab[slot * 64 + vi] = make_float4(lv[h].r, lv[h].g, lv[h].b, 0.0f);
+        int corner = -1;
+        if (vi == 0) corner = 0; else if (vi == 56) corner = 1; else if (vi == 63) corner = 2; else if (vi == 7) corner = 3;
+        if (corner >= 0) { Vtx c = lv[h]; c.r = 0.f; c.g = 0.f; c.b = 0.f; sh.corners[corner] = c; }
+      }
+      __syncwarp();
+      if (lane < 2) {
+        const Vtx& c0 = sh.corners[0];
+        const Vtx& c1 = sh.corners[lane == 0 ? 1 : 2];
+        const Vtx& c2 = sh.corners[lane == 0 ? 2 : 3];
+        process_triangle(ec, c0, c1, c2, base_id + lane, tex, slot);
+      }
+      bin_large(ec, lane);
+    } else {
+      // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
+      for (int k0 = 0; k0 < 98; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < 98) {
+          const int quad = k >> 1, half = k & 1, a = quad / 7, b = quad - 7 * a;
           Vtx v[3];
 #pragma unroll
-          for (int j = 0; j < 3; j++)
-            v[j] = shade_vertex(x, sh, p[3 * j], p[3 * j + 1], p[3 * j + 2], n[3 * j], n[3 * j + 1], n[3 * j + 2],
-                                c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
-          process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti], -1);
+          for (int j = 0; j < 3; j++) {
+            const int aa = j == 0 ? a : (j == 1 ? a + 1 : (half == 0 ? a + 1 : a));
+            const int bb = j == 0 ? b : (j == 1 ? (half == 0 ? b : b + 1) : b + 1);
+            const float lx = (float)(-ts / 2 + ((double)aa / 7.0) * ts), lz = (float)(-ts / 2 + ((double)bb / 7.0) * ts);
+            v[j] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)aa / 7.0),
+                                (float)(1.0 - (double)bb / 7.0));
+          }
+          process_triangle(ec, v[0], v[1], v[2], base_id + k, tex, -1);
         }
+        bin_large(ec, lane);
       }
     }
-    __syncthreads();
-    const int n_prims = min(sh.n_prims, max_prims);
-#ifdef DTS_STATS
-    if (tid == 0) { atomicAdd(&err[18], n_prims); atomicAdd(&err[19], 1); }
-#endif
-    const float clr[3] = {sh.ep.horizon[0], sh.ep.horizon[1], sh.ep.horizon[2]};
-    // ---------------------------------------------------------------- macro tiles of <= 20 x 32 coarse bins
-    const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH;
-    for (int mby0 = 0; mby0 < cbins_y; mby0 += kMtBinsY)
-      for (int mbx0 = 0; mbx0 < cbins_x; mbx0 += kMtBinsX) {
-        const int mbx1 = min(mbx0 + kMtBinsX, cbins_x) - 1, mby1 = min(mby0 + kMtBinsY, cbins_y) - 1;
-        const int mw = mbx1 - mbx0 + 1, mh = mby1 - mby0 + 1, n_bins = mw * mh;
-        // ------------------------------------------------------------ B: count, scan, scatter (coarse bins)
-        for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
-        if (tid == 0) { sh.n_large = 0; sh.next_bin = 0; }
-        __syncthreads();
-        for (int pass = 0; pass < 2; pass++) {
-          // small prims: one thread each
-          for (int p = tid; p < n_prims; p += kThreads) {
-            const int2 bb = *reinterpret_cast<const int2*>(&prims[p].pxmin);
-            const BinRange r = prim_bins(bb.x, bb.y, mbx0, mby0, mbx1, mby1);
-            if (r.bx0 > r.bx1 || r.by0 > r.by1) continue;
-            const int nb = (r.bx1 - r.bx0 + 1) * (r.by1 - r.by0 + 1);
-            if (nb > 4) {
-              if (pass == 0) { const int s = atomicAdd(&sh.n_large, 1); if (s < kMaxLarge) sh.large[s] = (uint16_t)p; else sh.overflow = 1; }
-              continue;
-            }
-            for (int by = r.by0; by <= r.by1; by++)
-              for (int bx = r.bx0; bx <= r.bx1; bx++) {
-                const int b = (by - mby0) * mw + (bx - mbx0);
-                const int pos = atomicAdd(&bin_count[b], 1);
-                if (pass == 1) pairs[bin_start[b] + pos] = (uint16_t)p;
-              }
-          }
-          __syncthreads();
-          // large prims: one warp each, lanes over the bins of the bounding box, exact edge test
-          const int n_large = min(sh.n_large, kMaxLarge);
-          for (int l = warp; l < n_large; l += kWarps) {
-            const int p = sh.large[l];
-            const PrimRec& pr = prims[p];
-            const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
-            const BinRange r = prim_bins(pr.pxmin, pr.pxmax, mbx0, mby0, mbx1, mby1);
-            const int bw = r.bx1 - r.bx0 + 1, nb = bw * (r.by1 - r.by0 + 1);
-            for (int q = lane; q < nb; q += 32) {
-              const int by = r.by0 + q / bw, bx = r.bx0 + q % bw;
-              if (!bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
-              const int b = (by - mby0) * mw + (bx - mbx0);
-              const int pos = atomicAdd(&bin_count[b], 1);
-              if (pass == 1) pairs[bin_start[b] + pos] = (uint16_t)p;
-            }
-          }
-          __syncthreads();
-          if (pass == 0) {
-            if (warp == 0) {  // exclusive scan of bin_count by one warp
-              int carry = 0;
-              for (int b0 = 0; b0 < n_bins; b0 += 32) {
-                const int b = b0 + lane;
-                const int v = b < n_bins ? bin_count[b] : 0;
-                int inc = v;
+  } else {
+    // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
+    const int o = item - 1 - n_tiles;
+    if (sh.ep.hidden[o >> 5] >> (o & 31) & 1u) return;
+    const DObject& ob = m.objects[o];
+    double sn, cs;
+    sincos((double)ob.y_rot_deg * kDeg2Rad, &sn, &cs);
+    model_view(sh.V, (double)ob.pos[0], (double)ob.pos[1], (double)ob.pos[2], (double)ob.scale, cs, sn, x);
+    {  // conservative bounding-sphere cull in eye space against the four side planes and near
+      const float cx_ = x.MV[0] * ob.centre[0] + x.MV[1] * ob.centre[1] + x.MV[2] * ob.centre[2] + x.MV[3];
+      const float cy_ = x.MV[4] * ob.centre[0] + x.MV[5] * ob.centre[1] + x.MV[6] * ob.centre[2] + x.MV[7];
+      const float cz_ = x.MV[8] * ob.centre[0] + x.MV[9] * ob.centre[1] + x.MV[10] * ob.centre[2] + x.MV[11];
+      const float rad = ob.bound_rad * ob.scale * 1.001f + 1e-4f;
+      const float hx = rsqrtf(sh.P00 * sh.P00 + 1.0f), hy = rsqrtf(sh.P11 * sh.P11 + 1.0f);
+      bool outside_ = cz_ - rad > -0.04f;                                  // entirely behind the near plane
+      outside_ |= (sh.P00 * cx_ + cz_) * hx > rad * 1.01f;                 // right plane: P00*x <= -z
+      outside_ |= (-sh.P00 * cx_ + cz_) * hx > rad * 1.01f;
+      outside_ |= (sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
+      outside_ |= (-sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
+      if (outside_) return;
+    }
+    int base_id = 2 + tris_per_tile * n_tiles;
+    for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
+    for (int k0 = 0; k0 < ob.tri_count; k0 += 32) {
+      const int k = k0 + lane;
+      if (k < ob.tri_count) {
+        const size_t ti = (size_t)ob.tri_offset + k;
+        const float* p = m.tri_pos + ti * 9;
+        const float* n = m.tri_nrm + ti * 9;
+        const float* uv = m.tri_uv + ti * 6;
+        const float* c = m.tri_col + ti * 9;
+        Vtx v[3];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
-                if (b < n_bins) bin_start[b] = carry + inc - v;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
-              }
-              if (lane == 0) { sh.n_pairs = carry; if (carry > max_pairs) sh.overflow = 1; }
-            }
-            __syncthreads();
-            if (sh.n_pairs > max_pairs) break;   // uniform: lists would not fit, render the clear colour
-            for (int b = tid; b < n_bins; b += kThreads) bin_count[b] = 0;
-            __syncthreads();
-          }
-        }
-        const bool pairs_ok = sh.n_pairs <= max_pairs;
-        __syncthreads();
-        // ------------------------------------------------------------ R: raster, warps pull coarse bins
-        const unsigned inv_mw = (65536u + (unsigned)mw - 1u) / (unsigned)mw;   // bin / mw for bin < 3276
-        const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
-        BinPrim* stage = sh.stage[warp];
-        int bin = 0;
-        if (lane == 0) bin = atomicAdd(&sh.next_bin, 1);
-        bin = __shfl_sync(0xffffffffu, bin, 0);
-        while (bin < n_bins) {
-          int next_bin = 0;
-          if (lane == 0) next_bin = atomicAdd(&sh.next_bin, 1);   // consumed after this bin: latency hidden
-          const int brow = (int)(((unsigned)bin * inv_mw) >> 16);
-          const int cbx = mbx0 + (bin - brow * mw), cby = mby0 + brow;
-          const int count = pairs_ok ? bin_count[bin] : 0;
-          const int start = bin_start[bin];
-          const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
-          const bool single = count <= kStage;
+        for (int j = 0; j < 3; j++)
+          v[j] = shade_vertex(x, sh, p[3 * j], p[3 * j + 1], p[3 * j + 2], n[3 * j], n[3 * j + 1], n[3 * j + 2],
+                              c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
+        process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti], -1);
+      }
+      bin_large(ec, lane);
+    }
+  }
+  if (lane == 0 && ctx.overflow) atomicOr(err, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ k_raster
+__global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
+k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, uint8_t* __restrict__ obs,
+         int max_prims, int cap, int max_lat, int32_t* __restrict__ err) {
+  __shared__ __align__(16) BinPrim stages[kWarps][kStage];
+  const int W = rc.width, H = rc.height;
+  const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
+  const size_t frame_bytes = (size_t)W * H * 3;
+  const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
+  BinPrim* stage = stages[warp];
+  const int n_work = rc.n_envs * cbins_y;   // work item = one row of coarse bins of one env
+  int work = 0;
+  if (lane == 0) work = atomicAdd(fm.work, 1);
+  work = __shfl_sync(0xffffffffu, work, 0);
+  while (work < n_work) {
+    int next_work = 0;
+    if (lane == 0) next_work = atomicAdd(fm.work, 1);   // consumed after this row: latency hidden
+    const int env = work / cbins_y, cby = work - env * cbins_y;
+    const DMap& m = maps[S.map_id[env]];
+    const PrimRec* prims = fm.prims + (size_t)env * max_prims;
+    const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
+    uint8_t* out = (fisheye ? fm.undist : obs) + (size_t)env * frame_bytes;
+    const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
+    const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
+    for (int cbx = 0; cbx < cbins_x; cbx++) {
+      const int cb = cby * cbins_x + cbx;
+      const int listed = fm.bin_count[(size_t)env * cbins + cb];
+      const bool scan_all = listed > cap;   // overflowed list (e.g. a whole distant mesh inside one bin): test every prim
+      const int count = scan_all ? min(fm.ctx[env].n_prims, max_prims) : listed;
+      const uint16_t* list = fm.lists + ((size_t)env * cbins + cb) * cap;
+      const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
+      const bool single = count <= kStage;
 #ifdef DTS_STATS
-          if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count); }
+      if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count); }
 #endif
-          int my_id = 0x7fffffff, my_flags = 0;
-          if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins
-            __syncwarp();
-            if (lane < count) { my_id = stage_prim(prims[pairs[start + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
-            __syncwarp();
-          }
+      int my_id = 0x7fffffff, my_flags = 0;
+      if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins
+        __syncwarp();
+        if (lane < count) { my_id = stage_prim(prims[scan_all ? lane : (int)list[lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
+        __syncwarp();
+      }
 #pragma unroll 1
-          for (int f = 0; f < kCFX * kCFY; f++) {
-            const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
-            if (bx * kBinW >= W || by * kBinH >= H) continue;
-            if (count == 0) { store_bin(out, clear_rgb, lane, bx, by, W, H); continue; }
-            const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
-            float z[4], cr[4], cg[4], cb[4];
-            int wid[4];
+      for (int f = 0; f < kCFX * kCFY; f++) {
+        const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
+        if (bx * kBinW >= W || by * kBinH >= H) continue;
+        if (count == 0) { store_bin(out, clear_rgb, lane, bx, by, W, H); continue; }
+        const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
+        float z[4], cr[4], cg[4], cb_[4];
+        int wid[4];
 #pragma unroll
-            for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb[s] = clr[2]; wid[s] = 0x7fffffff; }
-            bool simple_done = false;
-            for (int c0 = 0; c0 < count; c0 += kStage) {
-              const int nch = min(kStage, count - c0);
-              if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
-                __syncwarp();
-                my_id = 0x7fffffff; my_flags = 0;
-                if (lane < nch) { my_id = stage_prim(prims[pairs[start + c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
-                __syncwarp();
-              }
-              const bool live = (my_flags >> (8 + f)) & 1;
-              const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-              const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
+        for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb_[s] = clr[2]; wid[s] = 0x7fffffff; }
+        bool simple_done = false;
+        for (int c0 = 0; c0 < count; c0 += kStage) {
+          const int nch = min(kStage, count - c0);
+          if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
+            __syncwarp();
+            my_id = 0x7fffffff; my_flags = 0;
+            if (lane < nch) { my_id = stage_prim(prims[scan_all ? c0 + lane : (int)list[c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
+            __syncwarp();
+          }
+          const bool live = (my_flags >> (8 + f)) & 1;
+          const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+          const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
 #ifdef DTS_STATS
-              if (lane == 0) { atomicAdd(&err[11], __popc(live_mask)); atomicAdd(&err[12], __popc(ground_mask)); }
+          if (lane == 0) { atomicAdd(&err[11], __popc(live_mask)); atomicAdd(&err[12], __popc(ground_mask)); }
 #endif
-              if (single) {
-                // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
-                // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
-                // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
-                const unsigned full_mask = __ballot_sync(0xffffffffu, live && ((my_flags >> f) & 1));
-                const unsigned others = live_mask & ~ground_mask;
-                const unsigned pick = others ? others : live_mask;
-                if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
-                  const BinPrim& bp = stage[__ffs(pick) - 1];
-                  const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
-                  float c3[3];
-                  shade_pixel(bp, lat_tab, cdx, cdy, c3);
-                  store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
-                  simple_done = true;
+          if (single) {
+            // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
+            // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
+            // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
+            const unsigned full_mask = __ballot_sync(0xffffffffu, live && ((my_flags >> f) & 1));
+            const unsigned others = live_mask & ~ground_mask;
+            const unsigned pick = others ? others : live_mask;
+            if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
+              const BinPrim& bp = stage[__ffs(pick) - 1];
+              const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
+              float c3[3];
+              shade_pixel(bp, lat_tab, cdx, cdy, c3);
+              store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
+              simple_done = true;
 #ifdef DTS_STATS
-                  if (lane == 0) atomicAdd(&err[13], 1);
+              if (lane == 0) atomicAdd(&err[13], 1);
 #endif
-                  break;
-                }
-              }
-              // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
-              for (int phase = 0; phase < 2; phase++) {
-                unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
-                while (todo) {
-                  const int k = __ffs(todo) - 1;
-                  todo &= todo - 1;
-                  const BinPrim& bp = stage[k];
-#ifdef DTS_STATS
-                  if (lane == 0) { atomicAdd(&err[16], 1); if ((bp.flags >> f) & 1) atomicAdd(&err[17], 1); }
-#endif
-                  int mask = 15;
-                  if (!((bp.flags >> f) & 1)) {
-                    mask = 0;
-                    const int ec0 = bp.E0[0] + bp.A[0] * pxc + bp.B[0] * pyc;
-                    const int ec1 = bp.E0[1] + bp.A[1] * pxc + bp.B[1] * pyc;
-                    const int ec2 = bp.E0[2] + bp.A[2] * pxc + bp.B[2] * pyc;
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                      const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
-                      const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
-                      const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
-                      if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
-                    }
-                    if (!mask) continue;
-                  }
-                  // ---- early z: depth of the covered samples, GL_LESS in draw order
-                  const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
-                  float zs[4];
-                  int lt = 0, eq = 0;
-#pragma unroll
-                  for (int s = 0; s < 4; s++) {
-                    // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
-                    // identical to the spec's (float)(X_sample - x0) / 64
-                    const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
-                    zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
-                    lt |= (zs[s] < z[s]) << s;
-                    eq |= (zs[s] == z[s]) << s;
-                  }
-                  int pass_mask = mask & lt;
-                  const int tie = mask & eq;
-                  if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
-#pragma unroll
-                    for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
-                  }
-                  if (!pass_mask) continue;
-                  float c3[3];
-                  shade_pixel(bp, lat_tab, cdx, cdy, c3);
-#pragma unroll
-                  for (int s = 0; s < 4; s++)
-                    if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb[s] = c3[2]; }
-                }
-              }
-            }
-            // -------------------------------------------------------- O: resolve + store
-            if (!simple_done) {
-              const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
-              const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
-              const float b_ = ((cb[0] + cb[1]) + (cb[2] + cb[3])) * 0.25f;
-              store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
+              break;
             }
           }
-          bin = __shfl_sync(0xffffffffu, next_bin, 0);
+          // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
+          for (int phase = 0; phase < 2; phase++) {
+            unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+            while (todo) {
+              const int k = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const BinPrim& bp = stage[k];
+#ifdef DTS_STATS
+              if (lane == 0) { atomicAdd(&err[16], 1); if ((bp.flags >> f) & 1) atomicAdd(&err[17], 1); }
+#endif
+              int mask = 15;
+              if (!((bp.flags >> f) & 1)) {
+                mask = 0;
+                const int ec0 = bp.E0[0] + bp.A[0] * pxc + bp.B[0] * pyc;
+                const int ec1 = bp.E0[1] + bp.A[1] * pxc + bp.B[1] * pyc;
+                const int ec2 = bp.E0[2] + bp.A[2] * pxc + bp.B[2] * pyc;
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                  const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
+                  const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
+                  const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
+                  if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                }
+                if (!mask) continue;
+              }
+              // ---- early z: depth of the covered samples, GL_LESS in draw order
+              const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
+              float zs[4];
+              int lt = 0, eq = 0;
+#pragma unroll
+              for (int s = 0; s < 4; s++) {
+                // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
+                // identical to the spec's (float)(X_sample - x0) / 64
+                const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
+                zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
+                lt |= (zs[s] < z[s]) << s;
+                eq |= (zs[s] == z[s]) << s;
+              }
+              int pass_mask = mask & lt;
+              const int tie = mask & eq;
+              if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
+#pragma unroll
+                for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
+              }
+              if (!pass_mask) continue;
+              float c3[3];
+              shade_pixel(bp, lat_tab, cdx, cdy, c3);
+#pragma unroll
+              for (int s = 0; s < 4; s++)
+                if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb_[s] = c3[2]; }
+            }
+          }
         }
-        __syncthreads();
-      }
-    if (tid == 0 && sh.overflow) atomicOr(err, 1);
-    // ---------------------------------------------------------------- fisheye gather (distortion.py:118)
-    if (fisheye) {
-      __threadfence_block();
-      __syncthreads();
-      uint8_t* dst = obs + (size_t)env * frame_bytes;
-      for (int p = tid; p < W * H; p += kThreads) {
-        const int sx = (int)rintf(__ldg(lut_x + p)), sy = (int)rintf(__ldg(lut_y + p));
-        uint8_t r = 0, g = 0, b = 0;
-        if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
-          const uint8_t* s = my_undist + ((size_t)sy * W + sx) * 3;
-          r = s[0]; g = s[1]; b = s[2];
+        // -------------------------------------------------------- resolve + store
+        if (!simple_done) {
+          const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
+          const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
+          const float b_ = ((cb_[0] + cb_[1]) + (cb_[2] + cb_[3])) * 0.25f;
+          store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
         }
-        dst[(size_t)p * 3] = r; dst[(size_t)p * 3 + 1] = g; dst[(size_t)p * 3 + 2] = b;
       }
     }
+    work = __shfl_sync(0xffffffffu, next_work, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_fisheye
+__global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __restrict__ undist,
+                                                 const float* __restrict__ lut_x, const float* __restrict__ lut_y,
+                                                 uint8_t* __restrict__ obs) {
+  const int W = rc.width, H = rc.height;
+  const size_t npx = (size_t)W * H, total = npx * rc.n_envs;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t env = g / npx, p = g - env * npx;
+    const int sx = (int)rintf(__ldg(lut_x + p)), sy = (int)rintf(__ldg(lut_y + p));
+    uint8_t r = 0, gg = 0, b = 0;
+    if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
+      const uint8_t* s = undist + (env * npx + (size_t)sy * W + sx) * 3;
+      r = s[0]; gg = s[1]; b = s[2];
+    }
+    uint8_t* d = obs + g * 3;
+    d[0] = r; d[1] = gg; d[2] = b;
   }
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, int max_lat, const float* lut_x, const float* lut_y, int32_t* err_flag,
-                  cudaStream_t st) {
-  const size_t smem = ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)kMtBinsX * kMtBinsY * 2 * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
+                  int max_prims, int cap, int max_lat, int items_max, const float* lut_x, const float* lut_y,
+                  int32_t* err_flag, cudaStream_t st) {
+  const int W = rc.width, H = rc.height;
+  const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
+  const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
+  const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, cap, max_lat, fisheye ? (size_t)W * H * 3 : 0);
+  cudaMemsetAsync(fm.work, 0, 256, st);
+  cudaMemsetAsync(fm.bin_count, 0, (size_t)rc.n_envs * cbins * sizeof(int), st);
+  k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
+  const long long warps = (long long)rc.n_envs * items_max;
+  k_geometry<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(S, maps, rc, fm, items_max, max_prims, cap,
+                                                                              max_lat, err_flag);
+  k_raster<<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, cap, max_lat, err_flag);
+  int launches = 3;
+  if (fisheye) {
+    k_fisheye<<<148 * 8, 256, 0, st>>>(rc, fm.undist, lut_x, lut_y, obs);
+    launches++;
   }
-  uint8_t* undist = reinterpret_cast<uint8_t*>(scratch) + (size_t)n_ctas * render_slab_bytes(max_prims, max_pairs, max_lat);
-  k_render<<<n_ctas, kThreads, smem, st>>>(S, maps, rc, obs, reinterpret_cast<uint8_t*>(scratch), max_prims, max_pairs,
-                                           max_lat, undist, lut_x, lut_y, err_flag);
-  return 1;
+  return launches;
 }
 
 }  // namespace dts
