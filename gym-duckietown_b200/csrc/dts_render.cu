@@ -72,7 +72,7 @@ struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the curre
   const uint8_t* tex;            // nullptr = untextured
   int32_t tex_wh;                // w | h<<16
   int32_t lat;
-  int32_t pad[2];
+  float twf, thf;                // (float)tex_w, (float)tex_h
 };
 static_assert(sizeof(BinPrim) == 160, "BinPrim layout");
 
@@ -400,15 +400,16 @@ __device__ __forceinline__ int stage_prim(const PrimRec& r, BinPrim& bp, int ox,
       if (ef + lo < 0) inside &= ~(1u << f);
     }
   }
-  bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
-#pragma unroll
-  for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
   const int id = r.id_tex >> 8;
   bp.id = id;
   bp.flags = (int)((inside & live) | (live << 8));
+  if (live == 0) return id;   // touches no fine bin of this coarse bin: nothing else is read
+  bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
+#pragma unroll
+  for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
   const int tex = (r.id_tex & 255) - 1;
-  if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); }
-  else { bp.tex = nullptr; bp.tex_wh = 0; }
+  if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); bp.twf = (float)t.w; bp.thf = (float)t.h; }
+  else { bp.tex = nullptr; bp.tex_wh = 0; bp.twf = 0.f; bp.thf = 0.f; }
   bp.lat = r.lat;
   return id;
 }
@@ -447,7 +448,7 @@ __device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __r
   }
   if (bp.tex) {
     const int tw = bp.tex_wh & 0xffff, th = bp.tex_wh >> 16;
-    const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
+    const float tx = u * bp.twf - 0.5f, ty = v * bp.thf - 0.5f;
     const float txf = floorf(tx), tyf = floorf(ty);
     const float ffx = tx - txf, ffy = ty - tyf;
     const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg r
 }
 
 // ------------------------------------------------------------------------------------------------ k_geometry
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
            int cap, int max_lat, int32_t* __restrict__ err) {
   __shared__ GeoWarp gws[kWarps];
@@ -597,7 +598,23 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x);
     const int tex = m.tile_tex[idx];
     const int base_id = 2 + tris_per_tile * t;
-    // the tile's 8x8 lattice, two vertices per lane; also used to frustum-cull the whole tile
+    if (!rc.tessellate) {
+      // analytic tile: the prim is the quad of the 4 corners — cull on those before lighting the lattice
+      const int ca = (lane == 1 || lane == 2) ? 7 : 0, cb = (lane >= 2) ? 7 : 0;   // lanes 0..3: (0,0) (7,0) (7,7) (0,7)
+      const float lx = (float)(-ts / 2 + ((double)ca / 7.0) * ts), lz = (float)(-ts / 2 + ((double)cb / 7.0) * ts);
+      const Vtx v = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)ca / 7.0),
+                                 (float)(1.0 - (double)cb / 7.0));
+      const unsigned four = 0xFu;
+      bool culled4 = false;
+      culled4 |= (__ballot_sync(0xffffffffu, !(v.cz + v.cw >= 0.0f)) & four) == four;
+      culled4 |= (__ballot_sync(0xffffffffu, !(v.cw - v.cz >= 0.0f)) & four) == four;
+      culled4 |= (__ballot_sync(0xffffffffu, v.cx < -v.cw) & four) == four;
+      culled4 |= (__ballot_sync(0xffffffffu, v.cx > v.cw) & four) == four;
+      culled4 |= (__ballot_sync(0xffffffffu, v.cy < -v.cw) & four) == four;
+      culled4 |= (__ballot_sync(0xffffffffu, v.cy > v.cw) & four) == four;
+      if (culled4) return;
+    }
+    // the tile's 8x8 lattice, two vertices per lane (tessellated mode: also frustum-culls the whole tile)
     Vtx lv[2];
     int outside[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -610,10 +627,12 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
       outside[0] += !(v.cz + v.cw >= 0.0f); outside[1] += !(v.cw - v.cz >= 0.0f);
       outside[2] += v.cx < -v.cw; outside[3] += v.cx > v.cw; outside[4] += v.cy < -v.cw; outside[5] += v.cy > v.cw;
     }
-    bool culled = false;
+    if (rc.tessellate) {
+      bool culled = false;
 #pragma unroll
-    for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
-    if (culled) return;
+      for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
+      if (culled) return;
+    }
     if (!rc.tessellate) {
       // analytic tile (spec tile mode 1): lattice colours -> table, one quad (0,1,2)(0,2,3) of the corners
       int slot = 0;
@@ -751,9 +770,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
         const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
         float z[4], cr[4], cg[4], cb_[4];
         int wid[4];
-#pragma unroll
-        for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb_[s] = clr[2]; wid[s] = 0x7fffffff; }
-        bool simple_done = false;
+        bool simple_done = false, inited = false;
         for (int c0 = 0; c0 < count; c0 += kStage) {
           const int nch = min(kStage, count - c0);
           if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
@@ -787,6 +804,11 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
 #endif
               break;
             }
+          }
+          if (!inited) {   // per-sample state is only needed on the general path
+            inited = true;
+#pragma unroll
+            for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb_[s] = clr[2]; wid[s] = 0x7fffffff; }
           }
           // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
           for (int phase = 0; phase < 2; phase++) {
