@@ -548,7 +548,10 @@ __global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg r
 }
 
 // ------------------------------------------------------------------------------------------------ k_geometry
-__global__ void __launch_bounds__(kThreads, 3)
+#ifndef DTS_GEO_MIN_CTAS
+#define DTS_GEO_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, DTS_GEO_MIN_CTAS)
 k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
            int cap, int max_lat, int32_t* __restrict__ err) {
   __shared__ GeoWarp gws[kWarps];
