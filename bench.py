@@ -297,7 +297,7 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4, "d2h_bytes_per_step": E * (W * H * 3 + 4 + 1),
                 "steps": Ke, "api": "HostPipeline.submit/result, depth 2 (D2H of step k overlaps step k+1)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "render launches of one step: k_frame_setup + k_geometry + k_raster (k_raster dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": render_ms,
                      "compulsory_frac": (E * (W * H * 3 + 256) / (render_ms / 1000.0) / 1e9) / peak},

@@ -336,8 +336,8 @@ static int ensure_render(dts_sim* sim) {
   if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
   sim->max_lat = max_lat;
   sim->items_max = items_max;
-  sim->bin_cap = tess ? 512 : 96;    // entries per 32x8-px coarse bin; longer lists fall back to scanning all prims
   const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
+  sim->bin_cap = 3 * sim->max_prims + 8 * cbins + 256;   // (prim, coarse bin) pairs per env
   const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
   const size_t bytes = render_scratch_bytes(sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);

@@ -35,9 +35,9 @@ void launch_query(const DMap* maps, int map_id, int n, const double* q, const ui
 int render_ctas_per_sm();
 // scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
 // undistorted frames when the fisheye gather is on
-size_t render_scratch_bytes(int n, int max_prims, int cbins, int cap, int max_lat, size_t undist_frame);
+size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame);
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
-                  int max_prims, int cap, int max_lat, int items_max, const float* lut_x, const float* lut_y,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
                   int32_t* err_flag, cudaStream_t st);
 
 }  // namespace dts

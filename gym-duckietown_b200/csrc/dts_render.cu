@@ -84,14 +84,11 @@ struct __align__(16) FrameCtx {   // per env, global memory
   int32_t n_prims, n_lat, overflow, pad;
 };
 
-constexpr int kMaxLargeWarp = 32;
 struct __align__(16) GeoWarp {    // per warp of k_geometry, shared memory
   RenderEp ep;
   double V[12];
   float P00, P11, P22, P23;
   Vtx corners[4];
-  int n_large;
-  uint16_t large[kMaxLargeWarp];
 };
 using Shared = GeoWarp;           // shade_vertex reads ep and P from it
 
@@ -189,22 +186,12 @@ __device__ __forceinline__ int classify(const Vtx& a, const Vtx& b, const Vtx& c
   return need ? 1 : 0;
 }
 
-__device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int ox, int oy);
-
 struct EmitCtx {
   GeoWarp* gw;
   FrameCtx* ctx;
   PrimRec* prims;          // this env's slab
-  int* bin_count;          // [cbins] this env's cursors
-  uint16_t* lists;         // [cbins][cap]
-  int cap, max_prims, W, H, cbins_x;
+  int max_prims, W, H;
 };
-
-__device__ __forceinline__ void bin_append(const EmitCtx& ec, int b, int slot) {
-  // a list longer than `cap` is not an error: k_raster then scans all of the env's prims for that bin
-  const int pos = atomicAdd(&ec.bin_count[b], 1);
-  if (pos < ec.cap) ec.lists[(size_t)b * ec.cap + pos] = (uint16_t)slot;
-}
 
 // screen mapping + triangle setup (spec steps 5-7) and append to the slab
 __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
@@ -263,40 +250,6 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
   int4* dst = reinterpret_cast<int4*>(ec.prims + slot);
 #pragma unroll
   for (int k = 0; k < 8; k++) dst[k] = src[k];
-  // bin it: few coarse bins -> this lane appends; a large bounding box -> the whole warp does it afterwards
-  const int bx0 = px0 / kCoarseW, bx1 = px1 / kCoarseW, by0 = py0 / kCoarseH, by1 = py1 / kCoarseH;
-  if ((bx1 - bx0 + 1) * (by1 - by0 + 1) <= 4) {
-    for (int by = by0; by <= by1; by++)
-      for (int bx = bx0; bx <= bx1; bx++) bin_append(ec, by * ec.cbins_x + bx, slot);
-  } else {
-    const int l = atomicAdd(&ec.gw->n_large, 1);
-    if (l < kMaxLargeWarp) ec.gw->large[l] = (uint16_t)slot;
-    else {   // more large prims than the warp list holds: fall back to the bounding box
-      for (int by = by0; by <= by1; by++)
-        for (int bx = bx0; bx <= bx1; bx++) bin_append(ec, by * ec.cbins_x + bx, slot);
-    }
-  }
-}
-
-// after an item's triangles are emitted: all lanes bin the warp's large prims with the exact edge test
-__device__ __forceinline__ void bin_large(const EmitCtx& ec, int lane) {
-  __syncwarp();
-  const int nl = min(ec.gw->n_large, kMaxLargeWarp);
-  for (int l = 0; l < nl; l++) {
-    const int slot = ec.gw->large[l];
-    const PrimRec& pr = ec.prims[slot];
-    const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
-    const int bx0 = (pr.pxmin & 0xffff) / kCoarseW, by0 = (pr.pxmin >> 16) / kCoarseH;
-    const int bx1 = (pr.pxmax & 0xffff) / kCoarseW, by1 = (pr.pxmax >> 16) / kCoarseH;
-    const int bw = bx1 - bx0 + 1, nb = bw * (by1 - by0 + 1);
-    for (int q = lane; q < nb; q += 32) {
-      const int by = by0 + q / bw, bx = bx0 + q % bw;
-      if (bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) bin_append(ec, by * ec.cbins_x + bx, slot);
-    }
-  }
-  __syncwarp();
-  if (lane == 0) ec.gw->n_large = 0;
-  __syncwarp();
 }
 
 __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float din, float dout) {
@@ -364,14 +317,6 @@ __device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int
   return true;
 }
 
-struct BinRange { int bx0, by0, bx1, by1; };
-
-__device__ __forceinline__ BinRange prim_bins(int pxmin, int pxmax, int mbx0, int mby0, int mbx1, int mby1) {
-  BinRange r;
-  r.bx0 = max((pxmin & 0xffff) / kCoarseW, mbx0); r.by0 = max((pxmin >> 16) / kCoarseH, mby0);
-  r.bx1 = min((pxmax & 0xffff) / kCoarseW, mbx1); r.by1 = min((pxmax >> 16) / kCoarseH, mby1);
-  return r;
-}
 
 
 // Stage one prim for a coarse bin whose corner is (ox, oy) sub-pixels: edge functions re-based to the
@@ -502,8 +447,9 @@ int render_ctas_per_sm() { return DTS_RENDER_MIN_CTAS; }
 struct FrameMem {
   FrameCtx* ctx;        // [N]
   PrimRec* prims;       // [N][max_prims]
-  uint16_t* lists;      // [N][cbins][cap]
+  uint16_t* pairs;      // [N][max_pairs]  prim indices grouped by coarse bin (k_bin)
   int* bin_count;       // [N][cbins]
+  int* bin_start;       // [N][cbins]  offset of the bin's run inside the env's pairs
   float4* lat;          // [N][max_lat][64]
   uint8_t* undist;      // [N][H][W][3] (distortion only)
   int* work;            // [4] global work counters
@@ -511,22 +457,23 @@ struct FrameMem {
 
 __host__ __device__ inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 
-__host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int cap, int max_lat, size_t undist_frame) {
+__host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
   uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
   FrameMem f;
   f.work = reinterpret_cast<int*>(p); p += 256;
   f.ctx = reinterpret_cast<FrameCtx*>(p); p += align256((size_t)n * sizeof(FrameCtx));
   f.bin_count = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
+  f.bin_start = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
   f.prims = reinterpret_cast<PrimRec*>(p); p += align256((size_t)n * max_prims * sizeof(PrimRec));
-  f.lists = reinterpret_cast<uint16_t*>(p); p += align256((size_t)n * cbins * cap * sizeof(uint16_t));
+  f.pairs = reinterpret_cast<uint16_t*>(p); p += align256((size_t)n * max_pairs * sizeof(uint16_t));
   f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
   f.undist = undist_frame ? p : nullptr;
   return f;
 }
 
-size_t render_scratch_bytes(int n, int max_prims, int cbins, int cap, int max_lat, size_t undist_frame) {
-  return 256 + align256((size_t)n * sizeof(FrameCtx)) + align256((size_t)n * cbins * sizeof(int)) +
-         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * cbins * cap * sizeof(uint16_t)) +
+size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
+  return 256 + align256((size_t)n * sizeof(FrameCtx)) + 2 * align256((size_t)n * cbins * sizeof(int)) +
+         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * max_pairs * sizeof(uint16_t)) +
          align256((size_t)n * max_lat * 64 * sizeof(float4)) + (size_t)n * undist_frame + 256;
 }
 
@@ -553,7 +500,7 @@ __global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg r
 #endif
 __global__ void __launch_bounds__(kThreads, DTS_GEO_MIN_CTAS)
 k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
-           int cap, int max_lat, int32_t* __restrict__ err) {
+           int max_lat, int32_t* __restrict__ err) {
   __shared__ GeoWarp gws[kWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long gw_id = (long long)blockIdx.x * kWarps + wib;
@@ -563,16 +510,14 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   const int n_tiles = m.grid_w * m.grid_h;
   if (item >= 1 + n_tiles + m.n_objects) return;
   const int W = rc.width, H = rc.height;
-  const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
   GeoWarp& sh = gws[wib];
   FrameCtx& ctx = fm.ctx[env];
   for (int k = lane; k < (int)(sizeof(RenderEp) / 4); k += 32)
     reinterpret_cast<uint32_t*>(&sh.ep)[k] = reinterpret_cast<const uint32_t*>(&S.rep[env])[k];
   if (lane < 12) sh.V[lane] = ctx.V[lane];
-  if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; sh.n_large = 0; }
+  if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; }
   __syncwarp();
-  EmitCtx ec{&sh, &ctx, fm.prims + (size_t)env * max_prims, fm.bin_count + (size_t)env * cbins,
-             fm.lists + (size_t)env * cbins * cap, cap, max_prims, W, H, cbins_x};
+  EmitCtx ec{&sh, &ctx, fm.prims + (size_t)env * max_prims, max_prims, W, H};
   float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
   const int tris_per_tile = rc.tessellate ? 98 : 2;
   Xform x;
@@ -589,7 +534,6 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
       const Vtx c = shade_vertex(x, sh, P[i2][0], P[i2][1], P[i2][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
       process_triangle(ec, a, b, c, lane, -1, -1);
     }
-    bin_large(ec, lane);
   } else if (item <= n_tiles) {
     // road tile S:1852-1884: draw order i outer, j inner
     const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
@@ -657,8 +601,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
         const Vtx& c2 = sh.corners[lane == 0 ? 2 : 3];
         process_triangle(ec, c0, c1, c2, base_id + lane, tex, slot);
       }
-      bin_large(ec, lane);
-    } else {
+      } else {
       // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
       for (int k0 = 0; k0 < 98; k0 += 32) {
         const int k = k0 + lane;
@@ -675,8 +618,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
           }
           process_triangle(ec, v[0], v[1], v[2], base_id + k, tex, -1);
         }
-        bin_large(ec, lane);
-      }
+          }
     }
   } else {
     // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
@@ -716,16 +658,73 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
                               c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
         process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti], -1);
       }
-      bin_large(ec, lane);
-    }
+      }
   }
   if (lane == 0 && ctx.overflow) atomicOr(err, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ k_bin
+// warp per env: exact-size lists of prim indices per 32x8-px coarse bin — count, warp scan, scatter.  Prims with
+// a small bounding box are binned by it; larger ones test each bin of the box against their three edges.
+constexpr int kBinWarps = 4;
+__global__ void __launch_bounds__(kBinWarps * 32)
+k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restrict__ err) {
+  extern __shared__ int bin_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = blockIdx.x * kBinWarps + wib;
+  if (env >= rc.n_envs) return;
+  const int W = rc.width, H = rc.height;
+  const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
+  int* cnt = bin_smem + wib * 2 * cbins;
+  int* start = cnt + cbins;
+  const PrimRec* prims = fm.prims + (size_t)env * max_prims;
+  uint16_t* pairs = fm.pairs + (size_t)env * max_pairs;
+  const int n = min(fm.ctx[env].n_prims, max_prims);
+  bool ok = true;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int b = lane; b < cbins; b += 32) cnt[b] = 0;
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) {
+      const PrimRec& pr = prims[p];
+      const int bx0 = (pr.pxmin & 0xffff) / kCoarseW, by0 = (pr.pxmin >> 16) / kCoarseH;
+      const int bx1 = (pr.pxmax & 0xffff) / kCoarseW, by1 = (pr.pxmax >> 16) / kCoarseH;
+      const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
+      const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
+      for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) {
+          if (large && !bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
+          const int b = by * cbins_x + bx;
+          const int pos = atomicAdd(&cnt[b], 1);
+          if (pass == 1) pairs[start[b] + pos] = (uint16_t)p;
+        }
+    }
+    __syncwarp();
+    if (pass == 0) {
+      int carry = 0;
+      for (int b0 = 0; b0 < cbins; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = b < cbins ? cnt[b] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+        if (b < cbins) start[b] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      ok = carry <= max_pairs;
+      for (int b = lane; b < cbins; b += 32) {
+        fm.bin_count[(size_t)env * cbins + b] = ok ? cnt[b] : 0;   // lists that do not fit: the frame stays clear
+        fm.bin_start[(size_t)env * cbins + b] = start[b];
+      }
+      __syncwarp();
+      if (!ok) { if (lane == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); } return; }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, uint8_t* __restrict__ obs,
-         int max_prims, int cap, int max_lat, int32_t* __restrict__ err) {
+         int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
   __shared__ __align__(16) BinPrim stages[kWarps][kStage];
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
@@ -750,10 +749,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
     for (int cbx = 0; cbx < cbins_x; cbx++) {
       const int cb = cby * cbins_x + cbx;
-      const int listed = fm.bin_count[(size_t)env * cbins + cb];
-      const bool scan_all = listed > cap;   // overflowed list (e.g. a whole distant mesh inside one bin): test every prim
-      const int count = scan_all ? min(fm.ctx[env].n_prims, max_prims) : listed;
-      const uint16_t* list = fm.lists + ((size_t)env * cbins + cb) * cap;
+      const int count = fm.bin_count[(size_t)env * cbins + cb];
+      const uint16_t* list = fm.pairs + (size_t)env * max_pairs + fm.bin_start[(size_t)env * cbins + cb];
       const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
       const bool single = count <= kStage;
 #ifdef DTS_STATS
@@ -762,7 +759,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       int my_id = 0x7fffffff, my_flags = 0;
       if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins
         __syncwarp();
-        if (lane < count) { my_id = stage_prim(prims[scan_all ? lane : (int)list[lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
+        if (lane < count) { my_id = stage_prim(prims[list[lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
         __syncwarp();
       }
 #pragma unroll 1
@@ -779,7 +776,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
             __syncwarp();
             my_id = 0x7fffffff; my_flags = 0;
-            if (lane < nch) { my_id = stage_prim(prims[scan_all ? c0 + lane : (int)list[c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
+            if (lane < nch) { my_id = stage_prim(prims[list[c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
             __syncwarp();
           }
           const bool live = (my_flags >> (8 + f)) & 1;
@@ -899,20 +896,21 @@ __global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
-                  int max_prims, int cap, int max_lat, int items_max, const float* lut_x, const float* lut_y,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
                   int32_t* err_flag, cudaStream_t st) {
   const int W = rc.width, H = rc.height;
   const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
-  const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, cap, max_lat, fisheye ? (size_t)W * H * 3 : 0);
+  const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
   cudaMemsetAsync(fm.work, 0, 256, st);
-  cudaMemsetAsync(fm.bin_count, 0, (size_t)rc.n_envs * cbins * sizeof(int), st);
   k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
   const long long warps = (long long)rc.n_envs * items_max;
-  k_geometry<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(S, maps, rc, fm, items_max, max_prims, cap,
+  k_geometry<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(S, maps, rc, fm, items_max, max_prims,
                                                                               max_lat, err_flag);
-  k_raster<<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, cap, max_lat, err_flag);
-  int launches = 3;
+  k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, (size_t)kBinWarps * 2 * cbins * sizeof(int), st>>>(
+      rc, fm, max_prims, max_pairs, err_flag);
+  k_raster<<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
+  int launches = 4;
   if (fisheye) {
     k_fisheye<<<148 * 8, 256, 0, st>>>(rc, fm.undist, lut_x, lut_y, obs);
     launches++;
