@@ -239,3 +239,36 @@ def test_auto_reset_rollout_equals_reference_style_loop(torch_cuda):
                 assert s["step_count"][k] == o.step_count
     assert resets > 3 * N      # every env went through several episodes
     env.close()
+
+
+def test_frame_skip_and_dynamics_rand_vs_oracle(torch_cuda):
+    """frame_skip=3 (S:1673: three physics updates per action, step_count counts frames) and dynamics_rand
+    (per-env trim on the motor gains, S:746-748) against the oracle."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    N, T = 16, 40
+    env = make_env("small_loop", N, frame_skip=3, dynamics_rand=True, seed=321, max_steps=90)
+    captured = {}
+    orig = env.sim.reset
+    env.sim.reset = lambda mask, params, stream=0: (captured.update(params), orig(mask, params, stream))[1]
+    env.reset(render=False)
+    torch.cuda.synchronize()
+    assert np.abs(captured["trim"]).max() > 1e-4           # the Randomizer's normal(0, 0.02) draw is in use
+    st0 = {k: v.cpu().numpy().copy() for k, v in env.state.items()}
+    om = orc.OracleMap(maps.load_map("small_loop"))
+    cpu = [orc.OracleEnv(om, st0["pos_x"][k], st0["pos_z"][k], st0["angle"][k], wheel_dist=st0["wheel_dist"][k],
+                         frame_skip=3, max_steps=90, trim=float(captured["trim"][k])) for k in range(N)]
+    acts = np.random.default_rng(8).uniform(-1, 1, (T, N, 2)).astype(np.float32)
+    acts[:, :, 0] = 0.25
+    acts[:, :, 1] *= 0.2
+    for t in range(T):
+        _, rew, done, info = env.step(torch.from_numpy(acts[t]).to(env.device), render=False)
+        torch.cuda.synchronize()
+        s = {k: v.cpu().numpy() for k, v in info.items()}
+        for k in range(N):
+            o = cpu[k].step(acts[t, k])
+            assert s["step_count"][k] == o.step_count == 3 * (t + 1)
+            assert abs(s["pos_x"][k] - o.pos_x) <= 1e-5 and abs(s["pos_z"][k] - o.pos_z) <= 1e-5, (t, k)
+            assert s["done_code"][k] == o.done_code and abs(s["speed"][k] - o.speed) <= 1e-5, (t, k)
+    env.close()

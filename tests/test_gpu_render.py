@@ -166,3 +166,55 @@ def test_many_envs_per_cta_vs_oracle(torch_cuda):
     cpu = np.stack([sc.render(st["pos_x"][k], st["pos_z"][k], st["angle"][k], None, W, H, False) for k in sel])
     compare(obs2.cpu().numpy()[sel], cpu, "many_envs")
     env.close(); env2.close()
+
+
+def test_second_episode_stale_light_vs_oracle(torch_cuda):
+    """S:581: from the second reset on GL_LIGHT0's position is captured under the previous frame's camera
+    matrix.  Device auto-reset does that on its own; the oracle is handed the eye-space light the product reports."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+
+    N, W, H = 24, 160, 120
+    env = BatchedDuckietownEnv(N, "udem1", camera_width=W, camera_height=H, domain_rand=True, seed=40,
+                               device_reset=True, auto_reset=True)
+    env.reset()
+    obs = env.reset()          # second episode: stale modelview
+    torch.cuda.synchronize()
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    assert (st["episode"] == 2).all()
+    sc = orc.OracleScene(maps.load_map("udem1"))
+    gpu = obs.cpu().numpy()
+    cpu = []
+    lights = []
+    for k in range(N):
+        r = env.sim.debug_episode(k)
+        ep = orc.default_episode(cam_height=float(r["cam_height"]), cam_angle_deg=float(r["cam_angle_deg"]),
+                                 cam_fov_y_deg=float(r["cam_fov_y_deg"]), cam_noise=r["cam_noise"], horizon=r["horizon"],
+                                 ambient=r["ambient"], diffuse=r["diffuse"], light_eye=r["light_eye"], ground=r["ground"],
+                                 hidden=[int(v) for v in r["hidden"]])
+        lights.append(r["light_eye"].copy())
+        cpu.append(sc.render(st["pos_x"][k], st["pos_z"][k], st["angle"][k], ep, W, H, True))
+    lights = np.array(lights)
+    assert (lights[:, 3] == 0).all() and np.abs(lights[:, :3]).max() > 100   # directional DR light, rotated into eye space
+    assert np.abs(lights[:, 1] - np.clip(lights[:, 1], 170, 220)).max() > 1   # ... i.e. no longer the raw world-space draw
+    compare(gpu, np.stack(cpu), "stale_light")
+    env.close()
+
+
+def test_full_resolution_frame_vs_oracle(torch_cuda):
+    """640x480 (the reference's default camera), no distortion: many coarse bins, long far-field lists."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+    N, W, H = 6, 640, 480
+    env = BatchedDuckietownEnv(N, "udem1", camera_width=W, camera_height=H, domain_rand=False, seed=9)
+    obs = env.reset()
+    torch.cuda.synchronize()
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    sc = orc.OracleScene(maps.load_map("udem1"))
+    cpu = np.stack([sc.render(st["pos_x"][k], st["pos_z"][k], st["angle"][k], None, W, H, False) for k in range(N)])
+    compare(obs.cpu().numpy(), cpu, "full_res")
+    env.close()
