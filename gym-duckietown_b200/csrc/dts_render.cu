@@ -89,6 +89,7 @@ struct __align__(16) GeoWarp {    // per warp of k_geometry, shared memory
   double V[12];
   float P00, P11, P22, P23;
   Vtx corners[4];
+  Vtx poly[2][12];               // ping-pong polygon of the warp-parallel clipper
 };
 using Shared = GeoWarp;           // shade_vertex reads ep and P from it
 
@@ -263,43 +264,84 @@ __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float di
   return o;
 }
 
-// rare path: Sutherland-Hodgman against near, far and the guard band (spec step 4), then fan
-__device__ __noinline__ void clip_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                           int tex, int lat) {
-  Vtx poly[12], tmp[12];
-  float d[12];
-  poly[0] = a; poly[1] = b; poly[2] = c;
-  int n = 3;
+// Sutherland-Hodgman against near, far and the guard band (spec step 4), then a triangle fan — executed by the
+// WHOLE warp for one triangle: lane k owns polygon vertex k, neighbours' plane distances come by shuffle, output
+// slots by ballot prefix sums, so a plane costs a few dozen instructions instead of a serial loop over vertices.
+// Same arithmetic, same vertex order (hence the same fan) as the serial formulation of the spec.
+__device__ __forceinline__ void clip_and_emit_warp(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+                                                   int tex, int lat, int lane) {
   for (int p2 = 0; p2 < 6; p2++) {   // the spec's trivial reject looks at the ORIGINAL triangle, guard planes
-    int cnt = 0;
-    for (int k = 0; k < 3; k++) cnt += !(plane_dist(poly[k], p2) >= 0.0f);
+    const int cnt = !(plane_dist(a, p2) >= 0.0f) + !(plane_dist(b, p2) >= 0.0f) + !(plane_dist(c, p2) >= 0.0f);
     if (cnt == 3) return;
   }
+  GeoWarp& g = *ec.gw;
+  __syncwarp();
+  if (lane == 0) { g.poly[0][0] = a; g.poly[0][1] = b; g.poly[0][2] = c; }
+  __syncwarp();
+  int n = 3, cur = 0;
   for (int pl = 0; pl < 6; pl++) {
-    int any_out = 0;
-    for (int k = 0; k < n; k++) { d[k] = plane_dist(poly[k], pl); any_out |= !(d[k] >= 0.0f); }
-    if (!any_out) continue;
-    int m = 0;
-    for (int k = 0; k < n; k++) {
-      const int k2 = (k + 1 == n) ? 0 : k + 1;
-      const bool in1 = d[k] >= 0.0f, in2 = d[k2] >= 0.0f;
-      if (in1) tmp[m++] = poly[k];
-      if (in1 && !in2) tmp[m++] = clip_lerp(poly[k], poly[k2], d[k], d[k2]);
-      else if (!in1 && in2) tmp[m++] = clip_lerp(poly[k2], poly[k], d[k2], d[k]);
+    const Vtx* P = g.poly[cur];
+    const float dk = lane < n ? plane_dist(P[lane], pl) : 0.0f;
+    const bool in1 = dk >= 0.0f;
+    const unsigned valid = (1u << n) - 1u;
+    const unsigned out_mask = __ballot_sync(0xffffffffu, lane < n && !in1);
+    if (!out_mask) continue;
+    const int k2 = (lane + 1 == n) ? 0 : lane + 1;
+    const float dn = __shfl_sync(0xffffffffu, dk, k2 & 31);
+    const bool in2 = dn >= 0.0f;
+    const bool cross = lane < n && (in1 != in2);
+    const unsigned keep_mask = __ballot_sync(0xffffffffu, lane < n && in1) & valid;
+    const unsigned cross_mask = __ballot_sync(0xffffffffu, cross) & valid;
+    const unsigned below = (1u << lane) - 1u;
+    int pos = __popc(keep_mask & below) + __popc(cross_mask & below);
+    Vtx* T = g.poly[cur ^ 1];
+    if (lane < n) {
+      if (in1) T[pos++] = P[lane];
+      if (in1 && !in2) T[pos] = clip_lerp(P[lane], P[k2], dk, dn);
+      else if (!in1 && in2) T[pos] = clip_lerp(P[k2], P[lane], dn, dk);
     }
-    n = m;
-    for (int k = 0; k < n; k++) poly[k] = tmp[k];
+    n = __popc(keep_mask) + __popc(cross_mask);
+    cur ^= 1;
+    __syncwarp();
     if (n < 3) return;
   }
-  for (int k = 1; k + 1 < n; k++) setup_and_emit(ec, poly[0], poly[k], poly[k + 1], id, tex, lat);
+  const Vtx* P = g.poly[cur];
+  if (lane + 2 < n) setup_and_emit(ec, P[0], P[lane + 1], P[lane + 2], id, tex, lat);
+  __syncwarp();
 }
 
-__device__ __forceinline__ void process_triangle(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                                 int tex, int lat) {
+// one warp-uniform triangle (ground, analytic tile): classify once, lane 0 emits or the warp clips
+__device__ __forceinline__ void process_triangle_uniform(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c,
+                                                         int id, int tex, int lat, int lane) {
   const int cls = classify(a, b, c);
   if (cls == 2) return;
+  if (cls == 0) { if (lane == 0) setup_and_emit(ec, a, b, c, id, tex, lat); }
+  else clip_and_emit_warp(ec, a, b, c, id, tex, lat, lane);
+}
+
+// one triangle per lane (meshes, tessellated tiles): unclipped ones are emitted in place, the rare ones that
+// need clipping are broadcast lane by lane to the warp-parallel clipper
+__device__ __forceinline__ void process_triangle_lanes(const EmitCtx& ec, bool have, const Vtx& a, const Vtx& b,
+                                                       const Vtx& c, int id, int tex, int lat, int lane) {
+  const int cls = have ? classify(a, b, c) : 2;
   if (cls == 0) setup_and_emit(ec, a, b, c, id, tex, lat);
-  else clip_and_emit(ec, a, b, c, id, tex, lat);
+  unsigned need = __ballot_sync(0xffffffffu, cls == 1);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    Vtx va, vb, vc;
+    const float* fa = reinterpret_cast<const float*>(&a);
+    const float* fb = reinterpret_cast<const float*>(&b);
+    const float* fc = reinterpret_cast<const float*>(&c);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      reinterpret_cast<float*>(&va)[k] = __shfl_sync(0xffffffffu, fa[k], src);
+      reinterpret_cast<float*>(&vb)[k] = __shfl_sync(0xffffffffu, fb[k], src);
+      reinterpret_cast<float*>(&vc)[k] = __shfl_sync(0xffffffffu, fc[k], src);
+    }
+    const int sid = __shfl_sync(0xffffffffu, id, src), stex = __shfl_sync(0xffffffffu, tex, src);
+    clip_and_emit_warp(ec, va, vb, vc, sid, stex, lat, lane);
+  }
 }
 
 // conservative triangle / bin overlap: false only if one edge has the whole bin on its outside
@@ -495,17 +537,17 @@ __global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg r
 }
 
 // ------------------------------------------------------------------------------------------------ k_geometry
-#ifndef DTS_GEO_MIN_CTAS
-#define DTS_GEO_MIN_CTAS 3
-#endif
-__global__ void __launch_bounds__(kThreads, DTS_GEO_MIN_CTAS)
+// Small CTAs (2 warps) so that a slot is not held by one long warp (a clipped ground quad) while its siblings
+// (culled tiles) have long exited; warps are numbered item-major so neighbouring warps run the same code path.
+constexpr int kGeoWarps = 2;
+__global__ void __launch_bounds__(kGeoWarps * 32, 12)
 k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
            int max_lat, int32_t* __restrict__ err) {
-  __shared__ GeoWarp gws[kWarps];
+  __shared__ GeoWarp gws[kGeoWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long gw_id = (long long)blockIdx.x * kWarps + wib;
-  const int env = (int)(gw_id / items_max), item = (int)(gw_id % items_max);
-  if (env >= rc.n_envs) return;
+  const long long gw_id = (long long)blockIdx.x * kGeoWarps + wib;
+  const int item = (int)(gw_id / rc.n_envs), env = (int)(gw_id - (long long)item * rc.n_envs);
+  if (item >= items_max) return;
   const DMap& m = maps[S.map_id[env]];
   const int n_tiles = m.grid_w * m.grid_h;
   if (item >= 1 + n_tiles + m.n_objects) return;
@@ -523,17 +565,16 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   Xform x;
   if (item == 0) {
     // ground quad S:1805-1812: glScalef(50,0.01,50) applied to (+-1,-0.8,+-1), world-space +y normal
-    if (lane < 2) {
-      model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x);
-      const float gy = (float)(-0.8 * 0.01);
-      const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
-      const int i1 = lane == 0 ? 1 : 2, i2 = lane == 0 ? 2 : 3;
-      const float* g = sh.ep.ground;
-      const Vtx a = shade_vertex(x, sh, P[0][0], P[0][1], P[0][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-      const Vtx b = shade_vertex(x, sh, P[i1][0], P[i1][1], P[i1][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-      const Vtx c = shade_vertex(x, sh, P[i2][0], P[i2][1], P[i2][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
-      process_triangle(ec, a, b, c, lane, -1, -1);
-    }
+    model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x);
+    const float gy = (float)(-0.8 * 0.01);
+    const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
+    const float* g = sh.ep.ground;
+    const int pl_ = lane & 3;   // lanes 0..3 light the four corners, the two triangles (0,1,2)(0,2,3) are then warp-uniform
+    const Vtx mine = shade_vertex(x, sh, P[pl_][0], P[pl_][1], P[pl_][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
+    if (lane < 4) sh.corners[lane] = mine;
+    __syncwarp();
+    process_triangle_uniform(ec, sh.corners[0], sh.corners[1], sh.corners[2], 0, -1, -1, lane);
+    process_triangle_uniform(ec, sh.corners[0], sh.corners[2], sh.corners[3], 1, -1, -1, lane);
   } else if (item <= n_tiles) {
     // road tile S:1852-1884: draw order i outer, j inner
     const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
@@ -595,19 +636,15 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
         if (corner >= 0) { Vtx c = lv[h]; c.r = 0.f; c.g = 0.f; c.b = 0.f; sh.corners[corner] = c; }
       }
       __syncwarp();
-      if (lane < 2) {
-        const Vtx& c0 = sh.corners[0];
-        const Vtx& c1 = sh.corners[lane == 0 ? 1 : 2];
-        const Vtx& c2 = sh.corners[lane == 0 ? 2 : 3];
-        process_triangle(ec, c0, c1, c2, base_id + lane, tex, slot);
-      }
+      process_triangle_uniform(ec, sh.corners[0], sh.corners[1], sh.corners[2], base_id, tex, slot, lane);
+      process_triangle_uniform(ec, sh.corners[0], sh.corners[2], sh.corners[3], base_id + 1, tex, slot, lane);
       } else {
       // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
       for (int k0 = 0; k0 < 98; k0 += 32) {
         const int k = k0 + lane;
+        Vtx v[3];
         if (k < 98) {
           const int quad = k >> 1, half = k & 1, a = quad / 7, b = quad - 7 * a;
-          Vtx v[3];
 #pragma unroll
           for (int j = 0; j < 3; j++) {
             const int aa = j == 0 ? a : (j == 1 ? a + 1 : (half == 0 ? a + 1 : a));
@@ -616,8 +653,8 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
             v[j] = shade_vertex(x, sh, lx, 0.0f, lz, 0.f, 1.f, 0.f, 1.f, 1.f, 1.f, (float)((double)aa / 7.0),
                                 (float)(1.0 - (double)bb / 7.0));
           }
-          process_triangle(ec, v[0], v[1], v[2], base_id + k, tex, -1);
         }
+        process_triangle_lanes(ec, k < 98, v[0], v[1], v[2], base_id + k, tex, -1, lane);
           }
     }
   } else {
@@ -645,19 +682,21 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
     for (int k0 = 0; k0 < ob.tri_count; k0 += 32) {
       const int k = k0 + lane;
+      Vtx v[3];
+      int ttex = -1;
       if (k < ob.tri_count) {
         const size_t ti = (size_t)ob.tri_offset + k;
         const float* p = m.tri_pos + ti * 9;
         const float* n = m.tri_nrm + ti * 9;
         const float* uv = m.tri_uv + ti * 6;
         const float* c = m.tri_col + ti * 9;
-        Vtx v[3];
 #pragma unroll
         for (int j = 0; j < 3; j++)
           v[j] = shade_vertex(x, sh, p[3 * j], p[3 * j + 1], p[3 * j + 2], n[3 * j], n[3 * j + 1], n[3 * j + 2],
                               c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
-        process_triangle(ec, v[0], v[1], v[2], base_id + k, m.tri_tex[ti], -1);
+        ttex = m.tri_tex[ti];
       }
+      process_triangle_lanes(ec, k < ob.tri_count, v[0], v[1], v[2], base_id + k, ttex, -1, lane);
       }
   }
   if (lane == 0 && ctx.overflow) atomicOr(err, 1);
@@ -905,7 +944,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_
   cudaMemsetAsync(fm.work, 0, 256, st);
   k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
   const long long warps = (long long)rc.n_envs * items_max;
-  k_geometry<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(S, maps, rc, fm, items_max, max_prims,
+  k_geometry<<<(unsigned)((warps + kGeoWarps - 1) / kGeoWarps), kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims,
                                                                               max_lat, err_flag);
   k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, (size_t)kBinWarps * 2 * cbins * sizeof(int), st>>>(
       rc, fm, max_prims, max_pairs, err_flag);
