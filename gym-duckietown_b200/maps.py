@@ -134,6 +134,39 @@ class MapObject:
 
 
 @dataclass
+class DynObject:
+    """A `static: false` prop: DuckieObj pedestrian (objects.py:339-432) or DuckiebotObj lane follower
+    (objects.py:180-336).  Parameters are the reference's non-randomized defaults; under domain_rand the
+    reference draws them from the GLOBAL numpy RNG (unseeded), so callers may override."""
+    kind: int                 # 1 duckie, 2 duckiebot
+    object_index: int         # entry of MapData.objects (mesh, scale, initial pose)
+    pos: np.ndarray
+    angle: float
+    corners: np.ndarray       # [4,2] generate_corners of the mesh footprint (C:64-79)
+    axes: np.ndarray          # [2,2] generate_norm at load; the duckiebot never refreshes it (O:60-63, O:306-336)
+    safety_radius: float
+    # DuckieObj (O:339-366)
+    walk_distance: float = 0.0
+    vel: float = 0.02
+    wait_time: float = 8.0
+    wiggle: float = math.pi / 15
+    # DuckiebotObj (O:183-227)
+    follow_dist: float = 0.3
+    velocity: float = 0.1
+    gain: float = 2.0
+    trim: float = 0.0
+    radius: float = 0.0318
+    k: float = 27.0
+    limit: float = 1.0
+    wheel_dist: float = 0.102
+    robot_width: float = 0.13 + 0.02
+    robot_length: float = 0.18
+
+
+DYN_DUCKIE, DYN_DUCKIEBOT = 1, 2
+
+
+@dataclass
 class MapData:
     name: str
     tile_size: float
@@ -154,6 +187,7 @@ class MapData:
     start_tile: Optional[tuple] = None
     start_pose: Optional[list] = None
     meshes: List["assets.Mesh"] = field(default_factory=list)
+    dyn_objects: List[DynObject] = field(default_factory=list)
 
     @property
     def n_coll(self) -> int:
@@ -262,8 +296,8 @@ def _load_objects(md: MapData, map_data: dict) -> None:
         else:
             scale = desc.get("scale", 1.0)
         static = desc.get("static", True)
-        if not static:
-            raise InvalidMapException("dynamic objects are out of scope (SURVEY 8f-2)")
+        if not static and kind not in ("duckie", "duckiebot"):
+            raise InvalidMapException(f"Object kind unknown: dynamic {kind!r}")  # S:1013-1015
         corners = obb_corners(pos, mesh.min_coords, mesh.max_coords, angle, scale)
         axes = obb_axes(corners)
         ext = np.max([abs(mesh.min_coords), abs(mesh.max_coords)], axis=0)  # C:218
@@ -271,8 +305,13 @@ def _load_objects(md: MapData, map_data: dict) -> None:
         collidable = static and kind != "trafficlight"  # S:1027-1030
         md.objects.append(MapObject(
             kind=kind, mesh_id=mesh_ids[mesh_key], pos=pos, angle=angle, scale=float(scale),
-            optional=bool(desc.get("optional", False)), static=True, collidable=collidable,
+            optional=bool(desc.get("optional", False)), static=bool(static), collidable=collidable,
             corners=corners, axes=axes, safety_radius=radius, max_coords=mesh.max_coords))
+        if not static:
+            md.dyn_objects.append(DynObject(
+                kind=DYN_DUCKIE if kind == "duckie" else DYN_DUCKIEBOT, object_index=len(md.objects) - 1, pos=pos.copy(),
+                angle=angle, corners=corners.copy(), axes=axes.copy(), safety_radius=float(radius),
+                walk_distance=md.tile_size))   # DuckieObj(..., self.road_tile_size) S:1010
         if collidable:
             corners_l.append(corners.T)
             norms_l.append(axes)

@@ -66,6 +66,22 @@ typedef struct { /* mirrors the product's per-episode render record */
   uint32_t hidden[8];
 } orr_episode;
 
+typedef struct {   /* one dynamic obstacle (objects.py DuckieObj / DuckiebotObj) */
+  int32_t kind;      /* 1 duckie pedestrian, 2 duckiebot follower */
+  int32_t active;    /* DuckieObj.pedestrian_active */
+  double pos[3], angle, y_rot;
+  double corners[4][2];
+  double norm[4];    /* obj_norm rows */
+  double safety_radius;
+  double walk_distance, vel, wait_time, wiggle, time, start[3], heading[3];
+  double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length;
+} orc_dyn;
+
+int orc_closest_curve_point(const orc_map* m, double px, double pz, double angle, double pnt[3], double tan3[3]);
+void orc_agent_corners(double px, double pz, double angle, double cx[4], double cz[4]);
+void orc_dyn_step_all(const orc_map* m, orc_dyn* objs, int n, double dt);
+int orc_dyn_collision(const orc_dyn* objs, int n, double px, double pz, double angle);
+double orc_dyn_proximity(const orc_dyn* objs, int n, double px, double pz, double angle);
 void orc_action_map(double vel, double steer, double wheel_dist, double gain, double trim, double radius, double k,
                     double limit, double out_lr[2]);
 void orc_dyn_step(orc_dyn_state* s, const orc_dyn_params* p, const double cmd_lr[2], double dt);

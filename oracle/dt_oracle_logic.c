@@ -207,9 +207,9 @@ static void bez_point(const double* cp, double t, double out[3]) {  /* G:286-297
   }
 }
 
-/* closest_curve_point S:1337-1369 + get_lane_pos2 S:1371-1409. Returns 0 if not in a lane. */
-int orc_lane_pos(const orc_map* m, double px, double pz, double angle, double* dist, double* dot_dir,
-                 double* angle_rad) {
+/* closest_curve_point S:1337-1369: point on the best-aligned lane curve of the tile under (px,pz) and the
+ * unit tangent there.  Returns 0 when there is no drivable tile. */
+int orc_closest_curve_point(const orc_map* m, double px, double pz, double angle, double pnt[3], double tan3[3]) {
   int idx = tile_index(m, px, pz, 0, 0);
   if (idx < 0 || !m->tile_drivable[idx]) return 0;
   const double* cv = m->curves + (size_t)m->tile_curve_off[idx] * 12;
@@ -237,7 +237,7 @@ int orc_lane_pos(const orc_map* m, double px, double pz, double angle, double* d
     double dtp = sqrt((pt[0] - px) * (pt[0] - px) + pt[1] * pt[1] + (pt[2] - pz) * (pt[2] - pz));
     if (db < dtp) tt = mid; else tb = mid;
   }
-  double t = (tb + tt) * 0.5, pnt[3], tan3[3];
+  double t = (tb + tt) * 0.5;
   bez_point(cp, t, pnt);
   /* bezier_tangent G:300-313 */
   for (int k = 0; k < 3; k++) {
@@ -248,6 +248,15 @@ int orc_lane_pos(const orc_map* m, double px, double pz, double angle, double* d
   }
   double nrm = sqrt(tan3[0] * tan3[0] + tan3[1] * tan3[1] + tan3[2] * tan3[2]);
   for (int k = 0; k < 3; k++) tan3[k] /= nrm;
+  return 1;
+}
+
+/* get_lane_pos2 S:1371-1409. Returns 0 if not in a lane. */
+int orc_lane_pos(const orc_map* m, double px, double pz, double angle, double* dist, double* dot_dir,
+                 double* angle_rad) {
+  double pnt[3], tan3[3];
+  if (!orc_closest_curve_point(m, px, pz, angle, pnt, tan3)) return 0;
+  double dirx = cos(angle), dirz = -sin(angle);
   double dd = dirx * tan3[0] + dirz * tan3[2];
   if (dd > 1.0) dd = 1.0;
   if (dd < -1.0) dd = -1.0;

@@ -220,6 +220,48 @@ def gen_fisheye():
     print("fisheye: holes-free LUT", np.isnan(rx).sum() == 0, "out mean", out.mean())
 
 
+def gen_dynamic(name: str, steps=900, seed=21):
+    """Dynamic obstacles: DuckieObj / DuckiebotObj stepped by the reference's own code
+    (objects.py:180-432, update loop simulator.py:1570-1584), plus agent collision / proximity queries against
+    them.  domain_rand=False, so the only global-RNG draw is DuckieObj.wiggle (recorded as an input)."""
+    raw = raw_map(name)
+    md = maps.load_map(name)
+    np.random.seed(seed)   # objects.py draws from the GLOBAL numpy RNG (SURVEY app. B-10)
+    sim = refstub.build_reference_sim(raw, extents_for(raw))
+    S, C, G, O = refstub.modules()
+    dyn = [o for o in sim.objects if not o.static]
+    rec = {k: [] for k in ("pos", "angle", "y_rot", "corners", "active")}
+    rng = np.random.default_rng(seed)
+    q_pose, q_coll, q_prox, q_step = [], [], [], []
+    wiggle = np.array([float(np.ravel(getattr(o, "wiggle", 0.0))[0]) for o in dyn])
+    for t in range(steps):
+        for obj in sim.objects:   # S:1570-1584
+            if obj.kind == "duckiebot":
+                if not obj.static:
+                    obj.step_duckiebot(sim.delta_time, sim.closest_curve_point, [])
+            else:
+                obj.step(sim.delta_time)
+        rec["pos"].append([np.array(o.pos, float) for o in dyn])
+        rec["angle"].append([float(o.angle) for o in dyn])
+        rec["y_rot"].append([float(o.y_rot) for o in dyn])
+        rec["corners"].append([np.array(o.obj_corners, float) for o in dyn])
+        rec["active"].append([bool(getattr(o, "pedestrian_active", False)) for o in dyn])
+        if t % 5 == 0:   # probe agent poses around a dynamic object
+            o = dyn[rng.integers(len(dyn))]
+            r, a = rng.uniform(0, 0.3), rng.uniform(0, 2 * np.pi)
+            pos = np.array([o.pos[0] + r * np.cos(a), 0.0, o.pos[2] + r * np.sin(a)])
+            ang = rng.uniform(-np.pi, np.pi)
+            q_pose.append((pos[0], pos[2], ang)); q_step.append(t)
+            q_coll.append(sim._collision(S.get_agent_corners(pos, ang)))
+            q_prox.append(sim.proximity_penalty2(pos, ang))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(wiggle=wiggle, q_pose=np.array(q_pose), q_step=np.array(q_step), q_coll=np.array(q_coll), q_prox=np.array(q_prox),
+               dyn_index=np.array([sim.objects.index(o) for o in dyn]))
+    np.savez_compressed(os.path.join(OUT, f"dynamic_{name}.npz"), **out)
+    print(f"dynamic_{name}: {len(dyn)} dynamic objects x {steps} steps, collisions {np.mean(q_coll):.2f}, "
+          f"active {out['active'].mean():.2f}")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for m in MAPS:
@@ -228,3 +270,5 @@ if __name__ == "__main__":
     for m in ("small_loop", "loop_obstacles", "udem1"):
         gen_reset(m)
     gen_fisheye()
+    for m in ("loop_pedestrians", "loop_dyn_duckiebots"):
+        gen_dynamic(m)

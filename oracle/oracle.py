@@ -6,6 +6,7 @@ this module.  The product package never does.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 import sys
@@ -14,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liborc.so")
-SOURCES = ["dt_oracle_logic.c", "dt_oracle_raster.c", "dt_oracle_batch.c"]
+SOURCES = ["dt_oracle_logic.c", "dt_oracle_raster.c", "dt_oracle_batch.c", "dt_oracle_dynamic.c"]
 
 
 def build(force: bool = False) -> str:
@@ -38,6 +39,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.orc_proximity.restype = C.c_double
+        _lib.orc_dyn_proximity.restype = C.c_double
     return _lib
 
 
@@ -258,3 +260,49 @@ class OracleBatch:
                                   self.max_steps, C.c_double(1.2), self.eps, self.W, self.H, int(render), _p(self.obs),
                                   _p(self.reward), _p(self.done), self.threads)
         return self.obs, self.reward, self.done
+
+
+class OrcDyn(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("active", C.c_int32), ("pos", C.c_double * 3), ("angle", C.c_double),
+                ("y_rot", C.c_double), ("corners", (C.c_double * 2) * 4), ("norm", C.c_double * 4),
+                ("safety_radius", C.c_double), ("walk_distance", C.c_double), ("vel", C.c_double),
+                ("wait_time", C.c_double), ("wiggle", C.c_double), ("time", C.c_double), ("start", C.c_double * 3),
+                ("heading", C.c_double * 3)] + [(n, C.c_double) for n in (
+                    "follow_dist", "velocity", "gain", "trim", "radius", "k", "limit", "wheel_dist", "robot_width",
+                    "robot_length")]
+
+
+class OracleDynamics:
+    """The dynamic obstacles of one env (MapData.dyn_objects), stepped by the C oracle."""
+
+    def __init__(self, omap: OracleMap, wiggle=None):
+        md = omap.md
+        self.m, self.n = omap, len(md.dyn_objects)
+        self.objs = (OrcDyn * max(1, self.n))()
+        for i, d in enumerate(md.dyn_objects):
+            o = self.objs[i]
+            o.kind, o.active = d.kind, 0
+            for k in range(3):
+                o.pos[k] = float(d.pos[k]); o.start[k] = float(d.pos[k])
+            o.angle = d.angle
+            o.y_rot = float(np.rad2deg(d.angle))                       # O:57
+            for k in range(4):
+                o.corners[k][0], o.corners[k][1] = float(d.corners[k][0]), float(d.corners[k][1])
+            for k in range(4):
+                o.norm[k] = float(np.ravel(d.axes)[k])
+            o.safety_radius, o.walk_distance, o.vel, o.wait_time = d.safety_radius, d.walk_distance, d.vel, d.wait_time
+            o.wiggle = d.wiggle if wiggle is None else float(wiggle[i])
+            o.time = 0.0
+            o.heading[0], o.heading[1], o.heading[2] = math.cos(d.angle), 0.0, -math.sin(d.angle)   # heading_vec C:222
+            (o.follow_dist, o.velocity, o.gain, o.trim, o.radius, o.k, o.limit, o.wheel_dist, o.robot_width,
+             o.robot_length) = (d.follow_dist, d.velocity, d.gain, d.trim, d.radius, d.k, d.limit, d.wheel_dist,
+                                d.robot_width, d.robot_length)
+
+    def step(self, dt=1.0 / 30):
+        lib().orc_dyn_step_all(C.byref(self.m.c), self.objs, self.n, C.c_double(dt))
+
+    def collision(self, px, pz, angle) -> bool:
+        return bool(lib().orc_dyn_collision(self.objs, self.n, C.c_double(px), C.c_double(pz), C.c_double(angle)))
+
+    def proximity(self, px, pz, angle) -> float:
+        return float(lib().orc_dyn_proximity(self.objs, self.n, C.c_double(px), C.c_double(pz), C.c_double(angle)))

@@ -305,7 +305,8 @@ def build_reference_sim(map_data: dict, mesh_extents: dict, *, domain_rand=False
 
     _get_transform.grid_height = len(map_data["tiles"])
     with mock.patch.object(S, "get_mesh", fake_get_mesh), \
-            mock.patch.object(S, "get_duckiebot_mesh", lambda color: FakeMesh([0, 0, 0], [1, 1, 1])):
+            mock.patch.object(S, "get_duckiebot_mesh",
+                              lambda color: FakeMesh(*mesh_extents.get("duckiebot", ([0, 0, 0], [1, 1, 1])))):
         sim._interpret_map(map_data)
     # reset() needs these no-op GL-side collaborators (simulator.py:634-656, 760)
     sim.render_obs = lambda segment=False: np.zeros((sim.camera_height, sim.camera_width, 3), np.uint8)
