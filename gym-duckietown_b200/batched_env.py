@@ -32,8 +32,8 @@ class BatchedDuckietownEnv:
             raise L.DtsError("BatchedDuckietownEnv needs a CUDA device; there is no CPU implementation")
         if camera_rand:
             raise NotImplementedError("camera_rand needs carnivalmirror (distortion.py:58-83); out of scope")
-        names = [map_name] if isinstance(map_name, str) else list(map_name)
-        self.maps: List[MapData] = [load_map(n) for n in names]
+        names = [map_name] if isinstance(map_name, (str, MapData)) else list(map_name)
+        self.maps: List[MapData] = [n if isinstance(n, MapData) else load_map(n) for n in names]   # parsed maps pass through
         self.num_envs, self.device_index = num_envs, device
         self.device = torch.device("cuda", device)
         self.camera_width, self.camera_height = camera_width, camera_height
@@ -115,7 +115,7 @@ class BatchedDuckietownEnv:
 
     def _query_for(self, envs):
         def query(k, x, z, a, safety, hidden):
-            return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden)
+            return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden, dyn_env=int(envs[k]))
         return query
 
     def step(self, actions: torch.Tensor, render: bool = True, out=None):

@@ -156,6 +156,7 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   if (!b || map_id < 0 || map_id >= sim->cfg.max_maps) return sim->fail("bad map_id %d", map_id);
   if (b->n_objects > DTS_MAX_OBJECTS) return sim->fail("map has %d objects, limit %d", b->n_objects, DTS_MAX_OBJECTS);
   if (b->grid_w <= 0 || b->grid_h <= 0 || !(b->tile_size > 0)) return sim->fail("invalid tile grid");
+  if (b->n_dyn < 0 || b->n_dyn > DTS_MAX_DYN) return sim->fail("map has %d dynamic obstacles, limit %d", b->n_dyn, DTS_MAX_DYN);
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   DTS_CUDA(cudaDeviceSynchronize());
   auto& own = sim->map_allocs[map_id];
@@ -192,7 +193,9 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
     if (s.mesh_id < 0 || s.mesh_id >= b->n_meshes) return sim->fail("object %d: bad mesh_id", o);
     const dts_mesh& me = b->meshes[s.mesh_id];
     DObject& d = objs[o];
-    memcpy(d.pos, s.pos, sizeof d.pos);
+    for (int k = 0; k < 3; k++) { d.pos[k] = (float)s.pos[k]; d.dpos[k] = s.pos[k]; }   // glTranslatef takes floats
+    d.dyn_slot = s.dyn_slot;
+    if (s.dyn_slot >= b->n_dyn) return sim->fail("object %d: dyn_slot %d out of range", o, s.dyn_slot);
     d.scale = s.scale; d.y_rot_deg = s.y_rot_deg; d.mesh_id = s.mesh_id; d.optional = s.optional;
     d.tri_offset = me.tri_offset; d.tri_count = me.tri_count;
     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
@@ -227,6 +230,37 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   }
   m.n_textures = b->n_textures;
   bad |= sim->upload(&m.textures, tex.data(), tex.size(), &own);
+  // dynamic obstacles: constants + every env's copy of the load-time state ([field][slot][env])
+  m.n_dyn = b->n_dyn;
+  {
+    const size_t N = sim->cfg.num_envs, D = b->n_dyn;
+    std::vector<DDyn> par(D);
+    std::vector<double> st((size_t)DTS_DYN_FIELDS * D * N);
+    for (size_t s = 0; s < D; s++) {
+      const dts_dyn_object& q = b->dyn[s];
+      if (q.kind != DTS_DYN_DUCKIE && q.kind != DTS_DYN_DUCKIEBOT) return sim->fail("dyn %zu: bad kind %d", s, q.kind);
+      if (q.object_index < 0 || q.object_index >= b->n_objects || b->objects[q.object_index].dyn_slot != (int)s)
+        return sim->fail("dyn %zu: object_index %d does not point back to this slot", s, q.object_index);
+      DDyn& p = par[s];
+      p.kind = q.kind; p.object_index = q.object_index; p.pos_y = q.pos[1];
+      for (int k = 0; k < 4; k++) p.norms[k] = q.norms[k / 2][k % 2];
+      p.safety_radius = q.safety_radius; p.walk_distance = q.walk_distance; p.wiggle = q.wiggle; p.angle0 = q.angle;
+      p.follow_dist = q.follow_dist; p.velocity = q.velocity; p.gain = q.gain; p.trim = q.trim; p.radius = q.radius;
+      p.k = q.k; p.limit = q.limit; p.wheel_dist = q.wheel_dist; p.robot_width = q.robot_width; p.robot_length = q.robot_length;
+      double f[DTS_DYN_FIELDS] = {};
+      f[DTS_DYN_PX] = q.pos[0]; f[DTS_DYN_PZ] = q.pos[2]; f[DTS_DYN_ANGLE] = q.angle;
+      f[DTS_DYN_YROT] = q.angle * (180.0 / 3.14159265358979323846);       // np.rad2deg O:57
+      for (int k = 0; k < 4; k++) { f[DTS_DYN_CORNERS + 2 * k] = q.corners[k][0]; f[DTS_DYN_CORNERS + 2 * k + 1] = q.corners[k][1]; }
+      f[DTS_DYN_START_X] = q.pos[0]; f[DTS_DYN_START_Z] = q.pos[2];
+      f[DTS_DYN_WAIT] = q.wait_time; f[DTS_DYN_VEL] = q.vel; f[DTS_DYN_TIME] = 0.0; f[DTS_DYN_ACTIVE] = 0.0;
+      for (int k = 0; k < DTS_DYN_FIELDS; k++)
+        for (size_t e = 0; e < N; e++) st[((size_t)k * D + s) * N + e] = f[k];
+    }
+    bad |= sim->upload(&m.dyn, par.data(), par.size(), &own);
+    const double* dst = nullptr;
+    bad |= sim->upload(&dst, st.data(), st.size(), &own);
+    m.dyn_state = const_cast<double*>(dst);
+  }
   if (bad) return 1;
   m.valid = 1;
   sim->h_maps[map_id] = m;
@@ -387,10 +421,11 @@ int dts_get_state(dts_sim* sim, dts_state_view* v) {
   return 0;
 }
 
-int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const uint32_t* hidden, double* out_f64,
-                    int32_t* out_i32) {
+int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* query, const uint32_t* hidden,
+                    double* out_f64, int32_t* out_i32) {
   if (!sim) return 1;
   if (map_id < 0 || map_id >= sim->cfg.max_maps || !sim->h_maps[map_id].valid) return sim->fail("bad map_id %d", map_id);
+  if (dyn_env >= sim->cfg.num_envs) return sim->fail("dyn_env %d out of range", dyn_env);
   if (n <= 0) return 0;
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   if (n > sim->q_cap) {
@@ -404,11 +439,19 @@ int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const 
   }
   DTS_CUDA(cudaMemcpy(sim->q_in, query, (size_t)n * 32, cudaMemcpyHostToDevice));
   if (hidden) DTS_CUDA(cudaMemcpy(sim->q_hidden, hidden, (size_t)n * 32, cudaMemcpyHostToDevice));
-  launch_query(sim->d_maps, map_id, n, sim->q_in, hidden ? sim->q_hidden : nullptr, sim->q_outd, sim->q_outi, 0);
+  launch_query(sim->d_maps, map_id, dyn_env < 0 ? -1 : dyn_env, sim->cfg.num_envs, n, sim->q_in, hidden ? sim->q_hidden : nullptr, sim->q_outd, sim->q_outi, 0);
   sim->launches++;
   DTS_CUDA(cudaGetLastError());
   DTS_CUDA(cudaMemcpy(out_f64, sim->q_outd, (size_t)n * 32, cudaMemcpyDeviceToHost));
   DTS_CUDA(cudaMemcpy(out_i32, sim->q_outi, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dts_get_dyn_state(dts_sim* sim, int map_id, double** state_dev, int32_t* n_dyn) {
+  if (!sim) return 1;
+  if (map_id < 0 || map_id >= sim->cfg.max_maps || !sim->h_maps[map_id].valid) return sim->fail("bad map_id %d", map_id);
+  if (state_dev) *state_dev = sim->h_maps[map_id].n_dyn ? sim->h_maps[map_id].dyn_state : nullptr;
+  if (n_dyn) *n_dyn = sim->h_maps[map_id].n_dyn;
   return 0;
 }
 

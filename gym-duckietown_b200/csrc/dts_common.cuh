@@ -20,6 +20,18 @@ struct DObject {
   int32_t tri_offset, tri_count;
   float bound_rad;   // object-space bounding radius (culling)
   float centre[3];   // object-space bounding-sphere centre
+  int32_t dyn_slot;  // -1 static; else slot of the per-env dynamic state that supplies pos / y_rot
+  double dpos[3];    // float64 position (x.pos in _inconvenient_spawn S:1466)
+};
+
+// A dynamic obstacle's constants (dts_dyn_object); its evolving state lives in DMap::dyn_state.
+struct DDyn {
+  int32_t kind, object_index;
+  double pos_y;
+  double norms[4];
+  double safety_radius;
+  double walk_distance, wiggle, angle0;   // duckie: heading = heading_vec(angle at load) never changes (O:357)
+  double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length;
 };
 
 struct DTexture { const uint8_t* rgba; int32_t w, h; };
@@ -53,8 +65,24 @@ struct DMap {
   const int16_t* tri_tex;
   int32_t n_textures;
   const DTexture* textures;
+  int32_t n_dyn;
+  const DDyn* dyn;              // [n_dyn]
+  double* dyn_state;            // [DTS_DYN_FIELDS][n_dyn][num_envs]: mutable, per env, survives resets
   int32_t valid;
 };
+
+// One env's view of its map's dynamic obstacles.
+struct DynRef {
+  const DDyn* par;
+  double* st;
+  int32_t n_dyn, n_envs, e;
+  __device__ __forceinline__ double& f(int field, int slot) const {
+    return st[((size_t)field * n_dyn + slot) * n_envs + e];
+  }
+};
+__device__ __forceinline__ DynRef dyn_ref(const DMap& m, int n_envs, int e) {
+  return DynRef{m.dyn, m.dyn_state, e >= 0 ? m.n_dyn : 0, n_envs, e};
+}
 
 // ------------------------------------------------------------------ per-env state, SoA in HBM
 // One thread per env in the logic kernels: consecutive threads touch consecutive doubles.

@@ -28,8 +28,8 @@ void launch_reset_random(const DState& S, const DMap* maps, const StepCfg& c, in
                          cudaStream_t st);
 void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, const uint8_t* mask,
                          const ResetStaging& p, cudaStream_t st);
-void launch_query(const DMap* maps, int map_id, int n, const double* q, const uint32_t* hidden, double* outd,
-                  int32_t* outi, cudaStream_t st);
+void launch_query(const DMap* maps, int map_id, int dyn_env, int n_envs, int n, const double* q, const uint32_t* hidden,
+                  double* outd, int32_t* outi, cudaStream_t st);
 
 // render (dts_render.cu)
 int render_ctas_per_sm();

@@ -23,10 +23,11 @@ __device__ inline void evaluate_pose(const DState& S, const DMap& m, const StepC
                                      double ang, int step_count, float* reward, uint8_t* done) {
   int ti, tj;
   tile_at(m, px, pz, ti, tj);
+  const DynRef dyn = dyn_ref(m, S.n, e);
   const LanePose lp = lane_pose(m, px, pz, ang);
-  const double pen = proximity_penalty(m, px, pz, ang);
+  const double pen = proximity_penalty(m, px, pz, ang) + dynamic_proximity(dyn, px, pz, ang);   // S:1454-1457
   bool hit;
-  const bool ok = valid_pose(m, px, pz, ang, 1.0, &hit);
+  const bool ok = valid_pose(m, dyn, px, pz, ang, 1.0, &hit);
   double rew;
   uint8_t code;
   if (!ok) { rew = kRewardInvalidPose; code = DTS_INVALID_POSE; }
@@ -42,6 +43,19 @@ __device__ inline void evaluate_pose(const DState& S, const DMap& m, const StepC
   if (done) done[e] = code != DTS_IN_PROGRESS;
 }
 
+__device__ __forceinline__ void load_stream(const DState& S, int e, NpStream& rs) {
+  const int n = S.n;
+  rs.state = ((unsigned __int128)S.rng[0 * n + e] << 64) | S.rng[1 * n + e];
+  rs.inc = ((unsigned __int128)S.rng[2 * n + e] << 64) | S.rng[3 * n + e];
+  rs.has32 = (uint32_t)S.rng[4 * n + e];
+  rs.cache32 = (uint32_t)S.rng[5 * n + e];
+}
+__device__ __forceinline__ void store_stream(const DState& S, int e, const NpStream& rs) {
+  const int n = S.n;
+  S.rng[0 * n + e] = (uint64_t)(rs.state >> 64); S.rng[1 * n + e] = (uint64_t)rs.state;
+  S.rng[4 * n + e] = rs.has32; S.rng[5 * n + e] = rs.cache32;
+}
+
 __device__ inline void set_pose(const DState& S, const DMap& m, int e, double px, double pz, double ang) {
   S.pos_x[e] = px; S.pos_z[e] = pz; S.angle[e] = ang;
   S.cx[e] = px; S.cy[e] = m.grid_h * m.tile_size - pz; S.ctheta[e] = ang;   // cartesian_from_weird S:1629-1638
@@ -55,10 +69,7 @@ __device__ inline void set_pose(const DState& S, const DMap& m, int e, double px
 __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, int e) {
   const int n = S.n;
   NpStream rs;
-  rs.state = ((unsigned __int128)S.rng[0 * n + e] << 64) | S.rng[1 * n + e];
-  rs.inc = ((unsigned __int128)S.rng[2 * n + e] << 64) | S.rng[3 * n + e];
-  rs.has32 = (uint32_t)S.rng[4 * n + e];
-  rs.cache32 = (uint32_t)S.rng[5 * n + e];
+  load_stream(S, e, rs);
   const bool dr = (c.flags & DTS_FLAG_DOMAIN_RAND) != 0;
   RenderEp old = S.rep[e];
   double Vprev[12];
@@ -119,18 +130,12 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   if (m.start_i >= 0) { ti = m.start_i; tj = m.start_j; }
   else if (m.n_drivable > 0) { const int t = rs.integers(0, m.n_drivable); ti = m.drivable_ij[2 * t]; tj = m.drivable_ij[2 * t + 1]; }
   double px = 1.0, pz = 1.0, ang = 1.0;                                      // fallback S:735-736
+  const DynRef dyn = dyn_ref(m, n, e);
   for (int attempt = 0; attempt < kMaxSpawnAttempts && m.n_drivable > 0; attempt++) {
     const double x = rs.uniform((double)ti, (double)(ti + 1)) * m.tile_size, z = rs.uniform((double)tj, (double)(tj + 1)) * m.tile_size;
     const double a = rs.uniform(0.0, 2 * 3.141592653589793);
-    bool bad = false;                                                       // _inconvenient_spawn S:1461-1471
-    for (int o = 0; o < m.n_objects && !bad; o++) {
-      if (r.hidden[o >> 5] >> (o & 31) & 1u) continue;
-      const DObject& ob = m.objects[o];
-      const double dx = (double)ob.pos[0] - x, dy = (double)ob.pos[1], dz = (double)ob.pos[2] - z;
-      bad = sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad;
-    }
-    if (bad) continue;
-    if (!valid_pose(m, x, z, a, 1.3, nullptr)) continue;
+    if (inconvenient_spawn(m, dyn, r.hidden, x, z)) continue;
+    if (!valid_pose(m, dyn, x, z, a, 1.3, nullptr)) continue;
     const LanePose lp = lane_pose(m, x, z, a);
     if (!lp.in_lane) continue;
     const double deg = lp.angle_rad * 57.29577951308232;                    // np.rad2deg S:1406
@@ -140,8 +145,7 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   }
   set_pose(S, m, e, px, pz, ang);
   S.rep[e] = r;
-  S.rng[0 * n + e] = (uint64_t)(rs.state >> 64); S.rng[1 * n + e] = (uint64_t)rs.state;
-  S.rng[4 * n + e] = rs.has32; S.rng[5 * n + e] = rs.cache32;
+  store_stream(S, e, rs);
   S.episode[e] += 1;
 }
 
@@ -161,7 +165,11 @@ __global__ void __launch_bounds__(128) k_step_logic(DState S, const DMap* __rest
   int steps = S.step_count[e];
   const double trim = S.trim[e];
   const int D = c.dyn.delay_steps;
-  for (int f = 0; f < c.frame_skip; f++) {   // update_physics S:1551-1568
+  const DynRef dyn = dyn_ref(m, S.n, e);
+  NpStream rs;
+  const bool dyn_rand = dyn.n_dyn > 0 && (c.flags & DTS_FLAG_DOMAIN_RAND) && (S.rng[3 * S.n + e] & 1ull);  // seeded stream
+  if (dyn_rand) load_stream(S, e, rs);
+  for (int f = 0; f < c.frame_skip; f++) {   // update_physics S:1551-1584
     double l = ul, r = ur;
     if (D > 0) {  // delay line: the command issued now acts D steps later
       l = S.fifo[0 * S.n + e]; r = S.fifo[1 * S.n + e];
@@ -179,7 +187,9 @@ __global__ void __launch_bounds__(128) k_step_logic(DState S, const DMap* __rest
     ang = atan2(sn, cs);
     steps++;
     speed = sqrt((px - ppx) * (px - ppx) + (pz - ppz) * (pz - ppz)) / c.dt;
+    if (dyn.n_dyn > 0) dyn_step_all(m, dyn, c.dt, dyn_rand ? &rs : nullptr);   // S:1570-1584
   }
+  if (dyn_rand) store_stream(S, e, rs);
   S.cx[e] = x; S.cy[e] = y; S.ctheta[e] = th; S.vu[e] = u; S.vw[e] = w;
   S.pos_x[e] = px; S.pos_z[e] = pz; S.angle[e] = ang; S.speed[e] = speed; S.step_count[e] = steps;
   evaluate_pose(S, m, c, e, px, pz, ang, steps, reward, done);
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(128) k_reset_params(DState S, const DMap* __re
 
 // Batched pose predicates for host callers: _valid_pose / _collision / get_lane_pos2 /
 // proximity_penalty2 / _inconvenient_spawn of arbitrary poses (used by the host-side reset).
-__global__ void __launch_bounds__(128) k_query(const DMap* __restrict__ maps, int map_id, int n,
+__global__ void __launch_bounds__(128) k_query(const DMap* __restrict__ maps, int map_id, int dyn_env, int n_envs, int n,
                                                const double* __restrict__ q /*[n][4] x z angle safety*/,
                                                const uint32_t* __restrict__ hidden /*[n][8] or null*/,
                                                double* __restrict__ outd /*[n][4] dist dot angle prox*/,
@@ -242,23 +252,19 @@ __global__ void __launch_bounds__(128) k_query(const DMap* __restrict__ maps, in
   if (t >= n) return;
   const DMap& m = maps[map_id];
   const double x = q[4 * t], z = q[4 * t + 1], a = q[4 * t + 2], sf = q[4 * t + 3];
+  const DynRef dyn = dyn_ref(m, n_envs, dyn_env);
   bool hit2;
-  const bool ok = valid_pose(m, x, z, a, sf, &hit2);
+  const bool ok = valid_pose(m, dyn, x, z, a, sf, &hit2);
   double sn, cs;
   sincos(a, &sn, &cs);
-  const bool hit1 = agent_hits_static(m, x + kCentreOff * cs, z + kCentreOff * -sn, a);  // run_tests.py:50 usage
+  const bool hit1 = agent_hits_static(m, x + kCentreOff * cs, z + kCentreOff * -sn, a) ||   // run_tests.py:50 usage
+                    agent_hits_dynamic(dyn, x + kCentreOff * cs, z + kCentreOff * -sn, a);
   const LanePose lp = lane_pose(m, x, z, a);
-  bool bad = false;
-  for (int o = 0; o < m.n_objects && !bad; o++) {
-    if (hidden && (hidden[8 * t + (o >> 5)] >> (o & 31) & 1u)) continue;
-    const DObject& ob = m.objects[o];
-    const double dx = ob.pos[0] - x, dy = ob.pos[1], dz = ob.pos[2] - z;
-    bad = sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad;
-  }
+  const bool bad = inconvenient_spawn(m, dyn, hidden ? hidden + 8 * t : nullptr, x, z);
   int ti, tj;
   const int idx = tile_at(m, x, z, ti, tj);
   outd[4 * t] = lp.dist; outd[4 * t + 1] = lp.dot_dir; outd[4 * t + 2] = lp.angle_rad;
-  outd[4 * t + 3] = proximity_penalty(m, x, z, a);
+  outd[4 * t + 3] = proximity_penalty(m, x, z, a) + dynamic_proximity(dyn, x, z, a);
   outi[8 * t] = ok; outi[8 * t + 1] = hit1; outi[8 * t + 2] = hit2; outi[8 * t + 3] = lp.in_lane;
   outi[8 * t + 4] = bad; outi[8 * t + 5] = ti; outi[8 * t + 6] = tj;
   outi[8 * t + 7] = idx >= 0 && m.tile_drivable[idx];
@@ -277,9 +283,9 @@ void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, co
                          const ResetStaging& p, cudaStream_t st) {
   k_reset_params<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, c, mask, p);
 }
-void launch_query(const DMap* maps, int map_id, int n, const double* q, const uint32_t* hidden, double* outd,
-                  int32_t* outi, cudaStream_t st) {
-  k_query<<<(n + 127) / 128, 128, 0, st>>>(maps, map_id, n, q, hidden, outd, outi);
+void launch_query(const DMap* maps, int map_id, int dyn_env, int n_envs, int n, const double* q, const uint32_t* hidden,
+                  double* outd, int32_t* outi, cudaStream_t st) {
+  k_query<<<(n + 127) / 128, 128, 0, st>>>(maps, map_id, dyn_env, n_envs, n, q, hidden, outd, outi);
 }
 
 }  // namespace dts

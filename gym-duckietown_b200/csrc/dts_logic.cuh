@@ -100,9 +100,12 @@ __device__ inline bool agent_hits_static(const DMap& m, double bx, double bz, do
   return false;
 }
 
+__device__ inline bool agent_hits_dynamic(const DynRef& d, double bx, double bz, double angle);
+
 // _valid_pose S:1494-1534.  NB the collision box is built from the already-shifted centre and
 // get_agent_corners shifts it again (S:1502 + S:1521 -> S:2114): offset applied twice.
-__device__ inline bool valid_pose(const DMap& m, double px, double pz, double angle, double safety, bool* collided) {
+__device__ inline bool valid_pose(const DMap& m, const DynRef& d, double px, double pz, double angle, double safety,
+                                  bool* collided) {
   double sn, cs;
   sincos(angle, &sn, &cs);
   const double fx = cs, fz = -sn, rx = sn, rz = cs;
@@ -110,7 +113,8 @@ __device__ inline bool valid_pose(const DMap& m, double px, double pz, double an
   const double sw = safety * 0.5 * kRobotWidth, sl = safety * 0.5 * kRobotLength;
   const bool all_drivable = drivable_at(m, qx, qz) && drivable_at(m, qx - sw * rx, qz - sw * rz) &&
                             drivable_at(m, qx + sw * rx, qz + sw * rz) && drivable_at(m, qx + sl * fx, qz + sl * fz);
-  const bool hit = agent_hits_static(m, qx + kCentreOff * fx, qz + kCentreOff * fz, angle);
+  const bool hit = agent_hits_static(m, qx + kCentreOff * fx, qz + kCentreOff * fz, angle) ||
+                   agent_hits_dynamic(d, qx + kCentreOff * fx, qz + kCentreOff * fz, angle);   // S:1481-1489
   if (collided) *collided = hit;
   return !hit && all_drivable;
 }
@@ -144,14 +148,11 @@ __device__ __forceinline__ void bezier_at(const double* cp, double t, double& x,
   z = b0 * cp[2]; z += b1 * cp[5]; z += b2 * cp[8]; z += b3 * cp[11];
 }
 
-// closest_curve_point S:1337-1369 + get_lane_pos2 S:1371-1409
-__device__ inline LanePose lane_pose(const DMap& m, double px, double pz, double angle) {
-  LanePose r;
-  r.dist = r.dot_dir = r.angle_rad = __longlong_as_double(0x7ff8000000000000LL);
-  r.in_lane = false;
+// closest_curve_point S:1337-1369: point q and unit tangent t of the tile's best-aligned curve; false off-road.
+__device__ inline bool closest_curve_point(const DMap& m, double px, double pz, double angle, double q[3], double t3[3]) {
   int ti, tj;
   const int idx = tile_at(m, px, pz, ti, tj);
-  if (idx < 0 || !m.tile_drivable[idx]) return r;
+  if (idx < 0 || !m.tile_drivable[idx]) return false;
   const double* cv = m.curves + (size_t)m.tile_curve_off[idx] * 12;
   const int nc = m.tile_curve_cnt[idx];
   double sn, cs;
@@ -184,21 +185,191 @@ __device__ inline LanePose lane_pose(const DMap& m, double px, double pz, double
     if (dlo < dhi) hi = mid; else lo = mid;
   }
   const double t = (lo + hi) * 0.5, s = 1 - t;
-  double qx, qy, qz;
-  bezier_at(cp, t, qx, qy, qz);
+  bezier_at(cp, t, q[0], q[1], q[2]);
   double tx = 3 * (s * s) * (cp[3] - cp[0]); tx += 6 * s * t * (cp[6] - cp[3]); tx += 3 * (t * t) * (cp[9] - cp[6]);   // G:300-313
   double ty = 3 * (s * s) * (cp[4] - cp[1]); ty += 6 * s * t * (cp[7] - cp[4]); ty += 3 * (t * t) * (cp[10] - cp[7]);
   double tz = 3 * (s * s) * (cp[5] - cp[2]); tz += 6 * s * t * (cp[8] - cp[5]); tz += 3 * (t * t) * (cp[11] - cp[8]);
   const double nrm = sqrt(tx * tx + ty * ty + tz * tz);
-  tx /= nrm; tz /= nrm;
+  t3[0] = tx / nrm; t3[1] = ty / nrm; t3[2] = tz / nrm;
+  return true;
+}
+
+// get_lane_pos2 S:1371-1409
+__device__ inline LanePose lane_pose(const DMap& m, double px, double pz, double angle) {
+  LanePose r;
+  r.dist = r.dot_dir = r.angle_rad = __longlong_as_double(0x7ff8000000000000LL);
+  r.in_lane = false;
+  double q[3], t3[3];
+  if (!closest_curve_point(m, px, pz, angle, q, t3)) return r;
+  double sn, cs;
+  sincos(angle, &sn, &cs);
+  const double dirx = cs, dirz = -sn, tx = t3[0], tz = t3[2];
   const double dd = clampd(dirx * tx + dirz * tz, -1.0, 1.0);
   const double rvx = -tz, rvz = tx;  // cross(tangent, +y)
-  r.dist = (px - qx) * rvx + (pz - qz) * rvz;
+  r.dist = (px - q[0]) * rvx + (pz - q[2]) * rvz;
   r.angle_rad = acos(dd);
   if (dirx * rvx + dirz * rvz < 0) r.angle_rad = -r.angle_rad;
   r.dot_dir = dd;
   r.in_lane = true;
   return r;
+}
+
+// ------------------------------------------------------------------ dynamic obstacles (objects.py, O:)
+// DuckieObj.step O:396-422 + finish_walk O:424-432.  `rs` != nullptr: domain_rand draws (the reference takes them
+// from the global numpy RNG; here the env's stream supplies them).
+__device__ inline void duckie_step(const DynRef& d, int s, double dt, NpStream* rs) {
+  const DDyn& p = d.par[s];
+  const double time = d.f(DTS_DYN_TIME, s) + dt;
+  d.f(DTS_DYN_TIME, s) = time;
+  if (d.f(DTS_DYN_ACTIVE, s) == 0.0) {
+    const double w = d.f(DTS_DYN_WAIT, s) - dt;
+    d.f(DTS_DYN_WAIT, s) = w;
+    if (w <= 0) d.f(DTS_DYN_ACTIVE, s) = 1.0;
+    return;
+  }
+  double sn, cs;
+  sincos(p.angle0, &sn, &cs);
+  double vel = d.f(DTS_DYN_VEL, s);
+  const double vx = cs * vel, vz = -sn * vel;                         // heading_vec C:222 * vel
+  const double px = d.f(DTS_DYN_PX, s) + vx, pz = d.f(DTS_DYN_PZ, s) + vz;
+  d.f(DTS_DYN_PX, s) = px; d.f(DTS_DYN_PZ, s) = pz;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { d.f(DTS_DYN_CORNERS + 2 * k, s) += vx; d.f(DTS_DYN_CORNERS + 2 * k + 1, s) += vz; }
+  const double dx = px - d.f(DTS_DYN_START_X, s), dz = pz - d.f(DTS_DYN_START_Z, s);
+  double angle = d.f(DTS_DYN_ANGLE, s);
+  if (sqrt(dx * dx + 0.0 + dz * dz) > p.walk_distance) {
+    d.f(DTS_DYN_START_X, s) = px; d.f(DTS_DYN_START_Z, s) = pz;
+    angle += 3.141592653589793;
+    d.f(DTS_DYN_ANGLE, s) = angle;
+    d.f(DTS_DYN_ACTIVE, s) = 0.0;
+    if (rs) {
+      vel = -1 * (vel > 0 ? 1.0 : (vel < 0 ? -1.0 : 0.0)) * fabs(rs->normal(0.02, 0.005));
+      d.f(DTS_DYN_WAIT, s) = (double)(3 + rs->integers(0, 17));        // randint(3, 20)
+    } else {
+      vel *= -1;
+      d.f(DTS_DYN_WAIT, s) = 8.0;
+    }
+    d.f(DTS_DYN_VEL, s) = vel;
+  }
+  d.f(DTS_DYN_YROT, s) = (angle + p.wiggle * sin(48 * time)) * (180 / 3.141592653589793);
+}
+
+// DuckiebotObj.step_duckiebot O:229-263 + _update_pos O:281-336
+__device__ inline void duckiebot_step(const DMap& m, const DynRef& d, int s, double dt) {
+  const DDyn& p = d.par[s];
+  const double px = d.f(DTS_DYN_PX, s), pz = d.f(DTS_DYN_PZ, s), angle = d.f(DTS_DYN_ANGLE, s);
+  double cp[3], ct[3], cur[3], tmp[3];
+  if (!closest_curve_point(m, px, pz, angle, cp, ct)) return;         // the reference raises; here the bot stops
+  double lookup = p.follow_dist;
+  bool found = false;
+  for (int it = 0; it < 1000 && !found; it++) {
+    found = closest_curve_point(m, cp[0] + ct[0] * lookup, cp[2] + ct[2] * lookup, angle, cur, tmp);
+    if (!found) lookup *= 0.5;
+  }
+  if (!found) return;
+  double vx = cur[0] - px, vy = cur[1] - p.pos_y, vz = cur[2] - pz;
+  const double nn = sqrt(vx * vx + vy * vy + vz * vz);
+  vx /= nn; vy /= nn; vz /= nn;
+  double sn, cs;
+  sincos(angle, &sn, &cs);
+  const double steer = p.gain * -(sn * vx + 0 * vy + cs * vz);
+  const double k_r_inv = (p.gain + p.trim) / p.k, k_l_inv = (p.gain - p.trim) / p.k;
+  const double omega_r = (p.velocity + 0.5 * steer * p.wheel_dist) / p.radius;
+  const double omega_l = (p.velocity - 0.5 * steer * p.wheel_dist) / p.radius;
+  const double ur = fmax(fmin(omega_r * k_r_inv, p.limit), -p.limit), ul = fmax(fmin(omega_l * k_l_inv, p.limit), -p.limit);
+  if (ul == ur) {                                                      // O:305-307: box and y_rot not refreshed
+    d.f(DTS_DYN_PX, s) = px + dt * ul * cs;
+    d.f(DTS_DYN_PZ, s) = pz + dt * ul * -sn;
+    return;
+  }
+  const double w = (ur - ul) / p.wheel_dist;
+  const double r = (p.wheel_dist * (ul + ur)) / (2 * (ul - ur));
+  const double rot = w * dt;
+  const double icx = px + r * sn, icz = pz + r * cs;
+  double srot, crot;
+  sincos(rot, &srot, &crot);
+  const double ddx = px - icx, ddy = pz - icz;                          // rotate_point G:254-265
+  const double ndx = ddx * crot + ddy * srot, ndy = ddy * crot - ddx * srot;
+  const double nx = icx + ndx, nz = icz + ndy, na = angle + rot;
+  d.f(DTS_DYN_PX, s) = nx; d.f(DTS_DYN_PZ, s) = nz; d.f(DTS_DYN_ANGLE, s) = na;
+  d.f(DTS_DYN_YROT, s) += rot * 180 / 3.141592653589793;
+  sincos(na, &sn, &cs);
+  const double fx = cs, fz = -sn, sx = sn, sz = cs, hw = 0.5 * p.robot_width, hl = 0.5 * p.robot_length;
+  d.f(DTS_DYN_CORNERS + 0, s) = nx - hw * sx - hl * fx; d.f(DTS_DYN_CORNERS + 1, s) = nz - hw * sz - hl * fz;
+  d.f(DTS_DYN_CORNERS + 2, s) = nx + hw * sx - hl * fx; d.f(DTS_DYN_CORNERS + 3, s) = nz + hw * sz - hl * fz;
+  d.f(DTS_DYN_CORNERS + 4, s) = nx + hw * sx + hl * fx; d.f(DTS_DYN_CORNERS + 5, s) = nz + hw * sz + hl * fz;
+  d.f(DTS_DYN_CORNERS + 6, s) = nx - hw * sx + hl * fx; d.f(DTS_DYN_CORNERS + 7, s) = nz - hw * sz + hl * fz;
+}
+
+// the object loop of update_physics S:1570-1584
+__device__ inline void dyn_step_all(const DMap& m, const DynRef& d, double dt, NpStream* rs) {
+  for (int s = 0; s < d.n_dyn; s++) {
+    if (d.par[s].kind == DTS_DYN_DUCKIEBOT) duckiebot_step(m, d, s, dt);
+    else duckie_step(d, s, dt, rs);
+  }
+}
+
+// check_collision O:265-269 / O:368-372 -> intersects_single_obj C:162-186, agent box centred at (bx,bz)
+__device__ inline bool agent_hits_dynamic(const DynRef& d, double bx, double bz, double angle) {
+  if (d.n_dyn == 0) return false;
+  double sn, cs;
+  sincos(angle, &sn, &cs);
+  const double fx = cs, fz = -sn, rx = sn, rz = cs, hw = 0.5 * kRobotWidth, hl = 0.5 * kRobotLength;
+  double ax[4], az[4];
+  ax[0] = bx - hw * rx - hl * fx; az[0] = bz - hw * rz - hl * fz;
+  ax[1] = bx + hw * rx - hl * fx; az[1] = bz + hw * rz - hl * fz;
+  ax[2] = bx + hw * rx + hl * fx; az[2] = bz + hw * rz + hl * fz;
+  ax[3] = bx - hw * rx + hl * fx; az[3] = bz - hw * rz + hl * fz;
+  double aR0, aR1, aF0, aF1;
+  project4(rx, rz, ax, az, aR0, aR1);
+  project4(fx, fz, ax, az, aF0, aF1);
+  for (int s = 0; s < d.n_dyn; s++) {
+    double ox[4], oz[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ox[k] = d.f(DTS_DYN_CORNERS + 2 * k, s); oz[k] = d.f(DTS_DYN_CORNERS + 2 * k + 1, s); }
+    const double* on = d.par[s].norms;
+    double lo, hi, lo2, hi2;
+    project4(rx, rz, ox, oz, lo, hi);
+    if (!intervals_touch(aR0, aR1, lo, hi)) continue;
+    project4(fx, fz, ox, oz, lo, hi);
+    if (!intervals_touch(aF0, aF1, lo, hi)) continue;
+    project4(on[0], on[1], ax, az, lo, hi);
+    project4(on[0], on[1], ox, oz, lo2, hi2);
+    if (!intervals_touch(lo, hi, lo2, hi2)) continue;
+    project4(on[2], on[3], ax, az, lo, hi);
+    project4(on[2], on[3], ox, oz, lo2, hi2);
+    if (!intervals_touch(lo, hi, lo2, hi2)) continue;
+    return true;
+  }
+  return false;
+}
+
+// obj.proximity O:271-279 / O:374-383 summed as in S:1455-1457
+__device__ inline double dynamic_proximity(const DynRef& d, double px, double pz, double angle) {
+  if (d.n_dyn == 0) return 0.0;
+  double sn, cs;
+  sincos(angle, &sn, &cs);
+  const double qx = px + kCentreOff * cs, qz = pz + kCentreOff * -sn;
+  double acc = 0.0;
+  for (int s = 0; s < d.n_dyn; s++) {
+    const double dx = qx - d.f(DTS_DYN_PX, s), dy = 0 - d.par[s].pos_y, dz = qz - d.f(DTS_DYN_PZ, s);
+    const double sc = sqrt(dx * dx + dy * dy + dz * dz) - kAgentSafetyRad - d.par[s].safety_radius;
+    acc += sc < 0 ? sc : 0.0;
+  }
+  return acc;
+}
+
+// _inconvenient_spawn S:1461-1471 over the visible objects, dynamic ones where they currently are
+__device__ inline bool inconvenient_spawn(const DMap& m, const DynRef& d, const uint32_t* hidden, double x, double z) {
+  for (int o = 0; o < m.n_objects; o++) {
+    if (hidden && (hidden[o >> 5] >> (o & 31) & 1u)) continue;
+    const DObject& ob = m.objects[o];
+    double ox = ob.dpos[0], oz = ob.dpos[2];
+    if (ob.dyn_slot >= 0 && d.n_dyn > 0) { ox = d.f(DTS_DYN_PX, ob.dyn_slot); oz = d.f(DTS_DYN_PZ, ob.dyn_slot); }
+    const double dx = ox - x, dy = ob.dpos[1], dz = oz - z;
+    if (sqrt(dx * dx + dy * dy + dz * dz) < (double)ob.spawn_rad) return true;
+  }
+  return false;
 }
 
 // One integration step of the restated duckietown_world model (DESIGN.md "dynamics"; call site S:2083-2086).

@@ -662,9 +662,16 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     const int o = item - 1 - n_tiles;
     if (sh.ep.hidden[o >> 5] >> (o & 31) & 1u) return;
     const DObject& ob = m.objects[o];
+    float opx = ob.pos[0], opz = ob.pos[2], orot = ob.y_rot_deg;
+    if (ob.dyn_slot >= 0) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
+      const size_t nd = m.n_dyn, ne = rc.n_envs;
+      opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
+      opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
+      orot = (float)m.dyn_state[((size_t)DTS_DYN_YROT * nd + ob.dyn_slot) * ne + env];
+    }
     double sn, cs;
-    sincos((double)ob.y_rot_deg * kDeg2Rad, &sn, &cs);
-    model_view(sh.V, (double)ob.pos[0], (double)ob.pos[1], (double)ob.pos[2], (double)ob.scale, cs, sn, x);
+    sincos((double)orot * kDeg2Rad, &sn, &cs);
+    model_view(sh.V, (double)opx, (double)ob.pos[1], (double)opz, (double)ob.scale, cs, sn, x);
     {  // conservative bounding-sphere cull in eye space against the four side planes and near
       const float cx_ = x.MV[0] * ob.centre[0] + x.MV[1] * ob.centre[1] + x.MV[2] * ob.centre[2] + x.MV[3];
       const float cy_ = x.MV[4] * ob.centre[0] + x.MV[5] * ob.centre[1] + x.MV[6] * ob.centre[2] + x.MV[7];

@@ -14,7 +14,7 @@ from .maps import KIND_ID, TILE_KINDS, MapData
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdtsim.so")
 
-DTS_ABI_VERSION = 1
+DTS_ABI_VERSION = 2
 ACTION_PWM, ACTION_VEL_STEER = 0, 1
 FLAG_AUTO_RESET, FLAG_DOMAIN_RAND, FLAG_DISTORTION, FLAG_DYNAMICS_RAND, FLAG_TESSELLATE = 1, 2, 4, 8, 16
 IN_PROGRESS, INVALID_POSE, MAX_STEPS = 0, 1, 2
@@ -44,8 +44,21 @@ class Texture(C.Structure):
 
 
 class Object(C.Structure):
-    _fields_ = [("pos", C.c_float * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("mesh_id", C.c_int32),
-                ("optional", C.c_int32)]
+    _fields_ = [("pos", C.c_double * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("mesh_id", C.c_int32),
+                ("optional", C.c_int32), ("dyn_slot", C.c_int32), ("reserved", C.c_int32)]
+
+
+_DYN_SCALARS = ["safety_radius", "walk_distance", "vel", "wait_time", "wiggle", "follow_dist", "velocity", "gain",
+                "trim", "radius", "k", "limit", "wheel_dist", "robot_width", "robot_length"]
+DYN_FIELDS = 18   # DTS_DYN_FIELDS: px pz angle y_rot corners[8] start_x start_z wait vel time active
+DYN_PX, DYN_PZ, DYN_ANGLE, DYN_YROT, DYN_CORNERS, DYN_START_X, DYN_START_Z, DYN_WAIT, DYN_VEL, DYN_TIME, DYN_ACTIVE = \
+    0, 1, 2, 3, 4, 12, 13, 14, 15, 16, 17
+
+
+class DynObjectC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("object_index", C.c_int32), ("pos", C.c_double * 3), ("angle", C.c_double),
+                ("corners", (C.c_double * 2) * 4), ("norms", (C.c_double * 2) * 2)] + \
+               [(n, C.c_double) for n in _DYN_SCALARS]
 
 
 class Mesh(C.Structure):
@@ -61,7 +74,8 @@ class MapBlob(C.Structure):
         ("coll_radii", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p), ("n_meshes", C.c_int32),
         ("meshes", C.c_void_p), ("n_tris", C.c_int32), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p),
         ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p), ("tri_tex", C.c_void_p), ("n_textures", C.c_int32),
-        ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2),
+        ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2), ("n_dyn", C.c_int32), ("reserved", C.c_int32),
+        ("dyn", C.c_void_p),
     ]
 
 
@@ -117,7 +131,8 @@ def load() -> C.CDLL:
     lib.dts_step.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dts_render.argtypes = [vp, vp, vp]
     lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
-    lib.dts_query_poses.argtypes = [vp, i, i, vp, vp, vp, vp]
+    lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp]
+    lib.dts_get_dyn_state.argtypes = [vp, i, C.POINTER(vp), C.POINTER(C.c_int32)]
     lib.dts_comm_load.argtypes = [vp, C.c_char_p]
     lib.dts_comm_unique_id.argtypes = [vp, vp]
     lib.dts_comm_init.argtypes = [vp, vp, i, i]
@@ -135,7 +150,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_get_dyn_state", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_last_error", "dts_destroy"]
 
 
@@ -181,9 +196,23 @@ class MapBlobHolder:
         k["tuv"] = cat(uv, (0, 3, 2), np.float32); k["tcol"] = cat(col, (0, 3, 3), np.float32)
         k["ttex"] = cat(ttex, (0,), np.int16)
         objs = (Object * max(1, len(md.objects)))()
+        slot_of = {d.object_index: s for s, d in enumerate(md.dyn_objects)}
         for oi, o in enumerate(md.objects):
-            objs[oi] = Object((C.c_float * 3)(*[float(v) for v in o.pos]), float(o.scale),
-                              float(np.rad2deg(o.angle)), o.mesh_id, int(o.optional))  # y_rot O:57
+            objs[oi] = Object((C.c_double * 3)(*[float(v) for v in o.pos]), float(o.scale),
+                              float(np.rad2deg(o.angle)), o.mesh_id, int(o.optional), slot_of.get(oi, -1), 0)  # y_rot O:57
+        dyn = (DynObjectC * max(1, len(md.dyn_objects)))()
+        for s, d in enumerate(md.dyn_objects):
+            c = dyn[s]
+            c.kind, c.object_index, c.angle = int(d.kind), int(d.object_index), float(d.angle)
+            for i in range(3):
+                c.pos[i] = float(d.pos[i])
+            for i in range(4):
+                c.corners[i][0], c.corners[i][1] = float(d.corners[i][0]), float(d.corners[i][1])
+            for i in range(2):
+                c.norms[i][0], c.norms[i][1] = float(d.axes[i][0]), float(d.axes[i][1])
+            for n in _DYN_SCALARS:
+                setattr(c, n, float(getattr(d, n)))
+        k["dyn"] = dyn
         texs = (Texture * max(1, len(tex_imgs)))()
         for ti, im in enumerate(tex_imgs):
             texs[ti] = Texture(im.shape[1], im.shape[0], im.ctypes.data)
@@ -194,7 +223,8 @@ class MapBlobHolder:
             _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(md.meshes),
             C.cast(meshes, C.c_void_p), off, _ptr(k["tpos"]), _ptr(k["tnrm"]), _ptr(k["tuv"]), _ptr(k["tcol"]),
             _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p),
-            (C.c_int32 * 2)(*(md.start_tile if md.start_tile is not None else (-1, -1))))
+            (C.c_int32 * 2)(*(md.start_tile if md.start_tile is not None else (-1, -1))), len(md.dyn_objects), 0,
+            C.cast(dyn, C.c_void_p))
 
 
 class _CudaArray:
@@ -271,15 +301,24 @@ class Sim:
         self._check(self.lib.dts_get_state(self.h, C.byref(v)), "dts_get_state")
         return {n: _CudaArray(getattr(v, n), self.cfg.num_envs, dt) for n, dt in _STATE_FIELDS}
 
-    def query_poses(self, map_id: int, x, z, angle, safety=1.0, hidden=None):
+    def query_poses(self, map_id: int, x, z, angle, safety=1.0, hidden=None, dyn_env: int = -1):
+        """dyn_env: the env whose dynamic obstacles the predicates see (-1: static scene only)."""
         q = np.empty((len(x), 4), np.float64)
         q[:, 0], q[:, 1], q[:, 2], q[:, 3] = x, z, angle, safety
         outd = np.empty((len(x), 4), np.float64)
         outi = np.empty((len(x), 8), np.int32)
         hid = None if hidden is None else np.ascontiguousarray(hidden, np.uint32)
-        self._check(self.lib.dts_query_poses(self.h, map_id, len(x), _ptr(q), _ptr(hid), _ptr(outd), _ptr(outi)),
+        self._check(self.lib.dts_query_poses(self.h, map_id, int(dyn_env), len(x), _ptr(q), _ptr(hid), _ptr(outd), _ptr(outi)),
                     "dts_query_poses")
         return outd, outi
+
+    def dyn_state(self, map_id: int = 0):
+        """(device array f64[DYN_FIELDS * n_dyn * num_envs], n_dyn) of map `map_id`'s dynamic obstacles, or (None, 0)."""
+        p, nd = C.c_void_p(), C.c_int32()
+        self._check(self.lib.dts_get_dyn_state(self.h, map_id, C.byref(p), C.byref(nd)), "dts_get_dyn_state")
+        if not nd.value:
+            return None, 0
+        return _CudaArray(p.value, DYN_FIELDS * nd.value * self.cfg.num_envs, np.float64), nd.value
 
     def launch_count(self) -> int:
         return int(self.lib.dts_launch_count(self.h))

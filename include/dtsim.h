@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTS_ABI_VERSION 1
+#define DTS_ABI_VERSION 2
 #define DTS_MAX_DELAY 8      /* command-delay line depth (steps) */
 #define DTS_MAX_OBJECTS 256  /* per map; visibility bitmask is 8 x u32 */
 
@@ -66,13 +66,36 @@ typedef struct {
 
 typedef struct { int32_t width, height; const uint8_t* rgba; /* [height][width][4], row 0 = t=0 */ } dts_texture;
 
-typedef struct {            /* one placed static prop: objects.py:33-66 (WorldObj), render O:123-148 */
-  float pos[3];
+typedef struct {            /* one placed prop: objects.py:33-66 (WorldObj), render O:123-148 */
+  double pos[3];            /* float64 like WorldObj.pos (_inconvenient_spawn S:1461-1471); rendered as float32 */
   float scale;
   float y_rot_deg;
   int32_t mesh_id;
   int32_t optional;         /* hidden w.p. 1/2 at reset under domain_rand (S:653-654) */
+  int32_t dyn_slot;         /* -1: static; else index into dts_map_blob.dyn — pose comes from the per-env state */
+  int32_t reserved;
 } dts_object;
+
+/* One `static: false` obstacle (S:973-1017): DuckieObj pedestrian O:339-432 or DuckiebotObj lane follower
+ * O:180-336, with its state at map load.  Every env carries its own copy of the evolving state (per map), which
+ * like the reference's object list survives resets.  Under domain_rand the reference draws vel / wait_time /
+ * follow_dist ... from the GLOBAL numpy RNG at construction (O:348-350, O:197-205): the host supplies them. */
+enum { DTS_DYN_DUCKIE = 1, DTS_DYN_DUCKIEBOT = 2 };
+#define DTS_MAX_DYN 32
+typedef struct {
+  int32_t kind;             /* DTS_DYN_* */
+  int32_t object_index;     /* entry of objects[] carrying mesh / scale / height */
+  double pos[3], angle;     /* WorldObj.pos, .angle O:54-57 */
+  double corners[4][2];     /* obj_corners (x,z) O:60 */
+  double norms[2][2];       /* obj_norm rows O:61 — the duckiebot never refreshes them (O:306-336) */
+  double safety_radius;     /* O:66 */
+  double walk_distance, vel, wait_time, wiggle;                       /* DuckieObj O:343-366 */
+  double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length; /* O:196-227 */
+} dts_dyn_object;
+
+/* Per-env state of one dynamic obstacle: DTS_DYN_FIELDS doubles, device layout [field][slot][env]. */
+enum { DTS_DYN_PX = 0, DTS_DYN_PZ, DTS_DYN_ANGLE, DTS_DYN_YROT, DTS_DYN_CORNERS /* 8: x0 z0 .. x3 z3 */,
+       DTS_DYN_START_X = 12, DTS_DYN_START_Z, DTS_DYN_WAIT, DTS_DYN_VEL, DTS_DYN_TIME, DTS_DYN_ACTIVE, DTS_DYN_FIELDS };
 
 typedef struct { int32_t tri_offset, tri_count; } dts_mesh;
 
@@ -108,6 +131,9 @@ typedef struct {
   int32_t n_textures;
   const dts_texture* textures;
   int32_t start_tile[2];          /* map `start_tile` (simulator.py:867-871) or {-1,-1}: device resets spawn there */
+  int32_t n_dyn;                  /* <= DTS_MAX_DYN */
+  int32_t reserved;
+  const dts_dyn_object* dyn;      /* [n_dyn] in the order of the map's object list (update order S:1570-1584) */
 } dts_map_blob;
 
 /* Per-episode inputs produced by Simulator.reset() (simulator.py:528-763), one
@@ -178,9 +204,13 @@ int dts_get_state(dts_sim* sim, dts_state_view* out);
  * HOST pointers, synchronous. query[n][4] = x, z, angle, safety_factor; hidden[n][8] object-visibility
  * bitmasks or NULL; out_f64[n][4] = lane dist, dot_dir, angle_rad (NaN when not in a lane), proximity;
  * out_i32[n][8] = valid, collision (offset once), collision (as _valid_pose sees it), in_lane,
- * inconvenient_spawn, tile_i, tile_j, drivable. */
-int dts_query_poses(dts_sim* sim, int map_id, int n, const double* query, const uint32_t* hidden, double* out_f64,
-                    int32_t* out_i32);
+ * inconvenient_spawn, tile_i, tile_j, drivable.  Dynamic obstacles are taken where env `dyn_env` currently has
+ * them (check_collision O:265/368, proximity O:271/374, x.pos in S:1466); dyn_env < 0 ignores them. */
+int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* query, const uint32_t* hidden,
+                    double* out_f64, int32_t* out_i32);
+/* Device pointer to the dynamic-obstacle state of map `map_id`: f64[DTS_DYN_FIELDS][n_dyn][num_envs] (NULL, 0 for a
+ * map without dynamic obstacles).  Re-uploading the map puts every env's obstacles back to their load-time state. */
+int dts_get_dyn_state(dts_sim* sim, int map_id, double** state_dev, int32_t* n_dyn);
 /* End-of-rollout observation all-gather across the GPU shards of one box; the step path
  * itself has no collective.  libnccl is dlopen'ed from `libnccl_path` (the torch-bundled copy); rank 0
  * creates a unique id, the caller broadcasts its 128 bytes (torch.distributed), every rank inits.

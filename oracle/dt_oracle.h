@@ -82,11 +82,21 @@ void orc_agent_corners(double px, double pz, double angle, double cx[4], double 
 void orc_dyn_step_all(const orc_map* m, orc_dyn* objs, int n, double dt);
 int orc_dyn_collision(const orc_dyn* objs, int n, double px, double pz, double angle);
 double orc_dyn_proximity(const orc_dyn* objs, int n, double px, double pz, double angle);
+int orc_valid_pose_dyn(const orc_map* m, const orc_dyn* objs, int n, double px, double pz, double angle,
+                       double safety_factor, uint8_t* collided);
+void orc_step_dynamic(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int* step_count, double* last_px,
+                      double* last_pz, const double action[2], int action_mode, double wheel_dist,
+                      const double env5[5], int frame_skip, double dt, int max_steps, double robot_speed,
+                      orc_dyn* objs, int n, orc_step_out* o);
 void orc_action_map(double vel, double steer, double wheel_dist, double gain, double trim, double radius, double k,
                     double limit, double out_lr[2]);
 void orc_dyn_step(orc_dyn_state* s, const orc_dyn_params* p, const double cmd_lr[2], double dt);
 void orc_weird_from_cartesian(const orc_map* m, const orc_dyn_state* s, double* px, double* pz, double* ang);
 void orc_cartesian_from_weird(const orc_map* m, double px, double pz, double ang, orc_dyn_state* s);
+int orc_valid_pose(const orc_map* m, double px, double pz, double angle, double safety_factor, uint8_t* collided,
+                   uint8_t* all_drivable);
+void orc_done_reward(const orc_map* m, double px, double pz, double angle, int step_count, int max_steps,
+                     double robot_speed, orc_step_out* o);
 void orc_step(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int* step_count, double* last_px,
               double* last_pz, const double action[2], int action_mode, double wheel_dist, const double env5[5],
               int frame_skip, double dt, int max_steps, double robot_speed, orc_step_out* o);

@@ -137,3 +137,50 @@ double orc_dyn_proximity(const orc_dyn* objs, int n, double px, double pz, doubl
   }
   return tot;
 }
+
+/* _valid_pose S:1494-1534 with the dynamic half of _collision: the agent box is built from the already
+ * shifted centre (like orc_valid_pose). */
+int orc_valid_pose_dyn(const orc_map* m, const orc_dyn* objs, int n, double px, double pz, double angle,
+                       double safety_factor, uint8_t* collided) {
+  uint8_t col = 0, drv = 0;
+  orc_valid_pose(m, px, pz, angle, safety_factor, &col, &drv);
+  if (!col) {
+    double off = 0.066 - (0.18 / 2);
+    col = (uint8_t)orc_dyn_collision(objs, n, px + off * cos(angle), pz + off * -sin(angle), angle);
+  }
+  if (collided) *collided = col;
+  return !col && drv;
+}
+
+/* Simulator.step S:1669-1683 on a map with dynamic obstacles: per physics update the agent moves, then every
+ * object steps (S:1551-1584); done/reward (S:1685-1705, S:1654-1667) see the moved objects. */
+void orc_step_dynamic(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int* step_count, double* last_px,
+                      double* last_pz, const double action[2], int action_mode, double wheel_dist,
+                      const double env5[5], int frame_skip, double dt, int max_steps, double robot_speed,
+                      orc_dyn* objs, int n, orc_step_out* o) {
+  double cmd[2] = {action[0], action[1]};
+  if (action_mode == 1) orc_action_map(action[0], action[1], wheel_dist, env5[0], env5[1], env5[2], env5[3], env5[4], cmd);
+  cmd[0] = fmax(-1.0, fmin(1.0, cmd[0]));
+  cmd[1] = fmax(-1.0, fmin(1.0, cmd[1]));
+  double px = *last_px, pz = *last_pz, ang = 0, speed = 0;
+  for (int f = 0; f < frame_skip; f++) {
+    double ppx = px, ppz = pz;
+    orc_dyn_step(s, dp, cmd, dt);
+    orc_weird_from_cartesian(m, s, &px, &pz, &ang);
+    (*step_count)++;
+    speed = sqrt((px - ppx) * (px - ppx) + (pz - ppz) * (pz - ppz)) / dt;
+    orc_dyn_step_all(m, objs, n, dt);
+  }
+  *last_px = px; *last_pz = pz;
+  orc_done_reward(m, px, pz, ang, *step_count, max_steps, robot_speed, o);   /* static part + lane pose */
+  o->speed = speed;
+  o->prox += orc_dyn_proximity(objs, n, px, pz, ang);
+  int valid = orc_valid_pose_dyn(m, objs, n, px, pz, ang, 1.0, &o->collided);
+  if (!valid) { o->done = 1; o->done_code = 1; o->reward = -1000.0; }
+  else if (*step_count >= max_steps) { o->done = 1; o->done_code = 2; o->reward = 0.0; }
+  else {
+    o->done = 0; o->done_code = 0;
+    if (o->in_lane) o->reward = +1.0 * robot_speed * o->lane_dot + -10 * fabs(o->lane_dist) + +40 * o->prox;
+    else o->reward = 40 * o->prox;
+  }
+}

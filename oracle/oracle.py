@@ -122,8 +122,10 @@ class OracleEnv:
     """One reference-style env stepped by the C oracle: the CPU side of every trajectory parity test."""
 
     def __init__(self, omap: OracleMap, px, pz, angle, *, wheel_dist=0.102, action_mode=1, max_steps=1500,
-                 frame_skip=1, dt=1.0 / 30, robot_speed=1.2, env5=(1.0, 0.0, 0.0318, 27.0, 1.0), trim=0.0):
+                 frame_skip=1, dt=1.0 / 30, robot_speed=1.2, env5=(1.0, 0.0, 0.0318, 27.0, 1.0), trim=0.0,
+                 dynamics=None):
         self.m = omap
+        self.dynamics = dynamics          # OracleDynamics: this env's moving obstacles (stepped with the agent)
         self.dp = default_dyn_params(dt, 0.15, trim)
         self.s = OrcDynState()
         lib().orc_cartesian_from_weird(C.byref(omap.c), C.c_double(px), C.c_double(pz), C.c_double(angle), C.byref(self.s))
@@ -136,6 +138,14 @@ class OracleEnv:
     def step(self, action) -> OrcStepOut:
         o = OrcStepOut()
         a = (C.c_double * 2)(float(action[0]), float(action[1]))
+        if self.dynamics is not None:
+            d = self.dynamics
+            lib().orc_step_dynamic(C.byref(self.m.c), C.byref(self.dp), C.byref(self.s), C.byref(self.step_count),
+                                   C.byref(self.px), C.byref(self.pz), a, C.c_int(self.action_mode),
+                                   C.c_double(self.wheel_dist), self.env5, C.c_int(self.frame_skip),
+                                   C.c_double(self.dt), C.c_int(self.max_steps), C.c_double(self.robot_speed),
+                                   d.objs, C.c_int(d.n), C.byref(o))
+            return o
         lib().orc_step(C.byref(self.m.c), C.byref(self.dp), C.byref(self.s), C.byref(self.step_count),
                        C.byref(self.px), C.byref(self.pz), a, C.c_int(self.action_mode), C.c_double(self.wheel_dist),
                        self.env5, C.c_int(self.frame_skip), C.c_double(self.dt), C.c_int(self.max_steps),
@@ -197,13 +207,19 @@ class OracleScene:
         for i, o in enumerate(md.objects):
             src = k["objs"][i]
             me = k["meshes"][o.mesh_id]
-            self.objs[i] = OrrObject(src.pos, src.scale, src.y_rot_deg, me.tri_offset, me.tri_count)
+            self.objs[i] = OrrObject((C.c_float * 3)(*[float(v) for v in src.pos]), src.scale, src.y_rot_deg, me.tri_offset, me.tri_count)
         self.texs = (OrrTexture * max(1, len(k["tex_imgs"])))()
         for i, im in enumerate(k["tex_imgs"]):
             self.texs[i] = OrrTexture(im.shape[1], im.shape[0], im.ctypes.data)
         self.c = OrrScene(md.tile_size, md.grid_w, md.grid_h, _p(k["kind"]), _p(k["angle"]), _p(k["tex"]),
                           len(md.objects), C.cast(self.objs, C.c_void_p), _p(k["tpos"]), _p(k["tnrm"]), _p(k["tuv"]),
                           _p(k["tcol"]), _p(k["ttex"]), len(k["tex_imgs"]), C.cast(self.texs, C.c_void_p))
+
+    def set_object_pose(self, i, pos, y_rot_deg):
+        """Move object i (a dynamic obstacle of one env) before rendering that env's frame."""
+        for k in range(3):
+            self.objs[i].pos[k] = float(pos[k])
+        self.objs[i].y_rot_deg = float(y_rot_deg)
 
     def render(self, px, pz, angle, ep: OrrEpisode = None, W=160, H=120, domain_rand=False, lut=None) -> np.ndarray:
         ep = ep or default_episode()

@@ -35,15 +35,17 @@ def test_ctypes_struct_layout_matches_header():
     #include <stdio.h>
     #include <stddef.h>
     #include "dtsim.h"
-    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(dts_config), offsetof(dts_config, frame_rate),
-      offsetof(dts_config, seed), sizeof(dts_map_blob), sizeof(dts_episode_params), sizeof(dts_state_view), sizeof(dts_object)); return 0; }
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d\n", sizeof(dts_config), offsetof(dts_config, frame_rate),
+      offsetof(dts_config, seed), sizeof(dts_map_blob), sizeof(dts_episode_params), sizeof(dts_state_view), sizeof(dts_object),
+      sizeof(dts_dyn_object), offsetof(dts_dyn_object, safety_radius), offsetof(dts_map_blob, dyn), (int)DTS_DYN_FIELDS); return 0; }
     '''
     exe = os.path.join(ROOT, "tests", "_layout_probe")
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True, check=True)
     vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     os.remove(exe)
     assert vals == [ctypes.sizeof(L.Config), L.Config.frame_rate.offset, L.Config.seed.offset, ctypes.sizeof(L.MapBlob),
-                    ctypes.sizeof(L.EpisodeParams), ctypes.sizeof(L.StateView), ctypes.sizeof(L.Object)]
+                    ctypes.sizeof(L.EpisodeParams), ctypes.sizeof(L.StateView), ctypes.sizeof(L.Object),
+                    ctypes.sizeof(L.DynObjectC), L.DynObjectC.safety_radius.offset, L.MapBlob.dyn.offset, L.DYN_FIELDS]
 
 
 def test_product_never_imports_the_oracle():
