@@ -31,6 +31,7 @@ class Mesh:
     tri_col: np.ndarray  # f32 [F,3,3]
     tri_tex: np.ndarray  # i16 [F]   index into `textures`, -1 = untextured chunk
     textures: List[np.ndarray] = field(default_factory=list)  # RGBA8 [h,w,4], row 0 = t=0
+    alt_textures: Dict[int, np.ndarray] = field(default_factory=dict)  # texture slot -> the image a TrafficLightObj swaps in
     min_coords: np.ndarray = None
     max_coords: np.ndarray = None
 
@@ -200,13 +201,38 @@ def _build_sign(kind: str):
     return s.mesh("sign_generic:" + kind, textures=[_sign_texture(kind)])
 
 
+def _trafficlight_card(pattern: int) -> np.ndarray:
+    """Stand-in for trafficlight_card{0,1}.jpg (O:438-441): a dark card with a red and a green lamp whose lit one
+    depends on the pattern; the card wraps the four faces of the head, so opposite directions see opposite lamps."""
+    n = 64
+    img = np.zeros((n, n, 4), np.uint8)
+    img[..., :3] = (28, 28, 30)
+    img[..., 3] = 255
+    yy, xx = np.mgrid[0:n, 0:n]
+    for half in (0, 1):                       # left half of the card: N/S faces, right half: E/W faces
+        lit_green = (pattern == 0) == (half == 0)
+        cx = 16 + 32 * half
+        for cy, col_on, col_off, on in ((44, (235, 40, 30), (70, 14, 12), not lit_green),
+                                        (20, (40, 230, 60), (14, 66, 20), lit_green)):
+            img[(xx - cx) ** 2 + (yy - cy) ** 2 <= 81, :3] = col_on if on else col_off
+    return img
+
+
 def _build_trafficlight():
     s = _Soup()
     s.box((-0.01, 0.0, -0.01), (0.01, 0.30, 0.01), (0.2, 0.2, 0.2))
-    s.box((-0.04, 0.30, -0.04), (0.04, 0.42, 0.04), (0.15, 0.15, 0.15))
-    s.box((-0.015, 0.37, 0.04), (0.015, 0.40, 0.042), (0.9, 0.1, 0.1))
-    s.box((-0.015, 0.32, 0.04), (0.015, 0.35, 0.042), (0.1, 0.9, 0.1))
-    return s.mesh("trafficlight")
+    x0, x1, y0, y1 = -0.04, 0.04, 0.30, 0.42
+    white = (1.0, 1.0, 1.0)
+    # head: four card faces (material 0 of the mesh — the texture TrafficLightObj swaps, O:453,462), plain lids
+    s.quad((x0, y0, x1), (x1, y0, x1), (x1, y1, x1), (x0, y1, x1), white, 0, ((0.0, 0), (0.5, 0), (0.5, 1), (0.0, 1)))   # +z
+    s.quad((x1, y0, x0), (x0, y0, x0), (x0, y1, x0), (x1, y1, x0), white, 0, ((0.0, 0), (0.5, 0), (0.5, 1), (0.0, 1)))   # -z
+    s.quad((x1, y0, x1), (x1, y0, x0), (x1, y1, x0), (x1, y1, x1), white, 0, ((0.5, 0), (1.0, 0), (1.0, 1), (0.5, 1)))   # +x
+    s.quad((x0, y0, x0), (x0, y0, x1), (x0, y1, x1), (x0, y1, x0), white, 0, ((0.5, 0), (1.0, 0), (1.0, 1), (0.5, 1)))   # -x
+    s.quad((x0, y1, x1), (x1, y1, x1), (x1, y1, x0), (x0, y1, x0), (0.15, 0.15, 0.15))
+    s.quad((x0, y0, x0), (x1, y0, x0), (x1, y0, x1), (x0, y0, x1), (0.15, 0.15, 0.15))
+    m = s.mesh("trafficlight", textures=[_trafficlight_card(0)])
+    m.alt_textures = {0: _trafficlight_card(1)}
+    return m
 
 
 _BUILDERS = {

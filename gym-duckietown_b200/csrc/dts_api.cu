@@ -195,6 +195,8 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
     DObject& d = objs[o];
     for (int k = 0; k < 3; k++) { d.pos[k] = (float)s.pos[k]; d.dpos[k] = s.pos[k]; }   // glTranslatef takes floats
     d.dyn_slot = s.dyn_slot;
+    d.alt_from = s.alt_tex_from; d.alt_to = s.alt_tex_to;
+    if (s.alt_tex_to >= b->n_textures || s.alt_tex_from >= b->n_textures) return sim->fail("object %d: alt texture out of range", o);
     if (s.dyn_slot >= b->n_dyn) return sim->fail("object %d: dyn_slot %d out of range", o, s.dyn_slot);
     d.scale = s.scale; d.y_rot_deg = s.y_rot_deg; d.mesh_id = s.mesh_id; d.optional = s.optional;
     d.tri_offset = me.tri_offset; d.tri_count = me.tri_count;
@@ -238,7 +240,7 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
     std::vector<double> st((size_t)DTS_DYN_FIELDS * D * N);
     for (size_t s = 0; s < D; s++) {
       const dts_dyn_object& q = b->dyn[s];
-      if (q.kind != DTS_DYN_DUCKIE && q.kind != DTS_DYN_DUCKIEBOT) return sim->fail("dyn %zu: bad kind %d", s, q.kind);
+      if (q.kind != DTS_DYN_DUCKIE && q.kind != DTS_DYN_DUCKIEBOT && q.kind != DTS_DYN_TRAFFICLIGHT) return sim->fail("dyn %zu: bad kind %d", s, q.kind);
       if (q.object_index < 0 || q.object_index >= b->n_objects || b->objects[q.object_index].dyn_slot != (int)s)
         return sim->fail("dyn %zu: object_index %d does not point back to this slot", s, q.object_index);
       DDyn& p = par[s];
@@ -253,9 +255,17 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
       for (int k = 0; k < 4; k++) { f[DTS_DYN_CORNERS + 2 * k] = q.corners[k][0]; f[DTS_DYN_CORNERS + 2 * k + 1] = q.corners[k][1]; }
       f[DTS_DYN_START_X] = q.pos[0]; f[DTS_DYN_START_Z] = q.pos[2];
       f[DTS_DYN_WAIT] = q.wait_time; f[DTS_DYN_VEL] = q.vel; f[DTS_DYN_TIME] = 0.0; f[DTS_DYN_ACTIVE] = 0.0;
+      p.freq = q.freq; p.tl_first = -1; p.pad = 0;
+      if (q.kind == DTS_DYN_TRAFFICLIGHT) f[DTS_DYN_PATTERN] = q.pattern ? 1.0 : 0.0;
       for (int k = 0; k < DTS_DYN_FIELDS; k++)
         for (size_t e = 0; e < N; e++) st[((size_t)k * D + s) * N + e] = f[k];
     }
+    int tl_first = -1, tl_last = -1;
+    for (size_t s = 0; s < D; s++)
+      if (par[s].kind == DTS_DYN_TRAFFICLIGHT) { if (tl_first < 0) tl_first = (int)s; tl_last = (int)s; }
+    for (size_t s = 0; s < D; s++) par[s].tl_first = tl_first;
+    if (tl_first >= 0)   // every constructor assigns the shared mesh's card (O:453): the last light's pattern shows
+      for (size_t e = 0; e < N; e++) st[((size_t)DTS_DYN_SHOWN * D + tl_first) * N + e] = b->dyn[tl_last].pattern ? 1.0 : 0.0;
     bad |= sim->upload(&m.dyn, par.data(), par.size(), &own);
     const double* dst = nullptr;
     bad |= sim->upload(&dst, st.data(), st.size(), &own);

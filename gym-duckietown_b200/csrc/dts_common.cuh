@@ -20,7 +20,8 @@ struct DObject {
   int32_t tri_offset, tri_count;
   float bound_rad;   // object-space bounding radius (culling)
   float centre[3];   // object-space bounding-sphere centre
-  int32_t dyn_slot;  // -1 static; else slot of the per-env dynamic state that supplies pos / y_rot
+  int32_t dyn_slot;  // -1 static; else slot of the per-env dynamic state that supplies pos / y_rot / card
+  int32_t alt_from, alt_to;   // traffic-light card swap (texture ids), -1 none
   double dpos[3];    // float64 position (x.pos in _inconvenient_spawn S:1466)
 };
 
@@ -32,6 +33,9 @@ struct DDyn {
   double safety_radius;
   double walk_distance, wiggle, angle0;   // duckie: heading = heading_vec(angle at load) never changes (O:357)
   double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length;
+  double freq;        // traffic light
+  int32_t tl_first;   // slot of the map's first traffic light (holds the shared card), -1 if none
+  int32_t pad;
 };
 
 struct DTexture { const uint8_t* rgba; int32_t w, h; };

@@ -301,10 +301,25 @@ __device__ inline void duckiebot_step(const DMap& m, const DynRef& d, int s, dou
   d.f(DTS_DYN_CORNERS + 6, s) = nx - hw * sx + hl * fx; d.f(DTS_DYN_CORNERS + 7, s) = nz - hw * sz + hl * fz;
 }
 
+// TrafficLightObj.step O:455-462: `round(time, 3) % freq == 0` flips the pattern and re-assigns the SHARED mesh's card
+__device__ inline void trafficlight_step(const DynRef& d, int s, double dt) {
+  const DDyn& p = d.par[s];
+  const double time = d.f(DTS_DYN_TIME, s) + dt;
+  d.f(DTS_DYN_TIME, s) = time;
+  const long long ms = llrint(time * 1000.0), per = llrint(p.freq * 1000.0);
+  if (per > 0 && ms % per == 0) {
+    const double pat = d.f(DTS_DYN_PATTERN, s) == 0.0 ? 1.0 : 0.0;
+    d.f(DTS_DYN_PATTERN, s) = pat;
+    d.f(DTS_DYN_SHOWN, p.tl_first) = pat;
+  }
+}
+
 // the object loop of update_physics S:1570-1584
 __device__ inline void dyn_step_all(const DMap& m, const DynRef& d, double dt, NpStream* rs) {
   for (int s = 0; s < d.n_dyn; s++) {
-    if (d.par[s].kind == DTS_DYN_DUCKIEBOT) duckiebot_step(m, d, s, dt);
+    const int kind = d.par[s].kind;
+    if (kind == DTS_DYN_DUCKIEBOT) duckiebot_step(m, d, s, dt);
+    else if (kind == DTS_DYN_TRAFFICLIGHT) trafficlight_step(d, s, dt);
     else duckie_step(d, s, dt, rs);
   }
 }
@@ -324,6 +339,7 @@ __device__ inline bool agent_hits_dynamic(const DynRef& d, double bx, double bz,
   project4(rx, rz, ax, az, aR0, aR1);
   project4(fx, fz, ax, az, aF0, aF1);
   for (int s = 0; s < d.n_dyn; s++) {
+    if (d.par[s].kind == DTS_DYN_TRAFFICLIGHT) continue;   // a static WorldObj: check_collision is False (O:150-158)
     double ox[4], oz[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { ox[k] = d.f(DTS_DYN_CORNERS + 2 * k, s); oz[k] = d.f(DTS_DYN_CORNERS + 2 * k + 1, s); }
@@ -352,6 +368,7 @@ __device__ inline double dynamic_proximity(const DynRef& d, double px, double pz
   const double qx = px + kCentreOff * cs, qz = pz + kCentreOff * -sn;
   double acc = 0.0;
   for (int s = 0; s < d.n_dyn; s++) {
+    if (d.par[s].kind == DTS_DYN_TRAFFICLIGHT) continue;   // static WorldObj.proximity is 0 (O:160-168)
     const double dx = qx - d.f(DTS_DYN_PX, s), dy = 0 - d.par[s].pos_y, dz = qz - d.f(DTS_DYN_PZ, s);
     const double sc = sqrt(dx * dx + dy * dy + dz * dz) - kAgentSafetyRad - d.par[s].safety_radius;
     acc += sc < 0 ? sc : 0.0;

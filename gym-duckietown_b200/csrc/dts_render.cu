@@ -663,7 +663,11 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     if (sh.ep.hidden[o >> 5] >> (o & 31) & 1u) return;
     const DObject& ob = m.objects[o];
     float opx = ob.pos[0], opz = ob.pos[2], orot = ob.y_rot_deg;
-    if (ob.dyn_slot >= 0) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
+    int alt_from = -2;        // traffic-light card on pattern 1: swap this texture id for ob.alt_to
+    if (ob.dyn_slot >= 0 && m.dyn[ob.dyn_slot].kind == DTS_DYN_TRAFFICLIGHT) {
+      const size_t nd = m.n_dyn, ne = rc.n_envs;
+      if (m.dyn_state[((size_t)DTS_DYN_SHOWN * nd + m.dyn[ob.dyn_slot].tl_first) * ne + env] != 0.0) alt_from = ob.alt_from;
+    } else if (ob.dyn_slot >= 0) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
       const size_t nd = m.n_dyn, ne = rc.n_envs;
       opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
       opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
@@ -702,6 +706,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
           v[j] = shade_vertex(x, sh, p[3 * j], p[3 * j + 1], p[3 * j + 2], n[3 * j], n[3 * j + 1], n[3 * j + 2],
                               c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
         ttex = m.tri_tex[ti];
+        if (ttex == alt_from) ttex = ob.alt_to;
       }
       process_triangle_lanes(ec, k < ob.tri_count, v[0], v[1], v[2], base_id + k, ttex, -1, lane);
       }

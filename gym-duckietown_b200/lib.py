@@ -45,7 +45,8 @@ class Texture(C.Structure):
 
 class Object(C.Structure):
     _fields_ = [("pos", C.c_double * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("mesh_id", C.c_int32),
-                ("optional", C.c_int32), ("dyn_slot", C.c_int32), ("reserved", C.c_int32)]
+                ("optional", C.c_int32), ("dyn_slot", C.c_int32), ("alt_tex_from", C.c_int32), ("alt_tex_to", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 _DYN_SCALARS = ["safety_radius", "walk_distance", "vel", "wait_time", "wiggle", "follow_dist", "velocity", "gain",
@@ -53,12 +54,13 @@ _DYN_SCALARS = ["safety_radius", "walk_distance", "vel", "wait_time", "wiggle", 
 DYN_FIELDS = 18   # DTS_DYN_FIELDS: px pz angle y_rot corners[8] start_x start_z wait vel time active
 DYN_PX, DYN_PZ, DYN_ANGLE, DYN_YROT, DYN_CORNERS, DYN_START_X, DYN_START_Z, DYN_WAIT, DYN_VEL, DYN_TIME, DYN_ACTIVE = \
     0, 1, 2, 3, 4, 12, 13, 14, 15, 16, 17
+DYN_PATTERN, DYN_SHOWN = DYN_ACTIVE, DYN_WAIT   # traffic lights (see dtsim.h)
 
 
 class DynObjectC(C.Structure):
     _fields_ = [("kind", C.c_int32), ("object_index", C.c_int32), ("pos", C.c_double * 3), ("angle", C.c_double),
                 ("corners", (C.c_double * 2) * 4), ("norms", (C.c_double * 2) * 2)] + \
-               [(n, C.c_double) for n in _DYN_SCALARS]
+               [(n, C.c_double) for n in _DYN_SCALARS] + [("freq", C.c_double), ("pattern", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Mesh(C.Structure):
@@ -184,9 +186,13 @@ class MapBlobHolder:
         meshes = (Mesh * max(1, len(md.meshes)))()
         pos, nrm, uv, col, ttex = [], [], [], [], []
         off = 0
+        alt_of_mesh = {}
         for mi, m in enumerate(md.meshes):
             base = len(tex_imgs)
             tex_imgs.extend(np.ascontiguousarray(t) for t in m.textures)
+            for slot, img in getattr(m, "alt_textures", {}).items():   # traffic-light card for pattern 1
+                alt_of_mesh[mi] = (base + slot, len(tex_imgs))
+                tex_imgs.append(np.ascontiguousarray(img))
             meshes[mi] = Mesh(off, len(m.tri_pos))
             off += len(m.tri_pos)
             pos.append(m.tri_pos); nrm.append(m.tri_nrm); uv.append(m.tri_uv); col.append(m.tri_col)
@@ -199,7 +205,8 @@ class MapBlobHolder:
         slot_of = {d.object_index: s for s, d in enumerate(md.dyn_objects)}
         for oi, o in enumerate(md.objects):
             objs[oi] = Object((C.c_double * 3)(*[float(v) for v in o.pos]), float(o.scale),
-                              float(np.rad2deg(o.angle)), o.mesh_id, int(o.optional), slot_of.get(oi, -1), 0)  # y_rot O:57
+                              float(np.rad2deg(o.angle)), o.mesh_id, int(o.optional), slot_of.get(oi, -1),
+                              *(alt_of_mesh.get(o.mesh_id, (-1, -1)) if o.kind == "trafficlight" else (-1, -1)), 0)  # y_rot O:57
         dyn = (DynObjectC * max(1, len(md.dyn_objects)))()
         for s, d in enumerate(md.dyn_objects):
             c = dyn[s]
@@ -212,6 +219,7 @@ class MapBlobHolder:
                 c.norms[i][0], c.norms[i][1] = float(d.axes[i][0]), float(d.axes[i][1])
             for n in _DYN_SCALARS:
                 setattr(c, n, float(getattr(d, n)))
+            c.freq, c.pattern = float(d.freq), int(d.pattern)
         k["dyn"] = dyn
         texs = (Texture * max(1, len(tex_imgs)))()
         for ti, im in enumerate(tex_imgs):

@@ -138,7 +138,7 @@ class DynObject:
     """A `static: false` prop: DuckieObj pedestrian (objects.py:339-432) or DuckiebotObj lane follower
     (objects.py:180-336).  Parameters are the reference's non-randomized defaults; under domain_rand the
     reference draws them from the GLOBAL numpy RNG (unseeded), so callers may override."""
-    kind: int                 # 1 duckie, 2 duckiebot
+    kind: int                 # 1 duckie, 2 duckiebot, 3 traffic light (static, only its card texture changes)
     object_index: int         # entry of MapData.objects (mesh, scale, initial pose)
     pos: np.ndarray
     angle: float
@@ -161,9 +161,12 @@ class DynObject:
     wheel_dist: float = 0.102
     robot_width: float = 0.13 + 0.02
     robot_length: float = 0.18
+    # TrafficLightObj (O:434-462): seconds between card flips and the starting pattern
+    freq: float = 5.0
+    pattern: int = 0
 
 
-DYN_DUCKIE, DYN_DUCKIEBOT = 1, 2
+DYN_DUCKIE, DYN_DUCKIEBOT, DYN_TRAFFICLIGHT = 1, 2, 3
 
 
 @dataclass
@@ -312,6 +315,10 @@ def _load_objects(md: MapData, map_data: dict) -> None:
                 kind=DYN_DUCKIE if kind == "duckie" else DYN_DUCKIEBOT, object_index=len(md.objects) - 1, pos=pos.copy(),
                 angle=angle, corners=corners.copy(), axes=axes.copy(), safety_radius=float(radius),
                 walk_distance=md.tile_size))   # DuckieObj(..., self.road_tile_size) S:1010
+        elif kind == "trafficlight":   # TrafficLightObj S:999-1000: stepped like the others, never collides
+            md.dyn_objects.append(DynObject(
+                kind=DYN_TRAFFICLIGHT, object_index=len(md.objects) - 1, pos=pos.copy(), angle=angle,
+                corners=corners.copy(), axes=axes.copy(), safety_radius=float(radius)))
         if collidable:
             corners_l.append(corners.T)
             norms_l.append(axes)

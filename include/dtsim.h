@@ -72,7 +72,9 @@ typedef struct {            /* one placed prop: objects.py:33-66 (WorldObj), ren
   float y_rot_deg;
   int32_t mesh_id;
   int32_t optional;         /* hidden w.p. 1/2 at reset under domain_rand (S:653-654) */
-  int32_t dyn_slot;         /* -1: static; else index into dts_map_blob.dyn — pose comes from the per-env state */
+  int32_t dyn_slot;         /* -1: static; else index into dts_map_blob.dyn — pose / card come from the per-env state */
+  int32_t alt_tex_from;     /* traffic light: triangles textured `alt_tex_from` show `alt_tex_to` while the shared */
+  int32_t alt_tex_to;       /*   card is on pattern 1 (mesh.textures[0] = texs[pattern] O:453,462); -1 = none */
   int32_t reserved;
 } dts_object;
 
@@ -80,7 +82,8 @@ typedef struct {            /* one placed prop: objects.py:33-66 (WorldObj), ren
  * O:180-336, with its state at map load.  Every env carries its own copy of the evolving state (per map), which
  * like the reference's object list survives resets.  Under domain_rand the reference draws vel / wait_time /
  * follow_dist ... from the GLOBAL numpy RNG at construction (O:348-350, O:197-205): the host supplies them. */
-enum { DTS_DYN_DUCKIE = 1, DTS_DYN_DUCKIEBOT = 2 };
+enum { DTS_DYN_DUCKIE = 1, DTS_DYN_DUCKIEBOT = 2,
+       DTS_DYN_TRAFFICLIGHT = 3 /* TrafficLightObj O:434-462: static, never collides; flips its card every freq s */ };
 #define DTS_MAX_DYN 32
 typedef struct {
   int32_t kind;             /* DTS_DYN_* */
@@ -91,11 +94,17 @@ typedef struct {
   double safety_radius;     /* O:66 */
   double walk_distance, vel, wait_time, wiggle;                       /* DuckieObj O:343-366 */
   double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length; /* O:196-227 */
+  double freq;              /* TrafficLightObj O:445-450 (5; randint(4,7) under domain_rand) */
+  int32_t pattern;          /* starting pattern (0; randint(0,2) under domain_rand) */
+  int32_t reserved;
 } dts_dyn_object;
 
 /* Per-env state of one dynamic obstacle: DTS_DYN_FIELDS doubles, device layout [field][slot][env]. */
 enum { DTS_DYN_PX = 0, DTS_DYN_PZ, DTS_DYN_ANGLE, DTS_DYN_YROT, DTS_DYN_CORNERS /* 8: x0 z0 .. x3 z3 */,
-       DTS_DYN_START_X = 12, DTS_DYN_START_Z, DTS_DYN_WAIT, DTS_DYN_VEL, DTS_DYN_TIME, DTS_DYN_ACTIVE, DTS_DYN_FIELDS };
+       DTS_DYN_START_X = 12, DTS_DYN_START_Z, DTS_DYN_WAIT, DTS_DYN_VEL, DTS_DYN_TIME, DTS_DYN_ACTIVE, DTS_DYN_FIELDS,
+       /* traffic lights reuse two fields: their own pattern, and — in the FIRST light's slot — the card the mesh
+        * they all share currently shows (every flip assigns it; the last writer wins, like the reference) */
+       DTS_DYN_PATTERN = DTS_DYN_ACTIVE, DTS_DYN_SHOWN = DTS_DYN_WAIT };
 
 typedef struct { int32_t tri_offset, tri_count; } dts_mesh;
 

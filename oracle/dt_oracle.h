@@ -41,7 +41,10 @@ typedef struct {
 } orc_step_out;
 
 typedef struct { int32_t w, h; const uint8_t* rgba; } orr_texture;
-typedef struct { float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count; } orr_object;
+typedef struct {
+  float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count;
+  int32_t tex_from, tex_to; /* triangles textured tex_from draw tex_to instead (traffic-light card); -1 = off */
+} orr_object;
 
 typedef struct {
   double tile_size;
@@ -67,7 +70,7 @@ typedef struct { /* mirrors the product's per-episode render record */
 } orr_episode;
 
 typedef struct {   /* one dynamic obstacle (objects.py DuckieObj / DuckiebotObj) */
-  int32_t kind;      /* 1 duckie pedestrian, 2 duckiebot follower */
+  int32_t kind;      /* 1 duckie pedestrian, 2 duckiebot follower, 3 traffic light */
   int32_t active;    /* DuckieObj.pedestrian_active */
   double pos[3], angle, y_rot;
   double corners[4][2];
@@ -75,6 +78,9 @@ typedef struct {   /* one dynamic obstacle (objects.py DuckieObj / DuckiebotObj)
   double safety_radius;
   double walk_distance, vel, wait_time, wiggle, time, start[3], heading[3];
   double follow_dist, velocity, gain, trim, radius, k, limit, wheel_dist, robot_width, robot_length;
+  double freq;       /* kind 3 (TrafficLightObj): `active` is its pattern */
+  int32_t tl_first;  /* index of the first traffic light: its `shown` is the card of the mesh they all share */
+  int32_t shown;
 } orc_dyn;
 
 int orc_closest_curve_point(const orc_map* m, double px, double pz, double angle, double pnt[3], double tan3[3]);

@@ -88,10 +88,22 @@ static void duckiebot_step(const orc_map* m, orc_dyn* o, double dt) {
   duckiebot_update_pos(o, o->velocity, steering, dt);
 }
 
+/* TrafficLightObj.step O:455-462.  Python's round(time, 3) is restated as rint(time*1000)/1000: the same value
+ * unless time*1000 sits within an ulp of a .5 tie, which multiples of 1/frame_rate never do. */
+static void trafficlight_step(orc_dyn* objs, orc_dyn* o, double dt) {
+  o->time += dt;
+  double r = rint(o->time * 1000.0) / 1000.0;
+  if (fmod(r, o->freq) == 0) {
+    o->active ^= 1;
+    objs[o->tl_first].shown = o->active;   /* self.mesh.textures[0] = ... on the mesh all lights share */
+  }
+}
+
 /* the update loop of update_physics S:1570-1584 for the dynamic objects of one env */
 void orc_dyn_step_all(const orc_map* m, orc_dyn* objs, int n, double dt) {
   for (int i = 0; i < n; i++) {
     if (objs[i].kind == 2) duckiebot_step(m, &objs[i], dt);
+    else if (objs[i].kind == 3) trafficlight_step(objs, &objs[i], dt);
     else duckie_step(&objs[i], dt);
   }
 }
@@ -110,6 +122,7 @@ int orc_dyn_collision(const orc_dyn* objs, int n, double px, double pz, double a
   orc_agent_corners(px, pz, angle, cx, cz);
   const double an[2][2] = {{sin(angle), cos(angle)}, {cos(angle), -sin(angle)}};
   for (int i = 0; i < n; i++) {
+    if (objs[i].kind == 3) continue;   /* static WorldObj.check_collision -> False (O:150-158) */
     double ox[4], oz[4];
     for (int k = 0; k < 4; k++) { ox[k] = objs[i].corners[k][0]; oz[k] = objs[i].corners[k][1]; }
     int hit = 1;
@@ -131,6 +144,7 @@ double orc_dyn_proximity(const orc_dyn* objs, int n, double px, double pz, doubl
   double ax = px + off * cos(angle), az = pz + off * -sin(angle);
   double r1 = (fmax(0.18, 0.13 + 0.02) / 2) * 1.8, tot = 0.0;
   for (int i = 0; i < n; i++) {
+    if (objs[i].kind == 3) continue;   /* static WorldObj.proximity -> 0 (O:160-168) */
     double dx = ax - objs[i].pos[0], dy = 0 - objs[i].pos[1], dz = az - objs[i].pos[2];
     double score = sqrt(dx * dx + dy * dy + dz * dz) - r1 - objs[i].safety_radius;
     tot += score < 0 ? score : 0;

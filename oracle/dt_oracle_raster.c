@@ -437,7 +437,9 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
     model_view(V, t, (double)ob->scale, cos(th), sin(th), x.MV, x.N);
     for (int k = 0; k < ob->tri_count; k++) {
       size_t ti = (size_t)ob->tri_offset + k;
-      const orr_texture* tex = sc->tri_tex[ti] >= 0 ? &sc->textures[sc->tri_tex[ti]] : NULL;
+      int tid = sc->tri_tex[ti];
+      if (tid >= 0 && tid == ob->tex_from) tid = ob->tex_to;   /* TrafficLightObj card swap O:453,462 */
+      const orr_texture* tex = tid >= 0 ? &sc->textures[tid] : NULL;
       draw_triangle(&fb, &x, sc->tri_pos + ti * 9, sc->tri_nrm + ti * 9, sc->tri_uv + ti * 6, sc->tri_col + ti * 9, tex);
     }
   }

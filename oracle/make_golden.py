@@ -14,7 +14,9 @@ Files written
 from __future__ import annotations
 
 import hashlib
+import functools
 import os
+from unittest import mock
 import sys
 
 import numpy as np
@@ -262,6 +264,43 @@ def gen_dynamic(name: str, steps=900, seed=21):
           f"active {out['active'].mean():.2f}")
 
 
+def gen_trafficlight(name="loop_trafficlights", steps=1300, seed=5):
+    """TrafficLightObj (objects.py:434-476) stepped by the reference's own code: pattern per light, and which card
+    the SHARED mesh shows (every light assigns mesh.textures[0]; the last writer wins).  Two runs: the
+    non-randomized defaults (freq 5, pattern 0) and domain_rand=True, where the reference draws freq / pattern from
+    the global numpy RNG at construction (recorded as inputs)."""
+    raw = raw_map(name)
+    out = {}
+    for tag, dr in (("plain", False), ("dr", True)):
+        np.random.seed(seed)
+        S, C, G, O = refstub.modules()
+        # graphics.load_texture is lru_cached per path (G:69); under the pyglet mock every call returns the same
+        # MagicMock, so give each path its own token
+        with mock.patch.object(O, "load_texture", functools.lru_cache(maxsize=None)(lambda path, *a, **k: ("tex", path))), \
+                mock.patch.object(O, "get_resource_path", lambda fn: fn):     # duckietown_world is a mock too
+            sim = refstub.build_reference_sim(raw, extents_for(raw), domain_rand=dr)
+        tls = [o for o in sim.objects if isinstance(o, O.TrafficLightObj)]
+        assert len({id(o.mesh) for o in tls}) == 1 and tls[0].texs[0] is not tls[0].texs[1]
+
+        def shown():
+            tex = tls[0].mesh.textures[0]
+            return [j for o in tls for j in (0, 1) if o.texs[j] is tex][0]
+        out[f"{tag}_freq"] = np.array([o.freq for o in tls])
+        out[f"{tag}_pattern0"] = np.array([o.pattern for o in tls])
+        out[f"{tag}_shown0"] = np.array(shown())
+        pat, shw = [], []
+        for t in range(steps):
+            for obj in sim.objects:   # S:1570-1584
+                obj.step(sim.delta_time)
+            pat.append([o.pattern for o in tls])
+            shw.append(shown())
+        out[f"{tag}_pattern"], out[f"{tag}_shown"] = np.array(pat, np.int8), np.array(shw, np.int8)
+        out["tl_index"] = np.array([sim.objects.index(o) for o in tls])
+        print(f"trafficlight_{name}[{tag}]: freq {out[f'{tag}_freq']}, pattern0 {out[f'{tag}_pattern0']}, "
+              f"flips {np.abs(np.diff(out[f'{tag}_pattern'], axis=0)).sum(0)}, shown flips {np.abs(np.diff(shw)).sum()}")
+    np.savez_compressed(os.path.join(OUT, f"trafficlight_{name}.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for m in MAPS:
@@ -272,3 +311,4 @@ if __name__ == "__main__":
     gen_fisheye()
     for m in ("loop_pedestrians", "loop_dyn_duckiebots"):
         gen_dynamic(m)
+    gen_trafficlight()

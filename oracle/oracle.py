@@ -164,7 +164,7 @@ class OrrTexture(C.Structure):
 
 class OrrObject(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("tri_offset", C.c_int32),
-                ("tri_count", C.c_int32)]
+                ("tri_count", C.c_int32), ("tex_from", C.c_int32), ("tex_to", C.c_int32)]
 
 
 class OrrScene(C.Structure):
@@ -207,13 +207,20 @@ class OracleScene:
         for i, o in enumerate(md.objects):
             src = k["objs"][i]
             me = k["meshes"][o.mesh_id]
-            self.objs[i] = OrrObject((C.c_float * 3)(*[float(v) for v in src.pos]), src.scale, src.y_rot_deg, me.tri_offset, me.tri_count)
+            self.objs[i] = OrrObject((C.c_float * 3)(*[float(v) for v in src.pos]), src.scale, src.y_rot_deg, me.tri_offset, me.tri_count, -1, -1)
         self.texs = (OrrTexture * max(1, len(k["tex_imgs"])))()
         for i, im in enumerate(k["tex_imgs"]):
             self.texs[i] = OrrTexture(im.shape[1], im.shape[0], im.ctypes.data)
         self.c = OrrScene(md.tile_size, md.grid_w, md.grid_h, _p(k["kind"]), _p(k["angle"]), _p(k["tex"]),
                           len(md.objects), C.cast(self.objs, C.c_void_p), _p(k["tpos"]), _p(k["tnrm"]), _p(k["tuv"]),
                           _p(k["tcol"]), _p(k["ttex"]), len(k["tex_imgs"]), C.cast(self.texs, C.c_void_p))
+
+    def set_trafficlight_card(self, pattern: int):
+        """Which card the mesh shared by all traffic lights shows (TrafficLightObj O:453,462)."""
+        src = self.holder.keep["objs"]
+        for i in range(self.c.n_objects):
+            on = pattern and src[i].alt_tex_from >= 0
+            self.objs[i].tex_from, self.objs[i].tex_to = (src[i].alt_tex_from, src[i].alt_tex_to) if on else (-1, -1)
 
     def set_object_pose(self, i, pos, y_rot_deg):
         """Move object i (a dynamic obstacle of one env) before rendering that env's frame."""
@@ -285,13 +292,14 @@ class OrcDyn(C.Structure):
                 ("wait_time", C.c_double), ("wiggle", C.c_double), ("time", C.c_double), ("start", C.c_double * 3),
                 ("heading", C.c_double * 3)] + [(n, C.c_double) for n in (
                     "follow_dist", "velocity", "gain", "trim", "radius", "k", "limit", "wheel_dist", "robot_width",
-                    "robot_length")]
+                    "robot_length", "freq")] + [("tl_first", C.c_int32), ("shown", C.c_int32)]
 
 
 class OracleDynamics:
     """The dynamic obstacles of one env (MapData.dyn_objects), stepped by the C oracle."""
 
-    def __init__(self, omap: OracleMap, wiggle=None):
+    def __init__(self, omap: OracleMap, wiggle=None, freq=None, pattern=None):
+        """wiggle / freq / pattern: per dynamic object overrides of what the reference draws from the global RNG."""
         md = omap.md
         self.m, self.n = omap, len(md.dyn_objects)
         self.objs = (OrcDyn * max(1, self.n))()
@@ -308,11 +316,25 @@ class OracleDynamics:
                 o.norm[k] = float(np.ravel(d.axes)[k])
             o.safety_radius, o.walk_distance, o.vel, o.wait_time = d.safety_radius, d.walk_distance, d.vel, d.wait_time
             o.wiggle = d.wiggle if wiggle is None else float(wiggle[i])
+            o.freq = d.freq if freq is None else float(freq[i])
+            if d.kind == 3:
+                o.active = int(d.pattern if pattern is None else pattern[i])
             o.time = 0.0
             o.heading[0], o.heading[1], o.heading[2] = math.cos(d.angle), 0.0, -math.sin(d.angle)   # heading_vec C:222
             (o.follow_dist, o.velocity, o.gain, o.trim, o.radius, o.k, o.limit, o.wheel_dist, o.robot_width,
              o.robot_length) = (d.follow_dist, d.velocity, d.gain, d.trim, d.radius, d.k, d.limit, d.wheel_dist,
                                 d.robot_width, d.robot_length)
+
+        tls = [i for i, d in enumerate(md.dyn_objects) if d.kind == 3]
+        for i in range(self.n):
+            self.objs[i].tl_first = tls[0] if tls else -1
+        if tls:
+            self.objs[tls[0]].shown = self.objs[tls[-1]].active     # constructors assign in order: the last one shows
+
+    @property
+    def shown_card(self) -> int:
+        t = self.objs[0].tl_first
+        return int(self.objs[t].shown) if t >= 0 else 0
 
     def step(self, dt=1.0 / 30):
         lib().orc_dyn_step_all(C.byref(self.m.c), self.objs, self.n, C.c_double(dt))

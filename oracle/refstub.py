@@ -299,9 +299,16 @@ def build_reference_sim(map_data: dict, mesh_extents: dict, *, domain_rand=False
     sim.wheelVels = np.array([0, 0])
     sim.map_name = "standin"
 
+    mesh_cache = {}
+
     def fake_get_mesh(kind, segment=False, change_materials=None):
-        lo, hi = mesh_extents[kind]
-        return FakeMesh(lo, hi)
+        # cached per kind like ObjMesh.get (objmesh.py:28-62): TrafficLightObj instances SHARE their mesh, and
+        # with it the card texture they assign in step() (objects.py:453,462)
+        key = (kind, repr(change_materials))
+        if key not in mesh_cache:
+            lo, hi = mesh_extents[kind]
+            mesh_cache[key] = FakeMesh(lo, hi)
+        return mesh_cache[key]
 
     _get_transform.grid_height = len(map_data["tiles"])
     with mock.patch.object(S, "get_mesh", fake_get_mesh), \

@@ -224,3 +224,60 @@ def test_domain_rand_finish_walk_draws(golden_dir, torch_cuda):
     assert len(np.unique(np.round(wait * 30))) > 10
     assert len(np.unique(vel)) > N            # per env, per duckie draws
     env.close()
+
+
+@pytest.mark.parametrize("tag", ["plain", "dr"])
+def test_traffic_lights_vs_reference_golden(tag, golden_dir, torch_cuda):
+    """TrafficLightObj (O:434-462) on the device: per-light pattern and the card of the shared mesh, step for step
+    against the reference's own objects; frames with either card against the raster oracle."""
+    torch = torch_cuda
+    import copy
+    import oracle as orc
+    from gym_duckietown_b200 import lib as L, maps
+    g = np.load(os.path.join(golden_dir, "trafficlight_loop_trafficlights.npz"))
+    md = copy.deepcopy(maps.load_map("loop_trafficlights"))
+    tl = [i for i, d in enumerate(md.dyn_objects) if d.kind == maps.DYN_TRAFFICLIGHT]
+    for k, i in enumerate(tl):
+        md.dyn_objects[i].freq, md.dyn_objects[i].pattern = float(g[f"{tag}_freq"][k]), int(g[f"{tag}_pattern0"][k])
+    N = 4
+    env = make_env(md, N)
+    env.reset(render=False)
+    # look at the first light from 0.6 m
+    o = md.objects[md.dyn_objects[tl[0]].object_index]
+    a = np.array([0.2, 1.7, 3.3, 4.9])
+    px, pz = o.pos[0] - 0.6 * np.cos(a), o.pos[2] + 0.6 * np.sin(a)
+    env.sim.reset(None, dict(pos_x=px, pos_z=pz, angle=a))
+    st = dyn_host(env, torch)
+    assert np.all(st[L.DYN_SHOWN, tl[0], :] == g[f"{tag}_shown0"])
+    zero = torch.zeros(N, 2, device=env.device)
+    scene = orc.OracleScene(md)
+    frames = {}
+    T = len(g[f"{tag}_shown"])
+    want_frames = {100, int(np.flatnonzero(np.diff(g[f"{tag}_shown"]))[0]) + 5}
+    for t in range(T):
+        obs, *_ = env.step(zero, render=t in want_frames)
+        if t in want_frames:
+            frames[t] = (obs.cpu().numpy().copy(), dyn_host(env, torch))
+        if t % 7 == 0 or t in want_frames or t > T - 5:
+            st = dyn_host(env, torch)
+            for e in (0, N - 1):
+                assert np.array_equal(st[L.DYN_PATTERN, tl, e], g[f"{tag}_pattern"][t]), t
+                assert st[L.DYN_SHOWN, tl[0], e] == g[f"{tag}_shown"][t], t
+    state = {k: v.cpu().numpy() for k, v in env.state.items()}
+    cards = set()
+    for t, (got, dst) in frames.items():
+        card = int(g[f"{tag}_shown"][t])
+        cards.add(card)
+        scene.set_trafficlight_card(card)
+        for e in range(N):
+            for s, d in enumerate(md.dyn_objects):      # the walking duckie of this map: where env e has it
+                if d.kind != maps.DYN_TRAFFICLIGHT:
+                    scene.set_object_pose(d.object_index, (dst[L.DYN_PX, s, e], d.pos[1], dst[L.DYN_PZ, s, e]), dst[L.DYN_YROT, s, e])
+            want = scene.render(state["pos_x"][e], state["pos_z"][e], state["angle"][e])
+            diff = np.abs(got[e].astype(int) - want.astype(int))
+            assert diff.max() <= 1, (t, e, int((diff > 0).sum()))
+        scene.set_trafficlight_card(1 - card)
+        other = scene.render(state["pos_x"][0], state["pos_z"][0], state["angle"][0])
+        assert np.any(other != got[0])            # the card is in view: the other pattern would look different
+    assert cards == {0, 1}
+    env.close()

@@ -33,3 +33,22 @@ def test_dynamic_objects_vs_reference(name, golden_dir):
             assert abs(prox - g["q_prox"][qi]) <= 1e-12, (t, qi)
             qi += 1
     assert qi == len(g["q_step"]) and g["q_coll"].any() and not g["q_coll"].all()
+
+
+@pytest.mark.parametrize("tag", ["plain", "dr"])
+def test_traffic_lights_vs_reference(tag, golden_dir):
+    """TrafficLightObj.step (O:455-462): per-light pattern and the card of the mesh all lights share."""
+    g = np.load(os.path.join(golden_dir, "trafficlight_loop_trafficlights.npz"))
+    md = maps.load_map("loop_trafficlights")
+    om = orc.OracleMap(md)
+    tl = [i for i, d in enumerate(md.dyn_objects) if d.kind == maps.DYN_TRAFFICLIGHT]
+    assert [md.dyn_objects[i].object_index for i in tl] == list(g["tl_index"])
+    freq, pat = [5.0] * len(md.dyn_objects), [0] * len(md.dyn_objects)
+    for k, i in enumerate(tl):
+        freq[i], pat[i] = float(g[f"{tag}_freq"][k]), int(g[f"{tag}_pattern0"][k])
+    dyn = orc.OracleDynamics(om, freq=freq, pattern=pat)
+    assert dyn.shown_card == int(g[f"{tag}_shown0"])
+    for t in range(len(g[f"{tag}_shown"])):
+        dyn.step()
+        assert [dyn.objs[i].active for i in tl] == list(g[f"{tag}_pattern"][t]), t
+        assert dyn.shown_card == g[f"{tag}_shown"][t], t
