@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--domain-rand", action="store_true", help="BASELINE config 4: domain randomization on")
     ap.add_argument("--distortion", action="store_true", help="BASELINE config 4: fused fisheye gather")
+    ap.add_argument("--obs-format", default="hwc_uint8",
+                    help="fused wrapper output (SURVEY 8f-3): <hwc|chw|cwh>_<uint8|float32>; default is render_obs's own")
     ap.add_argument("--cycle-maps", action="store_true", help="BASELINE config 5: --map a,b cycled on reset (MultiMap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -193,6 +195,10 @@ def main():
     env = BatchedDuckietownEnv(E, map_arg, device=local_rank, camera_width=W, camera_height=H,
                                domain_rand=args.domain_rand, distortion=args.distortion, cycle_maps=args.cycle_maps,
                                seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E)
+    if args.obs_format != "hwc_uint8":
+        lay, dt = args.obs_format.split("_")
+        env.set_output_format(obs_layout=lay, obs_dtype=dt)
+        config["obs_format"] = args.obs_format
     env.reset()
     K, Wm = args.steps, max(3, args.warmup)
     gen = torch.Generator(device=dev)
@@ -202,7 +208,7 @@ def main():
     if world > 1:
         from gym_duckietown_b200.dist import ObsAllGather
         ag = ObsAllGather(env, rank, world)
-        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=torch.uint8, device=dev)
+        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=env.obs.dtype, device=dev)
 
     def barrier():
         if world > 1:
@@ -294,7 +300,7 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 logic / f32 raster / u8 obs", "data": "synthetic", "config": config,
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4, "d2h_bytes_per_step": E * (W * H * 3 + 4 + 1),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4, "d2h_bytes_per_step": E * (W * H * 3 * env.obs.element_size() + 4 + 1),
                 "steps": Ke, "api": "HostPipeline.submit/result, depth 2 (D2H of step k overlaps step k+1)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "render launches of one step: k_frame_setup + k_geometry + k_raster (k_raster dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -72,7 +72,33 @@ class BatchedDuckietownEnv:
             user_tile_start=user_tile_start)
         self.map_ids = np.zeros(num_envs, np.int32)
         self._first_reset = True
+        self.output_format = dict(obs_layout="hwc", obs_dtype="uint8", reward="raw", discrete_actions=False,
+                                  action_vel_scale=1.0)
         self.seed(seed)
+
+    def set_output_format(self, obs_layout: Optional[str] = None, obs_dtype: Optional[str] = None,
+                          reward: Optional[str] = None, discrete_actions: Optional[bool] = None,
+                          action_vel_scale: Optional[float] = None):
+        """Fuse the reference's wrapper stack into the step kernels (dts_set_output_format): obs_layout 'hwc' |
+        'chw' (ImgWrapper) | 'cwh' (PyTorchObsWrapper), obs_dtype 'uint8' | 'float32' (NormalizeWrapper: /255),
+        reward 'raw' | 'dt' (DtRewardWrapper), discrete_actions (DiscreteWrapper: ids in actions[:, 0]),
+        action_vel_scale (ActionWrapper: 0.8).  Re-allocates `self.obs` in the new shape / dtype."""
+        f = self.output_format
+        for key, val in (("obs_layout", obs_layout), ("obs_dtype", obs_dtype), ("reward", reward),
+                         ("discrete_actions", discrete_actions), ("action_vel_scale", action_vel_scale)):
+            if val is not None:
+                f[key] = val
+        lay = {"hwc": L.OBS_HWC, "chw": L.OBS_CHW, "cwh": L.OBS_CWH}[f["obs_layout"]]
+        dt = {"uint8": L.OBS_U8, "float32": L.OBS_F32_UNIT}[f["obs_dtype"]]
+        rw = {"raw": L.REWARD_RAW, "dt": L.REWARD_DT}[f["reward"]]
+        self.sim.set_output_format(lay, dt, rw, L.ACTIONS_DISCRETE3 if f["discrete_actions"] else L.ACTIONS_CONTINUOUS,
+                                   f["action_vel_scale"])
+        H, W = self.camera_height, self.camera_width
+        shape = {"hwc": (H, W, 3), "chw": (3, H, W), "cwh": (3, W, H)}[f["obs_layout"]]
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((self.num_envs,) + shape, device=self.device,
+                                   dtype=torch.uint8 if dt == L.OBS_U8 else torch.float32)
+        return self
 
     # ------------------------------------------------------------------ gym-like surface
     def seed(self, seed=None):
@@ -170,7 +196,7 @@ class HostPipeline:
             self.slots.append(dict(
                 act=torch.empty((n, 2), dtype=torch.float32, device=dev),
                 obs=torch.empty_like(env.obs), rew=torch.empty_like(env.reward), done=torch.empty_like(env._done_u8),
-                h_obs=torch.empty(tuple(env.obs.shape), dtype=torch.uint8).pin_memory(),
+                h_obs=torch.empty(tuple(env.obs.shape), dtype=env.obs.dtype).pin_memory(),
                 h_rew=torch.empty(n, dtype=torch.float32).pin_memory(),
                 h_done=torch.empty(n, dtype=torch.uint8).pin_memory(),
                 computed=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False))

@@ -43,6 +43,7 @@ struct dts_sim {
   void* nccl_lib = nullptr; void* nccl_comm = nullptr;
   uint64_t launches = 0;
   bool seeded = false;
+  dts_output_format fmt{DTS_OBS_HWC, DTS_OBS_U8, DTS_REWARD_RAW, DTS_ACTIONS_CONTINUOUS, 1.0};
   std::string err;
 
   int fail(const char* fmt, ...) {
@@ -109,6 +110,7 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   c.dyn.delay_steps = d;
   c.frame_skip = cfg->frame_skip; c.max_steps = cfg->max_steps; c.action_mode = cfg->action_mode; c.flags = cfg->flags;
   c.seed = cfg->seed; c.env_id_offset = cfg->env_id_offset;
+  c.reward_mode = DTS_REWARD_RAW; c.action_map = DTS_ACTIONS_CONTINUOUS; c.action_vel_scale = 1.0;
   DState& S = sim->S;
   S.n = n;
   int bad = 0;
@@ -389,7 +391,7 @@ static int ensure_render(dts_sim* sim) {
   return 0;
 }
 
-int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
+int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
   if (!sim) return 1;
   if (!obs_dev) return sim->fail("obs_dev is NULL");
   if (check_maps(sim)) return 1;
@@ -397,7 +399,7 @@ int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
   if (ensure_render(sim)) return 1;
   if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->lut_x) return sim->fail("distortion enabled but no fisheye LUT set");
   RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
-               (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0};
+               (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0, sim->fmt.obs_layout, sim->fmt.obs_dtype};
   const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
                               sim->bin_cap, sim->max_lat, sim->items_max, sim->lut_x, sim->lut_y, sim->d_err,
                               (cudaStream_t)stream);
@@ -406,7 +408,7 @@ int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream) {
   return 0;
 }
 
-int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* reward_dev, uint8_t* done_dev,
+int dts_step(dts_sim* sim, const float* actions_dev, void* obs_dev, float* reward_dev, uint8_t* done_dev,
              void* stream) {
   if (!sim) return 1;
   if (!actions_dev) return sim->fail("actions_dev is NULL");
@@ -454,6 +456,21 @@ int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* 
   DTS_CUDA(cudaGetLastError());
   DTS_CUDA(cudaMemcpy(out_f64, sim->q_outd, (size_t)n * 32, cudaMemcpyDeviceToHost));
   DTS_CUDA(cudaMemcpy(out_i32, sim->q_outi, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dts_set_output_format(dts_sim* sim, const dts_output_format* f) {
+  if (!sim) return 1;
+  if (!f) return sim->fail("format is NULL");
+  if (f->obs_layout < DTS_OBS_HWC || f->obs_layout > DTS_OBS_CWH) return sim->fail("bad obs_layout %d", f->obs_layout);
+  if (f->obs_dtype != DTS_OBS_U8 && f->obs_dtype != DTS_OBS_F32_UNIT) return sim->fail("bad obs_dtype %d", f->obs_dtype);
+  if (f->reward_mode != DTS_REWARD_RAW && f->reward_mode != DTS_REWARD_DT) return sim->fail("bad reward_mode %d", f->reward_mode);
+  if (f->action_map != DTS_ACTIONS_CONTINUOUS && f->action_map != DTS_ACTIONS_DISCRETE3) return sim->fail("bad action_map %d", f->action_map);
+  if (f->action_map == DTS_ACTIONS_DISCRETE3 && sim->cfg.action_mode != DTS_ACTION_VEL_STEER)
+    return sim->fail("discrete actions are [vel, steering] pairs (DiscreteWrapper wraps DuckietownEnv): action_mode must be VEL_STEER");
+  sim->fmt = *f;
+  sim->step_cfg.reward_mode = f->reward_mode; sim->step_cfg.action_map = f->action_map;
+  sim->step_cfg.action_vel_scale = f->action_vel_scale;
   return 0;
 }
 

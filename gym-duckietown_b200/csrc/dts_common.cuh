@@ -123,6 +123,8 @@ struct StepCfg {
   double gain, trim, radius, k, limit;
   DynParams dyn;
   int32_t frame_skip, max_steps, action_mode, flags;
+  int32_t reward_mode, action_map;      // dts_output_format
+  double action_vel_scale;
   uint64_t seed;
   int64_t env_id_offset;
 };

@@ -20,6 +20,7 @@ struct RenderCfg {
   int32_t flags;
   int32_t n_envs;
   int32_t tessellate;         // 1: literal 98 triangles per road tile (spec tile mode 0)
+  int32_t obs_layout, obs_dtype;   // DTS_OBS_* (dts_output_format)
 };
 
 void launch_step_logic(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const float* actions,
@@ -36,7 +37,7 @@ int render_ctas_per_sm();
 // scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
 // undistorted frames when the fisheye gather is on
 size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame);
-int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
+int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
                   int32_t* err_flag, cudaStream_t st);
 

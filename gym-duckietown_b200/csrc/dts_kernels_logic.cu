@@ -39,7 +39,11 @@ __device__ inline void evaluate_pose(const DState& S, const DMap& m, const StepC
   S.tile_i[e] = ti; S.tile_j[e] = tj;
   S.lane_dist[e] = lp.dist; S.lane_dot[e] = lp.dot_dir; S.lane_angle[e] = lp.angle_rad; S.in_lane[e] = lp.in_lane;
   S.prox[e] = pen; S.collided[e] = hit; S.reward[e] = rew; S.done_code[e] = code;
-  if (reward) reward[e] = (float)rew;
+  if (reward) {
+    double out = rew;
+    if (c.reward_mode == DTS_REWARD_DT) out = rew == -1000.0 ? -10.0 : (rew > 0 ? rew + 10 : rew + 4);   // LW:94-102
+    reward[e] = (float)out;
+  }
   if (done) done[e] = code != DTS_IN_PROGRESS;
 }
 
@@ -156,8 +160,15 @@ __global__ void __launch_bounds__(128) k_step_logic(DState S, const DMap* __rest
   if (e >= S.n) return;
   const DMap& m = maps[S.map_id[e]];
   const float2 act = reinterpret_cast<const float2*>(actions)[e];
-  double ul = (double)act.x, ur = (double)act.y;
-  if (c.action_mode == DTS_ACTION_VEL_STEER) action_to_pwm((double)act.x, (double)act.y, S.wheel_dist[e], c, ul, ur);
+  double a0 = (double)act.x, a1 = (double)act.y;
+  if (c.action_map == DTS_ACTIONS_DISCRETE3) {            // DiscreteWrapper.action W:18-30
+    const int id = (int)act.x;
+    a0 = id == 2 ? 0.7 : 0.6;
+    a1 = id == 0 ? 1.0 : (id == 1 ? -1.0 : 0.0);
+  }
+  a0 = a0 * c.action_vel_scale;                           // ActionWrapper.action LW:110-112 (scale 1.0: exact no-op)
+  double ul = a0, ur = a1;
+  if (c.action_mode == DTS_ACTION_VEL_STEER) action_to_pwm(a0, a1, S.wheel_dist[e], c, ul, ur);
   ul = clampd(ul, -1.0, 1.0);   // np.clip S:1670
   ur = clampd(ur, -1.0, 1.0);
   double x = S.cx[e], y = S.cy[e], th = S.ctheta[e], u = S.vu[e], w = S.vw[e];

@@ -480,6 +480,29 @@ __device__ __forceinline__ void store_bin(uint8_t* __restrict__ out, unsigned rg
   }
 }
 
+// One pixel in a wrapper layout / dtype (dts_output_format): element index of channel c at (x, y)
+__device__ __forceinline__ size_t fmt_index(int layout, int x, int y, int c, int W, int H) {
+  return layout == DTS_OBS_CHW ? ((size_t)c * H + y) * W + x
+       : layout == DTS_OBS_CWH ? ((size_t)c * W + x) * H + y
+                               : ((size_t)y * W + x) * 3 + c;
+}
+__device__ __forceinline__ void store_px_fmt(void* frame, int layout, int dtype, int x, int y, int W, int H, unsigned rgb) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const unsigned v = (rgb >> (8 * c)) & 255u;
+    const size_t i = fmt_index(layout, x, y, c, W, H);
+    if (dtype == DTS_OBS_F32_UNIT) reinterpret_cast<float*>(frame)[i] = (float)v / 255.0f;   // NormalizeWrapper LW:66-70
+    else reinterpret_cast<uint8_t*>(frame)[i] = (uint8_t)v;
+  }
+}
+// Fine-bin store: the packed u8 HWC fast path, or the wrapper format straight from the resolve registers.
+__device__ __forceinline__ void store_bin_any(uint8_t* __restrict__ out, int fmt, unsigned rgb, int lane, int bx, int by,
+                                              int W, int H) {
+  if (fmt == 0) { store_bin(out, rgb, lane, bx, by, W, H); return; }
+  const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
+  if (gx < W && gy < H) store_px_fmt(out, fmt & 3, fmt >> 2, gx, gy, W, H, rgb);
+}
+
 }  // namespace
 
 
@@ -773,6 +796,7 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
+template <bool kWrapFmt>   // true: a dts_output_format other than packed u8 HWC is written by the resolve
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, uint8_t* __restrict__ obs,
          int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
@@ -782,6 +806,9 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
   const size_t frame_bytes = (size_t)W * H * 3;
+  // wrapper output format (0 = packed u8 HWC); with the fisheye gather the raster writes the u8 HWC intermediate
+  const int out_fmt = (!kWrapFmt || fisheye) ? 0 : (rc.obs_layout | (rc.obs_dtype << 2));
+  const size_t out_elem = (kWrapFmt && !fisheye && rc.obs_dtype == DTS_OBS_F32_UNIT) ? 4 : 1;
   const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
   BinPrim* stage = stages[warp];
   const int n_work = rc.n_envs * cbins_y;   // work item = one row of coarse bins of one env
@@ -795,7 +822,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     const DMap& m = maps[S.map_id[env]];
     const PrimRec* prims = fm.prims + (size_t)env * max_prims;
     const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
-    uint8_t* out = (fisheye ? fm.undist : obs) + (size_t)env * frame_bytes;
+    uint8_t* out = fisheye ? fm.undist + (size_t)env * frame_bytes : obs + (size_t)env * frame_bytes * out_elem;
     const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
     for (int cbx = 0; cbx < cbins_x; cbx++) {
@@ -817,7 +844,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       for (int f = 0; f < kCFX * kCFY; f++) {
         const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
         if (bx * kBinW >= W || by * kBinH >= H) continue;
-        if (count == 0) { store_bin(out, clear_rgb, lane, bx, by, W, H); continue; }
+        if (count == 0) { store_bin_any(out, out_fmt, clear_rgb, lane, bx, by, W, H); continue; }
         const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
         float z[4], cr[4], cg[4], cb_[4];
         int wid[4];
@@ -848,7 +875,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
               float c3[3];
               shade_pixel(bp, lat_tab, cdx, cdy, c3);
-              store_bin(out, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
+              store_bin_any(out, out_fmt, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
               simple_done = true;
 #ifdef DTS_STATS
               if (lane == 0) atomicAdd(&err[13], 1);
@@ -919,7 +946,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
           const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
           const float b_ = ((cb_[0] + cb_[1]) + (cb_[2] + cb_[3])) * 0.25f;
-          store_bin(out, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
+          store_bin_any(out, out_fmt, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
         }
       }
     }
@@ -933,6 +960,7 @@ __global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __
                                                  uint8_t* __restrict__ obs) {
   const int W = rc.width, H = rc.height;
   const size_t npx = (size_t)W * H, total = npx * rc.n_envs;
+  const int fmt = rc.obs_layout | (rc.obs_dtype << 2);
   for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
     const size_t env = g / npx, p = g - env * npx;
     const int sx = (int)rintf(__ldg(lut_x + p)), sy = (int)rintf(__ldg(lut_y + p));
@@ -941,15 +969,22 @@ __global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __
       const uint8_t* s = undist + (env * npx + (size_t)sy * W + sx) * 3;
       r = s[0]; gg = s[1]; b = s[2];
     }
-    uint8_t* d = obs + g * 3;
-    d[0] = r; d[1] = gg; d[2] = b;
+    if (fmt == 0) {
+      uint8_t* d = obs + g * 3;
+      d[0] = r; d[1] = gg; d[2] = b;
+    } else {
+      const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+      store_px_fmt(obs + env * npx * 3 * (rc.obs_dtype == DTS_OBS_F32_UNIT ? 4 : 1), rc.obs_layout, rc.obs_dtype, x, y, W, H,
+                   (unsigned)r | ((unsigned)gg << 8) | ((unsigned)b << 16));
+    }
   }
 }
 
-int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_t* obs, void* scratch, int n_ctas,
+int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs_any, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
                   int32_t* err_flag, cudaStream_t st) {
   const int W = rc.width, H = rc.height;
+  uint8_t* obs = reinterpret_cast<uint8_t*>(obs_any);
   const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
   const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
@@ -960,7 +995,10 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, uint8_
                                                                               max_lat, err_flag);
   k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, (size_t)kBinWarps * 2 * cbins * sizeof(int), st>>>(
       rc, fm, max_prims, max_pairs, err_flag);
-  k_raster<<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
+  if (!fisheye && (rc.obs_layout | rc.obs_dtype) != 0)
+    k_raster<true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
+  else
+    k_raster<false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
   int launches = 4;
   if (fisheye) {
     k_fisheye<<<148 * 8, 256, 0, st>>>(rc, fm.undist, lut_x, lut_y, obs);

@@ -63,6 +63,17 @@ class DynObjectC(C.Structure):
                [(n, C.c_double) for n in _DYN_SCALARS] + [("freq", C.c_double), ("pattern", C.c_int32), ("reserved", C.c_int32)]
 
 
+OBS_HWC, OBS_CHW, OBS_CWH = 0, 1, 2
+OBS_U8, OBS_F32_UNIT = 0, 1
+REWARD_RAW, REWARD_DT = 0, 1
+ACTIONS_CONTINUOUS, ACTIONS_DISCRETE3 = 0, 1
+
+
+class OutputFormat(C.Structure):
+    _fields_ = [("obs_layout", C.c_int32), ("obs_dtype", C.c_int32), ("reward_mode", C.c_int32),
+                ("action_map", C.c_int32), ("action_vel_scale", C.c_double)]
+
+
 class Mesh(C.Structure):
     _fields_ = [("tri_offset", C.c_int32), ("tri_count", C.c_int32)]
 
@@ -134,6 +145,7 @@ def load() -> C.CDLL:
     lib.dts_render.argtypes = [vp, vp, vp]
     lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
     lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp]
+    lib.dts_set_output_format.argtypes = [vp, C.POINTER(OutputFormat)]
     lib.dts_get_dyn_state.argtypes = [vp, i, C.POINTER(vp), C.POINTER(C.c_int32)]
     lib.dts_comm_load.argtypes = [vp, C.c_char_p]
     lib.dts_comm_unique_id.argtypes = [vp, vp]
@@ -152,7 +164,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_get_dyn_state", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_last_error", "dts_destroy"]
 
 
@@ -303,6 +315,11 @@ class Sim:
 
     def render(self, obs_ptr: int, stream: int = 0):
         self._check(self.lib.dts_render(self.h, obs_ptr, stream), "dts_render")
+
+    def set_output_format(self, obs_layout=OBS_HWC, obs_dtype=OBS_U8, reward_mode=REWARD_RAW,
+                          action_map=ACTIONS_CONTINUOUS, action_vel_scale=1.0):
+        f = OutputFormat(obs_layout, obs_dtype, reward_mode, action_map, float(action_vel_scale))
+        self._check(self.lib.dts_set_output_format(self.h, C.byref(f)), "dts_set_output_format")
 
     def state_arrays(self) -> dict:
         v = StateView()

@@ -108,6 +108,23 @@ enum { DTS_DYN_PX = 0, DTS_DYN_PZ, DTS_DYN_ANGLE, DTS_DYN_YROT, DTS_DYN_CORNERS 
 
 typedef struct { int32_t tri_offset, tri_count; } dts_mesh;
 
+/* What the reference's wrapper stacks do to actions, observations and rewards, fused into the step kernels
+ * (SURVEY 8f-3).  W = src/gym_duckietown/wrappers.py, LW = learning/utils/wrappers.py. */
+enum { DTS_OBS_HWC = 0,     /* render_obs S:1953-1972: [H][W][3] */
+       DTS_OBS_CHW = 1,     /* ImgWrapper LW:73-87 transpose(2,0,1): [3][H][W] */
+       DTS_OBS_CWH = 2      /* PyTorchObsWrapper W:93-110 transpose(2,1,0): [3][W][H] */ };
+enum { DTS_OBS_U8 = 0,
+       DTS_OBS_F32_UNIT = 1 /* NormalizeWrapper LW:56-70: (obs - 0) / (255 - 0) as float32 */ };
+enum { DTS_REWARD_RAW = 0,
+       DTS_REWARD_DT = 1    /* DtRewardWrapper LW:90-102: -1000 -> -10, r > 0 -> r + 10, else r + 4 */ };
+enum { DTS_ACTIONS_CONTINUOUS = 0,
+       DTS_ACTIONS_DISCRETE3 = 1 /* DiscreteWrapper W:8-33: 0 left [0.6,+1], 1 right [0.6,-1], 2 forward [0.7,0];
+                                    actions[e][0] carries the id, actions[e][1] is ignored */ };
+typedef struct {
+  int32_t obs_layout, obs_dtype, reward_mode, action_map;
+  double action_vel_scale;  /* ActionWrapper LW:106-112: action[0] * 0.8 before the env sees it (1.0 = off) */
+} dts_output_format;
+
 /* Everything the hot path reads about one map, prepared on the host (maps.py):
  * tile grid S:788-860, curves S:1151-1335, static collidables S:1019-1038 / S:919-931,
  * meshes objmesh.py:65-293, textures graphics.py:70-169. All pointers are HOST memory, copied. */
@@ -202,10 +219,13 @@ int dts_seed_streams(dts_sim* sim, const uint8_t* mask_host, const uint64_t* str
 int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream);
 /* Simulator.step() (simulator.py:1669-1683) for all envs: actions f32[N][2] -> obs u8[N][H][W][3]
  * (NULL = skip rendering), reward f32[N], done u8[N]. All DEVICE pointers. */
-int dts_step(dts_sim* sim, const float* actions_dev, uint8_t* obs_dev, float* reward_dev, uint8_t* done_dev,
+int dts_step(dts_sim* sim, const float* actions_dev, void* obs_dev, float* reward_dev, uint8_t* done_dev,
              void* stream);
 /* Simulator.render_obs() (simulator.py:1953-1972) of the current state. */
-int dts_render(dts_sim* sim, uint8_t* obs_dev, void* stream);
+int dts_render(dts_sim* sim, void* obs_dev, void* stream);
+/* Select the fused wrapper behaviour for subsequent dts_step / dts_render calls (default: all zero, scale 1).
+ * obs_dev then holds num_envs * 3 * H * W elements of uint8 or float32 in the chosen layout. */
+int dts_set_output_format(dts_sim* sim, const dts_output_format* fmt);
 int dts_get_state(dts_sim* sim, dts_state_view* out);
 /* Batched pose predicates for host callers — the de-facto public helpers of Simulator:
  * _valid_pose (S:1494), _collision(get_agent_corners()) (S:1473, run_tests.py:50), get_lane_pos2 (S:1371),
