@@ -58,13 +58,14 @@ struct __align__(16) PrimRec {   // 128 B in the CTA's slab
   int32_t id_tex;                // draw id << 8 | (texture index + 1)
   int32_t pxmin, pxmax;          // pixel bbox (x | y<<16); 8-byte aligned, read as one int2 by the binner
   int32_t lat;                   // lattice slot of an analytic road tile, -1 otherwise
-  int32_t pad;
+  int32_t quad;                  // 1: convex quad X[0..2] + a 4th vertex kept in the bits of f0[4], f0[5] (an analytic
+                                 //    tile takes its colour from the lattice, so its r,g,b planes are free)
 };
 static_assert(offsetof(PrimRec, pxmin) % 8 == 0, "pxmin/pxmax are loaded as int2");
 static_assert(sizeof(PrimRec) == 128, "PrimRec must be 128 bytes");
 
 struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the current bin
-  int32_t E0[3], A[3], B[3];     // E_k(x,y) = E0_k + A_k*x + B_k*y, x,y in 1/64 px from the bin corner
+  int32_t E0[4], A[4], B[4];     // E_k(x,y) = E0_k + A_k*x + B_k*y, x,y in 1/64 px from the bin corner (triangles: E_3 = 0)
   int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
   float f0[7], fx[7], fy[7];
   int32_t id;                    // draw id
@@ -74,7 +75,7 @@ struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the curre
   int32_t lat;
   float twf, thf;                // (float)tex_w, (float)tex_h
 };
-static_assert(sizeof(BinPrim) == 160, "BinPrim layout");
+static_assert(sizeof(BinPrim) == 176, "BinPrim layout");
 
 struct Xform { float MV[12], N[9]; };
 
@@ -195,8 +196,11 @@ struct EmitCtx {
 };
 
 // screen mapping + triangle setup (spec steps 5-7) and append to the slab
-__device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
-                                               int tex, int lat) {
+// With `d` the prim is the QUAD a,b,c,d (spec tile mode 1: an unclipped road tile): planes of triangle (a,b,c),
+// coverage by four edges.  Returns false — nothing emitted — if the snapped quad is not strictly convex; the
+// caller then draws the two triangles (a,b,c)(a,c,d) instead.
+__device__ __forceinline__ bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+                                               int tex, int lat, const Vtx* d = nullptr) {
   const Vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
   float zw[3], q[3];
@@ -213,14 +217,29 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
     q[k] = iw;
   }
   const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
-  if (area2 == 0) return;
+  if (area2 == 0) return false;
   const int i1 = area2 < 0 ? 2 : 1, i2 = area2 < 0 ? 1 : 2;
   const int x0 = X[0], y0 = Y[0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
-  const int minx = min(x0, min(x1, x2)), maxx = max(x0, max(x1, x2));
-  const int miny = min(y0, min(y1, y2)), maxy = max(y0, max(y1, y2));
+  int minx = min(x0, min(x1, x2)), maxx = max(x0, max(x1, x2));
+  int miny = min(y0, min(y1, y2)), maxy = max(y0, max(y1, y2));
+  int qx[4] = {x0, x1, x2, 0}, qy[4] = {y0, y1, y2, 0};   // quad: cyclic order with positive orientation
+  if (d) {
+    const float iw = 1.0f / d->cw;
+    const float sx = ((d->cx * iw) * 0.5f + 0.5f) * Wf, sy = (0.5f - (d->cy * iw) * 0.5f) * Hf;
+    const int X3 = (int)rintf(sx * 64.0f), Y3 = (int)rintf(sy * 64.0f);
+    if (area2 > 0) { qx[1] = X[1]; qy[1] = Y[1]; qx[2] = X[2]; qy[2] = Y[2]; qx[3] = X3; qy[3] = Y3; }       // a b c d
+    else { qx[1] = X3; qy[1] = Y3; qx[2] = X[2]; qy[2] = Y[2]; qx[3] = X[1]; qy[3] = Y[1]; }                 // a d c b
+#pragma unroll
+    for (int k = 0; k < 4; k++) {   // strictly convex: every corner turns the same (positive) way
+      const int k1 = (k + 1) & 3, k2 = (k + 2) & 3;
+      const long long cr = (long long)(qx[k1] - qx[k]) * (qy[k2] - qy[k1]) - (long long)(qx[k2] - qx[k1]) * (qy[k1] - qy[k]);
+      if (cr <= 0) return false;
+    }
+    minx = min(minx, X3); maxx = max(maxx, X3); miny = min(miny, Y3); maxy = max(maxy, Y3);
+  }
   const int px0 = max(minx >> 6, 0), px1 = min(maxx >> 6, ec.W - 1);
   const int py0 = max(miny >> 6, 0), py1 = min(maxy >> 6, ec.H - 1);
-  if (px0 > px1 || py0 > py1) return;
+  if (px0 > px1 || py0 > py1) return true;   // off screen: emitted nothing, and nothing is what it covers
   PrimRec r;
   r.X[0] = x0; r.X[1] = x1; r.X[2] = x2;
   r.Y[0] = y0; r.Y[1] = y1; r.Y[2] = y2;
@@ -244,13 +263,28 @@ __device__ __forceinline__ void setup_and_emit(const EmitCtx& ec, const Vtx& a, 
   r.lat = lat;
   r.pxmin = px0 | (py0 << 16);
   r.pxmax = px1 | (py1 << 16);
-  r.pad = 0;
+  r.quad = 0;
+  if (d) {   // vertices in cyclic order; planes stay those of triangle (a,b,c) anchored at a
+    r.quad = 1;
+    r.X[1] = qx[1]; r.Y[1] = qy[1]; r.X[2] = qx[2]; r.Y[2] = qy[2];
+    r.f0[4] = __int_as_float(qx[3]); r.f0[5] = __int_as_float(qy[3]);
+  }
   const int slot = atomicAdd(&ec.ctx->n_prims, 1);
-  if (slot >= ec.max_prims) { ec.ctx->overflow = 1; return; }
+  if (slot >= ec.max_prims) { ec.ctx->overflow = 1; return true; }
   const int4* src = reinterpret_cast<const int4*>(&r);
   int4* dst = reinterpret_cast<int4*>(ec.prims + slot);
 #pragma unroll
   for (int k = 0; k < 8; k++) dst[k] = src[k];
+  return true;
+}
+
+// the prim's vertices in cyclic order (3, or 4 for a quad)
+__device__ __forceinline__ int prim_vertices(const PrimRec& r, int qx[4], int qy[4]) {
+  qx[0] = r.X[0]; qx[1] = r.X[1]; qx[2] = r.X[2]; qy[0] = r.Y[0]; qy[1] = r.Y[1]; qy[2] = r.Y[2];
+  qx[3] = qx[0]; qy[3] = qy[0];
+  if (!r.quad) return 3;
+  qx[3] = __float_as_int(r.f0[4]); qy[3] = __float_as_int(r.f0[5]);
+  return 4;
 }
 
 __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float din, float dout) {
@@ -344,16 +378,17 @@ __device__ __forceinline__ void process_triangle_lanes(const EmitCtx& ec, bool h
   }
 }
 
-// conservative triangle / bin overlap: false only if one edge has the whole bin on its outside
-__device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int ox, int oy) {
-  const int ax[3] = {X[1], X[2], X[0]}, ay[3] = {Y[1], Y[2], Y[0]}, bx[3] = {X[2], X[0], X[1]}, by[3] = {Y[2], Y[0], Y[1]};
+// conservative prim / bin overlap: false only if one edge has the whole bin on its outside
+__device__ __forceinline__ bool bin_overlaps(const int qx[4], const int qy[4], int n, int ox, int oy) {
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int dx = bx[k] - ax[k], dy = by[k] - ay[k];
+  for (int k = 0; k < 4; k++) {
+    if (k >= n) break;
+    const int k1 = (k + 1) & 3;   // a triangle's vertex 3 aliases vertex 0
+    const int dx = qx[k1] - qx[k], dy = qy[k1] - qy[k];
     // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the coarse bin's sample span
     const int xs = (-dy > 0) ? ox + (kCoarseW - 1) * kSub + 56 : ox + 8;
     const int ys = (dx > 0) ? oy + (kCoarseH - 1) * kSub + 56 : oy + 8;
-    const long long e = (long long)dx * (ys - ay[k]) - (long long)dy * (xs - ax[k]);
+    const long long e = (long long)dx * (ys - qy[k]) - (long long)dy * (xs - qx[k]);
     if (e < 0) return false;
   }
   return true;
@@ -365,14 +400,18 @@ __device__ __forceinline__ bool bin_overlaps(const int X[3], const int Y[3], int
 // corner (exact in 64 bits, then int32: inside the coarse bin |A*x + B*y| < 2^30), per-fine-bin exact
 // reject / trivial-accept bits, planes and texture.  Returns the prim's draw id.
 __device__ __forceinline__ int stage_prim(const PrimRec& r, BinPrim& bp, int ox, int oy, const DMap& m) {
-  const int X0 = r.X[0], X1 = r.X[1], X2 = r.X[2], Y0 = r.Y[0], Y1 = r.Y[1], Y2 = r.Y[2];
-  const int ax[3] = {X1, X2, X0}, ay[3] = {Y1, Y2, Y0}, bxv[3] = {X2, X0, X1}, byv[3] = {Y2, Y0, Y1};
+  int qx[4], qy[4];
+  const int nv = prim_vertices(r, qx, qy);
+  const int X0 = qx[0], Y0 = qy[0];
   unsigned live = 0xffu, inside = 0xffu;
+  bp.E0[3] = 0; bp.A[3] = 0; bp.B[3] = 0;   // triangles: a fourth edge that every sample passes
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int dx = bxv[k] - ax[k], dy = byv[k] - ay[k];
+  for (int k = 0; k < 4; k++) {
+    if (k >= nv) break;
+    const int ka = k, kb = (k + 1) & 3;   // edge k: vertex k -> k+1 (a triangle's vertex 3 aliases vertex 0)
+    const int dx = qx[kb] - qx[ka], dy = qy[kb] - qy[ka];
     const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
-    long long e0 = (long long)dx * (oy - ay[k]) - (long long)dy * (ox - ax[k]) - bias;
+    long long e0 = (long long)dx * (oy - qy[ka]) - (long long)dy * (ox - qx[ka]) - bias;
     if (e0 < -(1LL << 30)) live = 0;          // negative for every sample of the coarse bin
     if (e0 > (1LL << 30)) e0 = (1LL << 30);   // positive for every sample: keep the sign, stay in int32
     const int A = -dy, B = dx, e = (int)e0;
@@ -418,16 +457,14 @@ __device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __r
     ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
     const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
     const float4* L = lat_tab + bp.lat * 64 + ia * 8 + ib;
-    const float4 c00 = L[0], c01 = L[1], c10 = L[8], c11 = L[9];
-    if (fb <= fa) {
-      c3[0] = fmaf(fb, c11.x - c10.x, fmaf(fa, c10.x - c00.x, c00.x));
-      c3[1] = fmaf(fb, c11.y - c10.y, fmaf(fa, c10.y - c00.y, c00.y));
-      c3[2] = fmaf(fb, c11.z - c10.z, fmaf(fa, c10.z - c00.z, c00.z));
-    } else {
-      c3[0] = fmaf(fa, c11.x - c01.x, fmaf(fb, c01.x - c00.x, c00.x));
-      c3[1] = fmaf(fa, c11.y - c01.y, fmaf(fb, c01.y - c00.y, c00.y));
-      c3[2] = fmaf(fa, c11.z - c01.z, fmaf(fb, c01.z - c00.z, c00.z));
-    }
+    // the cell's two triangles share c00 and c11; pick the third corner and the order of the two weights
+    // instead of branching (same arithmetic, three loads instead of four)
+    const bool lower = fb <= fa;
+    const float4 c00 = L[0], c11 = L[9], cm = L[lower ? 8 : 1];
+    const float t1 = lower ? fa : fb, t2 = lower ? fb : fa;
+    c3[0] = fmaf(t2, c11.x - cm.x, fmaf(t1, cm.x - c00.x, c00.x));
+    c3[1] = fmaf(t2, c11.y - cm.y, fmaf(t1, cm.y - c00.y, c00.y));
+    c3[2] = fmaf(t2, c11.z - cm.z, fmaf(t1, cm.z - c00.z, c00.z));
   } else {
     c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
     c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
@@ -659,8 +696,16 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
         if (corner >= 0) { Vtx c = lv[h]; c.r = 0.f; c.g = 0.f; c.b = 0.f; sh.corners[corner] = c; }
       }
       __syncwarp();
-      process_triangle_uniform(ec, sh.corners[0], sh.corners[1], sh.corners[2], base_id, tex, slot, lane);
-      process_triangle_uniform(ec, sh.corners[0], sh.corners[2], sh.corners[3], base_id + 1, tex, slot, lane);
+      // a tile that needs no clipping is ONE quad prim (its diagonal then splits no bin); otherwise two triangles
+      bool as_quad = false;
+      if (classify(sh.corners[0], sh.corners[1], sh.corners[2]) == 0 && classify(sh.corners[0], sh.corners[2], sh.corners[3]) == 0) {
+        if (lane == 0) as_quad = setup_and_emit(ec, sh.corners[0], sh.corners[1], sh.corners[2], base_id, tex, slot, &sh.corners[3]);
+        as_quad = __shfl_sync(0xffffffffu, (int)as_quad, 0) != 0;
+      }
+      if (!as_quad) {
+        process_triangle_uniform(ec, sh.corners[0], sh.corners[1], sh.corners[2], base_id, tex, slot, lane);
+        process_triangle_uniform(ec, sh.corners[0], sh.corners[2], sh.corners[3], base_id + 1, tex, slot, lane);
+      }
       } else {
       // literal vertex list S:407-433 (spec tile mode 0): 7x7 quads, (0,1,2)(0,2,3) split, 3 shades / triangle
       for (int k0 = 0; k0 < 98; k0 += 32) {
@@ -763,10 +808,11 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
       const int bx0 = (pr.pxmin & 0xffff) / kCoarseW, by0 = (pr.pxmin >> 16) / kCoarseH;
       const int bx1 = (pr.pxmax & 0xffff) / kCoarseW, by1 = (pr.pxmax >> 16) / kCoarseH;
       const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
-      const int X[3] = {pr.X[0], pr.X[1], pr.X[2]}, Y[3] = {pr.Y[0], pr.Y[1], pr.Y[2]};
+      int qx[4], qy[4];
+      const int nv = prim_vertices(pr, qx, qy);
       for (int by = by0; by <= by1; by++)
         for (int bx = bx0; bx <= bx1; bx++) {
-          if (large && !bin_overlaps(X, Y, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
+          if (large && !bin_overlaps(qx, qy, nv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
           const int b = by * cbins_x + bx;
           const int pos = atomicAdd(&cnt[b], 1);
           if (pass == 1) pairs[start[b] + pos] = (uint16_t)p;
@@ -891,6 +937,11 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
           for (int phase = 0; phase < 2; phase++) {
             unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+            // every sample of the bin already belongs to a surface above the ground plane: the ground quad
+            // (y = -0.008, below everything else) cannot pass GL_LESS anywhere — same argument as the simple bin
+            if (phase == 1 && todo && c0 + kStage >= count &&
+                __all_sync(0xffffffffu, (wid[0] | wid[1] | wid[2] | wid[3]) != 0x7fffffff && wid[0] >= 2 && wid[1] >= 2 && wid[2] >= 2 && wid[3] >= 2))
+              todo = 0;
             while (todo) {
               const int k = __ffs(todo) - 1;
               todo &= todo - 1;
@@ -904,12 +955,14 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 const int ec0 = bp.E0[0] + bp.A[0] * pxc + bp.B[0] * pyc;
                 const int ec1 = bp.E0[1] + bp.A[1] * pxc + bp.B[1] * pyc;
                 const int ec2 = bp.E0[2] + bp.A[2] * pxc + bp.B[2] * pyc;
+                const int ec3 = bp.E0[3] + bp.A[3] * pxc + bp.B[3] * pyc;
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                   const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
                   const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
                   const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
-                  if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                  const int e3 = ec3 + bp.A[3] * sample_x(s) + bp.B[3] * sample_y(s);
+                  if ((e0 | e1 | e2 | e3) >= 0) mask |= 1 << s;
                 }
                 if (!mask) continue;
               }

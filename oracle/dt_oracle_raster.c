@@ -182,7 +182,10 @@ static int clip_polygon(vtx* poly, int n) {
 static inline float tex_byte(const orr_texture* t, int i, int j, int c) { return (float)t->rgba[((size_t)j * t->w + i) * 4 + c]; }
 
 /* one screen-space triangle (already clipped); `id` only documents draw order (drawn in order, GL_LESS) */
-static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat) {
+/* Rasterise triangle (a,b,c) — or, with `d`, the QUAD a,b,c,d of an unclipped road tile (spec tile mode 1):
+ * attribute planes of triangle (a,b,c), coverage by the quad's four edges.  Returns 0 without drawing when the
+ * snapped quad is not strictly convex: the caller then draws (a,b,c)(a,c,d). */
+static int raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat, const vtx* d) {
   vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
   float zw[3], q[3];
@@ -198,15 +201,30 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
     q[k] = iw;
   }
   int64_t area2 = (int64_t)(X[1] - X[0]) * (Y[2] - Y[0]) - (int64_t)(X[2] - X[0]) * (Y[1] - Y[0]);
-  if (area2 == 0) return;
+  if (area2 == 0) return 0;
   int i0 = 0, i1 = 1, i2 = 2;
   if (area2 < 0) { i1 = 2; i2 = 1; }
   const int ix[3] = {i0, i1, i2};
   int x0 = X[i0], y0 = Y[i0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
-  /* edges: e0 v1->v2, e1 v2->v0, e2 v0->v1 ; E(x,y) = (xb-xa)(y-ya) - (yb-ya)(x-xa) >= 0 inside */
-  const int ax[3] = {x1, x2, x0}, ay[3] = {y1, y2, y0}, bx[3] = {x2, x0, x1}, by[3] = {y2, y0, y1};
-  int bias[3];
-  for (int k = 0; k < 3; k++) {
+  /* polygon in positive orientation, edge k: vertex k -> k+1 ; E(x,y) = (xb-xa)(y-ya) - (yb-ya)(x-xa) >= 0 inside */
+  int nv = 3, qx[4] = {x0, x1, x2, 0}, qy[4] = {y0, y1, y2, 0};
+  if (d) {
+    float iw = 1.0f / d->cw;
+    float sx = ((d->cx * iw) * 0.5f + 0.5f) * Wf, sy = (0.5f - (d->cy * iw) * 0.5f) * Hf;
+    int X3 = (int)rintf(sx * 64.0f), Y3 = (int)rintf(sy * 64.0f);
+    nv = 4;
+    if (area2 > 0) { qx[1] = X[1]; qy[1] = Y[1]; qx[2] = X[2]; qy[2] = Y[2]; qx[3] = X3; qy[3] = Y3; }   /* a b c d */
+    else { qx[1] = X3; qy[1] = Y3; qx[2] = X[2]; qy[2] = Y[2]; qx[3] = X[1]; qy[3] = Y[1]; }             /* a d c b */
+    for (int k = 0; k < 4; k++) { /* strictly convex */
+      int k1 = (k + 1) & 3, k2 = (k + 2) & 3;
+      int64_t cr = (int64_t)(qx[k1] - qx[k]) * (qy[k2] - qy[k1]) - (int64_t)(qx[k2] - qx[k1]) * (qy[k1] - qy[k]);
+      if (cr <= 0) return 0;
+    }
+  }
+  int ax[4], ay[4], bx[4], by[4], bias[4];
+  for (int k = 0; k < nv; k++) {
+    int k1 = (k + 1) % nv;
+    ax[k] = qx[k]; ay[k] = qy[k]; bx[k] = qx[k1]; by[k] = qy[k1];
     int dx = bx[k] - ax[k], dy = by[k] - ay[k];
     bias[k] = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;  /* non-owner edges exclude E == 0 */
   }
@@ -240,6 +258,11 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
   int maxx = x0 > x1 ? x0 : x1; maxx = maxx > x2 ? maxx : x2;
   int miny = y0 < y1 ? y0 : y1; miny = miny < y2 ? miny : y2;
   int maxy = y0 > y1 ? y0 : y1; maxy = maxy > y2 ? maxy : y2;
+  if (nv == 4) {
+    int X3 = area2 > 0 ? qx[3] : qx[1], Y3 = area2 > 0 ? qy[3] : qy[1];
+    minx = minx < X3 ? minx : X3; maxx = maxx > X3 ? maxx : X3;
+    miny = miny < Y3 ? miny : Y3; maxy = maxy > Y3 ? maxy : Y3;
+  }
   int px0 = minx >> 6, px1 = maxx >> 6, py0 = miny >> 6, py1 = maxy >> 6;
   if (px0 < 0) px0 = 0;
   if (py0 < 0) py0 = 0;
@@ -251,7 +274,7 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
       for (int s = 0; s < 4; s++) {
         int sx = px * 64 + SX[s], sy = py * 64 + SY[s];
         int inside = 1;
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < nv; k++) {
           int64_t E = (int64_t)(bx[k] - ax[k]) * (sy - ay[k]) - (int64_t)(by[k] - ay[k]) * (sx - ax[k]);
           if (E - bias[k] < 0) inside = 0;
         }
@@ -309,6 +332,22 @@ static void raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture
         }
       }
     }
+  return 1;
+}
+
+/* 0 = visible without clipping, 1 = needs the clipper, 2 = outside one true-frustum plane (invisible) */
+static int classify3(const vtx* a, const vtx* b, const vtx* c) {
+  const vtx* v[3] = {a, b, c};
+  int out[6] = {0, 0, 0, 0, 0, 0}, need = 0;
+  for (int k = 0; k < 3; k++) {
+    float x = v[k]->cx, y = v[k]->cy, z = v[k]->cz, w = v[k]->cw;
+    out[0] += !(z + w >= 0.0f); out[1] += !(w - z >= 0.0f);
+    out[2] += x < -w; out[3] += x > w; out[4] += y < -w; out[5] += y > w;
+    need |= !(x + GUARD * w >= 0.0f) | !(GUARD * w - x >= 0.0f) | !(y + GUARD * w >= 0.0f) | !(GUARD * w - y >= 0.0f);
+  }
+  need |= out[0] | out[1];
+  for (int p = 0; p < 6; p++) if (out[p] == 3) return 2;
+  return need ? 1 : 0;
 }
 
 static void draw_shaded(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* tex, const float* lat);
@@ -328,7 +367,7 @@ static void draw_shaded(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture* te
     if (out == 3) return;
   }
   int m = clip_polygon(poly, 3);
-  for (int k = 1; k + 1 < m; k++) raster_triangle(fb, poly[0], poly[k], poly[k + 1], tex, lat);
+  for (int k = 1; k + 1 < m; k++) raster_triangle(fb, poly[0], poly[k], poly[k + 1], tex, lat, NULL);
 }
 
 /* Render one env. out: u8 [H][W][3], row 0 = top.  lut_x/lut_y: NULL or fisheye LUT [H][W]. */
@@ -408,6 +447,10 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
             for (int k = 0; k < 4; k++) if (a == ca[k] && b == cb[k]) corner[k] = v;
           }
         for (int k = 0; k < 4; k++) { corner[k].r = 0.0f; corner[k].g = 0.0f; corner[k].b = 0.0f; }
+        /* a tile that needs no clipping is ONE quad prim; otherwise (or if the snapped quad is not convex) two triangles */
+        if (classify3(&corner[0], &corner[1], &corner[2]) == 0 && classify3(&corner[0], &corner[2], &corner[3]) == 0 &&
+            raster_triangle(&fb, corner[0], corner[1], corner[2], tex, lat_rgb, &corner[3]))
+          continue;
         draw_shaded(&fb, corner[0], corner[1], corner[2], tex, lat_rgb);
         draw_shaded(&fb, corner[0], corner[2], corner[3], tex, lat_rgb);
         continue;
