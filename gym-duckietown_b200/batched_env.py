@@ -55,7 +55,7 @@ class BatchedDuckietownEnv:
             env_id_offset=env_id_offset)
         self.sim = L.Sim(self.cfg)
         for i, md in enumerate(self.maps):
-            self.sim.upload_map(i, md)
+            self.sim.upload_map(i, md, tuple(user_tile_start) if user_tile_start else None)
         if distortion:
             from .distortion import Distortion
             self.camera_model = Distortion(camera_width, camera_height)

@@ -186,6 +186,8 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
       if (b->tile_kind[j * b->grid_w + i] >= 0 && b->tile_drivable[j * b->grid_w + i]) { drv.push_back(i); drv.push_back(j); }
   m.start_i = b->start_tile[0]; m.start_j = b->start_tile[1];
   if (m.start_i < 0 || m.start_j < 0 || m.start_i >= b->grid_w || m.start_j >= b->grid_h) { m.start_i = -1; m.start_j = -1; }
+  m.has_start_pose = b->has_start_pose != 0;
+  for (int k = 0; k < 3; k++) m.start_pose[k] = b->start_pose[k];
   m.n_drivable = (int)drv.size() / 2;
   bad |= sim->upload(&m.drivable_ij, drv.data(), drv.size(), &own);
   // objects: add spawn radius (S:1467) and a bounding sphere per placed mesh

@@ -56,7 +56,9 @@ struct DMap {
   const double* coll_norms;     // [K][2][2]
   const double* coll_centers;   // [K][3]
   const double* coll_radii;     // [K]
-  int32_t start_i, start_j;     // map `start_tile` (S:867-871) or -1
+  int32_t start_i, start_j;     // user_tile_start / map `start_tile` (S:659-671) or -1
+  int32_t has_start_pose;       // map `start_pose` S:679-686
+  double start_pose[3];         // x, z offset inside the start tile, angle
   int32_t n_drivable;
   const int32_t* drivable_ij;   // [n_drivable][2] in reference scan order (S:806-860)
   int32_t n_objects;

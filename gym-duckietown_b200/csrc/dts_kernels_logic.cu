@@ -135,7 +135,10 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   else if (m.n_drivable > 0) { const int t = rs.integers(0, m.n_drivable); ti = m.drivable_ij[2 * t]; tj = m.drivable_ij[2 * t + 1]; }
   double px = 1.0, pz = 1.0, ang = 1.0;                                      // fallback S:735-736
   const DynRef dyn = dyn_ref(m, n, e);
-  for (int attempt = 0; attempt < kMaxSpawnAttempts && m.n_drivable > 0; attempt++) {
+  if (m.has_start_pose) {   // S:679-686: the map fixes the pose inside the start tile; nothing is drawn
+    px = ti * m.tile_size + m.start_pose[0]; pz = tj * m.tile_size + m.start_pose[1]; ang = m.start_pose[2];
+  }
+  for (int attempt = 0; attempt < kMaxSpawnAttempts && m.n_drivable > 0 && !m.has_start_pose; attempt++) {
     const double x = rs.uniform((double)ti, (double)(ti + 1)) * m.tile_size, z = rs.uniform((double)tj, (double)(tj + 1)) * m.tile_size;
     const double a = rs.uniform(0.0, 2 * 3.141592653589793);
     if (inconvenient_spawn(m, dyn, r.hidden, x, z)) continue;

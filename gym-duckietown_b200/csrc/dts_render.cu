@@ -104,7 +104,7 @@ __device__ __forceinline__ void model_view(const double* V, double tx, double ty
     for (int k = 0; k < 3; k++) {
       const double a = V[4 * r + 0] * R[0 + k] + V[4 * r + 1] * R[3 + k] + V[4 * r + 2] * R[6 + k];
       x.MV[4 * r + k] = (float)(a * sc);
-      x.N[3 * r + k] = (float)(a / sc);
+      x.N[3 * r + k] = (float)(sc == 1.0 ? a : a / sc);   // x / 1.0 == x exactly
     }
     x.MV[4 * r + 3] = (float)(V[4 * r + 0] * tx + V[4 * r + 1] * ty + V[4 * r + 2] * tz + V[4 * r + 3]);
   }
@@ -596,6 +596,24 @@ __global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg r
   c.n_prims = 0; c.n_lat = 0; c.overflow = 0; c.pad = 0;
 }
 
+// Conservative bounding-sphere cull in eye space against the four side planes and near: true only if the sphere
+// — hence everything inside it — lies outside one plane (margins cover the f32 rounding of the test itself).
+__device__ __forceinline__ bool sphere_outside(float P00, float P11, float cx_, float cy_, float cz_, float rad) {
+  const float hx = rsqrtf(P00 * P00 + 1.0f), hy = rsqrtf(P11 * P11 + 1.0f);
+  bool out = cz_ - rad > -0.04f;                                  // entirely behind the near plane
+  out |= (P00 * cx_ + cz_) * hx > rad * 1.01f;                    // right plane: P00*x <= -z
+  out |= (-P00 * cx_ + cz_) * hx > rad * 1.01f;
+  out |= (P11 * cy_ + cz_) * hy > rad * 1.01f;
+  out |= (-P11 * cy_ + cz_) * hy > rad * 1.01f;
+  return out;
+}
+// world point -> eye space with the f64 camera matrix (row-major 3x4)
+__device__ __forceinline__ void eye_point(const double* V, double wx, double wy, double wz, float& ex, float& ey, float& ez) {
+  ex = (float)(V[0] * wx + V[1] * wy + V[2] * wz + V[3]);
+  ey = (float)(V[4] * wx + V[5] * wy + V[6] * wz + V[7]);
+  ez = (float)(V[8] * wx + V[9] * wy + V[10] * wz + V[11]);
+}
+
 // ------------------------------------------------------------------------------------------------ k_geometry
 // Small CTAs (2 warps) so that a slot is not held by one long warp (a clipped ground quad) while its siblings
 // (culled tiles) have long exited; warps are numbered item-major so neighbouring warps run the same code path.
@@ -614,6 +632,37 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   const int W = rc.width, H = rc.height;
   GeoWarp& sh = gws[wib];
   FrameCtx& ctx = fm.ctx[env];
+  // ---- pre-cull on a bounding sphere before anything else is loaded or transformed: most (env, item) pairs end here
+  int dyn_kind = 0;
+  float opx = 0.f, opz = 0.f, orot = 0.f;
+  if (item >= 1 && item <= n_tiles) {
+    const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
+    if (m.tile_kind[tj * m.grid_w + ti] < 0) return;
+    const double ts = m.tile_size;
+    float ex, ey, ez;
+    eye_point(ctx.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, ex, ey, ez);
+    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, (float)(ts * 0.7071067811865476) * 1.001f + 1e-4f)) return;
+  } else if (item > n_tiles) {
+    const int o = item - 1 - n_tiles;
+    if (S.rep[env].hidden[o >> 5] >> (o & 31) & 1u) return;
+    const DObject& ob = m.objects[o];
+    opx = ob.pos[0]; opz = ob.pos[2]; orot = ob.y_rot_deg;
+    if (ob.dyn_slot >= 0) {
+      dyn_kind = m.dyn[ob.dyn_slot].kind;
+      if (dyn_kind != DTS_DYN_TRAFFICLIGHT) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
+        const size_t nd = m.n_dyn, ne = rc.n_envs;
+        opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
+        opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
+        orot = (float)m.dyn_state[((size_t)DTS_DYN_YROT * nd + ob.dyn_slot) * ne + env];
+      }
+    }
+    double sn, cs;
+    sincos((double)orot * kDeg2Rad, &sn, &cs);
+    const double sc = (double)ob.scale, ccx = ob.centre[0], ccy = ob.centre[1], ccz = ob.centre[2];
+    float ex, ey, ez;   // T(pos) S(scale) Ry(rot) applied to the bounding-sphere centre
+    eye_point(ctx.V, (double)opx + sc * (cs * ccx + sn * ccz), (double)ob.pos[1] + sc * ccy, (double)opz + sc * (-sn * ccx + cs * ccz), ex, ey, ez);
+    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, ob.bound_rad * ob.scale * 1.002f + 2e-4f)) return;
+  }
   for (int k = lane; k < (int)(sizeof(RenderEp) / 4); k += 32)
     reinterpret_cast<uint32_t*>(&sh.ep)[k] = reinterpret_cast<const uint32_t*>(&S.rep[env])[k];
   if (lane < 12) sh.V[lane] = ctx.V[lane];
@@ -639,7 +688,6 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     // road tile S:1852-1884: draw order i outer, j inner
     const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
     const int idx = tj * m.grid_w + ti;
-    if (m.tile_kind[idx] < 0) return;
     const int quarter = (m.tile_angle[idx] + 2) & 3;                     // glRotatef(angle*90+180) S:1873
     const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
     const double ts = m.tile_size;
@@ -728,35 +776,15 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   } else {
     // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
     const int o = item - 1 - n_tiles;
-    if (sh.ep.hidden[o >> 5] >> (o & 31) & 1u) return;
     const DObject& ob = m.objects[o];
-    float opx = ob.pos[0], opz = ob.pos[2], orot = ob.y_rot_deg;
     int alt_from = -2;        // traffic-light card on pattern 1: swap this texture id for ob.alt_to
-    if (ob.dyn_slot >= 0 && m.dyn[ob.dyn_slot].kind == DTS_DYN_TRAFFICLIGHT) {
+    if (dyn_kind == DTS_DYN_TRAFFICLIGHT) {
       const size_t nd = m.n_dyn, ne = rc.n_envs;
       if (m.dyn_state[((size_t)DTS_DYN_SHOWN * nd + m.dyn[ob.dyn_slot].tl_first) * ne + env] != 0.0) alt_from = ob.alt_from;
-    } else if (ob.dyn_slot >= 0) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
-      const size_t nd = m.n_dyn, ne = rc.n_envs;
-      opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
-      opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
-      orot = (float)m.dyn_state[((size_t)DTS_DYN_YROT * nd + ob.dyn_slot) * ne + env];
     }
     double sn, cs;
     sincos((double)orot * kDeg2Rad, &sn, &cs);
     model_view(sh.V, (double)opx, (double)ob.pos[1], (double)opz, (double)ob.scale, cs, sn, x);
-    {  // conservative bounding-sphere cull in eye space against the four side planes and near
-      const float cx_ = x.MV[0] * ob.centre[0] + x.MV[1] * ob.centre[1] + x.MV[2] * ob.centre[2] + x.MV[3];
-      const float cy_ = x.MV[4] * ob.centre[0] + x.MV[5] * ob.centre[1] + x.MV[6] * ob.centre[2] + x.MV[7];
-      const float cz_ = x.MV[8] * ob.centre[0] + x.MV[9] * ob.centre[1] + x.MV[10] * ob.centre[2] + x.MV[11];
-      const float rad = ob.bound_rad * ob.scale * 1.001f + 1e-4f;
-      const float hx = rsqrtf(sh.P00 * sh.P00 + 1.0f), hy = rsqrtf(sh.P11 * sh.P11 + 1.0f);
-      bool outside_ = cz_ - rad > -0.04f;                                  // entirely behind the near plane
-      outside_ |= (sh.P00 * cx_ + cz_) * hx > rad * 1.01f;                 // right plane: P00*x <= -z
-      outside_ |= (-sh.P00 * cx_ + cz_) * hx > rad * 1.01f;
-      outside_ |= (sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
-      outside_ |= (-sh.P11 * cy_ + cz_) * hy > rad * 1.01f;
-      if (outside_) return;
-    }
     int base_id = 2 + tris_per_tile * n_tiles;
     for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
     for (int k0 = 0; k0 < ob.tri_count; k0 += 32) {
@@ -878,7 +906,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
       const bool single = count <= kStage;
 #ifdef DTS_STATS
-      if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count); }
+      if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count);
+                       if (count > kStage) { atomicAdd(&err[14], 1); atomicAdd(&err[15], count); } }
 #endif
       int my_id = 0x7fffffff, my_flags = 0;
       if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins

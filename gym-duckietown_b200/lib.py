@@ -87,8 +87,8 @@ class MapBlob(C.Structure):
         ("coll_radii", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p), ("n_meshes", C.c_int32),
         ("meshes", C.c_void_p), ("n_tris", C.c_int32), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p),
         ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p), ("tri_tex", C.c_void_p), ("n_textures", C.c_int32),
-        ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2), ("n_dyn", C.c_int32), ("reserved", C.c_int32),
-        ("dyn", C.c_void_p),
+        ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2), ("n_dyn", C.c_int32), ("has_start_pose", C.c_int32),
+        ("dyn", C.c_void_p), ("start_pose", C.c_double * 3),
     ]
 
 
@@ -176,7 +176,7 @@ class MapBlobHolder:
     """Flattens a MapData (tiles, curves, OBBs, placed meshes, textures) into a dts_map_blob and keeps
     the numpy buffers alive for the duration of the upload."""
 
-    def __init__(self, md: MapData):
+    def __init__(self, md: MapData, user_tile_start=None):
         k = self.keep = {}
         k["kind"] = np.ascontiguousarray(md.tile_kind, np.int8)
         k["angle"] = np.ascontiguousarray(md.tile_angle, np.int8)
@@ -243,8 +243,11 @@ class MapBlobHolder:
             _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(md.meshes),
             C.cast(meshes, C.c_void_p), off, _ptr(k["tpos"]), _ptr(k["tnrm"]), _ptr(k["tuv"]), _ptr(k["tcol"]),
             _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p),
-            (C.c_int32 * 2)(*(md.start_tile if md.start_tile is not None else (-1, -1))), len(md.dyn_objects), 0,
-            C.cast(dyn, C.c_void_p))
+            (C.c_int32 * 2)(*(user_tile_start if user_tile_start else
+                              (md.start_tile if md.start_tile is not None else (-1, -1)))),   # S:659-671
+            len(md.dyn_objects), int(md.start_pose is not None), C.cast(dyn, C.c_void_p),
+            (C.c_double * 3)(*((float(md.start_pose[0][0]), float(md.start_pose[0][2]), float(md.start_pose[1]))
+                               if md.start_pose is not None else (0.0, 0.0, 0.0))))
 
 
 class _CudaArray:
@@ -269,8 +272,8 @@ class Sim:
         if rc:
             raise DtsError(f"{what}: {self.lib.dts_last_error(self.h).decode()}")
 
-    def upload_map(self, map_id: int, md: MapData):
-        holder = MapBlobHolder(md)
+    def upload_map(self, map_id: int, md: MapData, user_tile_start=None):
+        holder = MapBlobHolder(md, user_tile_start)
         self._check(self.lib.dts_upload_map(self.h, map_id, C.byref(holder.blob)), "dts_upload_map")
 
     def set_fisheye_lut(self, rmapx: np.ndarray, rmapy: np.ndarray):

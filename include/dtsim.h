@@ -156,10 +156,11 @@ typedef struct {
   const int16_t* tri_tex;         /* [n_tris] texture index, -1 = untextured */
   int32_t n_textures;
   const dts_texture* textures;
-  int32_t start_tile[2];          /* map `start_tile` (simulator.py:867-871) or {-1,-1}: device resets spawn there */
+  int32_t start_tile[2];          /* `user_tile_start` (S:659-662) else map `start_tile` (S:867-871) else {-1,-1}: device resets spawn there */
   int32_t n_dyn;                  /* <= DTS_MAX_DYN */
-  int32_t reserved;
+  int32_t has_start_pose;         /* map `start_pose` (S:874-876): device resets then place the agent at start_pose */
   const dts_dyn_object* dyn;      /* [n_dyn] in the order of the map's object list (update order S:1570-1584) */
+  double start_pose[3];           /* x offset, z offset inside the start tile, angle (S:679-686) */
 } dts_map_blob;
 
 /* Per-episode inputs produced by Simulator.reset() (simulator.py:528-763), one

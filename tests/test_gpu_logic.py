@@ -272,3 +272,30 @@ def test_frame_skip_and_dynamics_rand_vs_oracle(torch_cuda):
             assert abs(s["pos_x"][k] - o.pos_x) <= 1e-5 and abs(s["pos_z"][k] - o.pos_z) <= 1e-5, (t, k)
             assert s["done_code"][k] == o.done_code and abs(s["speed"][k] - o.speed) <= 1e-5, (t, k)
     env.close()
+
+
+def test_device_reset_honours_user_tile_start_and_start_pose(torch_cuda):
+    """S:659-686: `user_tile_start` beats the map's start_tile and consumes no draw; a map `start_pose` fixes the
+    pose inside the start tile.  The device reset must land where the host replay of the reference's reset() does."""
+    torch = torch_cuda
+    import copy
+    from gym_duckietown_b200 import maps
+    N = 16
+    dev = make_env("udem1", N, device_reset=True, user_tile_start=(1, 1), seed=77)
+    host = make_env("udem1", N, device_reset=False, user_tile_start=(1, 1), seed=77)
+    dev.reset(render=False); host.reset(render=False)
+    torch.cuda.synchronize()
+    a = {k: v.cpu().numpy() for k, v in dev.state.items()}
+    b = {k: v.cpu().numpy() for k, v in host.state.items()}
+    assert np.all(a["tile_i"] == 1) and np.all(a["tile_j"] == 1)
+    for k in ("pos_x", "pos_z", "angle"):
+        assert np.array_equal(a[k], b[k]), k
+    dev.close(); host.close()
+    md = copy.deepcopy(maps.load_map("small_loop"))
+    md.start_tile, md.start_pose = (1, 1), [[0.31, 0.0, 0.22], 1.25]
+    env = make_env(md, 4, device_reset=True, seed=5)
+    env.reset(render=False)
+    s = {k: v.cpu().numpy() for k, v in env.state.items()}
+    assert np.all(s["pos_x"] == 1 * md.tile_size + 0.31) and np.all(s["pos_z"] == 1 * md.tile_size + 0.22)
+    assert np.all(s["angle"] == 1.25)
+    env.close()

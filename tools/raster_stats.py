@@ -12,6 +12,6 @@ torch.cuda.synchronize()
 c0 = env.sim.debug_counters().astype(np.int64)
 env.render_obs(); torch.cuda.synchronize()
 c = env.sim.debug_counters().astype(np.int64) - c0
-names = {8: "coarse bins", 9: "empty coarse", 10: "sum list len", 11: "live prims (per fine bin chunks)", 12: "ground live", 13: "simple fine bins", 16: "general prim iterations", 17: "…of which fully inside"}
+names = {8: "coarse bins", 9: "empty coarse", 10: "sum list len", 11: "live prims (per fine bin chunks)", 12: "ground live", 13: "simple fine bins", 14: "coarse bins with > 32 prims", 15: "…their list lengths", 16: "general prim iterations", 17: "…of which fully inside"}
 for k, v in names.items():
     print(f"{v:40s} {c[k]:12d}  per env {c[k]/4096:10.1f}")
