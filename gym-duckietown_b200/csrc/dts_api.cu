@@ -381,6 +381,7 @@ static int ensure_render(dts_sim* sim) {
   }
   sim->render_ctas = sms * render_ctas_per_sm();
   sim->max_prims = max_tris + max_tris / 4 + 64;  // clipping can add fan triangles
+  if (items_max > 65535) return sim->fail("scene too large: %d draw items per frame (limit 65535)", items_max);
   if (sim->max_prims > 65535) return sim->fail("scene too large: %d triangles per frame (limit 65535)", sim->max_prims);
   sim->max_lat = max_lat;
   sim->items_max = items_max;

@@ -52,6 +52,21 @@ __host__ __device__ constexpr int sample_y(int s) { return s == 0 ? 8 : (s == 1 
 
 struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 
+#ifndef DTS_GEO_INLINE
+#define DTS_GEO_INLINE 1
+#endif
+#if DTS_GEO_INLINE
+#define DTS_GEO_FN __forceinline__
+#else
+#define DTS_GEO_FN __noinline__
+#endif
+#ifndef DTS_GEO_WARPS
+#define DTS_GEO_WARPS 1
+#endif
+#ifndef DTS_GEO_MIN_CTAS
+#define DTS_GEO_MIN_CTAS 32
+#endif
+
 struct __align__(16) PrimRec {   // 128 B in the CTA's slab
   int32_t X[3], Y[3];            // snapped vertices, orientation normalised (area > 0)
   float f0[7], fx[7], fy[7];     // planes anchored at vertex 0: z, q=1/w, u*q, v*q, r*q, g*q, b*q
@@ -89,29 +104,33 @@ struct __align__(16) GeoWarp {    // per warp of k_geometry, shared memory
   RenderEp ep;
   double V[12];
   float P00, P11, P22, P23;
+  Xform x;                       // model-view / normal matrix of the warp's draw item (warp-uniform)
   Vtx corners[4];
   Vtx poly[2][12];               // ping-pong polygon of the warp-parallel clipper
 };
 using Shared = GeoWarp;           // shade_vertex reads ep and P from it
 
-// MV = V * T(t) * S(sc) * Ry(c,s), N = rot(V) * Ry / sc — float64 then rounded (spec)
+// MV = V * T(t) * S(sc) * Ry(c,s), N = rot(V) * Ry / sc — float64 then rounded (spec).  Lanes 0..11 each produce
+// one entry of the 3x4 matrix (and of N for the rotation part) into the warp's shared Xform.
 __device__ __forceinline__ void model_view(const double* V, double tx, double ty, double tz, double sc, double c,
-                                           double s, Xform& x) {
-  const double R[9] = {c, 0.0, s, 0.0, 1.0, 0.0, -s, 0.0, c};
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double a = V[4 * r + 0] * R[0 + k] + V[4 * r + 1] * R[3 + k] + V[4 * r + 2] * R[6 + k];
+                                           double s, Xform& x, int lane) {
+  __syncwarp();
+  if (lane < 12) {
+    const int r = lane >> 2, k = lane & 3;
+    if (k < 3) {
+      const double R0 = k == 0 ? c : (k == 1 ? 0.0 : s), R1 = k == 1 ? 1.0 : 0.0, R2 = k == 0 ? -s : (k == 1 ? 0.0 : c);
+      const double a = V[4 * r + 0] * R0 + V[4 * r + 1] * R1 + V[4 * r + 2] * R2;
       x.MV[4 * r + k] = (float)(a * sc);
       x.N[3 * r + k] = (float)(sc == 1.0 ? a : a / sc);   // x / 1.0 == x exactly
+    } else {
+      x.MV[4 * r + 3] = (float)(V[4 * r + 0] * tx + V[4 * r + 1] * ty + V[4 * r + 2] * tz + V[4 * r + 3]);
     }
-    x.MV[4 * r + 3] = (float)(V[4 * r + 0] * tx + V[4 * r + 1] * ty + V[4 * r + 2] * tz + V[4 * r + 3]);
   }
+  __syncwarp();
 }
 
 // fixed-function transform & lighting of one vertex (float32, operation order = spec)
-__device__ __forceinline__ Vtx shade_vertex(const Xform& x, const Shared& sh, float px, float py, float pz, float nx,
+__device__ DTS_GEO_FN Vtx shade_vertex(const Xform& x, const Shared& sh, float px, float py, float pz, float nx,
                                             float ny, float nz, float cr, float cg, float cb, float u, float v) {
   float e[3], ne[3];
 #pragma unroll
@@ -199,7 +218,7 @@ struct EmitCtx {
 // With `d` the prim is the QUAD a,b,c,d (spec tile mode 1: an unclipped road tile): planes of triangle (a,b,c),
 // coverage by four edges.  Returns false — nothing emitted — if the snapped quad is not strictly convex; the
 // caller then draws the two triangles (a,b,c)(a,c,d) instead.
-__device__ __forceinline__ bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+__device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
                                                int tex, int lat, const Vtx* d = nullptr) {
   const Vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
@@ -302,7 +321,7 @@ __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float di
 // WHOLE warp for one triangle: lane k owns polygon vertex k, neighbours' plane distances come by shuffle, output
 // slots by ballot prefix sums, so a plane costs a few dozen instructions instead of a serial loop over vertices.
 // Same arithmetic, same vertex order (hence the same fan) as the serial formulation of the spec.
-__device__ __forceinline__ void clip_and_emit_warp(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+__device__ DTS_GEO_FN void clip_and_emit_warp(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
                                                    int tex, int lat, int lane) {
   for (int p2 = 0; p2 < 6; p2++) {   // the spec's trivial reject looks at the ORIGINAL triangle, guard planes
     const int cnt = !(plane_dist(a, p2) >= 0.0f) + !(plane_dist(b, p2) >= 0.0f) + !(plane_dist(c, p2) >= 0.0f);
@@ -615,17 +634,19 @@ __device__ __forceinline__ void eye_point(const double* V, double wx, double wy,
 }
 
 // ------------------------------------------------------------------------------------------------ k_geometry
-// Small CTAs (2 warps) so that a slot is not held by one long warp (a clipped ground quad) while its siblings
-// (culled tiles) have long exited; warps are numbered item-major so neighbouring warps run the same code path.
-constexpr int kGeoWarps = 2;
-__global__ void __launch_bounds__(kGeoWarps * 32, 12)
+// One warp per CTA, 64 registers, 32 CTAs per SM: the kernel is latency-bound (short dependent chains, most warps
+// exit at the pre-cull), so resident warps matter more than spills — measured 1 warp x 32 CTAs 178 us, 2 x 12 (80
+// registers) 207 us, 4 x 8 192 us on the bench workload.  A slot is never held by a finished sibling warp, and the
+// grid is item-major (blockIdx.y = draw item) so neighbouring CTAs run the same code path.
+constexpr int kGeoWarps = DTS_GEO_WARPS;
+template <bool kTess>   // true: spec tile mode 0 (DTS_FLAG_TESSELLATE), the literal 98 triangles per road tile
+__global__ void __launch_bounds__(kGeoWarps * 32, DTS_GEO_MIN_CTAS)
 k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
            int max_lat, int32_t* __restrict__ err) {
   __shared__ GeoWarp gws[kGeoWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long gw_id = (long long)blockIdx.x * kGeoWarps + wib;
-  const int item = (int)(gw_id / rc.n_envs), env = (int)(gw_id - (long long)item * rc.n_envs);
-  if (item >= items_max) return;
+  const int item = blockIdx.y, env = blockIdx.x * kGeoWarps + wib;   // item-major: neighbouring CTAs run the same path
+  if (env >= rc.n_envs) return;
   const DMap& m = maps[S.map_id[env]];
   const int n_tiles = m.grid_w * m.grid_h;
   if (item >= 1 + n_tiles + m.n_objects) return;
@@ -670,11 +691,11 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   __syncwarp();
   EmitCtx ec{&sh, &ctx, fm.prims + (size_t)env * max_prims, max_prims, W, H};
   float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
-  const int tris_per_tile = rc.tessellate ? 98 : 2;
-  Xform x;
+  const int tris_per_tile = kTess ? 98 : 2;
+  Xform& x = sh.x;
   if (item == 0) {
     // ground quad S:1805-1812: glScalef(50,0.01,50) applied to (+-1,-0.8,+-1), world-space +y normal
-    model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x);
+    model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x, lane);
     const float gy = (float)(-0.8 * 0.01);
     const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
     const float* g = sh.ep.ground;
@@ -691,10 +712,10 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     const int quarter = (m.tile_angle[idx] + 2) & 3;                     // glRotatef(angle*90+180) S:1873
     const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
     const double ts = m.tile_size;
-    model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x);
+    model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x, lane);
     const int tex = m.tile_tex[idx];
     const int base_id = 2 + tris_per_tile * t;
-    if (!rc.tessellate) {
+    if (!kTess) {
       // analytic tile: the prim is the quad of the 4 corners — cull on those before lighting the lattice
       const int ca = (lane == 1 || lane == 2) ? 7 : 0, cb = (lane >= 2) ? 7 : 0;   // lanes 0..3: (0,0) (7,0) (7,7) (0,7)
       const float lx = (float)(-ts / 2 + ((double)ca / 7.0) * ts), lz = (float)(-ts / 2 + ((double)cb / 7.0) * ts);
@@ -723,13 +744,13 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
       outside[0] += !(v.cz + v.cw >= 0.0f); outside[1] += !(v.cw - v.cz >= 0.0f);
       outside[2] += v.cx < -v.cw; outside[3] += v.cx > v.cw; outside[4] += v.cy < -v.cw; outside[5] += v.cy > v.cw;
     }
-    if (rc.tessellate) {
+    if (kTess) {
       bool culled = false;
 #pragma unroll
       for (int p = 0; p < 6; p++) culled |= __all_sync(0xffffffffu, outside[p] == 2);
       if (culled) return;
     }
-    if (!rc.tessellate) {
+    if (!kTess) {
       // analytic tile (spec tile mode 1): lattice colours -> table, one quad (0,1,2)(0,2,3) of the corners
       int slot = 0;
       if (lane == 0) slot = atomicAdd(&ctx.n_lat, 1);
@@ -784,7 +805,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     }
     double sn, cs;
     sincos((double)orot * kDeg2Rad, &sn, &cs);
-    model_view(sh.V, (double)opx, (double)ob.pos[1], (double)opz, (double)ob.scale, cs, sn, x);
+    model_view(sh.V, (double)opx, (double)ob.pos[1], (double)opz, (double)ob.scale, cs, sn, x, lane);
     int base_id = 2 + tris_per_tile * n_tiles;
     for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
     for (int k0 = 0; k0 < ob.tri_count; k0 += 32) {
@@ -1072,9 +1093,9 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
   cudaMemsetAsync(fm.work, 0, 256, st);
   k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
-  const long long warps = (long long)rc.n_envs * items_max;
-  k_geometry<<<(unsigned)((warps + kGeoWarps - 1) / kGeoWarps), kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims,
-                                                                              max_lat, err_flag);
+  const dim3 geo_grid((unsigned)((rc.n_envs + kGeoWarps - 1) / kGeoWarps), (unsigned)items_max);
+  if (rc.tessellate) k_geometry<true><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
+  else k_geometry<false><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
   k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, (size_t)kBinWarps * 2 * cbins * sizeof(int), st>>>(
       rc, fm, max_prims, max_pairs, err_flag);
   if (!fisheye && (rc.obs_layout | rc.obs_dtype) != 0)

@@ -1,13 +1,19 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (here, no GPU needed): headline metrics, stall reasons, hottest source lines.
-usage: python profiles/ncu_summarize.py gpurun_out/prof.ncu-rep [top_n]"""
+usage: python profiles/ncu_summarize.py gpurun_out/prof.ncu-rep [top_n] [kernel-name substring]"""
 import csv, io, subprocess, sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+want = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-d = {h: (u, v) for h, u, v in zip(rows[0], rows[1], rows[2])}
+sel = 2
+if want:
+    ki = rows[0].index("Kernel Name")
+    sel = [i for i in range(2, len(rows)) if want in rows[i][ki]][0]
+d = {h: (u, v) for h, u, v in zip(rows[0], rows[1], rows[sel])}
+print("kernel:", d["Kernel Name"][1][:80])
 for k in ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
           "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
           "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -23,7 +29,13 @@ hdr = None
 cur = None
 agg = []
 stall_tot = {}
+active = want is None
 for r in rows:
+    if len(r) >= 2 and r[0] in ("Kernel Name", "Function Name"):
+        active = want is None or want in r[1]
+        continue
+    if not active:
+        continue
     if len(r) >= 2 and r[0] == "File Path":
         cur = r[1].split("/")[-1]
         continue
