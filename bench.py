@@ -239,6 +239,7 @@ def main():
     ev1.record()
     barrier()
     launches = env.launch_count() - launches0
+    env.check()   # no frame hit a capacity limit
     ms = ev0.elapsed_time(ev1)
     render_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(rs, re_)]))
     if world > 1:

@@ -173,6 +173,13 @@ class BatchedDuckietownEnv:
     def launch_count(self) -> int:
         return self.sim.launch_count()
 
+    def check(self):
+        """Synchronise and raise if any render since creation ran out of its frame-memory capacity (prim slab or bin
+        lists, sized from the scene's upper bounds at the first render) — such frames are left at the clear colour."""
+        torch.cuda.synchronize(self.device)
+        if int(self.sim.debug_counters()[0]) != 0:
+            raise L.DtsError("render frame memory overflowed: some frames were not drawn")
+
     def close(self):
         self.sim.close()
 

@@ -277,6 +277,7 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   }
   if (bad) return 1;
   m.valid = 1;
+  if (sim->render_scratch) { cudaFree(sim->render_scratch); sim->render_scratch = nullptr; }   // re-sized for the new scene on the next render
   sim->h_maps[map_id] = m;
   DTS_CUDA(cudaMemcpy(sim->d_maps + map_id, &m, sizeof(DMap), cudaMemcpyHostToDevice));
   return 0;
@@ -386,7 +387,8 @@ static int ensure_render(dts_sim* sim) {
   sim->max_lat = max_lat;
   sim->items_max = items_max;
   const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
-  sim->bin_cap = 3 * sim->max_prims + 8 * cbins + 256;   // (prim, coarse bin) pairs per env
+  sim->bin_cap = 3 * sim->max_prims + 24 * cbins + 256;  // (prim, coarse bin) pairs per env: the ground fan (<= 8 x cbins),
+                                                          // a few screen-filling tiles and one screen-filling prop
   const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
   const size_t bytes = render_scratch_bytes(sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
