@@ -204,6 +204,28 @@ def gen_reset(name: str, seeds=range(24)):
     print(f"reset_{name}: seeds={len(out['seeds'])} x 2 episodes x (dr off/on)")
 
 
+def gen_reset_start(name="udem1", seeds=range(12)):
+    """reset() with a fixed start: `user_tile_start` (S:659-666, beats the map's start_tile, no tile draw), the map's
+    `start_tile` (S:668-669) and `start_pose` (S:679-686, no spawn loop at all) — as executed by the reference."""
+    import copy
+    raw = raw_map(name)
+    out = {"seeds": np.array(list(seeds))}
+    cases = {"user": (raw, dict(user_tile_start=(1, 1))),
+             "tile": (dict(copy.deepcopy(raw), start_tile=[3, 1]), {}),
+             "pose": (dict(copy.deepcopy(raw), start_tile=[3, 1], start_pose=[[0.21, 0.0, 0.33], 1.4]), {})}
+    for tag, (mp, kw) in cases.items():
+        pos, ang = [], []
+        for seed in seeds:
+            sim = refstub.build_reference_sim(mp, extents_for(mp), domain_rand=False, seed=int(seed), **kw)
+            for episode in range(2):
+                sim.reset()
+                pos.append(np.array(sim.cur_pos, float)); ang.append(float(sim.cur_angle))
+        out[f"{tag}_cur_pos"], out[f"{tag}_cur_angle"] = np.array(pos), np.array(ang)
+    out["start_tile"], out["start_pose"], out["user_tile_start"] = np.array([3, 1]), np.array([0.21, 0.0, 0.33, 1.4]), np.array([1, 1])
+    np.savez_compressed(os.path.join(OUT, f"reset_start_{name}.npz"), **out)
+    print(f"reset_start_{name}: {len(out['seeds'])} seeds x 2 episodes x (user_tile_start, start_tile, start_pose)")
+
+
 def gen_fisheye():
     refstub.install()
     from gym_duckietown.distortion import Distortion
@@ -312,3 +334,4 @@ if __name__ == "__main__":
     for m in ("loop_pedestrians", "loop_dyn_duckiebots"):
         gen_dynamic(m)
     gen_trafficlight()
+    gen_reset_start()

@@ -299,3 +299,31 @@ def test_device_reset_honours_user_tile_start_and_start_pose(torch_cuda):
     assert np.all(s["pos_x"] == 1 * md.tile_size + 0.31) and np.all(s["pos_z"] == 1 * md.tile_size + 0.22)
     assert np.all(s["angle"] == 1.25)
     env.close()
+
+
+def test_device_reset_fixed_starts_vs_reference_golden(golden_dir, torch_cuda):
+    """Device-side reset with user_tile_start / start_tile / start_pose against the reference's own reset() (2 episodes)."""
+    torch = torch_cuda
+    import copy
+    from gym_duckietown_b200 import maps
+    g = np.load(os.path.join(golden_dir, "reset_start_udem1.npz"))
+    n = len(g["seeds"])
+    assert list(g["seeds"]) == list(range(n))
+    base = maps.load_map("udem1")
+    md_tile = copy.deepcopy(base); md_tile.start_tile = tuple(int(v) for v in g["start_tile"])
+    md_pose = copy.deepcopy(md_tile)
+    sp = g["start_pose"]
+    md_pose.start_pose = [[float(sp[0]), float(sp[1]), float(sp[2])], float(sp[3])]
+    cases = {"user": (base, dict(user_tile_start=tuple(int(v) for v in g["user_tile_start"]))),
+             "tile": (md_tile, {}), "pose": (md_pose, {})}
+    for tag, (md, kw) in cases.items():
+        env = make_env(md, n, device_reset=True, seed=0, **kw)
+        for ep in range(2):
+            env.reset(render=False)
+            torch.cuda.synchronize()
+            s = {k: v.cpu().numpy() for k, v in env.state.items()}
+            rows = np.arange(n) * 2 + ep
+            assert np.array_equal(s["pos_x"], g[f"{tag}_cur_pos"][rows, 0]), (tag, ep)
+            assert np.array_equal(s["pos_z"], g[f"{tag}_cur_pos"][rows, 2]), (tag, ep)
+            assert np.array_equal(s["angle"], g[f"{tag}_cur_angle"][rows]), (tag, ep)
+        env.close()

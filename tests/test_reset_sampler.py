@@ -69,3 +69,27 @@ def check_against_golden(name, golden_dir, make_query):
 @pytest.mark.parametrize("name", MAPS)
 def test_reset_draws_match_reference(name, golden_dir):
     check_against_golden(name, golden_dir, oracle_query)
+
+
+def test_fixed_starts_match_reference(golden_dir):
+    """user_tile_start / map start_tile / map start_pose (S:659-686) as executed by the reference's reset()."""
+    import copy
+    g = np.load(os.path.join(golden_dir, "reset_start_udem1.npz"))
+    base = maps.load_map("udem1")
+    seeds = [int(v) for v in g["seeds"]]
+    envs = list(range(len(seeds)))
+    md_tile = copy.deepcopy(base); md_tile.start_tile = tuple(int(v) for v in g["start_tile"])
+    md_pose = copy.deepcopy(md_tile)
+    sp = g["start_pose"]
+    md_pose.start_pose = [[float(sp[0]), float(sp[1]), float(sp[2])], float(sp[3])]
+    cases = {"user": (base, dict(user_tile_start=tuple(int(v) for v in g["user_tile_start"]))),
+             "tile": (md_tile, {}), "pose": (md_pose, {})}
+    for tag, (md, kw) in cases.items():
+        s = EpisodeSampler(len(seeds), domain_rand=False, **kw)
+        s.seed(seeds)
+        for ep in range(2):
+            out = s.sample(envs, [md] * len(envs), oracle_query(md))
+            rows = np.arange(len(envs)) * 2 + ep
+            assert np.array_equal(out["pos_x"], g[f"{tag}_cur_pos"][rows, 0]), tag
+            assert np.array_equal(out["pos_z"], g[f"{tag}_cur_pos"][rows, 2]), tag
+            assert np.array_equal(out["angle"], g[f"{tag}_cur_angle"][rows]), tag
