@@ -27,7 +27,8 @@ class BatchedDuckietownEnv:
                  color_ground=(0.15, 0.15, 0.15), color_sky=(0.45, 0.82, 1), num_tris_distractors: int = 12,
                  gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
                  action_mode: str = "vel_steer", auto_reset: bool = False, device_reset: bool = False,
-                 cycle_maps: bool = False, env_id_offset: int = 0, tessellate_tiles: bool = False):
+                 cycle_maps: bool = False, env_id_offset: int = 0, tessellate_tiles: bool = False,
+                 randomize_maps_on_reset: bool = False):
         if not torch.cuda.is_available():
             raise L.DtsError("BatchedDuckietownEnv needs a CUDA device; there is no CPU implementation")
         if camera_rand:
@@ -41,6 +42,9 @@ class BatchedDuckietownEnv:
         self.frame_rate, self.delta_time, self.frame_skip = frame_rate, 1.0 / frame_rate, frame_skip
         self.robot_speed = robot_speed
         self.auto_reset, self.device_reset, self.cycle_maps = auto_reset, device_reset, cycle_maps
+        self.randomize_maps_on_reset = randomize_maps_on_reset
+        if cycle_maps and randomize_maps_on_reset:
+            raise ValueError("cycle_maps (MultiMapEnv) and randomize_maps_on_reset are two different reset policies")
         if auto_reset and not device_reset:
             raise ValueError("auto_reset re-spawns on the device: pass device_reset=True")
         flags = (L.FLAG_AUTO_RESET if auto_reset else 0) | (L.FLAG_DOMAIN_RAND if domain_rand else 0) | \
@@ -50,6 +54,7 @@ class BatchedDuckietownEnv:
             num_envs=num_envs, device=device, cam_width=camera_width, cam_height=camera_height, max_steps=max_steps,
             frame_skip=int(frame_skip), action_mode=L.ACTION_VEL_STEER if action_mode == "vel_steer" else L.ACTION_PWM,
             flags=flags, max_maps=len(self.maps), cycle_maps=len(self.maps) if cycle_maps else 0,
+            random_maps=len(self.maps) if randomize_maps_on_reset else 0,
             frame_rate=float(frame_rate), robot_speed=robot_speed, accept_start_angle_deg=float(accept_start_angle_deg),
             gain=gain, trim=trim, radius=radius, k=k, limit=limit, seed=0 if seed is None else int(seed),
             env_id_offset=env_id_offset)
@@ -126,6 +131,12 @@ class BatchedDuckietownEnv:
             if envs:
                 if self.cycle_maps and not self._first_reset:  # MultiMapEnv.reset, envs/multimap_env.py:46
                     self.map_ids[envs] = (self.map_ids[envs] + 1) % len(self.maps)
+                if self.randomize_maps_on_reset:   # np_random.choice(self.map_names) S:541-542: first draw of the reset
+                    for e in envs:
+                        self.map_ids[e] = int(self.sampler.rngs[e].integers(0, len(self.maps)))
+                    # _load_map (S:544) comes before the spawn loop: re-create the drawn maps' obstacles first, so that
+                    # the spawn predicates below see them at their load-time places
+                    self.sim.reset(mask_ptr, {"map_id": self.map_ids.copy()}, self._stream())
                 dense = self.sampler.sample(envs, [self.maps[self.map_ids[e]] for e in envs], self._query_for(envs))
                 params = {}
                 for key, val in dense.items():

@@ -110,6 +110,7 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   c.dyn.delay_steps = d;
   c.frame_skip = cfg->frame_skip; c.max_steps = cfg->max_steps; c.action_mode = cfg->action_mode; c.flags = cfg->flags;
   c.seed = cfg->seed; c.env_id_offset = cfg->env_id_offset;
+  c.random_maps = cfg->random_maps;
   c.reward_mode = DTS_REWARD_RAW; c.action_map = DTS_ACTIONS_CONTINUOUS; c.action_vel_scale = 1.0;
   DState& S = sim->S;
   S.n = n;
@@ -274,6 +275,10 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
     const double* dst = nullptr;
     bad |= sim->upload(&dst, st.data(), st.size(), &own);
     m.dyn_state = const_cast<double*>(dst);
+    std::vector<double> init((size_t)DTS_DYN_FIELDS * D);
+    for (int k = 0; k < DTS_DYN_FIELDS; k++)
+      for (size_t s = 0; s < D; s++) init[(size_t)k * D + s] = N ? st[((size_t)k * D + s) * N] : 0.0;
+    bad |= sim->upload(&m.dyn_init, init.data(), init.size(), &own);
   }
   if (bad) return 1;
   m.valid = 1;
@@ -295,11 +300,14 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
   return 0;
 }
 
+// > 0: round-robin over that many slots; < 0: uniform draw over -n slots; 0: the env keeps its map
+static int map_select(const dts_sim* sim) { return sim->cfg.random_maps > 0 ? -sim->cfg.random_maps : sim->cfg.cycle_maps; }
+
 static int check_maps(dts_sim* sim) {
   if (!sim->h_maps[0].valid) return sim->fail("no map uploaded in slot 0");
-  const int cyc = sim->cfg.cycle_maps;
+  const int cyc = sim->cfg.cycle_maps > sim->cfg.random_maps ? sim->cfg.cycle_maps : sim->cfg.random_maps;
   for (int k = 0; k < cyc; k++)
-    if (k >= sim->cfg.max_maps || !sim->h_maps[k].valid) return sim->fail("cycle_maps=%d but slot %d is empty", cyc, k);
+    if (k >= sim->cfg.max_maps || !sim->h_maps[k].valid) return sim->fail("cycle_maps / random_maps = %d but slot %d is empty", cyc, k);
   return 0;
 }
 
@@ -357,7 +365,7 @@ int dts_reset_random(dts_sim* sim, const uint8_t* mask_dev, void* stream) {
   if (check_maps(sim)) return 1;
   if (!sim->seeded) return sim->fail("dts_seed_streams must be called before a device-side reset");
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
-  launch_reset_random(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, mask_dev, (cudaStream_t)stream);
+  launch_reset_random(sim->S, sim->d_maps, sim->step_cfg, map_select(sim), mask_dev, (cudaStream_t)stream);
   sim->launches++;
   DTS_CUDA(cudaGetLastError());
   return 0;
@@ -421,7 +429,7 @@ int dts_step(dts_sim* sim, const float* actions_dev, void* obs_dev, float* rewar
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   if ((sim->cfg.flags & DTS_FLAG_AUTO_RESET) && !sim->seeded)
     return sim->fail("auto-reset needs seeded streams: call dts_seed_streams first");
-  launch_step_logic(sim->S, sim->d_maps, sim->step_cfg, sim->cfg.cycle_maps, actions_dev, reward_dev, done_dev,
+  launch_step_logic(sim->S, sim->d_maps, sim->step_cfg, map_select(sim), actions_dev, reward_dev, done_dev,
                     (cudaStream_t)stream);
   sim->launches++;
   DTS_CUDA(cudaGetLastError());

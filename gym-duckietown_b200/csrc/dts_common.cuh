@@ -74,6 +74,7 @@ struct DMap {
   int32_t n_dyn;
   const DDyn* dyn;              // [n_dyn]
   double* dyn_state;            // [DTS_DYN_FIELDS][n_dyn][num_envs]: mutable, per env, survives resets
+  const double* dyn_init;       // [DTS_DYN_FIELDS][n_dyn] load-time values (a map reload re-creates the obstacles)
   int32_t valid;
 };
 
@@ -126,6 +127,7 @@ struct StepCfg {
   DynParams dyn;
   int32_t frame_skip, max_steps, action_mode, flags;
   int32_t reward_mode, action_map;      // dts_output_format
+  int32_t random_maps, pad0;
   double action_vel_scale;
   uint64_t seed;
   int64_t env_id_offset;

@@ -68,6 +68,12 @@ __device__ inline void set_pose(const DState& S, const DMap& m, int e, double px
   S.step_count[e] = 0; S.speed[e] = 0.0;                                  // S:535-539
 }
 
+// _load_map re-creates the map's objects (S:541-544 under randomize_maps_on_reset): this env's obstacles go back
+// to their load-time state.
+__device__ inline void reinit_dynamic(const DMap& m, int n, int e) {
+  for (int k = 0; k < DTS_DYN_FIELDS * m.n_dyn; k++) m.dyn_state[(size_t)k * n + e] = m.dyn_init[k];
+}
+
 // Device-side Simulator.reset() (S:528-763): DR sampling + spawn rejection loop on the env's numpy-compatible
 // PCG64 stream, draw for draw in the reference's order (randomizer.py:46-89 sorted keys, then S:551-736).
 __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, int e) {
@@ -81,8 +87,10 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   const bool first = S.episode[e] == 0;
   int mid = S.map_id[e];
   if (n_maps_cycle > 0 && !first) mid = (mid + 1) % n_maps_cycle;   // MultiMapEnv.reset envs/multimap_env.py:44-49
+  if (n_maps_cycle < 0) mid = rs.integers(0, -n_maps_cycle);          // np_random.choice(map_names) S:541-542
   S.map_id[e] = mid;
   const DMap& m = maps[mid];
+  if (n_maps_cycle < 0) reinit_dynamic(m, n, e);                     // _load_map S:544
   RenderEp r;
   default_render_ep(r);
   // Randomizer.randomize: keys in sorted order — drawn whether or not DR is on (randomizer.py:33,46-89, S:546)
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(128) k_reset_params(DState S, const DMap* __re
   camera_view(S.pos_x[e], S.pos_z[e], S.angle[e], old, (c.flags & DTS_FLAG_DOMAIN_RAND) != 0, Vprev);
   if (p.map_id) S.map_id[e] = p.map_id[e];
   const DMap& m = maps[S.map_id[e]];
+  if (c.random_maps > 0) reinit_dynamic(m, S.n, e);   // the host drew the map (S:541-544): objects are re-created
   RenderEp r;
   default_render_ep(r);
   if (p.cam_height) r.cam_height = p.cam_height[e];

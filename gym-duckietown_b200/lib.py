@@ -29,7 +29,7 @@ class Config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("cam_width", C.c_int32),
         ("cam_height", C.c_int32), ("max_steps", C.c_int32), ("frame_skip", C.c_int32), ("action_mode", C.c_int32),
-        ("flags", C.c_int32), ("max_maps", C.c_int32), ("cycle_maps", C.c_int32), ("reserved0", C.c_int32),
+        ("flags", C.c_int32), ("max_maps", C.c_int32), ("cycle_maps", C.c_int32), ("random_maps", C.c_int32),
         ("frame_rate", C.c_double), ("robot_speed", C.c_double), ("accept_start_angle_deg", C.c_double),
         ("gain", C.c_double), ("trim", C.c_double), ("radius", C.c_double), ("k", C.c_double), ("limit", C.c_double),
         ("dyn_u1", C.c_double), ("dyn_u2", C.c_double), ("dyn_u3", C.c_double), ("dyn_w1", C.c_double),
@@ -379,7 +379,7 @@ def default_config(**kw) -> Config:
     """Reference defaults: Simulator.__init__ (S:207-232), DuckietownEnv.__init__ (E:15), DB18 nominal."""
     c = Config(
         abi_version=DTS_ABI_VERSION, num_envs=1, device=0, cam_width=640, cam_height=480, max_steps=1500, frame_skip=1,
-        action_mode=ACTION_VEL_STEER, flags=0, max_maps=1, cycle_maps=0, reserved0=0, frame_rate=30.0, robot_speed=1.2,
+        action_mode=ACTION_VEL_STEER, flags=0, max_maps=1, cycle_maps=0, random_maps=0, frame_rate=30.0, robot_speed=1.2,
         accept_start_angle_deg=60.0, gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
         dyn_u1=5.0, dyn_u2=0.0, dyn_u3=0.0, dyn_w1=4.0, dyn_w2=0.0, dyn_w3=0.0, dyn_uar=1.5, dyn_ual=1.5,
         dyn_war=15.0, dyn_wal=15.0, dyn_delay=0.15, seed=0, env_id_offset=0)

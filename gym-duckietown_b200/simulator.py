@@ -42,9 +42,9 @@ class Simulator(Env):
                  camera_rand: bool = False, randomize_maps_on_reset: bool = False, num_tris_distractors: int = 12,
                  color_ground=(0.15, 0.15, 0.15), color_sky=(0.45, 0.82, 1), style: str = "photos",
                  enable_leds: bool = False, device: int = 0, **env_kwargs):
-        if draw_curve or draw_bbox or randomize_maps_on_reset or enable_leds:
-            raise NotImplementedError("draw_curve / draw_bbox / randomize_maps_on_reset / enable_leds are debug "
-                                      "modes outside the hot path (SURVEY 8f-4)")
+        if draw_curve or draw_bbox or enable_leds:
+            raise NotImplementedError("draw_curve / draw_bbox / enable_leds are debug modes outside the hot path "
+                                      "(SURVEY 8f-4)")
         from .batched_env import BatchedDuckietownEnv  # needs torch + CUDA: fail here, loudly, if absent
         self.map_name = map_name
         self.max_steps, self.domain_rand, self.full_transparency = max_steps, domain_rand, full_transparency
@@ -53,16 +53,21 @@ class Simulator(Env):
         self.accept_start_angle_deg = accept_start_angle_deg
         self.distortion, self.undistort, self.dynamics_rand = distortion, False, dynamics_rand
         self.seed_value = seed
+        self.randomize_maps_on_reset = randomize_maps_on_reset
+        map_arg = map_name
+        if randomize_maps_on_reset:   # S:373-378: every map file except calibration* / regress*; reset() draws one
+            from .maps import list_maps
+            self.map_names = [m for m in list_maps() if not m.startswith(("calibration", "regress"))]
+            map_arg = self.map_names
+            env_kwargs = dict(env_kwargs, randomize_maps_on_reset=True)
         self._b = BatchedDuckietownEnv(
-            1, map_name, device=device, max_steps=max_steps, domain_rand=domain_rand, frame_rate=frame_rate,
+            1, map_arg, device=device, max_steps=max_steps, domain_rand=domain_rand, frame_rate=frame_rate,
             frame_skip=frame_skip, camera_width=camera_width, camera_height=camera_height, robot_speed=robot_speed,
             accept_start_angle_deg=accept_start_angle_deg, user_tile_start=user_tile_start, seed=seed,
             distortion=distortion, dynamics_rand=dynamics_rand, camera_rand=camera_rand,
             color_ground=color_ground, color_sky=color_sky, num_tris_distractors=num_tris_distractors,
             action_mode=self._action_mode, **env_kwargs)
-        md = self._b.maps[0]
-        self.road_tile_size, self.grid_width, self.grid_height = md.tile_size, md.grid_w, md.grid_h
-        self.drivable_tiles, self.objects = md.drivable_tiles, md.objects
+        self._adopt_map()
         self.action_space = spaces.Box(low=-1, high=1, shape=(2,), dtype=np.float32)              # S:309
         self.observation_space = spaces.Box(low=0, high=255, shape=(camera_height, camera_width, 3), dtype=np.uint8)
         self.reward_range = (-1000, 1000)
@@ -71,6 +76,17 @@ class Simulator(Env):
         self.wheelVels = np.array([0, 0])
         self.timestamp = 0.0
         self.reset()
+
+    def _map_index(self) -> int:
+        return int(self._b.map_ids[0]) if not self._b.device_reset else int(self._b.state["map_id"][0].item())
+
+    def _adopt_map(self):
+        """Map-dependent attributes of the reference Simulator (S:793-879) for the env's current map."""
+        md = self._b.maps[self._map_index()]
+        self.road_tile_size, self.grid_width, self.grid_height = md.tile_size, md.grid_w, md.grid_h
+        self.drivable_tiles, self.objects = md.drivable_tiles, md.objects
+        if self.randomize_maps_on_reset:
+            self.map_name = self.map_names[self._map_index()]
 
     # ------------------------------------------------------------------ gym.Env
     def seed(self, seed=None):
@@ -82,6 +98,7 @@ class Simulator(Env):
             raise NotImplementedError("segmentation rendering is a debug mode (SURVEY 8f-4)")
         obs = self._b.reset()
         self.timestamp = 0.0
+        self._adopt_map()
         return self._obs_numpy(obs)
 
     def step(self, action):
@@ -140,7 +157,7 @@ class Simulator(Env):
 
     # ------------------------------------------------------------------ helper methods callers use
     def _query(self, pos, angle, safety=1.0):
-        outd, outi = self._b.sim.query_poses(0, np.array([pos[0]]), np.array([pos[2]]), np.array([angle]), safety, dyn_env=0)
+        outd, outi = self._b.sim.query_poses(self._map_index(), np.array([pos[0]]), np.array([pos[2]]), np.array([angle]), safety, dyn_env=0)
         return outd[0], outi[0]
 
     def get_grid_coords(self, abs_pos) -> Tuple[int, int]:  # S:1134

@@ -49,7 +49,8 @@ typedef struct {
   int32_t max_maps;         /* slots for dts_upload_map */
   int32_t cycle_maps;       /* >0: every reset advances the env's map id modulo this count
                                (MultiMapEnv.reset round-robin, envs/multimap_env.py:44-49) */
-  int32_t reserved0;
+  int32_t random_maps;      /* >0: every reset draws the env's map uniformly from the first `random_maps` slots and
+                               re-creates its obstacles (randomize_maps_on_reset: np_random.choice + _load_map, S:541-544) */
   double frame_rate;        /* simulator.py:214 (30) */
   double robot_speed;       /* simulator.py:218 (1.2): the constant used in the reward, S:1702 */
   double accept_start_angle_deg; /* simulator.py:219 (60), device-side spawn only */

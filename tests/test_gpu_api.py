@@ -145,3 +145,22 @@ def test_host_pipeline_matches_sequential_stepping(torch_cuda):
     ho, hr, hd = pipe.result(tickets[-1])
     assert np.array_equal(ho.numpy(), ref[0]) and np.array_equal(hd.numpy(), ref[2])
     a.close(); b.close()
+
+
+def test_simulator_randomize_maps_on_reset(torch_cuda):
+    """Simulator(randomize_maps_on_reset=True) (S:373-378, 541-544): the map changes between resets and the
+    map-dependent attributes follow it."""
+    import gym_duckietown_b200 as gd
+    env = gd.Simulator("small_loop", randomize_maps_on_reset=True, camera_width=84, camera_height=84, seed=3, domain_rand=False)
+    names = set()
+    for _ in range(8):
+        obs = env.reset()
+        assert obs.shape == (84, 84, 3)
+        names.add(env.map_name)
+        md = gd.maps.load_map(env.map_name)
+        assert (env.grid_width, env.grid_height) == (md.grid_w, md.grid_h)
+        i, j = env.get_grid_coords(env.cur_pos)
+        assert md.tile_drivable[j * md.grid_w + i]
+        env.step([0.3, 0.3])
+    assert len(names) >= 3
+    env.close()

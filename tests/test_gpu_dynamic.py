@@ -281,3 +281,40 @@ def test_traffic_lights_vs_reference_golden(tag, golden_dir, torch_cuda):
         assert np.any(other != got[0])            # the card is in view: the other pattern would look different
     assert cards == {0, 1}
     env.close()
+
+
+def test_randomize_maps_on_reset_device_equals_host_and_recreates_obstacles(golden_dir, torch_cuda):
+    """S:541-544: every reset draws the map from the env's own stream and reloads it (obstacles back to load state)."""
+    torch = torch_cuda
+    from gym_duckietown_b200 import lib as L
+    names = ["small_loop", "loop_pedestrians", "udem1", "loop_dyn_duckiebots"]
+    N = 24
+    dev = make_env(names, N, device_reset=True, randomize_maps_on_reset=True, seed=300)
+    host = make_env(names, N, device_reset=False, randomize_maps_on_reset=True, seed=300)
+    zero = torch.zeros(N, 2, device=dev.device)
+    seen = set()
+    for ep in range(3):
+        dev.reset(render=False); host.reset(render=False)
+        torch.cuda.synchronize()
+        a = {k: v.cpu().numpy() for k, v in dev.state.items()}
+        b = {k: v.cpu().numpy() for k, v in host.state.items()}
+        assert np.array_equal(a["map_id"], b["map_id"]) and np.array_equal(a["map_id"], host.map_ids)
+        for k in ("pos_x", "pos_z", "angle"):
+            assert np.array_equal(a[k], b[k]), (ep, k)
+        seen |= set(a["map_id"].tolist())
+        for t in range(250):                       # past the pedestrians' 240-step wait: they are walking now
+            dev.step(zero, render=False)
+    assert len(seen) >= 3
+    st_before = dyn_host(dev, torch, 1)
+    e = int(np.flatnonzero(dev.state["map_id"].cpu().numpy() == 1)[0]) if (dev.state["map_id"] == 1).any() else None
+    if e is not None:
+        assert st_before[L.DYN_TIME, 0, e] > 8.0
+    dev.reset(render=False)                         # reload: envs that land on map 1 have fresh obstacles
+    torch.cuda.synchronize()
+    mid = dev.state["map_id"].cpu().numpy()
+    st = dyn_host(dev, torch, 1)
+    md = dev.maps[1]
+    for e in np.flatnonzero(mid == 1):
+        assert np.all(st[L.DYN_TIME, :, e] == 0.0) and np.all(st[L.DYN_ACTIVE, :, e] == 0.0)
+        assert np.array_equal(st[L.DYN_PX, :, e], np.array([d.pos[0] for d in md.dyn_objects]))
+    dev.close(); host.close()

@@ -93,3 +93,15 @@ def test_fixed_starts_match_reference(golden_dir):
             assert np.array_equal(out["pos_x"], g[f"{tag}_cur_pos"][rows, 0]), tag
             assert np.array_equal(out["pos_z"], g[f"{tag}_cur_pos"][rows, 2]), tag
             assert np.array_equal(out["angle"], g[f"{tag}_cur_angle"][rows]), tag
+
+
+def test_map_choice_draw_is_a_bounded_integer_draw():
+    """randomize_maps_on_reset picks the map with `np_random.choice(self.map_names)` (S:541-542): for a Generator that
+    is one `integers(0, n)` draw — which is what the host path and the device's Lemire sampler replay."""
+    names = [f"map{k}" for k in range(7)]
+    for seed in range(50):
+        a, b = np.random.default_rng(seed), np.random.default_rng(seed)
+        a.uniform(); b.uniform()                       # mid-stream, with numpy's cached 32-bit half possibly pending
+        for _ in range(5):
+            assert a.choice(names) == names[int(b.integers(0, len(names)))]
+        assert a.bit_generator.state == b.bit_generator.state
