@@ -99,3 +99,33 @@ def test_two_rank_sharding_is_rank_count_independent(tmp_path):
                        capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDING_OK" in r.stdout
+
+
+def test_map_blob_flattening_of_dynamic_objects_and_traffic_light_cards():
+    """Host logic only (no GPU): the dts_map_blob built for maps with `static: false` obstacles and traffic lights."""
+    import ctypes as C
+    from gym_duckietown_b200 import lib as L, maps
+    for name in ("loop_pedestrians", "loop_dyn_duckiebots", "loop_trafficlights", "udem1"):
+        md = maps.load_map(name)
+        h = L.MapBlobHolder(md)
+        b = h.blob
+        assert b.n_dyn == len(md.dyn_objects) <= 32 and b.n_objects == len(md.objects)
+        objs = C.cast(b.objects, C.POINTER(L.Object))
+        dyn = C.cast(b.dyn, C.POINTER(L.DynObjectC))
+        slots = [objs[i].dyn_slot for i in range(b.n_objects)]
+        assert sorted(s for s in slots if s >= 0) == list(range(b.n_dyn))          # every slot used exactly once
+        for s in range(b.n_dyn):
+            o = dyn[s].object_index
+            assert objs[o].dyn_slot == s and dyn[s].kind == md.dyn_objects[s].kind
+            assert [dyn[s].pos[k] for k in range(3)] == [float(v) for v in md.objects[o].pos]
+            if dyn[s].kind == maps.DYN_TRAFFICLIGHT:
+                assert 0 <= objs[o].alt_tex_from < b.n_textures and 0 <= objs[o].alt_tex_to < b.n_textures
+                assert objs[o].alt_tex_from != objs[o].alt_tex_to
+                assert not md.objects[o].collidable
+            else:
+                assert objs[o].alt_tex_from == -1 and not md.objects[o].static
+        # update order = object order (S:1570-1584)
+        assert [dyn[s].object_index for s in range(b.n_dyn)] == sorted(dyn[s].object_index for s in range(b.n_dyn))
+    md = maps.load_map("small_loop")
+    assert L.MapBlobHolder(md, user_tile_start=(2, 1)).blob.start_tile[:] == [2, 1]
+    assert L.MapBlobHolder(md).blob.start_tile[:] == [-1, -1] and L.MapBlobHolder(md).blob.has_start_pose == 0
