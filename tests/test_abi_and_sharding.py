@@ -129,3 +129,25 @@ def test_map_blob_flattening_of_dynamic_objects_and_traffic_light_cards():
     md = maps.load_map("small_loop")
     assert L.MapBlobHolder(md, user_tile_start=(2, 1)).blob.start_tile[:] == [2, 1]
     assert L.MapBlobHolder(md).blob.start_tile[:] == [-1, -1] and L.MapBlobHolder(md).blob.has_start_pose == 0
+
+
+def test_no_cpu_fallback_without_cuda():
+    """The product has no CPU path: on a box without a CUDA device every entry into the simulator classes raises
+    (loudly, with the reason) instead of computing something some other way."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    import gym_duckietown_b200 as gd
+    from gym_duckietown_b200 import gymshim, lib as L
+    with pytest.raises(L.DtsError, match="CUDA"):
+        gd.BatchedDuckietownEnv(2, "small_loop", camera_width=32, camera_height=24)
+    with pytest.raises(L.DtsError, match="CUDA"):
+        gd.Simulator("small_loop")
+    with pytest.raises(L.DtsError, match="CUDA"):
+        gymshim.make("Duckietown-small_loop-v0")
+    # the C ABI itself refuses too: no device -> dts_create fails with cudaSetDevice's message
+    lib = L.load()
+    h = ctypes.c_void_p()
+    cfg = L.default_config(num_envs=2, cam_width=32, cam_height=24)
+    assert lib.dts_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"cuda" in lib.dts_last_error(None).lower()
