@@ -29,6 +29,34 @@ class NotInLane(Exception):
 
 DEFAULT_MAP_NAME = "udem1"
 
+# module-level constants and helpers user scripts import from gym_duckietown.simulator (S:118-177, S:2056-2118)
+CAMERA_FORWARD_DIST, ROBOT_WIDTH, ROBOT_LENGTH, WHEEL_DIST = 0.066, 0.13 + 0.02, 0.18, 0.102
+DEFAULT_ROBOT_SPEED, DEFAULT_FRAMERATE, DEFAULT_MAX_STEPS = 1.20, 30, 1500
+REWARD_INVALID_POSE = -1000
+
+
+def get_dir_vec(cur_angle: float) -> np.ndarray:
+    """Unit vector the robot points along, x right / z towards the viewer (S:2056-2064)."""
+    return np.array([np.cos(cur_angle), 0.0, -np.sin(cur_angle)])
+
+
+def get_right_vec(cur_angle: float) -> np.ndarray:
+    """Unit vector to the robot's right (S:2066-2074)."""
+    return np.array([np.sin(cur_angle), 0.0, np.cos(cur_angle)])
+
+
+def _actual_center(pos, angle) -> np.ndarray:
+    """Centre of the robot's footprint: the camera sits CAMERA_FORWARD_DIST ahead of the rear end (S:2102-2110)."""
+    return np.asarray(pos, float) + (CAMERA_FORWARD_DIST - ROBOT_LENGTH / 2) * get_dir_vec(angle)
+
+
+def get_agent_corners(pos, angle) -> np.ndarray:
+    """[4,2] (x,z) corners of the robot's bounding box around `_actual_center(pos, angle)` (S:2113-2118, C:9-34)."""
+    c, f, r = _actual_center(pos, angle), get_dir_vec(angle), get_right_vec(angle)
+    hw, hl = 0.5 * ROBOT_WIDTH, 0.5 * ROBOT_LENGTH
+    pts = [c - hw * r - hl * f, c + hw * r - hl * f, c + hw * r + hl * f, c - hw * r + hl * f]
+    return np.array([[p_[0], p_[2]] for p_ in pts])
+
 
 class Simulator(Env):
     metadata = {"render.modes": ["rgb_array"], "video.frames_per_second": 30}

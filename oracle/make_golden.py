@@ -226,6 +226,20 @@ def gen_reset_start(name="udem1", seeds=range(12)):
     print(f"reset_start_{name}: {len(out['seeds'])} seeds x 2 episodes x (user_tile_start, start_tile, start_pose)")
 
 
+def gen_helpers(n=256, seed=9):
+    """Module-level helpers of simulator.py that user scripts import (S:2056-2118)."""
+    S, C, G, O = refstub.modules()
+    rng = np.random.default_rng(seed)
+    poses = np.stack([rng.uniform(0, 5, n), np.zeros(n), rng.uniform(0, 5, n)], 1)
+    angles = rng.uniform(-2 * np.pi, 2 * np.pi, n)
+    np.savez_compressed(os.path.join(OUT, "helpers.npz"), poses=poses, angles=angles,
+                        dir_vec=np.array([S.get_dir_vec(a) for a in angles]),
+                        right_vec=np.array([S.get_right_vec(a) for a in angles]),
+                        center=np.array([S._actual_center(p, a) for p, a in zip(poses, angles)]),
+                        corners=np.array([S.get_agent_corners(p, a) for p, a in zip(poses, angles)]))
+    print(f"helpers: {n} poses")
+
+
 def gen_fisheye():
     refstub.install()
     from gym_duckietown.distortion import Distortion
@@ -335,3 +349,4 @@ if __name__ == "__main__":
         gen_dynamic(m)
     gen_trafficlight()
     gen_reset_start()
+    gen_helpers()

@@ -151,3 +151,16 @@ def test_no_cpu_fallback_without_cuda():
     cfg = L.default_config(num_envs=2, cam_width=32, cam_height=24)
     assert lib.dts_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"cuda" in lib.dts_last_error(None).lower()
+
+
+def test_module_level_helpers_match_reference(golden_dir):
+    """get_dir_vec / get_right_vec / _actual_center / get_agent_corners (S:2056-2118), which user scripts import from
+    the simulator module, against values computed by the reference's own functions."""
+    import os
+    import numpy as np
+    from gym_duckietown_b200 import simulator as sim
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    for k, (p, a) in enumerate(zip(g["poses"], g["angles"])):
+        assert np.array_equal(sim.get_dir_vec(a), g["dir_vec"][k]) and np.array_equal(sim.get_right_vec(a), g["right_vec"][k])
+        assert np.array_equal(sim._actual_center(p, a), g["center"][k])
+        assert np.array_equal(sim.get_agent_corners(p, a), g["corners"][k])
