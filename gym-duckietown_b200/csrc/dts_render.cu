@@ -1096,7 +1096,10 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   const dim3 geo_grid((unsigned)((rc.n_envs + kGeoWarps - 1) / kGeoWarps), (unsigned)items_max);
   if (rc.tessellate) k_geometry<true><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
   else k_geometry<false><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
-  k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, (size_t)kBinWarps * 2 * cbins * sizeof(int), st>>>(
+  const size_t bin_smem_bytes = (size_t)kBinWarps * 2 * cbins * sizeof(int);
+  if (bin_smem_bytes > 48 * 1024)   // cameras beyond ~640x480 (cbins > 1536): opt in to large dynamic shared memory
+    cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
+  k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, bin_smem_bytes, st>>>(
       rc, fm, max_prims, max_pairs, err_flag);
   if (!fisheye && (rc.obs_layout | rc.obs_dtype) != 0)
     k_raster<true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
