@@ -136,6 +136,109 @@ def cpu_reference_run(map_name, w, h, steps, warmup, sample_envs, threads):
                                                    f"(oracle port: C logic + software rasteriser, {threads} OpenMP threads)")
 
 
+BASELINE_CONFIGS = {
+    # BASELINE.json configs[1..4] (configs[0] is the reference's own 1-env CPU case = the --impl reference arm)
+    "c2": dict(map="small_loop", envs=4096, width=160, height=120, domain_rand=False, distortion=False, cycle=False),
+    "c3": dict(map="loop_obstacles", envs=4096, width=160, height=120, domain_rand=False, distortion=False, cycle=False),
+    "c4": dict(map="udem1", envs=8192, width=640, height=480, domain_rand=True, distortion=True, cycle=False),
+    "c5": dict(map="small_loop,loop_obstacles,udem1,loop_pedestrians,loop_dyn_duckiebots,loop_trafficlights",
+               envs=4096, width=160, height=120, domain_rand=False, distortion=False, cycle=True),
+}
+PARITY_UNPINNED = ["dynamics (duckietown_world DB18 model restated, source absent)",
+                   "pixels (no OpenGL here: raster spec of DESIGN.md 5; render INPUTS pinned by tests/golden/gltrace_*.npz)"]
+
+
+def workload_text(c):
+    return (f"Duckietown-{c['map']}-v0 (stand-in map{'s, cycled on reset (MultiMap)' if c['cycle'] else ''}), {c['envs']} envs/GPU, "
+            f"{c['width']}x{c['height']} RGB, random [vel,steer] actions, domain_rand={c['domain_rand']}, "
+            f"distortion={c['distortion']}, device-side auto-reset")
+
+
+def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sampler=None, gather=True):
+    """Device-resident arm of one workload: W warm-up steps, K timed steps (k_step_logic + render) bracketed by
+    barrier + synchronize, + the end-of-rollout NCCL all-gather when world > 1.  Returns (result dict, env) —
+    the env is left alive for the caller's end-to-end arm."""
+    import torch
+    import torch.distributed as dist
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+
+    dev = torch.device("cuda", local_rank)
+    E, W, H = c["envs"], c["width"], c["height"]
+    names = c["map"].split(",")
+    env = BatchedDuckietownEnv(E, names if len(names) > 1 else names[0], device=local_rank, camera_width=W, camera_height=H,
+                               domain_rand=c["domain_rand"], distortion=c["distortion"], cycle_maps=c["cycle"],
+                               seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E)
+    if obs_format != "hwc_uint8":
+        lay, dt = obs_format.split("_")
+        env.set_output_format(obs_layout=lay, obs_dtype=dt)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.rand((K + Wm, E, 2), device=dev, generator=gen) * 2 - 1   # Box(-1,1,(2,)).sample() distribution
+    gathered = ag = None
+    if world > 1 and gather:
+        from gym_duckietown_b200.dist import ObsAllGather
+        ag = ObsAllGather(env, rank, world)
+        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=env.obs.dtype, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(Wm):
+        env.step(actions[t])
+    if ag is not None:
+        ag.all_gather(gathered)   # first collective on a communicator sets up channels: keep it out of the timed region
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.launch_count()
+    env.sim.profile(True)     # CUDA events around every render kernel, on the launching stream (roofline)
+    ev0.record()
+    for t in range(K):
+        env.step(actions[Wm + t])                 # dts_step: k_step_logic (+ device auto-reset) + the render kernels
+    if ag is not None:
+        ag.all_gather(gathered)                   # the single end-of-rollout NCCL all-gather (SURVEY 8e)
+    ev1.record()
+    barrier()
+    env.sim.profile(False)
+    launches = env.launch_count() - launches0
+    env.check()   # no frame hit a capacity limit
+    ms = ev0.elapsed_time(ev1)
+    kms, frames = env.sim.profile_read()
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * E * K / (ms / 1000.0)
+    per = {k: v / max(frames, 1) for k, v in kms.items()}
+    peak, peak_src = measured_peak()
+    raster_ms = per["k_raster"]
+    achieved = E * b_alg(W, H) / (raster_ms / 1000.0) / 1e9
+    render_ms = sum(per.values())
+    res = {
+        "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": Wm, "gpu_launches": int(launches),
+        "workload": workload_text(c),
+        "roofline": {"bound": "hbm", "kernel": "k_raster (dominant kernel of the step; CUDA events on the launching stream, mean over the timed steps)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": raster_ms,
+                     "compulsory_frac": (E * (W * H * 3 + 256) / (raster_ms / 1000.0) / 1e9) / peak,
+                     "all_render_kernels_ms": render_ms, "frac_all_render_kernels": (E * b_alg(W, H) / (render_ms / 1000.0) / 1e9) / peak},
+        "kernel_ms": per,
+    }
+    return res, env
+
+
+def bind_numa(local_rank):
+    try:
+        from gym_duckietown_b200.dist import bind_to_gpu_numa
+        return bind_to_gpu_numa(local_rank)
+    except Exception as e:   # affinity is an optimisation, never a reason to fail the bench
+        return {"error": str(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,7 +249,7 @@ def main():
     ap.add_argument("--map", default="small_loop")
     ap.add_argument("--width", type=int, default=160)
     ap.add_argument("--height", type=int, default=120)
-    ap.add_argument("--cpu-sample-envs", type=int, default=256)
+    ap.add_argument("--cpu-sample-envs", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--domain-rand", action="store_true", help="BASELINE config 4: domain randomization on")
     ap.add_argument("--distortion", action="store_true", help="BASELINE config 4: fused fisheye gather")
@@ -154,6 +257,10 @@ def main():
                     help="fused wrapper output (SURVEY 8f-3): <hwc|chw|cwh>_<uint8|float32>; default is render_obs's own")
     ap.add_argument("--pipeline-depth", type=int, default=2, help="HostPipeline slots in flight for the e2e arm")
     ap.add_argument("--cycle-maps", action="store_true", help="BASELINE config 5: --map a,b cycled on reset (MultiMap)")
+    ap.add_argument("--configs", default="auto",
+                    help="extra BASELINE configs timed after the headline and attached as \"configs\": comma list of "
+                         "c3,c4,c5, 'none', or 'auto' (N=1: c3,c4,c5; N>1: c5 with the NCCL all-gather)")
+    ap.add_argument("--c4-envs", type=int, default=8192)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,10 +269,10 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     W, H, E = args.width, args.height, args.envs
     cores = usable_cores()
-    map_arg = args.map.split(",") if "," in args.map else args.map
-    config = {"workload": f"Duckietown-{args.map}-v0 (stand-in map), {E} envs/GPU, {W}x{H} RGB, random [vel,steer] "
-                          f"actions, domain_rand={args.domain_rand}, distortion={args.distortion}, device-side auto-reset",
-              "envs_per_gpu": E, "width": W, "height": H, "map": args.map,
+    head = dict(map=args.map, envs=E, width=W, height=H, domain_rand=args.domain_rand, distortion=args.distortion,
+                cycle=args.cycle_maps)
+    config = {"workload": workload_text(head), "envs_per_gpu": E, "width": W, "height": H, "map": args.map,
+              "tile_mode": "1 (one quad per road tile + analytic 8x8 lattice lighting; mode 0 = literal 98 triangles differs by <= 2 LSB, tests/test_oracle_raster.py)",
               "l2": "obs batch written per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (E * W * H * 3 / 1e6)}
 
     if args.impl == "reference":
@@ -173,43 +280,27 @@ def main():
         # duckietown_world); the CPU arm is the oracle port of the same step on all host cores.
         if rank != 0:
             return
-        k = max(1, min(args.steps, 20))
-        w_ = max(1, min(args.warmup, 3))
-        val, secs, cores, desc = cpu_reference_run(args.map, W, H, k, w_, args.cpu_sample_envs, cores)
+        k, w_ = max(1, args.steps), max(0, args.warmup)   # the driver's step / warm-up counts, as given
+        val, secs, cores, desc = cpu_reference_run(args.map.split(",")[0], W, H, k, w_, args.cpu_sample_envs, cores)
         line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w_,
                 "ms_per_step": 1000 * secs / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 logic / f32 raster / u8 obs", "data": "synthetic", "config": config, "impl": "reference",
+                "baseline_is": "C port of the reference's CPU path (oracle/), NOT the Pyglet reference itself (cannot run here)",
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
 
+    numa = bind_numa(local_rank)   # before any pinned allocation: host buffers land on the GPU's NUMA node
     import torch
     import torch.distributed as dist
-    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    env = BatchedDuckietownEnv(E, map_arg, device=local_rank, camera_width=W, camera_height=H,
-                               domain_rand=args.domain_rand, distortion=args.distortion, cycle_maps=args.cycle_maps,
-                               seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E)
-    if args.obs_format != "hwc_uint8":
-        lay, dt = args.obs_format.split("_")
-        env.set_output_format(obs_layout=lay, obs_dtype=dt)
-        config["obs_format"] = args.obs_format
-    env.reset()
     K, Wm = args.steps, max(3, args.warmup)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    actions = torch.rand((K + Wm, E, 2), device=dev, generator=gen) * 2 - 1   # Box(-1,1,(2,)).sample() distribution
-    gathered = None
-    if world > 1:
-        from gym_duckietown_b200.dist import ObsAllGather
-        ag = ObsAllGather(env, rank, world)
-        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=env.obs.dtype, device=dev)
 
     def barrier():
         if world > 1:
@@ -217,105 +308,113 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm: `value` -------------------------------------------------------------
-    for t in range(Wm):
-        env.step(actions[t])
-    if world > 1:
-        ag.all_gather(gathered)   # first collective on a communicator sets up channels: keep it out of the timed region
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rs = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    re_ = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    launches0 = env.launch_count()
-    ev0.record()
-    for t in range(K):
-        env.step(actions[Wm + t], render=False)   # k_step_logic (+ device auto-reset)
-        rs[t].record()
-        env.render_obs()                          # k_render  — same two launches dts_step issues
-        re_[t].record()
-    if world > 1:
-        ag.all_gather(gathered)                   # the single end-of-rollout NCCL all-gather
-    ev1.record()
-    barrier()
-    launches = env.launch_count() - launches0
-    env.check()   # no frame hit a capacity limit
-    ms = ev0.elapsed_time(ev1)
-    render_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(rs, re_)]))
-    if world > 1:
-        tmax = torch.tensor([ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    value = world * E * K / (ms / 1000.0)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    res, env = run_config(head, K, Wm, rank, world, local_rank, args.obs_format, sampler)
+    if args.obs_format != "hwc_uint8":
+        config["obs_format"] = args.obs_format
 
     # ---- end-to-end arm: host buffers in/out through the public API -----------------------------------
     # HostPipeline.submit(): pinned-host actions -> device, dts_step, obs/reward/done -> pinned host on a copy
     # stream; result(): wait for that step's host buffers.  Two slots in flight, so the D2H of step k overlaps
     # the kernels of step k+1 (random-action rollout: actions do not depend on observations).
-    from gym_duckietown_b200.batched_env import HostPipeline
-    Ke = max(5, min(K, 50))
-    h_act = torch.empty((Ke + 3, E, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    pipe = HostPipeline(env, depth=args.pipeline_depth)
-    for t in range(3):
-        pipe.result(pipe.submit(h_act[t]))
-    barrier()
-    checksum = 0
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     from collections import deque
-    pend = deque()
+    from gym_duckietown_b200.batched_env import HostPipeline
 
-    def consume(tk):
-        ho, hr, hd = pipe.result(tk)
-        return int(ho.reshape(-1)[0]) + int(hd[0])       # the host really reads the step's result
+    def e2e_arm(env, Ke):
+        h_act = torch.empty((Ke + 3, env.num_envs, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        pipe = HostPipeline(env, depth=args.pipeline_depth)
+        for t in range(3):
+            pipe.result(pipe.submit(h_act[t]))
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pend = deque()
+        checksum = 0
 
-    for t in range(Ke):
-        pend.append(pipe.submit(h_act[3 + t]))
-        if len(pend) >= args.pipeline_depth:
+        def consume(tk):
+            ho, hr, hd = pipe.result(tk)
+            return int(ho.reshape(-1)[0]) + int(hd[0])       # the host really reads the step's result
+
+        for t in range(Ke):
+            pend.append(pipe.submit(h_act[3 + t]))
+            if len(pend) >= args.pipeline_depth:
+                checksum += consume(pend.popleft())
+        while pend:
             checksum += consume(pend.popleft())
-    while pend:
-        checksum += consume(pend.popleft())
-    e1.record()
-    barrier()
-    ems = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - t0) - 0.0)   # device and wall clock agree; take the larger
-    if world > 1:
-        tmax = torch.tensor([ems], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ems = float(tmax.item())
-    e2e = world * E * Ke / (ems / 1000.0)
-    if rank == 0:
+        e1.record()
+        barrier()
+        ems = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - t0))   # device and wall clock agree; take the larger
+        if world > 1:
+            tmax = torch.tensor([ems], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ems = float(tmax.item())
+        out_bytes = int(pipe.slots[0]["h_obs"].numel() * pipe.slots[0]["h_obs"].element_size())
+        return {"value": world * env.num_envs * Ke / (ems / 1000.0), "unit": UNIT, "h2d_bytes_per_step": env.num_envs * 2 * 4,
+                "d2h_bytes_per_step": out_bytes + env.num_envs * (4 + 1), "steps": Ke,
+                "api": f"HostPipeline.submit/result, depth {args.pipeline_depth} (D2H of step k overlaps step k+1)"}
+
+    Ke = max(5, min(K, 50))
+    e2e = e2e_arm(env, Ke)
+    e2e_resized = None
+    if hasattr(env, "set_resize"):   # fused ResizeWrapper (wrappers.py:111-141): the training stack's 84x84 payload
+        try:
+            env.set_resize(84, 84)
+            e2e_resized = e2e_arm(env, Ke)
+            e2e_resized["obs"] = "84x84 RGB resized on the device (cv2.INTER_CUBIC semantics of ResizeWrapper)"
+            env.set_resize(None, None)
+        except Exception as ex:
+            e2e_resized = {"error": str(ex)}
+    if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, same step count, device-resident ---------------------------------
+    extra = {}
+    want = args.configs
+    if want == "auto":
+        want = "c3,c4,c5" if world == 1 else "c5"
+    for name in [w for w in want.split(",") if w and w != "none"]:
+        c = dict(BASELINE_CONFIGS[name])
+        if name == "c4":
+            c["envs"] = args.c4_envs
+        try:
+            r, e_ = run_config(c, K, Wm, rank, world, local_rank, "hwc_uint8", None, gather=(name == "c5"))
+            e_.close()
+            del e_
+            extra[name] = r
+        except Exception as ex:
+            extra[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peak()
-    achieved = E * b_alg(W, H) / (render_ms / 1000.0) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "render_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("envs") == E and tj.get("width") == W and tj.get("map") == args.map:
             traffic = tj.get("dram_bytes_per_launch")
+    res["roofline"]["traffic"] = traffic
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 logic / f32 raster / u8 obs", "data": "synthetic", "config": config,
-        "clocks": sampler.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4, "d2h_bytes_per_step": E * (W * H * 3 * env.obs.element_size() + 4 + 1),
-                "steps": Ke, "api": f"HostPipeline.submit/result, depth {args.pipeline_depth} (D2H of step k overlaps step k+1)"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "render launches of one step: k_frame_setup + k_geometry + k_raster (k_raster dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": render_ms,
-                     "compulsory_frac": (E * (W * H * 3 + 256) / (render_ms / 1000.0) / 1e9) / peak},
+        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
+        "kernel_ms": res["kernel_ms"], "parity_unpinned": PARITY_UNPINNED, "numa": numa,
+        "baseline_is": "cpu_baseline / --impl reference = C port of the reference's CPU path (oracle/), not the Pyglet reference (cannot run here)",
     }
+    if e2e_resized is not None:
+        line["e2e_resized"] = e2e_resized
+    if extra:
+        line["configs"] = extra
     if not args.no_cpu_baseline:
-        val, secs, used, desc = cpu_reference_run(args.map.split(",")[0], W, H, 10, 2, args.cpu_sample_envs, cores)
+        val, secs, used, desc = cpu_reference_run(args.map.split(",")[0], W, H, 4, 1, args.cpu_sample_envs, cores)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": desc}
     print(json.dumps(line))
     if world > 1:

@@ -28,7 +28,7 @@ class BatchedDuckietownEnv:
                  gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
                  action_mode: str = "vel_steer", auto_reset: bool = False, device_reset: bool = False,
                  cycle_maps: bool = False, env_id_offset: int = 0, tessellate_tiles: bool = False,
-                 randomize_maps_on_reset: bool = False):
+                 randomize_maps_on_reset: bool = False, randomization_config=None):
         if not torch.cuda.is_available():
             raise L.DtsError("BatchedDuckietownEnv needs a CUDA device; there is no CPU implementation")
         if camera_rand:
@@ -57,7 +57,11 @@ class BatchedDuckietownEnv:
             random_maps=len(self.maps) if randomize_maps_on_reset else 0,
             frame_rate=float(frame_rate), robot_speed=robot_speed, accept_start_angle_deg=float(accept_start_angle_deg),
             gain=gain, trim=trim, radius=radius, k=k, limit=limit, seed=0 if seed is None else int(seed),
-            env_id_offset=env_id_offset)
+            env_id_offset=env_id_offset, num_tris_distractors=int(num_tris_distractors),
+            color_sky=tuple(color_sky), color_ground=tuple(color_ground))
+        if randomization_config is not None:   # Randomizer(randomization_config_fp=...) randomizer.py:19-33
+            from .episode import load_dr_config
+            L.set_dr_ops(self.cfg, L.dr_ops_from_config(load_dr_config(randomization_config)))
         self.sim = L.Sim(self.cfg)
         for i, md in enumerate(self.maps):
             self.sim.upload_map(i, md, tuple(user_tile_start) if user_tile_start else None)
@@ -74,7 +78,7 @@ class BatchedDuckietownEnv:
         self.sampler = EpisodeSampler(
             num_envs, domain_rand=domain_rand, dynamics_rand=dynamics_rand, accept_start_angle_deg=accept_start_angle_deg,
             num_tris_distractors=num_tris_distractors, color_ground=color_ground, color_sky=color_sky,
-            user_tile_start=user_tile_start)
+            user_tile_start=user_tile_start, randomization_config=randomization_config)
         self.map_ids = np.zeros(num_envs, np.int32)
         self._first_reset = True
         self.output_format = dict(obs_layout="hwc", obs_dtype="uint8", reward="raw", discrete_actions=False,
@@ -135,8 +139,10 @@ class BatchedDuckietownEnv:
                     for e in envs:
                         self.map_ids[e] = int(self.sampler.rngs[e].integers(0, len(self.maps)))
                     # _load_map (S:544) comes before the spawn loop: re-create the drawn maps' obstacles first, so that
-                    # the spawn predicates below see them at their load-time places
-                    self.sim.reset(mask_ptr, {"map_id": self.map_ids.copy()}, self._stream())
+                    # the spawn predicates below see them at their load-time places.  Only the map id and the
+                    # obstacles change here: pose / camera of the episode that just ended stay in place for the
+                    # stale-modelview light capture of the reset proper (S:581).
+                    self.sim.assign_maps(mask_ptr, self.map_ids.copy(), self._stream())
                 dense = self.sampler.sample(envs, [self.maps[self.map_ids[e]] for e in envs], self._query_for(envs))
                 params = {}
                 for key, val in dense.items():
@@ -152,7 +158,8 @@ class BatchedDuckietownEnv:
 
     def _query_for(self, envs):
         def query(k, x, z, a, safety, hidden):
-            return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden, dyn_env=int(envs[k]))
+            return self.sim.query_poses(int(self.map_ids[envs[k]]), x, z, a, safety, hidden, dyn_env=int(envs[k]),
+                                        stream=self._stream())
         return query
 
     def step(self, actions: torch.Tensor, render: bool = True, out=None):
@@ -188,7 +195,7 @@ class BatchedDuckietownEnv:
         """Synchronise and raise if any render since creation ran out of its frame-memory capacity (prim slab or bin
         lists, sized from the scene's upper bounds at the first render) — such frames are left at the clear colour."""
         torch.cuda.synchronize(self.device)
-        if int(self.sim.debug_counters()[0]) != 0:
+        if int(self.sim.debug_counters()[0]) != 0 or (self.sim.status() & 1):
             raise L.DtsError("render frame memory overflowed: some frames were not drawn")
 
     def close(self):

@@ -37,6 +37,12 @@ struct dts_sim {
   int render_ctas = 0, max_prims = 0, bin_cap = 0, max_lat = 0, items_max = 0;
   float *lut_x = nullptr, *lut_y = nullptr;
   int32_t* d_err = nullptr;
+  int32_t* h_status = nullptr;          // mapped pinned host word: bit 0 = a frame overflowed its frame memory
+  int32_t* d_status = nullptr;          // its device address
+  // per-kernel timing (dts_profile_*): event pairs recorded around the render launches
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events; // kProfMarks events per profiled frame
+  int64_t prof_frames = 0;
   // query scratch
   double* q_in = nullptr; double* q_outd = nullptr; int32_t* q_outi = nullptr; uint32_t* q_hidden = nullptr; int q_cap = 0;
   // nccl (dlopen'ed)
@@ -112,6 +118,32 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   c.seed = cfg->seed; c.env_id_offset = cfg->env_id_offset;
   c.random_maps = cfg->random_maps;
   c.reward_mode = DTS_REWARD_RAW; c.action_map = DTS_ACTIONS_CONTINUOUS; c.action_vel_scale = 1.0;
+  if (cfg->num_tris_distractors < 0 || cfg->n_dr_ops < 0 || cfg->n_dr_ops > DTS_MAX_DR_OPS) {
+    g_create_error = "num_tris_distractors / n_dr_ops out of range"; delete sim; return 1;
+  }
+  c.num_tris_distractors = cfg->num_tris_distractors;
+  for (int k = 0; k < 3; k++) { c.color_sky[k] = cfg->color_sky[k]; c.color_ground[k] = cfg->color_ground[k]; }
+  if (cfg->n_dr_ops > 0) {
+    c.n_dr_ops = cfg->n_dr_ops;
+    for (int k = 0; k < cfg->n_dr_ops; k++) {
+      c.dr_ops[k] = cfg->dr_ops[k];
+      const dts_dr_op& op = cfg->dr_ops[k];
+      if (op.type < DTS_DR_INT || op.type > DTS_DR_NORMAL || op.size < 0 || op.target < DTS_DR_NONE || op.target > DTS_DR_TRIM) {
+        g_create_error = "bad dts_dr_op"; delete sim; return 1;
+      }
+    }
+  } else {   // randomization/config/default_dr.json, keys sorted (randomizer.py:33)
+    const dts_dr_op def[7] = {
+        {DTS_DR_UNIFORM, 1, DTS_DR_CAMERA_ANGLE, 0, {0.8, 0, 0}, {1.2, 0, 0}},
+        {DTS_DR_UNIFORM, 1, DTS_DR_CAMERA_FOV_Y, 0, {0.8, 0, 0}, {1.2, 0, 0}},
+        {DTS_DR_UNIFORM, 1, DTS_DR_CAMERA_HEIGHT, 0, {0.92, 0, 0}, {1.08, 0, 0}},
+        {DTS_DR_UNIFORM, 3, DTS_DR_CAMERA_NOISE, 0, {-0.005, -0.005, -0.005}, {0.005, 0.005, 0.005}},
+        {DTS_DR_INT, 1, DTS_DR_HORZ_MODE, 0, {0, 0, 0}, {4, 0, 0}},
+        {DTS_DR_UNIFORM, 3, DTS_DR_LIGHT_POS, 0, {-150, 170, -150}, {150, 220, 150}},
+        {DTS_DR_NORMAL, 1, DTS_DR_TRIM, 0, {0, 0, 0}, {0.02, 0, 0}}};
+    c.n_dr_ops = 7;
+    for (int k = 0; k < 7; k++) c.dr_ops[k] = def[k];
+  }
   DState& S = sim->S;
   S.n = n;
   int bad = 0;
@@ -127,6 +159,12 @@ int dts_create(const dts_config* cfg, dts_sim** out) {
   bad |= sim->dalloc(&S.rep, n);
   bad |= sim->dalloc(&sim->d_maps, cfg->max_maps);
   bad |= sim->dalloc(&sim->d_err, 32);
+  if (cudaHostAlloc((void**)&sim->h_status, 64, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&sim->d_status, sim->h_status, 0) != cudaSuccess) {
+    sim->fail("cudaHostAlloc(mapped status word) failed"); bad = 1;
+  } else {
+    memset(sim->h_status, 0, 64);
+  }
   auto& st = sim->stage;
   bad |= sim->dalloc(&st.map_id, n);
   double** sd[] = {&st.pos_x, &st.pos_z, &st.angle, &st.wheel_dist, &st.trim};
@@ -151,6 +189,8 @@ void dts_destroy(dts_sim* sim) {
   for (auto& v : sim->map_allocs) for (void* p : v) cudaFree(p);
   void* extra[] = {sim->render_scratch, sim->lut_x, sim->lut_y, sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
   for (void* p : extra) if (p) cudaFree(p);
+  if (sim->h_status) cudaFreeHost(sim->h_status);
+  for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   delete sim;
 }
 
@@ -160,11 +200,31 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   if (b->n_objects > DTS_MAX_OBJECTS) return sim->fail("map has %d objects, limit %d", b->n_objects, DTS_MAX_OBJECTS);
   if (b->grid_w <= 0 || b->grid_h <= 0 || !(b->tile_size > 0)) return sim->fail("invalid tile grid");
   if (b->n_dyn < 0 || b->n_dyn > DTS_MAX_DYN) return sim->fail("map has %d dynamic obstacles, limit %d", b->n_dyn, DTS_MAX_DYN);
+  // validate the whole blob BEFORE the slot's previous allocations are released: a rejected upload leaves the
+  // old map intact
+  for (int o = 0; o < b->n_objects; o++) {
+    const dts_object& s = b->objects[o];
+    if (s.mesh_id < 0 || s.mesh_id >= b->n_meshes) return sim->fail("object %d: bad mesh_id", o);
+    if (s.alt_tex_to >= b->n_textures || s.alt_tex_from >= b->n_textures) return sim->fail("object %d: alt texture out of range", o);
+    if (s.dyn_slot >= b->n_dyn) return sim->fail("object %d: dyn_slot %d out of range", o, s.dyn_slot);
+  }
+  for (int t = 0; t < b->n_textures; t++) {
+    const dts_texture& s = b->textures[t];
+    if (s.width <= 0 || s.height <= 0 || (s.width & (s.width - 1)) || (s.height & (s.height - 1)))
+      return sim->fail("texture %d: %dx%d is not a power of two", t, s.width, s.height);
+  }
+  for (int s = 0; s < b->n_dyn; s++) {
+    const dts_dyn_object& q = b->dyn[s];
+    if (q.kind != DTS_DYN_DUCKIE && q.kind != DTS_DYN_DUCKIEBOT && q.kind != DTS_DYN_TRAFFICLIGHT) return sim->fail("dyn %d: bad kind %d", s, q.kind);
+    if (q.object_index < 0 || q.object_index >= b->n_objects || b->objects[q.object_index].dyn_slot != s)
+      return sim->fail("dyn %d: object_index %d does not point back to this slot", s, q.object_index);
+  }
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   DTS_CUDA(cudaDeviceSynchronize());
   auto& own = sim->map_allocs[map_id];
   for (void* p : own) cudaFree(p);
   own.clear();
+  sim->h_maps[map_id].valid = 0;   // until the new map is complete, the slot holds nothing (a failed cudaMalloc below leaves it empty)
   DMap m{};
   const size_t T = (size_t)b->grid_w * b->grid_h;
   m.tile_size = b->tile_size; m.grid_w = b->grid_w; m.grid_h = b->grid_h; m.n_tiles = (int)T;
@@ -280,7 +340,11 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
       for (size_t s = 0; s < D; s++) init[(size_t)k * D + s] = N ? st[((size_t)k * D + s) * N] : 0.0;
     bad |= sim->upload(&m.dyn_init, init.data(), init.size(), &own);
   }
-  if (bad) return 1;
+  if (bad) {
+    DMap empty{};
+    cudaMemcpy(sim->d_maps + map_id, &empty, sizeof(DMap), cudaMemcpyHostToDevice);
+    return 1;
+  }
   m.valid = 1;
   if (sim->render_scratch) { cudaFree(sim->render_scratch); sim->render_scratch = nullptr; }   // re-sized for the new scene on the next render
   sim->h_maps[map_id] = m;
@@ -413,9 +477,19 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
   if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->lut_x) return sim->fail("distortion enabled but no fisheye LUT set");
   RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
                (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0, sim->fmt.obs_layout, sim->fmt.obs_dtype};
+  if (*(volatile int32_t*)sim->h_status & 1)
+    return sim->fail("an earlier frame overflowed its render frame memory (prim slab / bin lists) and was left incomplete");
+  cudaEvent_t* marks = nullptr;
+  if (sim->profiling) {
+    const size_t base = sim->prof_events.size();
+    sim->prof_events.resize(base + kProfMarks);
+    for (int k = 0; k < kProfMarks; k++) DTS_CUDA(cudaEventCreate(&sim->prof_events[base + k]));
+    marks = sim->prof_events.data() + base;
+    sim->prof_frames++;
+  }
   const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
                               sim->bin_cap, sim->max_lat, sim->items_max, sim->lut_x, sim->lut_y, sim->d_err,
-                              (cudaStream_t)stream);
+                              sim->d_status, marks, (cudaStream_t)stream);
   sim->launches += k;
   DTS_CUDA(cudaGetLastError());
   return 0;
@@ -447,7 +521,8 @@ int dts_get_state(dts_sim* sim, dts_state_view* v) {
 }
 
 int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* query, const uint32_t* hidden,
-                    double* out_f64, int32_t* out_i32) {
+                    double* out_f64, int32_t* out_i32, void* stream) {
+  cudaStream_t qs = (cudaStream_t)stream;   // ordered after the caller's in-flight steps (they move the dynamic obstacles)
   if (!sim) return 1;
   if (map_id < 0 || map_id >= sim->cfg.max_maps || !sim->h_maps[map_id].valid) return sim->fail("bad map_id %d", map_id);
   if (dyn_env >= sim->cfg.num_envs) return sim->fail("dyn_env %d out of range", dyn_env);
@@ -462,13 +537,59 @@ int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* 
     DTS_CUDA(cudaMalloc(&sim->q_outi, (size_t)n * 32));
     DTS_CUDA(cudaMalloc(&sim->q_hidden, (size_t)n * 32));
   }
-  DTS_CUDA(cudaMemcpy(sim->q_in, query, (size_t)n * 32, cudaMemcpyHostToDevice));
-  if (hidden) DTS_CUDA(cudaMemcpy(sim->q_hidden, hidden, (size_t)n * 32, cudaMemcpyHostToDevice));
-  launch_query(sim->d_maps, map_id, dyn_env < 0 ? -1 : dyn_env, sim->cfg.num_envs, n, sim->q_in, hidden ? sim->q_hidden : nullptr, sim->q_outd, sim->q_outi, 0);
+  DTS_CUDA(cudaMemcpyAsync(sim->q_in, query, (size_t)n * 32, cudaMemcpyHostToDevice, qs));
+  if (hidden) DTS_CUDA(cudaMemcpyAsync(sim->q_hidden, hidden, (size_t)n * 32, cudaMemcpyHostToDevice, qs));
+  launch_query(sim->d_maps, map_id, dyn_env < 0 ? -1 : dyn_env, sim->cfg.num_envs, n, sim->q_in, hidden ? sim->q_hidden : nullptr, sim->q_outd, sim->q_outi, qs);
   sim->launches++;
   DTS_CUDA(cudaGetLastError());
-  DTS_CUDA(cudaMemcpy(out_f64, sim->q_outd, (size_t)n * 32, cudaMemcpyDeviceToHost));
-  DTS_CUDA(cudaMemcpy(out_i32, sim->q_outi, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  DTS_CUDA(cudaMemcpyAsync(out_f64, sim->q_outd, (size_t)n * 32, cudaMemcpyDeviceToHost, qs));
+  DTS_CUDA(cudaMemcpyAsync(out_i32, sim->q_outi, (size_t)n * 32, cudaMemcpyDeviceToHost, qs));
+  DTS_CUDA(cudaStreamSynchronize(qs));
+  return 0;
+}
+
+int dts_assign_maps(dts_sim* sim, const uint8_t* mask_dev, const int32_t* map_id_host, void* stream) {
+  if (!sim) return 1;
+  if (!map_id_host) return sim->fail("map_id_host is NULL");
+  const size_t n = sim->cfg.num_envs;
+  for (size_t e = 0; e < n; e++)
+    if (map_id_host[e] < 0 || map_id_host[e] >= sim->cfg.max_maps || !sim->h_maps[map_id_host[e]].valid)
+      return sim->fail("dts_assign_maps: map_id[%zu]=%d has no uploaded map", e, map_id_host[e]);
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DTS_CUDA(cudaMemcpyAsync(sim->stage.map_id, map_id_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  launch_assign_maps(sim->S, sim->d_maps, mask_dev, sim->stage.map_id, st);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  DTS_CUDA(cudaStreamSynchronize(st));   // pageable host source
+  return 0;
+}
+
+int dts_status(dts_sim* sim) { return (sim && sim->h_status) ? *(volatile int32_t*)sim->h_status : 0; }
+
+int dts_profile_enable(dts_sim* sim, int on) {
+  if (!sim) return 1;
+  sim->profiling = on != 0;
+  return 0;
+}
+
+int dts_profile_read(dts_sim* sim, double ms_out[8], int64_t* frames) {
+  if (!sim || !ms_out) return 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  for (int k = 0; k < 8; k++) ms_out[k] = 0.0;
+  const size_t per = kProfMarks;
+  for (size_t f = 0; f + per <= sim->prof_events.size(); f += per) {
+    DTS_CUDA(cudaEventSynchronize(sim->prof_events[f + per - 1]));
+    for (size_t k = 0; k + 1 < per; k++) {
+      float ms = 0.f;
+      DTS_CUDA(cudaEventElapsedTime(&ms, sim->prof_events[f + k], sim->prof_events[f + k + 1]));
+      ms_out[k] += ms;
+    }
+  }
+  if (frames) *frames = sim->prof_frames;
+  for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
+  sim->prof_events.clear();
+  sim->prof_frames = 0;
   return 0;
 }
 

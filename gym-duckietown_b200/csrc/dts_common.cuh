@@ -131,6 +131,10 @@ struct StepCfg {
   double action_vel_scale;
   uint64_t seed;
   int64_t env_id_offset;
+  // Simulator.__init__ keywords read by reset() (S:226-230) and the Randomizer table (randomizer.py:19-89)
+  int32_t num_tris_distractors, n_dr_ops;
+  double color_sky[3], color_ground[3];
+  dts_dr_op dr_ops[DTS_MAX_DR_OPS];
 };
 
 }  // namespace dts

@@ -29,6 +29,7 @@ void launch_reset_random(const DState& S, const DMap* maps, const StepCfg& c, in
                          cudaStream_t st);
 void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, const uint8_t* mask,
                          const ResetStaging& p, cudaStream_t st);
+void launch_assign_maps(const DState& S, const DMap* maps, const uint8_t* mask, const int32_t* map_id, cudaStream_t st);
 void launch_query(const DMap* maps, int map_id, int dyn_env, int n_envs, int n, const double* q, const uint32_t* hidden,
                   double* outd, int32_t* outi, cudaStream_t st);
 
@@ -37,8 +38,11 @@ int render_ctas_per_sm();
 // scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
 // undistorted frames when the fisheye gather is on
 size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame);
+// `marks`: NULL or kProfMarks events recorded on `st` before k_frame_setup and after each of k_frame_setup, k_geometry,
+// k_bin, k_raster and the post passes (dts_profile_*).  `status_dev`: device address of the mapped host status word.
+constexpr int kProfMarks = 6;
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
-                  int32_t* err_flag, cudaStream_t st);
+                  int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st);
 
 }  // namespace dts

@@ -93,26 +93,49 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
   if (n_maps_cycle < 0) reinit_dynamic(m, n, e);                     // _load_map S:544
   RenderEp r;
   default_render_ep(r);
-  // Randomizer.randomize: keys in sorted order — drawn whether or not DR is on (randomizer.py:33,46-89, S:546)
-  const double cam_angle = rs.uniform(0.8, 1.2), cam_fov = rs.uniform(0.8, 1.2), cam_h = rs.uniform(0.92, 1.08);
-  double noise[3];
-  for (int k = 0; k < 3; k++) noise[k] = rs.uniform(-0.005, 0.005);
-  const int horz = rs.integers(0, 4);
+  // Randomizer.randomize: every key of the table in sorted order — drawn whether or not DR is on
+  // (randomizer.py:33,46-89, S:546); c.dr_ops is default_dr.json unless the caller supplied its own table
+  double cam_angle = 1.0, cam_fov = 1.0, cam_h = 1.0, noise[3] = {0.0, 0.0, 0.0}, lp3[3] = {0.0, 3.0, 0.0}, trim = 0.0;
+  int horz = 0;
+  for (int oi = 0; oi < c.n_dr_ops; oi++) {
+    const dts_dr_op& op = c.dr_ops[oi];
+    for (int k = 0; k < op.size; k++) {
+      const int kk = (op.size <= 3) ? k : 0;
+      double v;
+      if (op.type == DTS_DR_INT) v = (double)rs.integers((int64_t)op.a[kk], (int64_t)op.b[kk]);
+      else if (op.type == DTS_DR_UNIFORM) v = rs.uniform(op.a[kk], op.b[kk]);
+      else v = rs.normal(op.a[kk], op.b[kk]);
+      switch (op.target) {
+        case DTS_DR_CAMERA_ANGLE: if (k == 0) cam_angle = v; break;
+        case DTS_DR_CAMERA_FOV_Y: if (k == 0) cam_fov = v; break;
+        case DTS_DR_CAMERA_HEIGHT: if (k == 0) cam_h = v; break;
+        case DTS_DR_CAMERA_NOISE: if (k < 3) noise[k] = v; break;
+        case DTS_DR_HORZ_MODE: if (k == 0) horz = (int)v; break;
+        case DTS_DR_LIGHT_POS: if (k < 3) lp3[k] = v; break;
+        case DTS_DR_TRIM: if (k == 0) trim = v; break;
+        default: break;
+      }
+    }
+  }
   float lpos[4] = {0.f, 3.f, 0.f, 1.f};
-  const double l0 = rs.uniform(-150, 150), l1 = rs.uniform(170, 220), l2 = rs.uniform(-150, 150);
-  const double trim = rs.normal(0.0, 0.02);
+  for (int k = 0; k < 3; k++) { r.horizon[k] = (float)c.color_sky[k]; r.ground[k] = (float)c.color_ground[k]; }   // S:562, S:594
   double wheel = 0.102;
   if (dr) {
-    const double base[4][3] = {{0.45, 0.82, 1.0}, {0.64, 0.71, 0.28}, {0.15, 0.15, 0.15}, {0.9, 0.9, 0.9}};
-    const double hs = horz < 2 ? 0.1 : 0.4;                                   // S:551-560
-    for (int k = 0; k < 3; k++) r.horizon[k] = (float)(base[horz][k] * rs.uniform(1.0 - hs, 1.0 + hs));
-    lpos[0] = (float)l0; lpos[1] = (float)l1; lpos[2] = (float)l2; lpos[3] = 0.f;  // 3 floats into a 4-array: w = 0
+    const double base[4][3] = {{c.color_sky[0], c.color_sky[1], c.color_sky[2]},
+                               {0.64, 0.71, 0.28}, {0.15, 0.15, 0.15}, {0.9, 0.9, 0.9}};
+    if (horz >= 0 && horz < 4) {                                              // S:551-560
+      const double hs = horz < 2 ? 0.1 : 0.4;
+      for (int k = 0; k < 3; k++) r.horizon[k] = (float)(base[horz][k] * rs.uniform(1.0 - hs, 1.0 + hs));
+    } else {
+      for (int k = 0; k < 3; k++) r.horizon[k] = old.horizon[k];              // no branch taken: the attribute keeps its value
+    }
+    lpos[0] = (float)lp3[0]; lpos[1] = (float)lp3[1]; lpos[2] = (float)lp3[2]; lpos[3] = 0.f;  // 3 floats into a 4-array: w = 0
     double p4[4];
     for (int k = 0; k < 4; k++) p4[k] = rs.uniform(1.0 - 0.3, 1.0 + 0.3);     // _perturb(ambient, 0.3) S:574
     for (int k = 0; k < 3; k++) r.ambient[k] = (float)(0.25 * p4[k]);
     for (int k = 0; k < 4; k++) p4[k] = rs.uniform(1.0 - 0.99, 1.0 + 0.99);   // _perturb(diffuse, 0.99) S:576
     for (int k = 0; k < 3; k++) r.diffuse[k] = (float)(0.35 * p4[k]);
-    for (int k = 0; k < 3; k++) r.ground[k] = (float)(0.15 * rs.uniform(1.0 - 0.3, 1.0 + 0.3));  // S:594
+    for (int k = 0; k < 3; k++) r.ground[k] = (float)(c.color_ground[k] * rs.uniform(1.0 - 0.3, 1.0 + 0.3));  // S:594
     wheel = 0.102 * rs.uniform(1.0 - 0.1, 1.0 + 0.1);                         // S:597
     r.cam_height = (float)(0.108 * cam_h);                                    // S:612-614
     r.cam_angle_deg = (float)(19.15 * cam_angle);
@@ -120,7 +143,7 @@ __device__ inline void respawn(const DState& S, const DMap* maps, const StepCfg&
     for (int k = 0; k < 3; k++) r.cam_noise[k] = (float)noise[k];
   }
   // distractor triangles S:621-629: never visible (below the ground plane) but their draws are consumed
-  for (int t = 0; t < 36; t++) {
+  for (int t = 0; t < 3 * c.num_tris_distractors; t++) {
     rs.next64(); rs.next64(); rs.next64();      // uniform(low=[-20,-0.6,-20], high=[20,-0.3,20], size=3)
     rs.next64();                                // c = uniform(0, 0.9)
     if (dr) { rs.next64(); rs.next64(); rs.next64(); }   // _perturb([c,c,c], 0.1)
@@ -240,6 +263,7 @@ __global__ void __launch_bounds__(128) k_reset_params(DState S, const DMap* __re
   if (c.random_maps > 0) reinit_dynamic(m, S.n, e);   // the host drew the map (S:541-544): objects are re-created
   RenderEp r;
   default_render_ep(r);
+  for (int k = 0; k < 3; k++) { r.horizon[k] = (float)c.color_sky[k]; r.ground[k] = (float)c.color_ground[k]; }
   if (p.cam_height) r.cam_height = p.cam_height[e];
   if (p.cam_angle_deg) r.cam_angle_deg = p.cam_angle_deg[e];
   if (p.cam_fov_y_deg) r.cam_fov_y_deg = p.cam_fov_y_deg[e];
@@ -262,6 +286,17 @@ __global__ void __launch_bounds__(128) k_reset_params(DState S, const DMap* __re
   S.rep[e] = r;
   S.episode[e] += 1;
   evaluate_pose(S, m, c, e, px, pz, ang, 0, nullptr, nullptr);
+}
+
+// randomize_maps_on_reset with a host-drawn map (S:541-544): new map id + its obstacles re-created (_load_map),
+// nothing else — pose, episode counter and render record stay those of the episode that just ended, so the reset
+// that follows captures GL_LIGHT0 under the right stale modelview (S:581).
+__global__ void __launch_bounds__(128) k_assign_maps(DState S, const DMap* __restrict__ maps,
+                                                     const uint8_t* __restrict__ mask, const int32_t* __restrict__ map_id) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.n || (mask && !mask[e])) return;
+  S.map_id[e] = map_id[e];
+  reinit_dynamic(maps[map_id[e]], S.n, e);
 }
 
 // Batched pose predicates for host callers: _valid_pose / _collision / get_lane_pos2 /
@@ -305,6 +340,9 @@ void launch_reset_random(const DState& S, const DMap* maps, const StepCfg& c, in
 void launch_reset_params(const DState& S, const DMap* maps, const StepCfg& c, const uint8_t* mask,
                          const ResetStaging& p, cudaStream_t st) {
   k_reset_params<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, c, mask, p);
+}
+void launch_assign_maps(const DState& S, const DMap* maps, const uint8_t* mask, const int32_t* map_id, cudaStream_t st) {
+  k_assign_maps<<<(S.n + 127) / 128, 128, 0, st>>>(S, maps, mask, map_id);
 }
 void launch_query(const DMap* maps, int map_id, int dyn_env, int n_envs, int n, const double* q, const uint32_t* hidden,
                   double* outd, int32_t* outi, cudaStream_t st) {

@@ -1,27 +1,30 @@
 // dts_render.cu — batched software rasteriser for the agent camera (Simulator._render_img,
 // simulator.py:1707-1951) on sm_100a.  No tensor cores: there is no dense contraction here.
 //
-// Three stream-ordered kernels per frame batch, no CTA-wide barrier anywhere:
+// Four stream-ordered kernels per frame batch, no CTA-wide barrier in any of them:
 //   k_frame_setup  thread per env: camera matrices (f64), gluPerspective, counters -> FrameCtx[env]
 //   k_geometry     warp per (env, draw item) over the whole GPU: ground / map tile / placed mesh.  Model-view
 //                  f64->f32, fixed-function per-vertex lighting, frustum cull, near + guard-band clip, snap to
-//                  1/64 px, triangle setup -> 128-byte PrimRec appended to the env's slab; the prim is binned
-//                  right away into 32x8-px coarse bins (small ones by the emitting lane, large ones by the whole
-//                  warp with an exact edge test) through per-bin atomic cursors.  A road tile is ONE quad: its
-//                  8x8 lit lattice goes to the env's table and the Gouraud interpolant is evaluated per pixel
+//                  1/64 px, triangle setup -> 128-byte PrimRec appended to the env's slab.  A road tile is ONE quad:
+//                  its 8x8 lit lattice goes to the env's table and the Gouraud interpolant is evaluated per pixel
 //                  (render spec tile mode 1); RenderCfg.tessellate switches to the literal 98 triangles (mode 0).
-//   k_raster       persistent warps pull rows of coarse bins (any env) from one global counter.  A coarse bin's
-//                  list is staged lane-parallel once (edge functions re-based so lanes work in int32, exact
-//                  reject / trivial-accept bits for each of its 8 fine 8x4 bins), then every lane owns one pixel
-//                  of a fine bin with its 4 MSAA samples (depth, colour, draw id) in registers; simple bins (one
-//                  fully covering prim) skip the depth machinery; early-z before shading; ground drawn last;
-//                  box resolve -> u8, rows packed with shuffles and stored as 32-bit words
-//   k_fisheye      (distortion only) out[y,x] = undistorted[rint(rmapy), rint(rmapx)]      distortion.py:118
+//   k_bin          warp per env: exact (prim, 32x8-px coarse bin) pairs — count, warp scan, scatter — then, dense
+//                  over the pairs (one pair per lane), the 80-byte BinRec each pair needs for visibility: edge
+//                  functions re-based to the bin corner (exact in 64 bits, then int32), per-fine-bin reject /
+//                  trivial-accept bits, the depth plane.  A bin's records are contiguous in HBM.
+//   k_raster       persistent warps pull rows of coarse bins (any env) from one global counter.  The bin's records
+//                  arrive in shared memory by bulk-async copy (cp.async.bulk + mbarrier, double-buffered per warp:
+//                  the next chunk of 32 records lands while the current one is rasterised).  Visibility first: every
+//                  lane owns one pixel of an 8x4 fine bin with its 4 MSAA samples (depth + winning prim) in
+//                  registers.  Shading is DEFERRED: once per distinct winner of the pixel (1 for interior pixels,
+//                  2 on an edge), fetched from the PrimRec by index — overdraw costs no shading.  Bins with one
+//                  fully covering prim skip the depth pass.  Box resolve -> u8, rows packed with shuffles and
+//                  stored as 32-bit words.
 // Arithmetic follows the render spec of DESIGN.md (the CPU checker implements the same spec) bit for bit
 // (compiled with -fmad=false; fmaf() is spelled out where the spec has one).
 //
-// HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / bin lists / lattice table
-// (tens of KB per env, written by k_geometry and read once by k_raster) + texels (shared, L2-resident).
+// HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / BinRec lists / lattice table
+// (tens of KB per env, written by k_geometry / k_bin and read once by k_raster) + texels (shared, L2-resident).
 #include <cstddef>
 
 #include "dts_camera.cuh"
@@ -67,30 +70,33 @@ struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 #define DTS_GEO_MIN_CTAS 32
 #endif
 
-struct __align__(16) PrimRec {   // 128 B in the CTA's slab
-  int32_t X[3], Y[3];            // snapped vertices, orientation normalised (area > 0)
-  float f0[7], fx[7], fy[7];     // planes anchored at vertex 0: z, q=1/w, u*q, v*q, r*q, g*q, b*q
-  int32_t id_tex;                // draw id << 8 | (texture index + 1)
-  int32_t pxmin, pxmax;          // pixel bbox (x | y<<16); 8-byte aligned, read as one int2 by the binner
-  int32_t lat;                   // lattice slot of an analytic road tile, -1 otherwise
-  int32_t quad;                  // 1: convex quad X[0..2] + a 4th vertex kept in the bits of f0[4], f0[5] (an analytic
-                                 //    tile takes its colour from the lattice, so its r,g,b planes are free)
+struct __align__(16) PrimRec {   // 128 B in the env's slab, words grouped for 128-bit loads
+  int32_t X0, Y0, X1, Y1;        // w0  snapped vertices in cyclic order, orientation normalised (area > 0)
+  int32_t X2, Y2, X3, Y3;        // w1  vertex 3: 4th corner of a quad, else a copy of vertex 0
+  float z0, zx, zy;              // w2  depth plane anchored at vertex 0 (f0, d/dx, d/dy per pixel)
+  int32_t id;                    //     draw id (GL_LESS ties go to the earlier draw)
+  float q0, qx, qy, u0;          // w3  q = 1/w, then u*q, v*q, r*q, g*q, b*q
+  float ux, uy, v0, vx;          // w4
+  float vy;                      // w5
+  int32_t ltq;                   //     (lattice slot + 1) | (texture index + 1) << 16 | quad << 24
+  float r0, rx;
+  float ry, g0, gx, gy;          // w6
+  float b0, bx, by;              // w7
+  int32_t pad;
 };
-static_assert(offsetof(PrimRec, pxmin) % 8 == 0, "pxmin/pxmax are loaded as int2");
 static_assert(sizeof(PrimRec) == 128, "PrimRec must be 128 bytes");
+static_assert(offsetof(PrimRec, q0) == 48 && offsetof(PrimRec, vy) == 80 && offsetof(PrimRec, ry) == 96, "PrimRec word groups");
 
-struct __align__(16) BinPrim {   // smem, per staged prim, re-based to the current bin
+struct __align__(16) BinRec {    // 80 B per (prim, coarse bin) pair: what visibility needs, re-based to the bin corner
   int32_t E0[4], A[4], B[4];     // E_k(x,y) = E0_k + A_k*x + B_k*y, x,y in 1/64 px from the bin corner (triangles: E_3 = 0)
-  int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
-  float f0[7], fx[7], fy[7];
+  float z0, zx, zy;              // depth plane
   int32_t id;                    // draw id
-  int32_t flags;                 // per fine bin f of the coarse bin: bit f = every sample inside, bit 8+f = may touch
-  const uint8_t* tex;            // nullptr = untextured
-  int32_t tex_wh;                // w | h<<16
-  int32_t lat;
-  float twf, thf;                // (float)tex_w, (float)tex_h
+  int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
+  uint32_t prim_flags;           // prim index | per fine bin f of the coarse bin: bit 16+f = may touch, bit 24+f = every sample inside
+  int32_t kind;                  // bit 0: quad (4 edges), bit 1: ground quad (draw id < 2)
 };
-static_assert(sizeof(BinPrim) == 176, "BinPrim layout");
+static_assert(sizeof(BinRec) == 80, "BinRec layout");
+constexpr unsigned kNoPrim = 0xffffu;   // sample not covered by any prim: clear colour
 
 struct Xform { float MV[12], N[9]; };
 
@@ -260,8 +266,7 @@ __device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const
   const int py0 = max(miny >> 6, 0), py1 = min(maxy >> 6, ec.H - 1);
   if (px0 > px1 || py0 > py1) return true;   // off screen: emitted nothing, and nothing is what it covers
   PrimRec r;
-  r.X[0] = x0; r.X[1] = x1; r.X[2] = x2;
-  r.Y[0] = y0; r.Y[1] = y1; r.Y[2] = y2;
+  r.X0 = x0; r.Y0 = y0; r.X1 = x1; r.Y1 = y1; r.X2 = x2; r.Y2 = y2; r.X3 = x0; r.Y3 = y0;
   const float dx1 = (float)(x1 - x0) * 0.015625f, dy1 = (float)(y1 - y0) * 0.015625f;
   const float dx2 = (float)(x2 - x0) * 0.015625f, dy2 = (float)(y2 - y0) * 0.015625f;
   const float areaf = dx1 * dy2 - dx2 * dy1;
@@ -271,22 +276,28 @@ __device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const
   const float v0[7] = {zw[0], q0, p0->u * q0, p0->v * q0, p0->r * q0, p0->g * q0, p0->b * q0};
   const float v1[7] = {zw[i1], q1, p1->u * q1, p1->v * q1, p1->r * q1, p1->g * q1, p1->b * q1};
   const float v2[7] = {zw[i2], q2, p2->u * q2, p2->v * q2, p2->r * q2, p2->g * q2, p2->b * q2};
+  float f0[7], fx[7], fy[7];
 #pragma unroll
   for (int at = 0; at < 7; at++) {
     const float d1 = v1[at] - v0[at], d2 = v2[at] - v0[at];
-    r.f0[at] = v0[at];
-    r.fx[at] = (d1 * dy2 - d2 * dy1) * ia;
-    r.fy[at] = (d2 * dx1 - d1 * dx2) * ia;
+    f0[at] = v0[at];
+    fx[at] = (d1 * dy2 - d2 * dy1) * ia;
+    fy[at] = (d2 * dx1 - d1 * dx2) * ia;
   }
-  r.id_tex = (id << 8) | (tex + 1);
-  r.lat = lat;
-  r.pxmin = px0 | (py0 << 16);
-  r.pxmax = px1 | (py1 << 16);
-  r.quad = 0;
+  r.z0 = f0[0]; r.zx = fx[0]; r.zy = fy[0];
+  r.q0 = f0[1]; r.qx = fx[1]; r.qy = fy[1];
+  r.u0 = f0[2]; r.ux = fx[2]; r.uy = fy[2];
+  r.v0 = f0[3]; r.vx = fx[3]; r.vy = fy[3];
+  r.r0 = f0[4]; r.rx = fx[4]; r.ry = fy[4];
+  r.g0 = f0[5]; r.gx = fx[5]; r.gy = fy[5];
+  r.b0 = f0[6]; r.bx = fx[6]; r.by = fy[6];
+  r.id = id;
+  r.ltq = (lat + 1) | ((tex + 1) << 16);
+  r.pad = 0;
+  (void)px0; (void)py0; (void)px1; (void)py1;
   if (d) {   // vertices in cyclic order; planes stay those of triangle (a,b,c) anchored at a
-    r.quad = 1;
-    r.X[1] = qx[1]; r.Y[1] = qy[1]; r.X[2] = qx[2]; r.Y[2] = qy[2];
-    r.f0[4] = __int_as_float(qx[3]); r.f0[5] = __int_as_float(qy[3]);
+    r.ltq |= 1 << 24;
+    r.X1 = qx[1]; r.Y1 = qy[1]; r.X2 = qx[2]; r.Y2 = qy[2]; r.X3 = qx[3]; r.Y3 = qy[3];
   }
   const int slot = atomicAdd(&ec.ctx->n_prims, 1);
   if (slot >= ec.max_prims) { ec.ctx->overflow = 1; return true; }
@@ -295,15 +306,6 @@ __device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const
 #pragma unroll
   for (int k = 0; k < 8; k++) dst[k] = src[k];
   return true;
-}
-
-// the prim's vertices in cyclic order (3, or 4 for a quad)
-__device__ __forceinline__ int prim_vertices(const PrimRec& r, int qx[4], int qy[4]) {
-  qx[0] = r.X[0]; qx[1] = r.X[1]; qx[2] = r.X[2]; qy[0] = r.Y[0]; qy[1] = r.Y[1]; qy[2] = r.Y[2];
-  qx[3] = qx[0]; qy[3] = qy[0];
-  if (!r.quad) return 3;
-  qx[3] = __float_as_int(r.f0[4]); qy[3] = __float_as_int(r.f0[5]);
-  return 4;
 }
 
 __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float din, float dout) {
@@ -415,67 +417,75 @@ __device__ __forceinline__ bool bin_overlaps(const int qx[4], const int qy[4], i
 
 
 
-// Stage one prim for a coarse bin whose corner is (ox, oy) sub-pixels: edge functions re-based to the
-// corner (exact in 64 bits, then int32: inside the coarse bin |A*x + B*y| < 2^30), per-fine-bin exact
-// reject / trivial-accept bits, planes and texture.  Returns the prim's draw id.
-__device__ __forceinline__ int stage_prim(const PrimRec& r, BinPrim& bp, int ox, int oy, const DMap& m) {
-  int qx[4], qy[4];
-  const int nv = prim_vertices(r, qx, qy);
-  const int X0 = qx[0], Y0 = qy[0];
+// The visibility record of prim `p` for the coarse bin whose corner is (ox, oy) sub-pixels: edge functions re-based
+// to the corner (exact in 64 bits, then int32: inside the coarse bin |A*x + B*y| < 2^30), exact reject /
+// trivial-accept bits for each of the bin's 8 fine bins, depth plane, draw id.
+__device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int p, int ox, int oy, BinRec* __restrict__ out) {
+  const int4 w0 = __ldg(reinterpret_cast<const int4*>(pr));
+  const int4 w1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+  const float4 w2 = __ldg(reinterpret_cast<const float4*>(pr) + 2);
+  const int quad = (__ldg(&pr->ltq) >> 24) & 1;
+  const int qx[4] = {w0.x, w0.z, w1.x, w1.z}, qy[4] = {w0.y, w0.w, w1.y, w1.w};
+  const int nv = quad ? 4 : 3;
   unsigned live = 0xffu, inside = 0xffu;
-  bp.E0[3] = 0; bp.A[3] = 0; bp.B[3] = 0;   // triangles: a fourth edge that every sample passes
+  int E0[4] = {0, 0, 0, 0}, A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};   // triangles: a fourth edge that every sample passes
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     if (k >= nv) break;
-    const int ka = k, kb = (k + 1) & 3;   // edge k: vertex k -> k+1 (a triangle's vertex 3 aliases vertex 0)
+    const int ka = k, kb = (k + 1) & 3;   // edge k: vertex k -> k+1 (a triangle's vertex 3 is a copy of vertex 0)
     const int dx = qx[kb] - qx[ka], dy = qy[kb] - qy[ka];
     const int bias = (dy > 0 || (dy == 0 && dx < 0)) ? 0 : 1;
     long long e0 = (long long)dx * (oy - qy[ka]) - (long long)dy * (ox - qx[ka]) - bias;
     if (e0 < -(1LL << 30)) live = 0;          // negative for every sample of the coarse bin
     if (e0 > (1LL << 30)) e0 = (1LL << 30);   // positive for every sample: keep the sign, stay in int32
-    const int A = -dy, B = dx, e = (int)e0;
-    bp.E0[k] = e; bp.A[k] = A; bp.B[k] = B;
+    if (e0 < -(1LL << 30)) e0 = -(1LL << 30);
+    const int a = -dy, b = dx, e = (int)e0;
+    E0[k] = e; A[k] = a; B[k] = b;
     // extremes of A*x + B*y over one fine bin's sample span x in [8, 504], y in [8, 248]
-    const int hi = (A > 0 ? A * 504 : A * 8) + (B > 0 ? B * 248 : B * 8);
-    const int lo = (A > 0 ? A * 8 : A * 504) + (B > 0 ? B * 8 : B * 248);
+    const int hi = (a > 0 ? a * 504 : a * 8) + (b > 0 ? b * 248 : b * 8);
+    const int lo = (a > 0 ? a * 8 : a * 504) + (b > 0 ? b * 8 : b * 248);
 #pragma unroll
     for (int f = 0; f < 8; f++) {
-      const int ef = e + A * ((f & 3) * kBinW * kSub) + B * ((f >> 2) * kBinH * kSub);
+      const int ef = e + a * ((f & 3) * kBinW * kSub) + b * ((f >> 2) * kBinH * kSub);
       if (ef + hi < 0) live &= ~(1u << f);
       if (ef + lo < 0) inside &= ~(1u << f);
     }
   }
-  const int id = r.id_tex >> 8;
-  bp.id = id;
-  bp.flags = (int)((inside & live) | (live << 8));
-  if (live == 0) return id;   // touches no fine bin of this coarse bin: nothing else is read
-  bp.x0 = X0 - ox; bp.y0 = Y0 - oy;
-#pragma unroll
-  for (int k = 0; k < 7; k++) { bp.f0[k] = r.f0[k]; bp.fx[k] = r.fx[k]; bp.fy[k] = r.fy[k]; }
-  const int tex = (r.id_tex & 255) - 1;
-  if (tex >= 0) { const DTexture t = m.textures[tex]; bp.tex = t.rgba; bp.tex_wh = t.w | (t.h << 16); bp.twf = (float)t.w; bp.thf = (float)t.h; }
-  else { bp.tex = nullptr; bp.tex_wh = 0; bp.twf = 0.f; bp.thf = 0.f; }
-  bp.lat = r.lat;
-  return id;
+  const int id = __float_as_int(w2.w);
+  int4* o = reinterpret_cast<int4*>(out);
+  o[0] = make_int4(E0[0], E0[1], E0[2], E0[3]);
+  o[1] = make_int4(A[0], A[1], A[2], A[3]);
+  o[2] = make_int4(B[0], B[1], B[2], B[3]);
+  o[3] = make_int4(__float_as_int(w2.x), __float_as_int(w2.y), __float_as_int(w2.z), id);
+  o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0));
 }
 
-// Fragment colour of one staged prim at a pixel centre (spec steps 5-6 and 8): perspective-correct
-// u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles, bilinear REPEAT texel, MODULATE.
-__device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __restrict__ lat_tab, float cdx,
-                                            float cdy, float c3[3]) {
-  float qq = fmaf(bp.fy[1], cdy, fmaf(bp.fx[1], cdx, bp.f0[1]));
+// Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
+// 5-6 and 8): perspective-correct u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles,
+// bilinear REPEAT texel, MODULATE.  Deferred shading: each lane may shade a different prim.
+__device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, unsigned w, const DTexture* __restrict__ textures,
+                                           const float4* __restrict__ lat_tab, int pxa, int pya, float c3[3]) {
+  const PrimRec* pr = prims + w;
+  const int2 xy0 = __ldg(reinterpret_cast<const int2*>(pr));
+  const float4 w3 = __ldg(reinterpret_cast<const float4*>(pr) + 3);   // q0 qx qy u0
+  const float4 w4 = __ldg(reinterpret_cast<const float4*>(pr) + 4);   // ux uy v0 vx
+  const float2 w5 = __ldg(reinterpret_cast<const float2*>(pr) + 10);  // vy ltq
+  const int ltq = __float_as_int(w5.y);
+  const float cdx = (float)(pxa + 32 - xy0.x) * 0.015625f, cdy = (float)(pya + 32 - xy0.y) * 0.015625f;
+  float qq = fmaf(w3.z, cdy, fmaf(w3.y, cdx, w3.x));
   if (!(qq > 1e-20f)) qq = 1e-20f;
   const float rq = 1.0f / qq;
-  const float u = fmaf(bp.fy[2], cdy, fmaf(bp.fx[2], cdx, bp.f0[2])) * rq;
-  const float v = fmaf(bp.fy[3], cdy, fmaf(bp.fx[3], cdx, bp.f0[3])) * rq;
-  if (bp.lat >= 0) {
+  const float u = fmaf(w4.y, cdy, fmaf(w4.x, cdx, w3.w)) * rq;
+  const float v = fmaf(w5.x, cdy, fmaf(w4.w, cdx, w4.z)) * rq;
+  const int lat = (ltq & 0xffff) - 1, tex = ((ltq >> 16) & 0xff) - 1;
+  if (lat >= 0) {
     // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
     const float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
     int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
     ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
     ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
     const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
-    const float4* L = lat_tab + bp.lat * 64 + ia * 8 + ib;
+    const float4* L = lat_tab + lat * 64 + ia * 8 + ib;
     // the cell's two triangles share c00 and c11; pick the third corner and the order of the two weights
     // instead of branching (same arithmetic, three loads instead of four)
     const bool lower = fb <= fa;
@@ -485,18 +495,22 @@ __device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __r
     c3[1] = fmaf(t2, c11.y - cm.y, fmaf(t1, cm.y - c00.y, c00.y));
     c3[2] = fmaf(t2, c11.z - cm.z, fmaf(t1, cm.z - c00.z, c00.z));
   } else {
-    c3[0] = fmaf(bp.fy[4], cdy, fmaf(bp.fx[4], cdx, bp.f0[4])) * rq;
-    c3[1] = fmaf(bp.fy[5], cdy, fmaf(bp.fx[5], cdx, bp.f0[5])) * rq;
-    c3[2] = fmaf(bp.fy[6], cdy, fmaf(bp.fx[6], cdx, bp.f0[6])) * rq;
+    const float2 w5b = __ldg(reinterpret_cast<const float2*>(pr) + 11);  // r0 rx
+    const float4 w6 = __ldg(reinterpret_cast<const float4*>(pr) + 6);    // ry g0 gx gy
+    const float4 w7 = __ldg(reinterpret_cast<const float4*>(pr) + 7);    // b0 bx by
+    c3[0] = fmaf(w6.x, cdy, fmaf(w5b.y, cdx, w5b.x)) * rq;
+    c3[1] = fmaf(w6.w, cdy, fmaf(w6.z, cdx, w6.y)) * rq;
+    c3[2] = fmaf(w7.z, cdy, fmaf(w7.y, cdx, w7.x)) * rq;
   }
-  if (bp.tex) {
-    const int tw = bp.tex_wh & 0xffff, th = bp.tex_wh >> 16;
-    const float tx = u * bp.twf - 0.5f, ty = v * bp.thf - 0.5f;
+  if (tex >= 0) {
+    const DTexture t = textures[tex];
+    const int tw = t.w, th = t.h;
+    const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
     const float txf = floorf(tx), tyf = floorf(ty);
     const float ffx = tx - txf, ffy = ty - tyf;
     const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
     const int tj0 = ((int)tyf) & (th - 1), tj1 = (tj0 + 1) & (th - 1);
-    const uchar4* tp = reinterpret_cast<const uchar4*>(bp.tex);
+    const uchar4* tp = reinterpret_cast<const uchar4*>(t.rgba);
     const uchar4 t00 = __ldg(tp + tj0 * tw + ti0), t10 = __ldg(tp + tj0 * tw + ti1);
     const uchar4 t01 = __ldg(tp + tj1 * tw + ti0), t11 = __ldg(tp + tj1 * tw + ti1);
     const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
@@ -509,6 +523,33 @@ __device__ __forceinline__ void shade_pixel(const BinPrim& bp, const float4* __r
       c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
     }
   }
+}
+
+// ---- bulk-async copy (TMA, 1-D) + mbarrier: global -> shared without register staging
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
 }
 
 // u8 = rint(255 * clamp(c)) packed r | g<<8 | b<<16 (resolve of 4 equal samples is the value itself)
@@ -568,12 +609,14 @@ int render_ctas_per_sm() { return DTS_RENDER_MIN_CTAS; }
 struct FrameMem {
   FrameCtx* ctx;        // [N]
   PrimRec* prims;       // [N][max_prims]
-  uint16_t* pairs;      // [N][max_pairs]  prim indices grouped by coarse bin (k_bin)
+  uint32_t* pairs;      // [N][max_pairs]  prim | coarse bin << 16, grouped by coarse bin (k_bin pass 1)
+  BinRec* recs;         // [N][max_pairs]  the pairs' visibility records, same order (k_bin pass 2)
   int* bin_count;       // [N][cbins]
-  int* bin_start;       // [N][cbins]  offset of the bin's run inside the env's pairs
+  int* bin_start;       // [N][cbins]  offset of the bin's run inside the env's pairs / recs
   float4* lat;          // [N][max_lat][64]
   uint8_t* undist;      // [N][H][W][3] (distortion only)
   int* work;            // [4] global work counters
+  int32_t* status;      // mapped host word (dts_status): bit 0 = a frame ran out of frame memory
 };
 
 __host__ __device__ inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
@@ -586,15 +629,18 @@ __host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_
   f.bin_count = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
   f.bin_start = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
   f.prims = reinterpret_cast<PrimRec*>(p); p += align256((size_t)n * max_prims * sizeof(PrimRec));
-  f.pairs = reinterpret_cast<uint16_t*>(p); p += align256((size_t)n * max_pairs * sizeof(uint16_t));
+  f.pairs = reinterpret_cast<uint32_t*>(p); p += align256((size_t)n * max_pairs * sizeof(uint32_t));
+  f.recs = reinterpret_cast<BinRec*>(p); p += align256((size_t)n * max_pairs * sizeof(BinRec));
   f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
   f.undist = undist_frame ? p : nullptr;
+  f.status = nullptr;
   return f;
 }
 
 size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
   return 256 + align256((size_t)n * sizeof(FrameCtx)) + 2 * align256((size_t)n * cbins * sizeof(int)) +
-         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * max_pairs * sizeof(uint16_t)) +
+         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * max_pairs * sizeof(uint32_t)) +
+         align256((size_t)n * max_pairs * sizeof(BinRec)) +
          align256((size_t)n * max_lat * 64 * sizeof(float4)) + (size_t)n * undist_frame + 256;
 }
 
@@ -828,12 +874,13 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
       process_triangle_lanes(ec, k < ob.tri_count, v[0], v[1], v[2], base_id + k, ttex, -1, lane);
       }
   }
-  if (lane == 0 && ctx.overflow) atomicOr(err, 1);
+  if (lane == 0 && ctx.overflow) { atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_bin
-// warp per env: exact-size lists of prim indices per 32x8-px coarse bin — count, warp scan, scatter.  Prims with
-// a small bounding box are binned by it; larger ones test each bin of the box against their three edges.
+// warp per env.  Pass 1: exact-size lists of (prim, 32x8-px coarse bin) pairs — count, warp scan, scatter; prims with
+// a small bounding box are binned by it, larger ones test each bin of the box against their edges.  Pass 2, dense
+// over the pairs (one per lane, so a screen-filling prim costs no more lanes than a sliver): the pair's BinRec.
 constexpr int kBinWarps = 4;
 __global__ void __launch_bounds__(kBinWarps * 32)
 k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restrict__ err) {
@@ -846,25 +893,28 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
   int* cnt = bin_smem + wib * 2 * cbins;
   int* start = cnt + cbins;
   const PrimRec* prims = fm.prims + (size_t)env * max_prims;
-  uint16_t* pairs = fm.pairs + (size_t)env * max_pairs;
+  uint32_t* pairs = fm.pairs + (size_t)env * max_pairs;
   const int n = min(fm.ctx[env].n_prims, max_prims);
-  bool ok = true;
+  int total = 0;
   for (int pass = 0; pass < 2; pass++) {
     for (int b = lane; b < cbins; b += 32) cnt[b] = 0;
     __syncwarp();
     for (int p = lane; p < n; p += 32) {
-      const PrimRec& pr = prims[p];
-      const int bx0 = (pr.pxmin & 0xffff) / kCoarseW, by0 = (pr.pxmin >> 16) / kCoarseH;
-      const int bx1 = (pr.pxmax & 0xffff) / kCoarseW, by1 = (pr.pxmax >> 16) / kCoarseH;
+      const int4 w0 = __ldg(reinterpret_cast<const int4*>(prims + p));
+      const int4 w1 = __ldg(reinterpret_cast<const int4*>(prims + p) + 1);
+      const int qx[4] = {w0.x, w0.z, w1.x, w1.z}, qy[4] = {w0.y, w0.w, w1.y, w1.w};
+      const int nv = ((__ldg(&prims[p].ltq) >> 24) & 1) ? 4 : 3;   // vertex 3 of a triangle repeats vertex 0
+      const int minx = min(min(qx[0], qx[1]), min(qx[2], qx[3])), maxx = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
+      const int miny = min(min(qy[0], qy[1]), min(qy[2], qy[3])), maxy = max(max(qy[0], qy[1]), max(qy[2], qy[3]));
+      const int bx0 = max(minx >> 6, 0) / kCoarseW, by0 = max(miny >> 6, 0) / kCoarseH;
+      const int bx1 = min(maxx >> 6, W - 1) / kCoarseW, by1 = min(maxy >> 6, H - 1) / kCoarseH;
       const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
-      int qx[4], qy[4];
-      const int nv = prim_vertices(pr, qx, qy);
       for (int by = by0; by <= by1; by++)
         for (int bx = bx0; bx <= bx1; bx++) {
           if (large && !bin_overlaps(qx, qy, nv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
           const int b = by * cbins_x + bx;
           const int pos = atomicAdd(&cnt[b], 1);
-          if (pass == 1) pairs[start[b] + pos] = (uint16_t)p;
+          if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
         }
     }
     __syncwarp();
@@ -879,14 +929,27 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
         if (b < cbins) start[b] = carry + inc - v;
         carry += __shfl_sync(0xffffffffu, inc, 31);
       }
-      ok = carry <= max_pairs;
+      total = carry;
+      const bool ok = total <= max_pairs;
       for (int b = lane; b < cbins; b += 32) {
         fm.bin_count[(size_t)env * cbins + b] = ok ? cnt[b] : 0;   // lists that do not fit: the frame stays clear
         fm.bin_start[(size_t)env * cbins + b] = start[b];
       }
       __syncwarp();
-      if (!ok) { if (lane == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); } return; }
+      if (!ok) {
+        if (lane == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
+        return;
+      }
     }
+  }
+  // pass 2: one pair per lane -> its visibility record (the pairs were written by other lanes of this warp:
+  // __syncwarp above orders those writes before these reads)
+  BinRec* recs = fm.recs + (size_t)env * max_pairs;
+  for (int i = lane; i < total; i += 32) {
+    const uint32_t pair = pairs[i];
+    const int p = (int)(pair & 0xffffu), b = (int)(pair >> 16);
+    const int cby = b / cbins_x, cbx = b - cby * cbins_x;
+    build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
   }
 }
 
@@ -895,7 +958,8 @@ template <bool kWrapFmt>   // true: a dts_output_format other than packed u8 HWC
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, uint8_t* __restrict__ obs,
          int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
-  __shared__ __align__(16) BinPrim stages[kWarps][kStage];
+  __shared__ __align__(128) BinRec stages[kWarps][2][kStage];   // per warp: two chunks of records in flight
+  __shared__ __align__(8) uint64_t bars[kWarps][2];
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -905,7 +969,11 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   const int out_fmt = (!kWrapFmt || fisheye) ? 0 : (rc.obs_layout | (rc.obs_dtype << 2));
   const size_t out_elem = (kWrapFmt && !fisheye && rc.obs_dtype == DTS_OBS_F32_UNIT) ? 4 : 1;
   const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
-  BinPrim* stage = stages[warp];
+  uint64_t* bar = bars[warp];
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  __syncwarp();
+  uint32_t parity = 0;   // bit s: the phase the next wait on slot s completes
+  int cs = 0, ps = 0;    // consumer / producer slot
   const int n_work = rc.n_envs * cbins_y;   // work item = one row of coarse bins of one env
   int work = 0;
   if (lane == 0) work = atomicAdd(fm.work, 1);
@@ -915,141 +983,213 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     if (lane == 0) next_work = atomicAdd(fm.work, 1);   // consumed after this row: latency hidden
     const int env = work / cbins_y, cby = work - env * cbins_y;
     const DMap& m = maps[S.map_id[env]];
+    const DTexture* textures = m.textures;
     const PrimRec* prims = fm.prims + (size_t)env * max_prims;
+    const BinRec* recs = fm.recs + (size_t)env * max_pairs;
     const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
     uint8_t* out = fisheye ? fm.undist + (size_t)env * frame_bytes : obs + (size_t)env * frame_bytes * out_elem;
     const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
-    for (int cbx = 0; cbx < cbins_x; cbx++) {
-      const int cb = cby * cbins_x + cbx;
-      const int count = fm.bin_count[(size_t)env * cbins + cb];
-      const uint16_t* list = fm.pairs + (size_t)env * max_pairs + fm.bin_start[(size_t)env * cbins + cb];
-      const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
-      const bool single = count <= kStage;
-#ifdef DTS_STATS
-      if (lane == 0) { atomicAdd(&err[8], 1); if (count == 0) atomicAdd(&err[9], 1); atomicAdd(&err[10], count);
-                       if (count > kStage) { atomicAdd(&err[14], 1); atomicAdd(&err[15], count); } }
-#endif
-      int my_id = 0x7fffffff, my_flags = 0;
-      if (single && count > 0) {   // the common case: stage the whole list once for all 8 fine bins
-        __syncwarp();
-        if (lane < count) { my_id = stage_prim(prims[list[lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
-        __syncwarp();
+    // lane l holds the list of coarse bin (cby, l)
+    int my_cnt = 0, my_start = 0;
+    if (lane < cbins_x) {
+      my_cnt = fm.bin_count[(size_t)env * cbins + cby * cbins_x + lane];
+      my_start = fm.bin_start[(size_t)env * cbins + cby * cbins_x + lane];
+    }
+    const unsigned nz = __ballot_sync(0xffffffffu, my_cnt > 0);
+    const unsigned fvalid_y = ((cby * kCFY + 1) * kBinH < H) ? 0xffu : 0x0fu;   // second row of fine bins inside the image?
+    // ---- producer: walks the row's chunk sequence one chunk ahead of the consumer.  A list of <= 32 records is
+    // ONE chunk shared by the bin's 8 fine bins; a longer list is streamed chunk by chunk for each fine bin in turn
+    // (the records are ready-made, re-reading them from L2 costs no arithmetic).
+    int pcbx = nz ? __ffs(nz) - 1 : 32, pf = 0, pc = 0;
+    auto fine_valid = [&](int cbx, int f) -> bool {
+      return ((fvalid_y >> f) & 1u) && (cbx * kCFX + (f & 3)) * kBinW < W;
+    };
+    auto next_bin = [&]() {
+      const unsigned rem = nz & ~((2u << pcbx) - 1u);
+      pcbx = rem ? __ffs(rem) - 1 : 32;
+      pf = 0; pc = 0;
+    };
+    auto issue = [&]() {
+      if (pcbx >= 32) return;
+      const int n = __shfl_sync(0xffffffffu, my_cnt, pcbx), st = __shfl_sync(0xffffffffu, my_start, pcbx);
+      if (n > kStage) while (pf < kCFX * kCFY && !fine_valid(pcbx, pf)) pf++;   // fine bins outside the image are not visited
+      if (n > kStage && pf >= kCFX * kCFY) { next_bin(); return; }               // (cannot happen: fine bin 0 is always inside)
+      const int nch = min(kStage, n - pc);
+      if (lane == 0) {
+        mbar_expect_tx(&bar[ps], (uint32_t)(nch * sizeof(BinRec)));
+        bulk_load(stages[warp][ps], recs + st + pc, (uint32_t)(nch * sizeof(BinRec)), &bar[ps]);
       }
+      ps ^= 1;
+      if (n <= kStage) { next_bin(); return; }
+      pc += kStage;
+      if (pc >= n) {
+        pc = 0; pf++;
+        while (pf < kCFX * kCFY && !fine_valid(pcbx, pf)) pf++;
+        if (pf >= kCFX * kCFY) next_bin();
+      }
+    };
+    issue();
+    for (int cbx = 0; cbx < cbins_x; cbx++) {
+      const int count = __shfl_sync(0xffffffffu, my_cnt, cbx);
+      if (count == 0) {
 #pragma unroll 1
-      for (int f = 0; f < kCFX * kCFY; f++) {
-        const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
-        if (bx * kBinW >= W || by * kBinH >= H) continue;
-        if (count == 0) { store_bin_any(out, out_fmt, clear_rgb, lane, bx, by, W, H); continue; }
-        const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
-        float z[4], cr[4], cg[4], cb_[4];
-        int wid[4];
-        bool simple_done = false, inited = false;
+        for (int f = 0; f < kCFX * kCFY; f++)
+          if (fine_valid(cbx, f)) store_bin_any(out, out_fmt, clear_rgb, lane, cbx * kCFX + (f & 3), cby * kCFY + (f >> 2), W, H);
+        continue;
+      }
+      const bool single = count <= kStage;
+      const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
+#pragma unroll 1
+      for (int g = 0; g < (single ? 1 : kCFX * kCFY); g++) {
+        if (!single && !fine_valid(cbx, g)) continue;
+        float z[4];
+        unsigned wn[4];   // per sample: depth and winning prim (index into the env's slab)
+#pragma unroll 1
         for (int c0 = 0; c0 < count; c0 += kStage) {
+          // ---- acquire this chunk; the next one starts loading into the other slot meanwhile
+          __syncwarp();   // every lane is done with the slot the producer is about to refill
+          issue();
+          mbar_wait(&bar[cs], (parity >> cs) & 1u);
+          parity ^= 1u << cs;
+          const BinRec* stage = stages[warp][cs];
+          cs ^= 1;
           const int nch = min(kStage, count - c0);
-          if (!single) {   // long lists (far field): re-stage chunk by chunk for every fine bin
-            __syncwarp();
-            my_id = 0x7fffffff; my_flags = 0;
-            if (lane < nch) { my_id = stage_prim(prims[list[c0 + lane]], stage[lane], ox, oy, m); my_flags = stage[lane].flags; }
-            __syncwarp();
-          }
-          const bool live = (my_flags >> (8 + f)) & 1;
-          const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-          const unsigned ground_mask = __ballot_sync(0xffffffffu, live && my_id < 2);
-#ifdef DTS_STATS
-          if (lane == 0) { atomicAdd(&err[11], __popc(live_mask)); atomicAdd(&err[12], __popc(ground_mask)); }
-#endif
-          if (single) {
-            // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
-            // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
-            // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
-            const unsigned full_mask = __ballot_sync(0xffffffffu, live && ((my_flags >> f) & 1));
-            const unsigned others = live_mask & ~ground_mask;
-            const unsigned pick = others ? others : live_mask;
-            if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
-              const BinPrim& bp = stage[__ffs(pick) - 1];
-              const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
-              float c3[3];
-              shade_pixel(bp, lat_tab, cdx, cdy, c3);
-              store_bin_any(out, out_fmt, pack_rgb(c3[0], c3[1], c3[2]), lane, bx, by, W, H);
-              simple_done = true;
-#ifdef DTS_STATS
-              if (lane == 0) atomicAdd(&err[13], 1);
-#endif
-              break;
+          uint2 mine = make_uint2(0u, 0u);
+          if (lane < nch) mine = *reinterpret_cast<const uint2*>(&stage[lane].prim_flags);
+          const bool first = c0 == 0, last = c0 + kStage >= count;
+#pragma unroll 1
+          for (int f = (single ? 0 : g); f < (single ? kCFX * kCFY : g + 1); f++) {
+            if (!fine_valid(cbx, f)) continue;
+            const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
+            const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
+            const bool live = (mine.x >> (16 + f)) & 1u;
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            const unsigned ground_mask = __ballot_sync(0xffffffffu, live && (mine.y & 2u));
+            bool simple = false;
+            if (single) {
+              // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
+              // All four samples then carry its colour (depth cleared to 1 passes, the ground lies below
+              // every other surface and fails GL_LESS), and the mean of four equal floats is exact.
+              const unsigned full_mask = __ballot_sync(0xffffffffu, live && ((mine.x >> (24 + f)) & 1u));
+              const unsigned others = live_mask & ~ground_mask;
+              const unsigned pick = others ? others : live_mask;
+              if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
+                simple = true;
+                const unsigned w = stage[__ffs(pick) - 1].prim_flags & 0xffffu;
+                wn[0] = w; wn[1] = w; wn[2] = w; wn[3] = w;
+              }
             }
-          }
-          if (!inited) {   // per-sample state is only needed on the general path
-            inited = true;
+            if (!simple) {
+              if (first) {
 #pragma unroll
-            for (int s = 0; s < 4; s++) { z[s] = 1.0f; cr[s] = clr[0]; cg[s] = clr[1]; cb_[s] = clr[2]; wid[s] = 0x7fffffff; }
-          }
-          // everything else first, the ground quad last (it is almost always hidden -> early-z kills it)
-          for (int phase = 0; phase < 2; phase++) {
-            unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
-            // every sample of the bin already belongs to a surface above the ground plane: the ground quad
-            // (y = -0.008, below everything else) cannot pass GL_LESS anywhere — same argument as the simple bin
-            if (phase == 1 && todo && c0 + kStage >= count &&
-                __all_sync(0xffffffffu, (wid[0] | wid[1] | wid[2] | wid[3]) != 0x7fffffff && wid[0] >= 2 && wid[1] >= 2 && wid[2] >= 2 && wid[3] >= 2))
-              todo = 0;
-            while (todo) {
-              const int k = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const BinPrim& bp = stage[k];
-#ifdef DTS_STATS
-              if (lane == 0) { atomicAdd(&err[16], 1); if ((bp.flags >> f) & 1) atomicAdd(&err[17], 1); }
-#endif
-              int mask = 15;
-              if (!((bp.flags >> f) & 1)) {
-                mask = 0;
-                const int ec0 = bp.E0[0] + bp.A[0] * pxc + bp.B[0] * pyc;
-                const int ec1 = bp.E0[1] + bp.A[1] * pxc + bp.B[1] * pyc;
-                const int ec2 = bp.E0[2] + bp.A[2] * pxc + bp.B[2] * pyc;
-                const int ec3 = bp.E0[3] + bp.A[3] * pxc + bp.B[3] * pyc;
+                for (int s = 0; s < 4; s++) { z[s] = 1.0f; wn[s] = kNoPrim; }
+              }
+              // ---- visibility: everything else first, the ground quad last (it is almost always hidden)
+#pragma unroll 1
+              for (int phase = 0; phase < 2; phase++) {
+                unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+                // every sample of the bin already belongs to a surface above the ground plane: the ground quad
+                // (y = -0.008, below everything else) cannot pass GL_LESS anywhere — same argument as the simple bin
+                if (phase == 1 && todo &&
+                    __all_sync(0xffffffffu, wn[0] != kNoPrim && wn[1] != kNoPrim && wn[2] != kNoPrim && wn[3] != kNoPrim))
+                  todo = 0;
+                while (todo) {
+                  const int k = __ffs(todo) - 1;
+                  todo &= todo - 1;
+                  const BinRec& br = stage[k];
+                  const uint32_t pflags = br.prim_flags;
+                  int mask = 15;
+                  if (!((pflags >> (24 + f)) & 1u)) {
+                    const int4 E = *reinterpret_cast<const int4*>(br.E0);
+                    const int4 A = *reinterpret_cast<const int4*>(br.A);
+                    const int4 B = *reinterpret_cast<const int4*>(br.B);
+                    const int ec0 = E.x + A.x * pxc + B.x * pyc;
+                    const int ec1 = E.y + A.y * pxc + B.y * pyc;
+                    const int ec2 = E.z + A.z * pxc + B.z * pyc;
+                    mask = 0;
+                    if (br.kind & 1) {
+                      const int ec3 = E.w + A.w * pxc + B.w * pyc;
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                  const int e0 = ec0 + bp.A[0] * sample_x(s) + bp.B[0] * sample_y(s);
-                  const int e1 = ec1 + bp.A[1] * sample_x(s) + bp.B[1] * sample_y(s);
-                  const int e2 = ec2 + bp.A[2] * sample_x(s) + bp.B[2] * sample_y(s);
-                  const int e3 = ec3 + bp.A[3] * sample_x(s) + bp.B[3] * sample_y(s);
-                  if ((e0 | e1 | e2 | e3) >= 0) mask |= 1 << s;
+                      for (int s = 0; s < 4; s++) {
+                        const int e0 = ec0 + A.x * sample_x(s) + B.x * sample_y(s);
+                        const int e1 = ec1 + A.y * sample_x(s) + B.y * sample_y(s);
+                        const int e2 = ec2 + A.z * sample_x(s) + B.z * sample_y(s);
+                        const int e3 = ec3 + A.w * sample_x(s) + B.w * sample_y(s);
+                        if ((e0 | e1 | e2 | e3) >= 0) mask |= 1 << s;
+                      }
+                    } else {
+#pragma unroll
+                      for (int s = 0; s < 4; s++) {
+                        const int e0 = ec0 + A.x * sample_x(s) + B.x * sample_y(s);
+                        const int e1 = ec1 + A.y * sample_x(s) + B.y * sample_y(s);
+                        const int e2 = ec2 + A.z * sample_x(s) + B.z * sample_y(s);
+                        if ((e0 | e1 | e2) >= 0) mask |= 1 << s;
+                      }
+                    }
+                    if (!mask) continue;
+                  }
+                  // ---- depth of the covered samples, GL_LESS in draw order
+                  const float4 zp = *reinterpret_cast<const float4*>(&br.z0);   // z0 zx zy id
+                  const int2 xy0 = *reinterpret_cast<const int2*>(&br.x0);
+                  const float cdx = (float)(pxc + 32 - xy0.x) * 0.015625f, cdy = (float)(pyc + 32 - xy0.y) * 0.015625f;
+                  float zs[4];
+                  int lt = 0, eq = 0;
+#pragma unroll
+                  for (int s = 0; s < 4; s++) {
+                    // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
+                    // identical to the spec's (float)(X_sample - x0) / 64
+                    const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
+                    zs[s] = fmaf(zp.z, sdy, fmaf(zp.y, sdx, zp.x));
+                    lt |= (zs[s] < z[s]) << s;
+                    eq |= (zs[s] == z[s]) << s;
+                  }
+                  int pass_mask = mask & lt;
+                  const int tie = mask & eq;
+                  if (tie) {   // exact depth ties are rare: the earlier draw keeps the sample (its id comes from the slab)
+                    const int my_id = __float_as_int(zp.w);
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+                      if ((tie >> s & 1) && wn[s] != kNoPrim && my_id < __ldg(&prims[wn[s]].id)) pass_mask |= 1 << s;
+                  }
+                  if (!pass_mask) continue;
+                  const unsigned me = pflags & 0xffffu;
+#pragma unroll
+                  for (int s = 0; s < 4; s++)
+                    if (pass_mask >> s & 1) { z[s] = zs[s]; wn[s] = me; }
                 }
-                if (!mask) continue;
               }
-              // ---- early z: depth of the covered samples, GL_LESS in draw order
-              const float cdx = (float)(pxc + 32 - bp.x0) * 0.015625f, cdy = (float)(pyc + 32 - bp.y0) * 0.015625f;
-              float zs[4];
-              int lt = 0, eq = 0;
-#pragma unroll
-              for (int s = 0; s < 4; s++) {
-                // sample offset from the pixel centre is a multiple of 1/64: cdx + off is exact, i.e.
-                // identical to the spec's (float)(X_sample - x0) / 64
-                const float sdx = cdx + (float)(sample_x(s) - 32) * 0.015625f, sdy = cdy + (float)(sample_y(s) - 32) * 0.015625f;
-                zs[s] = fmaf(bp.fy[0], sdy, fmaf(bp.fx[0], sdx, bp.f0[0]));
-                lt |= (zs[s] < z[s]) << s;
-                eq |= (zs[s] == z[s]) << s;
-              }
-              int pass_mask = mask & lt;
-              const int tie = mask & eq;
-              if (__any_sync(__activemask(), tie)) {   // exact depth ties are rare: draw order decides
-#pragma unroll
-                for (int s = 0; s < 4; s++) if ((tie >> s & 1) && bp.id < wid[s]) pass_mask |= 1 << s;
-              }
-              if (!pass_mask) continue;
-              float c3[3];
-              shade_pixel(bp, lat_tab, cdx, cdy, c3);
-#pragma unroll
-              for (int s = 0; s < 4; s++)
-                if (pass_mask >> s & 1) { z[s] = zs[s]; wid[s] = bp.id; cr[s] = c3[0]; cg[s] = c3[1]; cb_[s] = c3[2]; }
             }
+            if (!(last || simple)) continue;
+            // ---- deferred shading: once per distinct winner of this pixel, then the box resolve
+            const int pxa = ox + pxc, pya = oy + pyc;
+            const bool same = wn[1] == wn[0] && wn[2] == wn[0] && wn[3] == wn[0];
+            const bool all_same = __all_sync(0xffffffffu, same);
+            float s01[3] = {0.f, 0.f, 0.f}, s23[3] = {0.f, 0.f, 0.f};
+            unsigned rgb = 0;
+            unsigned pend = 0xfu;
+#pragma unroll 1
+            while (__any_sync(0xffffffffu, pend != 0u)) {
+              if (pend) {
+                const int s = __ffs(pend) - 1;
+                const unsigned w = s == 0 ? wn[0] : (s == 1 ? wn[1] : (s == 2 ? wn[2] : wn[3]));
+                float c3[3] = {clr[0], clr[1], clr[2]};
+                if (w != kNoPrim) shade_prim(prims, w, textures, lat_tab, pxa, pya, c3);
+                if (all_same) { rgb = pack_rgb(c3[0], c3[1], c3[2]); pend = 0u; }
+                else {
+#pragma unroll
+                  for (int t = 0; t < 4; t++)
+                    if ((pend >> t & 1u) && wn[t] == w) {
+                      pend &= ~(1u << t);
+                      if (t < 2) { s01[0] = s01[0] + c3[0]; s01[1] = s01[1] + c3[1]; s01[2] = s01[2] + c3[2]; }
+                      else { s23[0] = s23[0] + c3[0]; s23[1] = s23[1] + c3[1]; s23[2] = s23[2] + c3[2]; }
+                    }
+                }
+              }
+            }
+            if (!all_same) rgb = pack_rgb((s01[0] + s23[0]) * 0.25f, (s01[1] + s23[1]) * 0.25f, (s01[2] + s23[2]) * 0.25f);
+            store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
           }
-        }
-        // -------------------------------------------------------- resolve + store
-        if (!simple_done) {
-          const float r_ = ((cr[0] + cr[1]) + (cr[2] + cr[3])) * 0.25f;
-          const float g_ = ((cg[0] + cg[1]) + (cg[2] + cg[3])) * 0.25f;
-          const float b_ = ((cb_[0] + cb_[1]) + (cb_[2] + cb_[3])) * 0.25f;
-          store_bin_any(out, out_fmt, pack_rgb(r_, g_, b_), lane, bx, by, W, H);
         }
       }
     }
@@ -1085,31 +1225,40 @@ __global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs_any, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
-                  int32_t* err_flag, cudaStream_t st) {
+                  int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st) {
   const int W = rc.width, H = rc.height;
   uint8_t* obs = reinterpret_cast<uint8_t*>(obs_any);
   const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
-  const FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
+  FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
+  fm.status = status_dev;
+  int mk = 0;
+  auto mark = [&]() { if (marks) cudaEventRecord(marks[mk++], st); };
   cudaMemsetAsync(fm.work, 0, 256, st);
+  mark();
   k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
+  mark();
   const dim3 geo_grid((unsigned)((rc.n_envs + kGeoWarps - 1) / kGeoWarps), (unsigned)items_max);
   if (rc.tessellate) k_geometry<true><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
   else k_geometry<false><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
+  mark();
   const size_t bin_smem_bytes = (size_t)kBinWarps * 2 * cbins * sizeof(int);
   if (bin_smem_bytes > 48 * 1024)   // cameras beyond ~640x480 (cbins > 1536): opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
   k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, bin_smem_bytes, st>>>(
       rc, fm, max_prims, max_pairs, err_flag);
+  mark();
   if (!fisheye && (rc.obs_layout | rc.obs_dtype) != 0)
     k_raster<true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
   else
     k_raster<false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
+  mark();
   int launches = 4;
   if (fisheye) {
     k_fisheye<<<148 * 8, 256, 0, st>>>(rc, fm.undist, lut_x, lut_y, obs);
     launches++;
   }
+  mark();
   return launches;
 }
 

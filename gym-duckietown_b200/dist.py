@@ -12,6 +12,35 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (PCI sysfs), BEFORE pinned host buffers are
+    allocated: first-touch then places them on that node and the D2H stream does not cross the socket link.  One
+    process per GPU (torchrun) otherwise inherits an all-CPU mask.  Returns what was done (for the bench record)."""
+    import subprocess
+    bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                         capture_output=True, text=True, timeout=10).stdout.strip().lower()
+    if not bus:
+        return {"bound": False, "why": "nvidia-smi gave no bus id"}
+    if len(bus.split(":")[0]) == 8:   # 00000000:1B:00.0 -> 0000:1b:00.0
+        bus = bus[4:]
+    node_path = f"/sys/bus/pci/devices/{bus}/numa_node"
+    if not os.path.exists(node_path):
+        return {"bound": False, "why": f"{node_path} missing"}
+    node = int(open(node_path).read().strip())
+    if node < 0:
+        return {"bound": False, "why": "numa_node = -1 (single node)"}
+    txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+    cpus = set()
+    for part in txt.split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = cpus & set(os.sched_getaffinity(0))
+    if not allowed:
+        return {"bound": False, "why": f"no allowed CPU on node {node}"}
+    os.sched_setaffinity(0, allowed)
+    return {"bound": True, "node": node, "cpus": len(allowed)}
+
+
 def find_libnccl() -> str:
     """The NCCL that torch itself loaded (nvidia-nccl wheel), else the system one."""
     cands = []

@@ -27,6 +27,33 @@ DIM = 0.5
 CAMERA_ANGLE, CAMERA_FOV_Y, CAMERA_FLOOR_DIST, WHEEL_DIST = 19.15, 75, 0.108, 0.102
 MAX_SPAWN_ATTEMPTS = 5000
 _CHUNK = 16
+# randomization/config/default_dr.json (== randomizer.py DEFAULT_CONFIG)
+DEFAULT_DR_CONFIG = {
+    "horz_mode": {"type": "int", "low": 0, "high": 4},
+    "light_pos": {"type": "uniform", "low": [-150, 170, -150], "high": [150, 220, 150], "size": 3},
+    "camera_noise": {"type": "uniform", "low": -0.005, "high": 0.005, "size": 3},
+    "trim": {"type": "normal", "loc": 0, "scale": 0.02},
+    "camera_height": {"type": "uniform", "low": 0.92, "high": 1.08},
+    "camera_angle": {"type": "uniform", "low": 0.8, "high": 1.2},
+    "camera_fov_y": {"type": "uniform", "low": 0.8, "high": 1.2},
+}
+_DR_REQUIRED = ("camera_angle", "camera_fov_y", "camera_height", "camera_noise", "horz_mode", "light_pos", "trim")
+
+
+def load_dr_config(cfg) -> dict:
+    """`Randomizer(randomization_config_fp=...)` (randomizer.py:19-33): a dict, a JSON file path, or None for
+    default_dr.json.  Every key the simulator reads must be present: the reference falls back to
+    DEFAULT_CONFIG[k]["default"], which does not exist (KeyError, randomizer.py:84)."""
+    if cfg is None:
+        return dict(DEFAULT_DR_CONFIG)
+    if not isinstance(cfg, dict):
+        import json
+        with open(cfg) as f:
+            cfg = json.load(f)
+    missing = [k for k in _DR_REQUIRED if k not in cfg]
+    if missing:
+        raise KeyError(f"randomization config lacks {missing}: the reference's Randomizer raises KeyError('default') for them")
+    return dict(cfg)
 
 
 def np_random(seed=None) -> np.random.Generator:
@@ -37,7 +64,7 @@ def np_random(seed=None) -> np.random.Generator:
 class EpisodeSampler:
     def __init__(self, num_envs: int, *, domain_rand: bool, dynamics_rand: bool = False, camera_rand: bool = False,
                  accept_start_angle_deg: float = 60.0, num_tris_distractors: int = 12,
-                 color_ground=(0.15, 0.15, 0.15), color_sky=BLUE_SKY, user_tile_start=None):
+                 color_ground=(0.15, 0.15, 0.15), color_sky=BLUE_SKY, user_tile_start=None, randomization_config=None):
         self.n = num_envs
         self.domain_rand = domain_rand
         self.dynamics_rand = dynamics_rand
@@ -47,6 +74,9 @@ class EpisodeSampler:
         self.color_ground = np.array(color_ground)
         self.color_sky = np.array(list(color_sky))
         self.user_tile_start = user_tile_start
+        self.dr_config = load_dr_config(randomization_config)
+        self.dr_keys = sorted(self.dr_config)   # randomizer.py:33
+        self.last_horizon = [np.array(self.color_sky, dtype=float) for _ in range(num_envs)]
         self.rngs: List[np.random.Generator] = [np_random(None) for _ in range(num_envs)]
         self.episodes = np.zeros(num_envs, np.int64)
 
@@ -64,17 +94,29 @@ class EpisodeSampler:
             noise[3] = 1
         return val * noise
 
-    def _pre_spawn(self, rng, md: MapData) -> dict:
+    def _randomize(self, rng) -> dict:
+        """Randomizer.randomize (randomizer.py:36-91): every key in sorted order with the reference's numpy calls."""
+        out = {}
+        for k in self.dr_keys:
+            d = self.dr_config[k]
+            size = d.get("size", 1)
+            if d["type"] == "int":
+                out[k] = rng.integers(low=d["low"], high=d["high"], size=size)
+            elif d["type"] == "uniform":
+                out[k] = rng.uniform(low=d["low"], high=d["high"], size=size)
+            elif d["type"] == "normal":
+                out[k] = rng.normal(loc=d["loc"], scale=d["scale"], size=size)
+            else:
+                raise NotImplementedError("You've specified an unsupported distribution type")
+        return out
+
+    def _pre_spawn(self, rng, md: MapData, env: int = 0) -> dict:
         """Everything reset() draws before the start tile (S:546-656), in order."""
         out = {}
         # Randomizer.randomize — keys sorted, drawn whether or not DR is on (randomizer.py:33,46-89)
-        camera_angle = rng.uniform(low=0.8, high=1.2, size=1)
-        camera_fov_y = rng.uniform(low=0.8, high=1.2, size=1)
-        camera_height = rng.uniform(low=0.92, high=1.08, size=1)
-        camera_noise = rng.uniform(low=-0.005, high=0.005, size=3)
-        horz_mode = rng.integers(low=0, high=4, size=1)
-        light_pos_r = rng.uniform(low=[-150, 170, -150], high=[150, 220, 150], size=3)
-        trim = rng.normal(loc=0, scale=0.02, size=1)
+        st = self._randomize(rng)
+        camera_angle, camera_fov_y, camera_height = st["camera_angle"], st["camera_fov_y"], st["camera_height"]
+        camera_noise, horz_mode, light_pos_r, trim = st["camera_noise"], st["horz_mode"], st["light_pos"], st["trim"]
         if self.domain_rand:  # S:551-562
             hm = int(horz_mode[0])
             if hm == 0:
@@ -83,8 +125,10 @@ class EpisodeSampler:
                 horizon = self._perturb(rng, WALL_COLOR)
             elif hm == 2:
                 horizon = self._perturb(rng, [0.15, 0.15, 0.15], 0.4)
-            else:
+            elif hm == 3:
                 horizon = self._perturb(rng, [0.9, 0.9, 0.9], 0.4)
+            else:
+                horizon = self.last_horizon[env]   # no branch assigns: the attribute keeps its previous value
             light_pos = np.array([light_pos_r[0], light_pos_r[1], light_pos_r[2], 0.0])  # 3 floats in a 4-array
         else:
             horizon = self.color_sky
@@ -112,6 +156,7 @@ class EpisodeSampler:
             if obj.optional and self.domain_rand:
                 if not (rng.integers(0, 2) == 0):
                     hidden[oi >> 5] |= np.uint32(1 << (oi & 31))
+        self.last_horizon[env] = np.array(horizon, dtype=float)
         out.update(cam_height=cam_height, cam_angle_deg=cam_angle, cam_fov_y_deg=cam_fov,
                    cam_noise=camera_noise if self.domain_rand else np.zeros(3), horizon_color=horizon,
                    light_ambient=ambient[:3], light_diffuse=diffuse[:3], light_pos=light_pos, ground_color=ground,
@@ -127,7 +172,7 @@ class EpisodeSampler:
         todo = []
         for k, e in enumerate(envs):
             rng, md = self.rngs[e], maps[k]
-            r = self._pre_spawn(rng, md)
+            r = self._pre_spawn(rng, md, e)
             if self.user_tile_start is not None:  # S:659-666
                 ti, tj = self.user_tile_start
                 if not (0 <= ti < md.grid_w and 0 <= tj < md.grid_h) or md.tile_kind[tj * md.grid_w + ti] < 0:

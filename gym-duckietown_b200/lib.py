@@ -14,7 +14,7 @@ from .maps import KIND_ID, TILE_KINDS, MapData
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdtsim.so")
 
-DTS_ABI_VERSION = 2
+DTS_ABI_VERSION = 3
 ACTION_PWM, ACTION_VEL_STEER = 0, 1
 FLAG_AUTO_RESET, FLAG_DOMAIN_RAND, FLAG_DISTORTION, FLAG_DYNAMICS_RAND, FLAG_TESSELLATE = 1, 2, 4, 8, 16
 IN_PROGRESS, INVALID_POSE, MAX_STEPS = 0, 1, 2
@@ -23,6 +23,17 @@ DONE_CODE_STR = {0: "in-progress", 1: "invalid-pose", 2: "max-steps-reached"}  #
 
 class DtsError(RuntimeError):
     pass
+
+
+DR_INT, DR_UNIFORM, DR_NORMAL = 0, 1, 2
+DR_TARGETS = {"camera_angle": 1, "camera_fov_y": 2, "camera_height": 3, "camera_noise": 4, "horz_mode": 5,
+              "light_pos": 6, "trim": 7}   # DTS_DR_*; any other key is drawn and discarded (DTS_DR_NONE)
+MAX_DR_OPS = 16
+
+
+class DrOp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("size", C.c_int32), ("target", C.c_int32), ("reserved", C.c_int32),
+                ("a", C.c_double * 3), ("b", C.c_double * 3)]
 
 
 class Config(C.Structure):
@@ -36,6 +47,8 @@ class Config(C.Structure):
         ("dyn_w2", C.c_double), ("dyn_w3", C.c_double), ("dyn_uar", C.c_double), ("dyn_ual", C.c_double),
         ("dyn_war", C.c_double), ("dyn_wal", C.c_double), ("dyn_delay", C.c_double),
         ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+        ("num_tris_distractors", C.c_int32), ("n_dr_ops", C.c_int32),
+        ("color_sky", C.c_double * 3), ("color_ground", C.c_double * 3), ("dr_ops", DrOp * MAX_DR_OPS),
     ]
 
 
@@ -123,13 +136,20 @@ _lib = None
 
 
 def load() -> C.CDLL:
-    """Load libdtsim.so; build it first if the source tree is newer (nvcc needed). Fails loudly."""
+    """Load libdtsim.so; (re)build it first when it is missing or older than csrc/ or dtsim.h and nvcc is on PATH
+    (build.build checks the mtimes).  Fails loudly: there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _b
-        _b.build()
+    import shutil
+    from . import build as _b
+    if shutil.which("nvcc"):
+        _b.build(force=False)
+    elif not os.path.exists(LIB_PATH):
+        raise DtsError(f"{LIB_PATH} is missing and nvcc is not available to build it")
+    elif _b.needs_build():
+        import warnings
+        warnings.warn("libdtsim.so is older than its sources and nvcc is not available: loading the stale library")
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:  # no fallback, by design
@@ -144,7 +164,11 @@ def load() -> C.CDLL:
     lib.dts_step.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dts_render.argtypes = [vp, vp, vp]
     lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
-    lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp]
+    lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp]
+    lib.dts_assign_maps.argtypes = [vp, vp, vp, vp]
+    lib.dts_status.argtypes = [vp]
+    lib.dts_profile_enable.argtypes = [vp, i]
+    lib.dts_profile_read.argtypes = [vp, vp, vp]
     lib.dts_set_output_format.argtypes = [vp, C.POINTER(OutputFormat)]
     lib.dts_get_dyn_state.argtypes = [vp, i, C.POINTER(vp), C.POINTER(C.c_int32)]
     lib.dts_comm_load.argtypes = [vp, C.c_char_p]
@@ -164,7 +188,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_last_error", "dts_destroy"]
 
 
@@ -329,16 +353,39 @@ class Sim:
         self._check(self.lib.dts_get_state(self.h, C.byref(v)), "dts_get_state")
         return {n: _CudaArray(getattr(v, n), self.cfg.num_envs, dt) for n, dt in _STATE_FIELDS}
 
-    def query_poses(self, map_id: int, x, z, angle, safety=1.0, hidden=None, dyn_env: int = -1):
-        """dyn_env: the env whose dynamic obstacles the predicates see (-1: static scene only)."""
+    def query_poses(self, map_id: int, x, z, angle, safety=1.0, hidden=None, dyn_env: int = -1, stream: int = 0):
+        """dyn_env: the env whose dynamic obstacles the predicates see (-1: static scene only).  Runs on `stream`,
+        i.e. after the steps already queued there, and returns when the answers are on the host."""
         q = np.empty((len(x), 4), np.float64)
         q[:, 0], q[:, 1], q[:, 2], q[:, 3] = x, z, angle, safety
         outd = np.empty((len(x), 4), np.float64)
         outi = np.empty((len(x), 8), np.int32)
         hid = None if hidden is None else np.ascontiguousarray(hidden, np.uint32)
-        self._check(self.lib.dts_query_poses(self.h, map_id, int(dyn_env), len(x), _ptr(q), _ptr(hid), _ptr(outd), _ptr(outi)),
-                    "dts_query_poses")
+        self._check(self.lib.dts_query_poses(self.h, map_id, int(dyn_env), len(x), _ptr(q), _ptr(hid), _ptr(outd), _ptr(outi),
+                                             stream), "dts_query_poses")
         return outd, outi
+
+    def assign_maps(self, mask_ptr: Optional[int], map_ids: np.ndarray, stream: int = 0):
+        """randomize_maps_on_reset (host-drawn): new map ids + re-created obstacles, nothing else (dts_assign_maps)."""
+        ids = np.ascontiguousarray(map_ids, np.int32)
+        if ids.shape != (self.cfg.num_envs,):
+            raise ValueError("map_ids must have one entry per env")
+        self._check(self.lib.dts_assign_maps(self.h, mask_ptr, _ptr(ids), stream), "dts_assign_maps")
+
+    def status(self) -> int:
+        """Sticky status bits, read without synchronising (bit 0: a frame overflowed its render frame memory)."""
+        return int(self.lib.dts_status(self.h))
+
+    def profile(self, on: bool):
+        self._check(self.lib.dts_profile_enable(self.h, int(bool(on))), "dts_profile_enable")
+
+    def profile_read(self):
+        """(dict kernel -> summed ms, frames) since the last read; synchronises."""
+        ms = np.zeros(8, np.float64)
+        fr = C.c_int64()
+        self._check(self.lib.dts_profile_read(self.h, _ptr(ms), C.byref(fr)), "dts_profile_read")
+        names = ["k_frame_setup", "k_geometry", "k_bin", "k_raster", "post"]
+        return {n: float(ms[k]) for k, n in enumerate(names)}, int(fr.value)
 
     def dyn_state(self, map_id: int = 0):
         """(device array f64[DYN_FIELDS * n_dyn * num_envs], n_dyn) of map `map_id`'s dynamic obstacles, or (None, 0)."""
@@ -382,9 +429,52 @@ def default_config(**kw) -> Config:
         action_mode=ACTION_VEL_STEER, flags=0, max_maps=1, cycle_maps=0, random_maps=0, frame_rate=30.0, robot_speed=1.2,
         accept_start_angle_deg=60.0, gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0,
         dyn_u1=5.0, dyn_u2=0.0, dyn_u3=0.0, dyn_w1=4.0, dyn_w2=0.0, dyn_w3=0.0, dyn_uar=1.5, dyn_ual=1.5,
-        dyn_war=15.0, dyn_wal=15.0, dyn_delay=0.15, seed=0, env_id_offset=0)
+        dyn_war=15.0, dyn_wal=15.0, dyn_delay=0.15, seed=0, env_id_offset=0, num_tris_distractors=12, n_dr_ops=0)
+    c.color_sky[:] = (0.45, 0.82, 1.0)      # BLUE_SKY S:108
+    c.color_ground[:] = (0.15, 0.15, 0.15)  # S:228
     for k_, v in kw.items():
         if not hasattr(c, k_):
             raise TypeError(f"unknown config field {k_}")
-        setattr(c, k_, v)
+        if k_ in ("color_sky", "color_ground"):
+            getattr(c, k_)[:] = [float(x) for x in v]
+        elif k_ == "dr_ops":
+            set_dr_ops(c, v)
+        else:
+            setattr(c, k_, v)
     return c
+
+
+def dr_ops_from_config(cfg: dict) -> list:
+    """Randomizer table (randomization/randomizer.py:19-89) -> list of (type, size, target, a[3], b[3]) in the
+    reference's draw order (sorted keys).  `cfg` is the parsed JSON: {key: {"type": "int" | "uniform" | "normal", ...}}."""
+    ops = []
+    for key in sorted(cfg):
+        d = cfg[key]
+        t = d["type"]
+        size = d.get("size", 1)
+        if t == "int":
+            ty, a, b = DR_INT, d["low"], d["high"]
+        elif t == "uniform":
+            ty, a, b = DR_UNIFORM, d["low"], d["high"]
+        elif t == "normal":
+            ty, a, b = DR_NORMAL, d["loc"], d["scale"]
+        else:
+            raise NotImplementedError("You've specified an unsupported distribution type")   # randomizer.py:79
+        a3 = np.broadcast_to(np.asarray(a, np.float64), (min(int(size), 3),) if np.ndim(a) == 0 else np.shape(a))
+        b3 = np.broadcast_to(np.asarray(b, np.float64), (min(int(size), 3),) if np.ndim(b) == 0 else np.shape(b))
+        if int(size) > 3 and (np.ndim(a) or np.ndim(b)):
+            raise ValueError(f"DR key {key}: array bounds with size > 3 are not supported")
+        av, bv = np.zeros(3), np.zeros(3)
+        av[:len(a3)], bv[:len(b3)] = a3, b3
+        ops.append((ty, int(size), DR_TARGETS.get(key, 0), av, bv))
+    if len(ops) > MAX_DR_OPS:
+        raise ValueError(f"at most {MAX_DR_OPS} randomization keys")
+    return ops
+
+
+def set_dr_ops(c: Config, ops: list):
+    c.n_dr_ops = len(ops)
+    for k, (ty, size, target, a, b) in enumerate(ops):
+        c.dr_ops[k].type, c.dr_ops[k].size, c.dr_ops[k].target = ty, size, target
+        c.dr_ops[k].a[:] = [float(x) for x in a]
+        c.dr_ops[k].b[:] = [float(x) for x in b]

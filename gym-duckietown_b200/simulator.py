@@ -185,7 +185,7 @@ class Simulator(Env):
 
     # ------------------------------------------------------------------ helper methods callers use
     def _query(self, pos, angle, safety=1.0):
-        outd, outi = self._b.sim.query_poses(self._map_index(), np.array([pos[0]]), np.array([pos[2]]), np.array([angle]), safety, dyn_env=0)
+        outd, outi = self._b.sim.query_poses(self._map_index(), np.array([pos[0]]), np.array([pos[2]]), np.array([angle]), safety, dyn_env=0, stream=self._b._stream())
         return outd[0], outi[0]
 
     def get_grid_coords(self, abs_pos) -> Tuple[int, int]:  # S:1134

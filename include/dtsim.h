@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTS_ABI_VERSION 2
+#define DTS_ABI_VERSION 3
 #define DTS_MAX_DELAY 8      /* command-delay line depth (steps) */
 #define DTS_MAX_OBJECTS 256  /* per map; visibility bitmask is 8 x u32 */
 
@@ -35,6 +35,21 @@ enum { DTS_FLAG_AUTO_RESET = 1,   /* done envs are re-spawned on device inside d
        DTS_FLAG_DYNAMICS_RAND = 8,/* simulator.py:224  per-env trim on the motor gains (S:746-748) */
        DTS_FLAG_TESSELLATE = 16   /* draw every road tile as the literal 7x7 quads of simulator.py:386-507
                                      instead of one quad + analytic lattice lighting (DESIGN.md render spec) */ };
+
+/* One entry of the reference's domain-randomization table (randomization/randomizer.py:19-89): Randomizer.randomize
+ * draws every key of the JSON config in SORTED key order from the env's np_random, whether or not domain_rand is on
+ * (S:546).  `target` says which render / dynamics parameter the draw feeds; keys the simulator never reads are still
+ * drawn (DTS_DR_NONE) so that the stream stays aligned with the reference. */
+enum { DTS_DR_INT = 0,      /* rng.integers(low, high, size)   randomizer.py:55-58 */
+       DTS_DR_UNIFORM = 1,  /* rng.uniform(low, high, size)    randomizer.py:69 */
+       DTS_DR_NORMAL = 2    /* rng.normal(loc, scale, size)    randomizer.py:77 */ };
+enum { DTS_DR_NONE = 0, DTS_DR_CAMERA_ANGLE, DTS_DR_CAMERA_FOV_Y, DTS_DR_CAMERA_HEIGHT, DTS_DR_CAMERA_NOISE,
+       DTS_DR_HORZ_MODE, DTS_DR_LIGHT_POS, DTS_DR_TRIM };
+#define DTS_MAX_DR_OPS 16
+typedef struct {
+  int32_t type, size, target, reserved;
+  double a[3], b[3];        /* low / loc and high / scale; element k of a size-3 draw uses a[k], b[k]; size > 3 uses [0] */
+} dts_dr_op;
 
 typedef struct {
   int32_t abi_version;      /* DTS_ABI_VERSION */
@@ -63,6 +78,12 @@ typedef struct {
   double dyn_delay;         /* 0.15 (S:748-750) */
   uint64_t seed;            /* device-side spawn/DR streams: stream k = hash(seed, global_env_id) */
   int64_t env_id_offset;    /* global index of local env 0 (multi-GPU shards keep seeds GPU-count independent) */
+  /* Simulator.__init__ keywords that reset() reads (simulator.py:226-230): device resets honour them */
+  int32_t num_tris_distractors; /* 12: 3*n vertices drawn per reset S:621-629 (never visible, draws consumed) */
+  int32_t n_dr_ops;         /* 0 = the reference's default_dr.json; else the custom table below, in sorted key order */
+  double color_sky[3];      /* BLUE_SKY S:108 (float64 like the Python floats _perturb multiplies) */
+  double color_ground[3];   /* (0.15, 0.15, 0.15) S:228 */
+  dts_dr_op dr_ops[DTS_MAX_DR_OPS];
 } dts_config;
 
 typedef struct { int32_t width, height; const uint8_t* rgba; /* [height][width][4], row 0 = t=0 */ } dts_texture;
@@ -238,7 +259,11 @@ int dts_get_state(dts_sim* sim, dts_state_view* out);
  * inconvenient_spawn, tile_i, tile_j, drivable.  Dynamic obstacles are taken where env `dyn_env` currently has
  * them (check_collision O:265/368, proximity O:271/374, x.pos in S:1466); dyn_env < 0 ignores them. */
 int dts_query_poses(dts_sim* sim, int map_id, int dyn_env, int n, const double* query, const uint32_t* hidden,
-                    double* out_f64, int32_t* out_i32);
+                    double* out_f64, int32_t* out_i32, void* stream);
+/* randomize_maps_on_reset, host-drawn (S:541-544): give the masked envs the map ids in map_id_host[N] and re-create
+ * those maps' obstacles for them (_load_map) WITHOUT touching pose, episode counter or render record — the reset that
+ * follows still sees the previous episode's last camera (stale GL_LIGHT0 position, S:581). */
+int dts_assign_maps(dts_sim* sim, const uint8_t* mask_dev, const int32_t* map_id_host, void* stream);
 /* Device pointer to the dynamic-obstacle state of map `map_id`: f64[DTS_DYN_FIELDS][n_dyn][num_envs] (NULL, 0 for a
  * map without dynamic obstacles).  Re-uploading the map puts every env's obstacles back to their load-time state. */
 int dts_get_dyn_state(dts_sim* sim, int map_id, double** state_dev, int32_t* n_dyn);
@@ -250,6 +275,16 @@ int dts_comm_load(dts_sim* sim, const char* libnccl_path);
 int dts_comm_unique_id(dts_sim* sim, uint8_t out[128]);
 int dts_comm_init(dts_sim* sim, const uint8_t id[128], int rank, int world);
 int dts_allgather_obs(dts_sim* sim, const void* send_dev, void* recv_dev, uint64_t bytes_per_rank, void* stream);
+/* Sticky status, readable WITHOUT synchronising (a mapped host word the kernels write): bit 0 = some frame since
+ * creation overflowed its render frame memory (prim slab / bin lists) and was left incomplete.  dts_step and
+ * dts_render return non-zero once it is set (the frame that overflowed may be one or two calls back). */
+int dts_status(dts_sim* sim);
+/* Per-kernel device timing of the render launches (bench.py's roofline): when enabled, every dts_render brackets its
+ * kernels with CUDA events on the caller's stream.  dts_profile_read synchronises, returns the summed milliseconds of
+ * [0] k_frame_setup, [1] k_geometry, [2] k_bin, [3] k_raster, [4] post passes (resize) and the number of frames
+ * they cover, and clears the accumulators. */
+int dts_profile_enable(dts_sim* sim, int on);
+int dts_profile_read(dts_sim* sim, double ms_out[8], int64_t* frames);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t dts_launch_count(dts_sim* sim);
 /* debug: the env's per-episode render record as 36 x 32-bit words (cam_height, cam_angle_deg, cam_fov_y_deg, -,

@@ -308,6 +308,7 @@ def build_reference_sim(map_data: dict, mesh_extents: dict, *, domain_rand=False
         if key not in mesh_cache:
             lo, hi = mesh_extents[kind]
             mesh_cache[key] = FakeMesh(lo, hi)
+            mesh_cache[key].kind = kind
         return mesh_cache[key]
 
     _get_transform.grid_height = len(map_data["tiles"])
