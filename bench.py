@@ -272,7 +272,7 @@ def main():
     head = dict(map=args.map, envs=E, width=W, height=H, domain_rand=args.domain_rand, distortion=args.distortion,
                 cycle=args.cycle_maps)
     config = {"workload": workload_text(head), "envs_per_gpu": E, "width": W, "height": H, "map": args.map,
-              "tile_mode": "1 (one quad per road tile + analytic 8x8 lattice lighting; mode 0 = literal 98 triangles differs by <= 2 LSB, tests/test_oracle_raster.py)",
+              "tile_mode": "1 (one quad per road tile + analytic 8x8 lattice lighting); vs mode 0 (the literal 98 triangles, DTS_FLAG_TESSELLATE): > 1 LSB on < 1 % of the channel values, all at tile outlines (tests/test_oracle_raster.py)",
               "l2": "obs batch written per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (E * W * H * 3 / 1e6)}
 
     if args.impl == "reference":

@@ -626,6 +626,22 @@ int dts_debug_episode(dts_sim* sim, int env, void* out144) {
   return 0;
 }
 
+/* debug: frame setup of `env` in the last dts_render (synchronises) */
+int dts_debug_frame(dts_sim* sim, int env, double V[12], float P[4], int32_t counts[4], float* lattice_by_cell, int n_cells) {
+  if (!sim) return 1;
+  if (env < 0 || env >= sim->cfg.num_envs) return sim->fail("env out of range");
+  if (!sim->render_scratch) return sim->fail("nothing rendered yet");
+  if (sim->cfg.flags & DTS_FLAG_TESSELLATE) return sim->fail("dts_debug_frame reads the analytic-tile lattice (tile mode 1)");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  DTS_CUDA(cudaDeviceSynchronize());
+  const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
+  const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
+  if (debug_frame_copy(sim->render_scratch, sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame, env, V, P,
+                       counts, lattice_by_cell, n_cells, 2))
+    return sim->fail("debug_frame_copy failed");
+  return 0;
+}
+
 /* debug: copy the 32 int32 diagnostic counters (word 0 = overflow flag; 8.. = DTS_STATS counters) */
 int dts_debug_counters(dts_sim* sim, int32_t out[32]) {
   if (!sim) return 1;

@@ -25,7 +25,7 @@ __host__ __device__ inline void camera_view(double px, double pz, double angle, 
   double L[12] = {sx, sy, sz, -(sx * ex + sy * ey + sz * ez),
                   ux, uy, uz, -(ux * ex + uy * ey + uz * ez),
                   -fx, -fy, -fz, (fx * ex + fy * ey + fz * ez)};
-  L[11] += 0.066;  // T(0,0,CAMERA_FORWARD_DIST) S:1784 (CAMERA_FORWARD_DIST S:131)
+  L[11] += (double)0.066f;  // glTranslatef(0, 0, CAMERA_FORWARD_DIST) S:1784: a GLfloat argument (S:131)
   const double th = (double)ep.cam_angle_deg * kDeg2Rad;
   const double c = cos(th), s = sin(th);
   for (int k = 0; k < 4; k++) {

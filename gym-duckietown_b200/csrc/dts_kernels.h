@@ -45,4 +45,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
                   int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
                   int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st);
 
+int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame,
+                     int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile);
+
 }  // namespace dts

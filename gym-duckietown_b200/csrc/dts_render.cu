@@ -758,7 +758,8 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     const int quarter = (m.tile_angle[idx] + 2) & 3;                     // glRotatef(angle*90+180) S:1873
     const double cs = quarter == 0 ? 1.0 : (quarter == 2 ? -1.0 : 0.0), sn = quarter == 1 ? 1.0 : (quarter == 3 ? -1.0 : 0.0);
     const double ts = m.tile_size;
-    model_view(sh.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, 1.0, cs, sn, x, lane);
+    // glTranslatef((i + 0.5) * TS, 0, (j + 0.5) * TS) S:1870 takes GLfloat arguments
+    model_view(sh.V, (double)(float)((ti + 0.5) * ts), 0.0, (double)(float)((tj + 0.5) * ts), 1.0, cs, sn, x, lane);
     const int tex = m.tile_tex[idx];
     const int base_id = 2 + tris_per_tile * t;
     if (!kTess) {
@@ -1221,6 +1222,40 @@ __global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __
                    (unsigned)r | ((unsigned)gg << 8) | ((unsigned)b << 16));
     }
   }
+}
+
+// Test hook (dts_debug_frame): what k_frame_setup / k_geometry left in frame memory for one env of the last render —
+// the camera model-view and projection, the prim / lattice counts, and the lit 8x8 lattice of every road tile that
+// was emitted, re-ordered by grid cell (i * grid_h + j; cells that were culled stay NaN).
+int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame,
+                     int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile) {
+  const FrameMem fm = carve(scratch, n, max_prims, cbins, max_pairs, max_lat, undist_frame);
+  FrameCtx c;
+  if (cudaMemcpy(&c, fm.ctx + env, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  for (int k = 0; k < 12; k++) V[k] = c.V[k];
+  P[0] = c.P00; P[1] = c.P11; P[2] = c.P22; P[3] = c.P23;
+  counts[0] = c.n_prims; counts[1] = c.n_lat; counts[2] = c.overflow; counts[3] = 0;
+  const int np = c.n_prims < max_prims ? c.n_prims : max_prims;
+  PrimRec* prims = new PrimRec[np > 0 ? np : 1];
+  float4* lat = new float4[(size_t)max_lat * 64];
+  int rc = 0;
+  if (np && cudaMemcpy(prims, fm.prims + (size_t)env * max_prims, (size_t)np * sizeof(PrimRec), cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+  if (cudaMemcpy(lat, fm.lat + (size_t)env * max_lat * 64, (size_t)max_lat * 64 * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+  for (int k = 0; k < n_cells * 64 * 3; k++) lattice_by_cell[k] = nanf("");
+  for (int p = 0; p < np && !rc; p++) {
+    const int slot = (prims[p].ltq & 0xffff) - 1;
+    if (slot < 0 || slot >= max_lat) continue;
+    const int cell = (prims[p].id - 2) / tris_per_tile;   // tiles are drawn i outer, j inner: cell = i * grid_h + j
+    if (cell < 0 || cell >= n_cells) continue;
+    for (int v = 0; v < 64; v++) {
+      lattice_by_cell[(cell * 64 + v) * 3 + 0] = lat[slot * 64 + v].x;
+      lattice_by_cell[(cell * 64 + v) * 3 + 1] = lat[slot * 64 + v].y;
+      lattice_by_cell[(cell * 64 + v) * 3 + 2] = lat[slot * 64 + v].z;
+    }
+  }
+  delete[] prims;
+  delete[] lat;
+  return rc;
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs_any, void* scratch, int n_ctas,

@@ -178,6 +178,7 @@ def load() -> C.CDLL:
     lib.dts_launch_count.argtypes = [vp]
     lib.dts_debug_counters.argtypes = [vp, vp]
     lib.dts_debug_episode.argtypes = [vp, i, vp]
+    lib.dts_debug_frame.argtypes = [vp, i, vp, vp, vp, vp, i]
     lib.dts_launch_count.restype = C.c_uint64
     lib.dts_last_error.argtypes = [vp]
     lib.dts_last_error.restype = C.c_char_p
@@ -189,7 +190,7 @@ def load() -> C.CDLL:
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
            "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
-           "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_last_error", "dts_destroy"]
+           "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_debug_frame", "dts_last_error", "dts_destroy"]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -404,6 +405,13 @@ class Sim:
         return dict(cam_height=raw[0], cam_angle_deg=raw[1], cam_fov_y_deg=raw[2], cam_noise=raw[4:7], horizon=raw[8:11],
                     ambient=raw[12:15], diffuse=raw[16:19], light_eye=raw[20:24], ground=raw[24:27],
                     hidden=raw[28:36].view(np.uint32))
+
+    def debug_frame(self, env: int, n_cells: int) -> dict:
+        """Frame setup of `env` in the last render: V f64[12], P f32[4], counts, lattice f32[n_cells, 64, 3] (NaN = culled)."""
+        V, P, cnt = np.zeros(12), np.zeros(4, np.float32), np.zeros(4, np.int32)
+        lat = np.zeros((n_cells, 64, 3), np.float32)
+        self._check(self.lib.dts_debug_frame(self.h, env, _ptr(V), _ptr(P), _ptr(cnt), _ptr(lat), n_cells), "dts_debug_frame")
+        return dict(V=V, P=P, n_prims=int(cnt[0]), n_lat=int(cnt[1]), overflow=int(cnt[2]), lattice=lat)
 
     def debug_counters(self) -> np.ndarray:
         out = np.zeros(32, np.int32)

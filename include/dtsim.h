@@ -290,6 +290,10 @@ uint64_t dts_launch_count(dts_sim* sim);
 /* debug: the env's per-episode render record as 36 x 32-bit words (cam_height, cam_angle_deg, cam_fov_y_deg, -,
  * cam_noise[3], -, horizon[3], -, ambient[3], -, diffuse[3], -, light_eye[4], ground[3], -, hidden u32[8]). */
 int dts_debug_episode(dts_sim* sim, int env, void* out144);
+/* debug (tests/test_gpu_gltrace.py): what k_frame_setup / k_geometry produced for `env` in the last dts_render — camera
+ * model-view V (row-major 3x4, float64), projection P00 P11 P22 P23, counts = {prims, lattices, overflow, 0}, and the lit
+ * 8x8 lattice [n_cells][64][3] of every emitted road tile by grid cell i * grid_h + j (NaN where culled).  Synchronises. */
+int dts_debug_frame(dts_sim* sim, int env, double V[12], float P[4], int32_t counts[4], float* lattice_by_cell, int n_cells);
 /* 32 diagnostic counters: [0] != 0 -> a render scratch buffer overflowed (frame incomplete). */
 int dts_debug_counters(dts_sim* sim, int32_t out[32]);
 const char* dts_last_error(dts_sim* sim); /* sim may be NULL: error of the last failed dts_create */

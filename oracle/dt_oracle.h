@@ -108,4 +108,6 @@ void orc_step(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int*
               int frame_skip, double dt, int max_steps, double robot_speed, orc_step_out* o);
 void orr_render(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                 int domain_rand, const float* lut_x, const float* lut_y, uint8_t* out);
+void orr_debug_frame(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
+                     int domain_rand, double* V_out, float* P_out, float* item_mv, float* item_n, float* lattice);
 #endif

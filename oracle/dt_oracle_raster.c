@@ -64,7 +64,7 @@ static void camera_view(double px, double pz, double angle, const orr_episode* e
   double ux = sy * fz - sz * fy, uy = sz * fx - sx * fz, uz = sx * fy - sy * fx;
   double L[12] = {sx, sy, sz, -(sx * ex + sy * ey + sz * ez), ux, uy, uz, -(ux * ex + uy * ey + uz * ez),
                   -fx, -fy, -fz, (fx * ex + fy * ey + fz * ez)};
-  L[11] += 0.066;
+  L[11] += (double)0.066f; /* glTranslatef(0, 0, CAMERA_FORWARD_DIST): a GLfloat argument */
   double th = (double)ep->cam_angle_deg * 0.017453292519943295;
   double c = cos(th), s = sin(th);
   for (int k = 0; k < 4; k++) {
@@ -430,7 +430,8 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
       /* glRotatef(angle*90+180, 0,1,0): multiples of 90 degrees -> exact cos/sin */
       int quarter = (sc->tile_angle[idx] + 2) & 3;
       const double cs[4] = {1, 0, -1, 0}, sn[4] = {0, 1, 0, -1};
-      const double t[3] = {(i + 0.5) * ts, 0.0, (j + 0.5) * ts};
+      /* glTranslatef((i + 0.5) * TS, 0, (j + 0.5) * TS) S:1870: GLfloat arguments */
+      const double t[3] = {(double)(float)((i + 0.5) * ts), 0.0, (double)(float)((j + 0.5) * ts)};
       model_view(V, t, 1.0, cs[quarter], sn[quarter], x.MV, x.N);
       const orr_texture* tex = sc->tile_tex[idx] >= 0 ? &sc->textures[sc->tile_tex[idx]] : NULL;
       const float white[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1}, up[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0};
@@ -506,6 +507,59 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
         out[((size_t)y * W + xx) * 3 + ch] = v;
       }
     }
+}
+
+/* Test hook for the GL call-trace golden (tests/golden/gltrace_*.npz): the transforms and the lit tile lattices this
+ * renderer uses for one frame.  item 0 = ground, 1.. = every grid cell in draw order (i outer, j inner; absent tiles
+ * zero), then the objects.  item_mv [items][12], item_n [items][9], lattice [cells][64][3] (a outer, b inner). */
+void orr_debug_frame(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
+                     int domain_rand, double* V_out, float* P_out, float* item_mv, float* item_n, float* lattice) {
+  double V[12];
+  camera_view(px, pz, angle, ep, domain_rand, V);
+  memcpy(V_out, V, sizeof V);
+  xform x;
+  x.ep = ep;
+  {
+    double f = 1.0 / tan((double)ep->cam_fov_y_deg * 0.017453292519943295 / 2.0), aspect = (double)W / (double)H;
+    double zn = 0.04, zf = 100.0;
+    x.P00 = (float)(f / aspect); x.P11 = (float)f;
+    x.P22 = (float)((zf + zn) / (zn - zf)); x.P23 = (float)(2.0 * zf * zn / (zn - zf));
+    P_out[0] = x.P00; P_out[1] = x.P11; P_out[2] = x.P22; P_out[3] = x.P23;
+  }
+  const double zero3[3] = {0, 0, 0};
+  int item = 0;
+  model_view(V, zero3, 1.0, 1.0, 0.0, x.MV, x.N);
+  memcpy(item_mv, x.MV, 48); memcpy(item_n, x.N, 36);
+  item++;
+  const double ts = sc->tile_size;
+  float lat[8];
+  for (int k = 0; k < 8; k++) lat[k] = (float)(-ts / 2 + ((double)k / 7.0) * ts);
+  for (int i = 0; i < sc->grid_w; i++)
+    for (int j = 0; j < sc->grid_h; j++, item++) {
+      int idx = j * sc->grid_w + i;
+      float* L = lattice + (size_t)(item - 1) * 64 * 3;
+      memset(item_mv + 12 * item, 0, 48); memset(item_n + 9 * item, 0, 36); memset(L, 0, 64 * 3 * 4);
+      if (sc->tile_kind[idx] < 0) continue;
+      int quarter = (sc->tile_angle[idx] + 2) & 3;
+      const double cs[4] = {1, 0, -1, 0}, sn[4] = {0, 1, 0, -1};
+      const double t[3] = {(double)(float)((i + 0.5) * ts), 0.0, (double)(float)((j + 0.5) * ts)};
+      model_view(V, t, 1.0, cs[quarter], sn[quarter], x.MV, x.N);
+      memcpy(item_mv + 12 * item, x.MV, 48); memcpy(item_n + 9 * item, x.N, 36);
+      const float white[3] = {1, 1, 1}, up[3] = {0, 1, 0};
+      for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++) {
+          const float p[3] = {lat[a], 0.0f, lat[b]};
+          vtx v = shade_vertex(&x, p, up, white, 0.f, 0.f);
+          L[(a * 8 + b) * 3] = v.r; L[(a * 8 + b) * 3 + 1] = v.g; L[(a * 8 + b) * 3 + 2] = v.b;
+        }
+    }
+  for (int o = 0; o < sc->n_objects; o++, item++) {
+    const orr_object* ob = &sc->objects[o];
+    const double t[3] = {ob->pos[0], ob->pos[1], ob->pos[2]};
+    const double th = (double)ob->y_rot_deg * 0.017453292519943295;
+    model_view(V, t, (double)ob->scale, cos(th), sin(th), x.MV, x.N);
+    memcpy(item_mv + 12 * item, x.MV, 48); memcpy(item_n + 9 * item, x.N, 36);
+  }
 }
 
 /* batch over envs (OpenMP): the cpu_baseline / --impl reference leg of bench.py */

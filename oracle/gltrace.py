@@ -156,7 +156,7 @@ class GLRecorder:
         t = np.eye(4)
         t[:3, 3] = -e
         self._mul(m @ t)
-        self.events.append(dict(kind="lookat", eye=e, center=c, up=up))
+        self.events.append(dict(kind="lookat", eye=e, center=c, up=up, modelview=self.stacks["GL_MODELVIEW"][-1].copy()))
 
     def glColor3f(self, r, g, b):
         self.color = np.array([_f32(r), _f32(g), _f32(b), 1.0])
@@ -282,6 +282,10 @@ def make_sim(rec: GLRecorder, raw_map: dict, mesh_extents: dict, *, domain_rand:
     from unittest import mock
 
     import refstub
+    # a new Simulator = a fresh GL context: identity matrices, default state
+    rec.mode = "GL_MODELVIEW"
+    rec.stacks = {"GL_MODELVIEW": [np.eye(4)], "GL_PROJECTION": [np.eye(4)], "GL_TEXTURE": [np.eye(4)]}
+    rec.enabled, rec.light, rec.texture = set(), {}, None
     sim = refstub.build_reference_sim(raw_map, mesh_extents, domain_rand=domain_rand, seed=seed)
     S, C, G, O = refstub.modules()
     S.load_texture = rec._fake_load_texture    # build_reference_sim installs a plain no-op loader: ours carries ids

@@ -10,6 +10,11 @@ Files written
   action_map.npz       DuckietownEnv.step [vel, steer] -> wheel duty  (envs/duckietown_env.py:36-59)
   reset_<map>.npz      Simulator.reset() outputs per seed, domain_rand off/on (simulator.py:528-763)
   fisheye.npz          Distortion LUT digest, sub-sampled LUT, one remapped test image (distortion.py)
+  gltrace_<map>.npz    what the reference's own _render_img / _init_vlists / WorldObj.render / reset() lighting ask
+                       OpenGL to do, recorded call by call (oracle/gltrace.py): per frame the projection arguments,
+                       look-at, model-view of every draw, GL_LIGHT0 (eye-space position, ambient, diffuse), current
+                       colour, bound texture, draw order; the vertex lists            (simulator.py:386-527, 564-586,
+                       1707-1951; objects.py:123-148)
 """
 from __future__ import annotations
 
@@ -337,7 +342,98 @@ def gen_trafficlight(name="loop_trafficlights", steps=1300, seed=5):
     np.savez_compressed(os.path.join(OUT, f"trafficlight_{name}.npz"), **out)
 
 
+def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, height=120):
+    """Run the reference's render path against the recording GL (oracle/gltrace.py): reset() + a short walk, twice per
+    seed (the second episode captures GL_LIGHT0 under the previous frame's model-view, S:581), domain_rand off and on."""
+    import gltrace
+    rec = gltrace.GLRecorder()
+    gltrace.attach(rec)
+    raw = raw_map(name)
+    S, C, G, O = refstub.modules()
+    frames, draws = [], []
+    vl = {}
+    tex_names = []
+
+    def tex_index(tid):
+        if tid is None:
+            return -1
+        nm = rec.tex_names[tid][0]
+        if nm not in tex_names:
+            tex_names.append(nm)
+        return tex_names.index(nm)
+
+    mesh_kinds = []
+    distractors = []
+    for dr in (False, True):
+        for seed in seeds:
+            sim = gltrace.make_sim(rec, raw, extents_for(raw), domain_rand=dr, seed=int(seed), width=width, height=height)
+            if not vl:
+                vl = dict(road_v=sim.road_vlist.attrs["v"], road_t=sim.road_vlist.attrs["t"], road_n=sim.road_vlist.attrs["n"],
+                          road_c=sim.road_vlist.attrs["c"], ground_v=sim.ground_vlist.attrs["v"])
+            rng = np.random.default_rng(1000 + seed)
+            for episode in range(2):
+                rec.take()
+                sim.reset()
+                distractors.append(np.concatenate([sim.tri_vlist.attrs["v"], sim.tri_vlist.attrs["c"]], 1))
+                for k in range(poses_per_episode + 1):
+                    if k > 0:   # a short walk from the spawn pose: rendering does not need a valid pose
+                        d = S.get_dir_vec(sim.cur_angle)
+                        sim.cur_pos = np.array(sim.cur_pos, float) + d * rng.uniform(0.02, 0.2)
+                        sim.cur_angle = float(sim.cur_angle) + rng.uniform(-0.5, 0.5)
+                        rec.take()
+                        sim.render_obs()
+                    ev = rec.take()
+                    lights = [e for e in ev if e["kind"] == "light"]
+                    clear = [e for e in ev if e["kind"] == "clear"][-1]
+                    look = [e for e in ev if e["kind"] == "lookat"][-1]
+                    dl = [e for e in ev if e["kind"] == "draw"]
+                    f = dict(dr=dr, seed=seed, episode=episode, k=k, pos=np.array(sim.cur_pos, float), angle=float(sim.cur_angle),
+                             clear=clear["color"], persp=np.array(rec.perspective), eye=look["eye"], center=look["center"],
+                             view=look["modelview"].reshape(-1), proj=dl[0]["projection"].reshape(-1),
+                             light_eye=dl[0]["light_pos_eye"], light_ambient=dl[0]["light_ambient"],
+                             light_diffuse=dl[0]["light_diffuse"], light_model_ambient=dl[0]["light_model_ambient"],
+                             light_raw=(lights[0]["values"] if lights else np.full(4, np.nan)),
+                             flags=np.array([dl[0]["lighting"], dl[0]["light0"], dl[0]["color_material"], dl[0]["normalize"],
+                                             dl[0]["rescale_normal"]], np.int8),
+                             cam_height=float(np.asarray(sim.cam_height).reshape(-1)[0]),
+                             cam_angle=float(np.asarray(sim.cam_angle[0]).reshape(-1)[0]),
+                             cam_fov_y=float(np.asarray(sim.cam_fov_y).reshape(-1)[0]),
+                             camera_noise=np.array(sim.randomization_settings["camera_noise"], float),
+                             horizon=np.array(sim.horizon_color, float), ground=np.array(sim.ground_color, float),
+                             draw0=len(draws), visible=np.array([o.visible for o in sim.objects], bool))
+                    for e in dl:
+                        if e["what"] == "vlist":
+                            v = rec.vlists[e["id"]]
+                            kind = 0 if v is sim.ground_vlist else (1 if v is sim.tri_vlist else 2)
+                            sub = -1
+                        else:
+                            kind = 3
+                            if e["id"] not in mesh_kinds:
+                                mesh_kinds.append(e["id"])
+                            sub = mesh_kinds.index(e["id"])
+                        draws.append(dict(frame=len(frames), kind=kind, sub=sub, mv=e["modelview"].reshape(-1), color=e["color"],
+                                          tex=tex_index(e["texture"]), lit=e["lighting"]))
+                    f["ndraws"] = len(draws) - f["draw0"]
+                    frames.append(f)
+    out = {f"f_{k}": np.array([fr[k] for fr in frames]) for k in frames[0] if k != "visible"}
+    nobj = max(len(fr["visible"]) for fr in frames)
+    out["f_visible"] = np.array([np.pad(fr["visible"], (0, nobj - len(fr["visible"]))) for fr in frames])
+    out.update({f"d_{k}": np.array([d[k] for d in draws]) for k in draws[0]})
+    out.update(vl)
+    out["distractors"] = np.array(distractors)
+    out["tex_names"] = np.array(tex_names)
+    out["mesh_kinds"] = np.array(mesh_kinds if mesh_kinds else [""])
+    out["width"], out["height"] = np.int32(width), np.int32(height)
+    np.savez_compressed(os.path.join(OUT, f"gltrace_{name}.npz"), **out)
+    print(f"gltrace_{name}: {len(frames)} frames, {len(draws)} draws, textures {tex_names}, meshes {mesh_kinds}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gltrace":
+        os.makedirs(OUT, exist_ok=True)
+        for m in MAPS:
+            gen_gltrace(m)
+        sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     for m in MAPS:
         gen_logic(m)
@@ -350,3 +446,5 @@ if __name__ == "__main__":
     gen_trafficlight()
     gen_reset_start()
     gen_helpers()
+    for m in MAPS:
+        gen_gltrace(m)

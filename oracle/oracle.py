@@ -238,6 +238,20 @@ class OracleScene:
                          int(domain_rand), _p(lx) if lx is not None else None, _p(ly) if ly is not None else None, _p(out))
         return out
 
+    def debug_frame(self, px, pz, angle, ep: OrrEpisode = None, W=160, H=120, domain_rand=False) -> dict:
+        """Transforms and lit tile lattices the raster oracle uses for one frame (orr_debug_frame): V f64[12], P f32[4]
+        (P00 P11 P22 P23), item_mv f32[items,12], item_n f32[items,9], lattice f32[cells,64,3]; items = ground, every
+        grid cell (i outer, j inner), objects."""
+        ep = ep or default_episode()
+        cells = self.c.grid_w * self.c.grid_h
+        items = 1 + cells + self.c.n_objects
+        V, P = np.zeros(12), np.zeros(4, np.float32)
+        mv, nn = np.zeros((items, 12), np.float32), np.zeros((items, 9), np.float32)
+        lat = np.zeros((cells, 64, 3), np.float32)
+        lib().orr_debug_frame(C.byref(self.c), C.c_double(px), C.c_double(pz), C.c_double(angle), C.byref(ep), W, H,
+                              int(domain_rand), _p(V), _p(P), _p(mv), _p(nn), _p(lat))
+        return dict(V=V, P=P, item_mv=mv, item_n=nn, lattice=lat)
+
     def render_batch(self, px, pz, angle, eps, W=160, H=120, domain_rand=False, lut=None, threads=1) -> np.ndarray:
         n = len(px)
         out = np.zeros((n, H, W, 3), np.uint8)

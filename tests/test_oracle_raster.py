@@ -28,10 +28,14 @@ def _poses(md, n, seed):
 def test_analytic_tiles_equal_literal_tessellation_up_to_edge_placement(name):
     """Tile mode 1 (one quad + analytic Gouraud lattice, the parity spec) vs mode 0 (the literal 98
     triangles of simulator.py:386-507): same image except rounding (+-1) and sub-1/64-px placement of
-    tile outlines.  Quantified: >=99 % of channel values within 1 LSB, mean abs diff < 0.15."""
+    tile outlines (mode 0 snaps the 8 lattice points of every tile border separately, so its outline is a 7-segment
+    polyline within 1/128 px of mode 1's straight edge; a sample inside that sliver belongs to the other tile).
+    There is NO 1-LSB bound between the two modes: a flipped sample changes its pixel by up to a quarter of the local
+    contrast, and two can flip in one pixel.  Hard bounds asserted here (measured: 0.5-0.8 % / 0.05-0.1 % / 0.01-0.04 %):
+    >1 LSB on < 1 % of the channel values, > 8 LSB on < 0.2 %, > 32 LSB on < 0.06 %, mean abs diff < 0.15 LSB."""
     md = maps.load_map(name)
     sc = orc.OracleScene(md)
-    tot = big = 0
+    tot = big = big8 = big32 = 0
     absdiff = 0.0
     for x, z, a in _poses(md, 16, 3):
         orc.lib().orr_set_tile_mode(0)
@@ -39,8 +43,9 @@ def test_analytic_tiles_equal_literal_tessellation_up_to_edge_placement(name):
         orc.lib().orr_set_tile_mode(1)
         ana = sc.render(x, z, a).astype(int)
         d = np.abs(lit - ana)
-        tot += d.size; big += int((d > 1).sum()); absdiff += d.sum()
+        tot += d.size; big += int((d > 1).sum()); big8 += int((d > 8).sum()); big32 += int((d > 32).sum()); absdiff += d.sum()
     assert big / tot < 0.01, big / tot
+    assert big8 / tot < 0.002 and big32 / tot < 0.0006, (big8 / tot, big32 / tot)
     assert absdiff / tot < 0.15
 
 
