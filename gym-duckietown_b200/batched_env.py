@@ -81,6 +81,7 @@ class BatchedDuckietownEnv:
             user_tile_start=user_tile_start, randomization_config=randomization_config)
         self.map_ids = np.zeros(num_envs, np.int32)
         self._first_reset = True
+        self.resize = None
         self.output_format = dict(obs_layout="hwc", obs_dtype="uint8", reward="raw", discrete_actions=False,
                                   action_vel_scale=1.0)
         self.seed(seed)
@@ -102,12 +103,37 @@ class BatchedDuckietownEnv:
         rw = {"raw": L.REWARD_RAW, "dt": L.REWARD_DT}[f["reward"]]
         self.sim.set_output_format(lay, dt, rw, L.ACTIONS_DISCRETE3 if f["discrete_actions"] else L.ACTIONS_CONTINUOUS,
                                    f["action_vel_scale"])
-        H, W = self.camera_height, self.camera_width
+        self._alloc_obs()
+        return self
+
+    @property
+    def obs_size(self):
+        """(height, width) of the observations the env emits: the camera's, or the fused ResizeWrapper's target."""
+        return (self.resize[1], self.resize[0]) if self.resize else (self.camera_height, self.camera_width)
+
+    def _alloc_obs(self):
+        f = self.output_format
+        H, W = self.obs_size
         shape = {"hwc": (H, W, 3), "chw": (3, H, W), "cwh": (3, W, H)}[f["obs_layout"]]
         with torch.cuda.device(self.device):
             self.obs = torch.zeros((self.num_envs,) + shape, device=self.device,
-                                   dtype=torch.uint8 if dt == L.OBS_U8 else torch.float32)
+                                   dtype=torch.uint8 if f["obs_dtype"] == "uint8" else torch.float32)
+
+    def set_resize(self, resize_w: Optional[int], resize_h: Optional[int]):
+        """ResizeWrapper (wrappers.py:111-141) on the device: render at the camera size, emit `resize_w` x `resize_h`
+        observations (cv2.INTER_CUBIC's 8-bit fixed-point arithmetic) in the current layout / dtype.  None switches off."""
+        self.resize = (int(resize_w), int(resize_h)) if resize_w else None
+        self.sim.set_resize(*(self.resize or (0, 0)))
+        self._alloc_obs()
         return self
+
+    def sim_resize_only(self, frames: torch.Tensor) -> torch.Tensor:
+        """The device ResizeWrapper pass on caller-supplied full-size frames u8[N, H, W, 3] -> self.obs."""
+        if tuple(frames.shape) != (self.num_envs, self.camera_height, self.camera_width, 3) or frames.dtype != torch.uint8:
+            raise ValueError("frames must be uint8 [num_envs, camera_height, camera_width, 3]")
+        frames = frames.to(self.device).contiguous()
+        self.sim.resize_frames(frames.data_ptr(), self.obs.data_ptr(), self._stream())
+        return self.obs
 
     # ------------------------------------------------------------------ gym-like surface
     def seed(self, seed=None):

@@ -35,10 +35,14 @@ struct dts_sim {
   // render
   void* render_scratch = nullptr;
   int render_ctas = 0, max_prims = 0, bin_cap = 0, max_lat = 0, items_max = 0;
-  float *lut_x = nullptr, *lut_y = nullptr;
+  FishTab fish{nullptr, nullptr, nullptr, nullptr};   // fused fisheye tables (dts_set_fisheye_lut)
   int32_t* d_err = nullptr;
   int32_t* h_status = nullptr;          // mapped pinned host word: bit 0 = a frame overflowed its frame memory
   int32_t* d_status = nullptr;          // its device address
+  // fused ResizeWrapper (dts_set_resize): full-size render target + tap tables
+  int resize_w = 0, resize_h = 0;
+  uint8_t* resize_src = nullptr;
+  int16_t *resize_xtab = nullptr, *resize_ytab = nullptr;
   // per-kernel timing (dts_profile_*): event pairs recorded around the render launches
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events; // kProfMarks events per profiled frame
@@ -187,8 +191,11 @@ void dts_destroy(dts_sim* sim) {
   cudaDeviceSynchronize();
   for (void* p : sim->allocs) cudaFree(p);
   for (auto& v : sim->map_allocs) for (void* p : v) cudaFree(p);
-  void* extra[] = {sim->render_scratch, sim->lut_x, sim->lut_y, sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
+  void* extra[] = {sim->render_scratch, (void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
+                   sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
   for (void* p : extra) if (p) cudaFree(p);
+  void* rz[] = {sim->resize_src, sim->resize_xtab, sim->resize_ytab};
+  for (void* p : rz) if (p) cudaFree(p);
   if (sim->h_status) cudaFreeHost(sim->h_status);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   delete sim;
@@ -354,13 +361,54 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
 
 int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, int width, int height) {
   if (!sim) return 1;
+  if (!rmapx || !rmapy) return sim->fail("fisheye LUT is NULL");
   if (width != sim->cfg.cam_width || height != sim->cfg.cam_height)
     return sim->fail("fisheye LUT is %dx%d but the camera is %dx%d", width, height, sim->cfg.cam_width, sim->cfg.cam_height);
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
-  const size_t n = (size_t)width * height;
-  if (!sim->lut_x) { DTS_CUDA(cudaMalloc(&sim->lut_x, n * 4)); DTS_CUDA(cudaMalloc(&sim->lut_y, n * 4)); }
-  DTS_CUDA(cudaMemcpy(sim->lut_x, rmapx, n * 4, cudaMemcpyHostToDevice));
-  DTS_CUDA(cudaMemcpy(sim->lut_y, rmapy, n * 4, cudaMemcpyHostToDevice));
+  // distortion.py:118 gathers img[rint(rmapy), rint(rmapx)].  The rasteriser renders those source pixels directly
+  // (FishTab): per output pixel the source position, per 8x4 fine / 32x8 coarse output bin / row of coarse bins the
+  // bounding box of its source pixels (the bins prims are sorted into).
+  const int W = width, H = height;
+  const int cbx_n = (W + 31) / 32, cby_n = (H + 7) / 8, cbins = cbx_n * cby_n;
+  std::vector<int32_t> src((size_t)W * H);
+  const short4 empty = make_short4(32767, 32767, -32768, -32768);
+  std::vector<short4> cbox(cbins, empty), fbox((size_t)cbins * 8, empty), rbox(cby_n, empty);
+  auto grow = [](short4& b, int x, int y) {
+    b.x = (short)(x < b.x ? x : b.x); b.y = (short)(y < b.y ? y : b.y);
+    b.z = (short)(x > b.z ? x : b.z); b.w = (short)(y > b.w ? y : b.w);
+  };
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const float fx = rmapx[(size_t)y * W + x], fy = rmapy[(size_t)y * W + x];
+      const int sx = (int)rintf(fx), sy = (int)rintf(fy);   // round-half-even like the kernel's rintf
+      const bool ok = fx == fx && fy == fy && sx >= 0 && sx < W && sy >= 0 && sy < H;
+      src[(size_t)y * W + x] = ok ? (int32_t)((uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16)) : (int32_t)0x80008000u;
+      if (!ok) continue;
+      const int cb = (y / 8) * cbx_n + x / 32, f = ((y & 7) >> 2) * 4 + ((x & 31) >> 3);
+      grow(cbox[cb], sx, sy); grow(fbox[(size_t)cb * 8 + f], sx, sy); grow(rbox[y / 8], sx, sy);
+    }
+  // int32 edge functions inside a coarse bin need |A x + B y| < 2^30 over its source box: |A| <= 5*64*H, |B| <= 5*64*W
+  // (4x guard band), x <= 64*w, y <= 64*h  ->  H*w + W*h < 2^30 / (5*64*64)
+  for (int b = 0; b < cbins; b++) {
+    if (cbox[b].z < cbox[b].x) continue;
+    const long long w = cbox[b].z - cbox[b].x + 2, h = cbox[b].w - cbox[b].y + 2;
+    if ((long long)H * w + (long long)W * h >= (1LL << 30) / (5 * 64 * 64))
+      return sim->fail("fisheye LUT sends output bin %d to a %lldx%lld px source region: too wide for the rasteriser's int32 edge functions", b, w, h);
+  }
+  void* old[] = {(void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox};
+  DTS_CUDA(cudaDeviceSynchronize());
+  for (void* p : old) if (p) cudaFree(p);
+  sim->fish = FishTab{nullptr, nullptr, nullptr, nullptr};
+  int32_t* d_src = nullptr; short4 *d_c = nullptr, *d_f = nullptr, *d_r = nullptr;
+  DTS_CUDA(cudaMalloc(&d_src, src.size() * sizeof(int32_t)));
+  DTS_CUDA(cudaMalloc(&d_c, cbox.size() * sizeof(short4)));
+  DTS_CUDA(cudaMalloc(&d_f, fbox.size() * sizeof(short4)));
+  DTS_CUDA(cudaMalloc(&d_r, rbox.size() * sizeof(short4)));
+  DTS_CUDA(cudaMemcpy(d_src, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(d_c, cbox.data(), cbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(d_f, fbox.data(), fbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(d_r, rbox.data(), rbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
+  sim->fish = FishTab{d_src, d_c, d_f, d_r};
   return 0;
 }
 
@@ -459,9 +507,20 @@ static int ensure_render(dts_sim* sim) {
   sim->max_lat = max_lat;
   sim->items_max = items_max;
   const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
-  sim->bin_cap = 3 * sim->max_prims + 24 * cbins + 256;  // (prim, coarse bin) pairs per env: the ground fan (<= 8 x cbins),
-                                                          // a few screen-filling tiles and one screen-filling prop
-  const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
+  // (prim, coarse bin) pairs.  Upper bound per env: the ground fan (<= 8 x cbins), a few screen-filling tiles and one
+  // screen-filling prop; under the fused fisheye the bins are overlapping source boxes (x ~4).  The batch shares ONE
+  // pool, each env taking exactly what its frame needs: capacity = that bound x num_envs, capped at DTS_PAIR_POOL_GB
+  // (default 16) of records — a typical frame uses a small fraction of its bound.
+  const long long per_env = (3LL * sim->max_prims + 24LL * cbins + 256) * ((sim->cfg.flags & DTS_FLAG_DISTORTION) ? 4 : 1);
+  double pool_gb = 16.0;
+  if (const char* e = getenv("DTS_PAIR_POOL_GB")) pool_gb = atof(e) > 0 ? atof(e) : pool_gb;
+  long long pool = per_env * sim->cfg.num_envs;
+  const long long cap = (long long)(pool_gb * 1073741824.0 / 84.0);
+  if (pool > cap) pool = cap;
+  if (pool > 2000000000LL) pool = 2000000000LL;
+  if (pool < per_env) pool = per_env;
+  sim->bin_cap = (int)pool;
+  const size_t frame = 0;   // the fisheye gather is fused: no undistorted intermediate
   const size_t bytes = render_scratch_bytes(sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
   if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -474,7 +533,7 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
   if (check_maps(sim)) return 1;
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   if (ensure_render(sim)) return 1;
-  if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->lut_x) return sim->fail("distortion enabled but no fisheye LUT set");
+  if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->fish.src_xy) return sim->fail("distortion enabled but no fisheye LUT set");
   RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
                (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0, sim->fmt.obs_layout, sim->fmt.obs_dtype};
   if (*(volatile int32_t*)sim->h_status & 1)
@@ -487,9 +546,20 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
     marks = sim->prof_events.data() + base;
     sim->prof_frames++;
   }
-  const int k = launch_render(sim->S, sim->d_maps, rc, obs_dev, sim->render_scratch, sim->render_ctas, sim->max_prims,
-                              sim->bin_cap, sim->max_lat, sim->items_max, sim->lut_x, sim->lut_y, sim->d_err,
-                              sim->d_status, marks, (cudaStream_t)stream);
+  void* target = obs_dev;
+  if (sim->resize_w) {   // render full size, packed u8 HWC, into the library's buffer; k_resize writes the caller's tensor
+    rc.obs_layout = DTS_OBS_HWC; rc.obs_dtype = DTS_OBS_U8;
+    target = sim->resize_src;
+  }
+  int k = launch_render(sim->S, sim->d_maps, rc, target, sim->render_scratch, sim->render_ctas, sim->max_prims,
+                        sim->bin_cap, sim->max_lat, sim->items_max, sim->fish, sim->d_err,
+                        sim->d_status, marks, (cudaStream_t)stream);
+  if (sim->resize_w) {
+    launch_resize(sim->resize_src, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
+                  sim->resize_xtab, sim->resize_ytab, obs_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, (cudaStream_t)stream);
+    k++;
+  }
+  if (marks) cudaEventRecord(marks[kProfMarks - 1], (cudaStream_t)stream);   // closes the "post" interval
   sim->launches += k;
   DTS_CUDA(cudaGetLastError());
   return 0;
@@ -565,6 +635,65 @@ int dts_assign_maps(dts_sim* sim, const uint8_t* mask_dev, const int32_t* map_id
   return 0;
 }
 
+// cv2.resize INTER_CUBIC tap table of one axis (OpenCV resize(): fx = (float)((d + 0.5) * scale - 0.5), interpolateCubic
+// with A = -0.75 in float32, taps = saturate_cast<short>(w * 2048), indices clamped to the image)
+static void cubic_axis_table(int src, int dst, std::vector<int16_t>& tab) {
+  tab.assign((size_t)dst * 8, 0);
+  const double inv = (double)dst / (double)src, scale = 1.0 / inv;
+  for (int d = 0; d < dst; d++) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    const int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    const float A = -0.75f, x = fx;
+    float c[4];
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+    for (int k = 0; k < 4; k++) {
+      int idx = sx - 1 + k;
+      idx = idx < 0 ? 0 : (idx > src - 1 ? src - 1 : idx);
+      tab[(size_t)d * 8 + k] = (int16_t)idx;
+      tab[(size_t)d * 8 + 4 + k] = (int16_t)lrintf(c[k] * 2048.0f);
+    }
+  }
+}
+
+int dts_set_resize(dts_sim* sim, int out_w, int out_h) {
+  if (!sim) return 1;
+  if (out_w < 0 || out_h < 0 || (out_w == 0) != (out_h == 0)) return sim->fail("bad resize target %dx%d", out_w, out_h);
+  if (out_w > 4096 || out_h > 4096) return sim->fail("resize target %dx%d too large", out_w, out_h);
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  DTS_CUDA(cudaDeviceSynchronize());
+  void* old[] = {sim->resize_src, sim->resize_xtab, sim->resize_ytab};
+  for (void* p : old) if (p) cudaFree(p);
+  sim->resize_src = nullptr; sim->resize_xtab = sim->resize_ytab = nullptr;
+  sim->resize_w = sim->resize_h = 0;
+  if (!out_w) return 0;
+  std::vector<int16_t> xt, yt;
+  cubic_axis_table(sim->cfg.cam_width, out_w, xt);
+  cubic_axis_table(sim->cfg.cam_height, out_h, yt);
+  DTS_CUDA(cudaMalloc(&sim->resize_src, (size_t)sim->cfg.num_envs * sim->cfg.cam_width * sim->cfg.cam_height * 3));
+  DTS_CUDA(cudaMalloc(&sim->resize_xtab, xt.size() * 2));
+  DTS_CUDA(cudaMalloc(&sim->resize_ytab, yt.size() * 2));
+  DTS_CUDA(cudaMemcpy(sim->resize_xtab, xt.data(), xt.size() * 2, cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(sim->resize_ytab, yt.data(), yt.size() * 2, cudaMemcpyHostToDevice));
+  sim->resize_w = out_w; sim->resize_h = out_h;
+  return 0;
+}
+
+int dts_resize_frames(dts_sim* sim, const uint8_t* src_dev, void* dst_dev, void* stream) {
+  if (!sim) return 1;
+  if (!sim->resize_w) return sim->fail("dts_set_resize first");
+  if (!src_dev || !dst_dev) return sim->fail("NULL frame pointer");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  launch_resize(src_dev, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
+                sim->resize_xtab, sim->resize_ytab, dst_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, (cudaStream_t)stream);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int dts_status(dts_sim* sim) { return (sim && sim->h_status) ? *(volatile int32_t*)sim->h_status : 0; }
 
 int dts_profile_enable(dts_sim* sim, int on) {
@@ -635,7 +764,7 @@ int dts_debug_frame(dts_sim* sim, int env, double V[12], float P[4], int32_t cou
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   DTS_CUDA(cudaDeviceSynchronize());
   const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
-  const size_t frame = (sim->cfg.flags & DTS_FLAG_DISTORTION) ? (size_t)sim->cfg.cam_width * sim->cfg.cam_height * 3 : 0;
+  const size_t frame = 0;
   if (debug_frame_copy(sim->render_scratch, sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame, env, V, P,
                        counts, lattice_by_cell, n_cells, 2))
     return sim->fail("debug_frame_copy failed");

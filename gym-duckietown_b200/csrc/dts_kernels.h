@@ -33,6 +33,16 @@ void launch_assign_maps(const DState& S, const DMap* maps, const uint8_t* mask, 
 void launch_query(const DMap* maps, int map_id, int dyn_env, int n_envs, int n, const double* q, const uint32_t* hidden,
                   double* outd, int32_t* outi, cudaStream_t st);
 
+// Fused fisheye gather (distortion.py:118, obs[y, x] = undistorted[rint(rmapy), rint(rmapx)]): the rasteriser renders
+// each OUTPUT pixel at the source position the LUT names, so no undistorted frame is ever written.  Prims are binned
+// against the source-pixel bounding boxes of the output bins.  All device pointers, built by dts_set_fisheye_lut.
+struct FishTab {
+  const int32_t* src_xy;   // [H][W]  sx | sy << 16 (int16 each); sx = -32768: source outside the image -> 0
+  const short4* cbox;      // [cbins]    source bounding box (x0, y0, x1, y1) of a 32x8 coarse output bin; x1 < x0: empty
+  const short4* fbox;      // [cbins][8] the same for each of its 8x4 fine bins
+  const short4* rbox;      // [cbins_y]  and for each row of coarse bins
+};
+
 // render (dts_render.cu)
 int render_ctas_per_sm();
 // scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
@@ -42,9 +52,12 @@ size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int 
 // k_bin, k_raster and the post passes (dts_profile_*).  `status_dev`: device address of the mapped host status word.
 constexpr int kProfMarks = 6;
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish,
                   int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st);
 
+// ResizeWrapper on the device: src u8[N][H][W][3] -> dst [N] x (ow x oh) in `layout` / `dtype` (dts_set_resize)
+void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
+                   void* dst, int layout, int dtype, cudaStream_t st);
 int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame,
                      int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile);
 

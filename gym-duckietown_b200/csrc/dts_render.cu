@@ -399,28 +399,33 @@ __device__ __forceinline__ void process_triangle_lanes(const EmitCtx& ec, bool h
   }
 }
 
-// conservative prim / bin overlap: false only if one edge has the whole bin on its outside
-__device__ __forceinline__ bool bin_overlaps(const int qx[4], const int qy[4], int n, int ox, int oy) {
+// conservative prim / box overlap: false only if one edge has every sample position of the box
+// [x_lo, x_hi] x [y_lo, y_hi] (sub-pixels) on its outside
+__device__ __forceinline__ bool box_overlaps(const int qx[4], const int qy[4], int n, int x_lo, int x_hi, int y_lo, int y_hi) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     if (k >= n) break;
     const int k1 = (k + 1) & 3;   // a triangle's vertex 3 aliases vertex 0
     const int dx = qx[k1] - qx[k], dy = qy[k1] - qy[k];
-    // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the coarse bin's sample span
-    const int xs = (-dy > 0) ? ox + (kCoarseW - 1) * kSub + 56 : ox + 8;
-    const int ys = (dx > 0) ? oy + (kCoarseH - 1) * kSub + 56 : oy + 8;
+    // E(x,y) = dx*(y-ay) - dy*(x-ax); maximise over the box
+    const int xs = (-dy > 0) ? x_hi : x_lo;
+    const int ys = (dx > 0) ? y_hi : y_lo;
     const long long e = (long long)dx * (ys - qy[k]) - (long long)dy * (xs - qx[k]);
     if (e < 0) return false;
   }
   return true;
 }
-
-
+__device__ __forceinline__ bool bin_overlaps(const int qx[4], const int qy[4], int n, int ox, int oy) {
+  return box_overlaps(qx, qy, n, ox + 8, ox + (kCoarseW - 1) * kSub + 56, oy + 8, oy + (kCoarseH - 1) * kSub + 56);
+}
 
 // The visibility record of prim `p` for the coarse bin whose corner is (ox, oy) sub-pixels: edge functions re-based
 // to the corner (exact in 64 bits, then int32: inside the coarse bin |A*x + B*y| < 2^30), exact reject /
 // trivial-accept bits for each of the bin's 8 fine bins, depth plane, draw id.
-__device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int p, int ox, int oy, BinRec* __restrict__ out) {
+// With `fb` (fused fisheye) the bin's pixels are wherever the LUT sends its output pixels: (ox, oy) is the corner of
+// their source bounding box and fb[f] the source box of fine bin f; the bits then speak about every pixel of that box.
+__device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int p, int ox, int oy, BinRec* __restrict__ out,
+                                             const short4* __restrict__ fb = nullptr) {
   const int4 w0 = __ldg(reinterpret_cast<const int4*>(pr));
   const int4 w1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
   const float4 w2 = __ldg(reinterpret_cast<const float4*>(pr) + 2);
@@ -441,14 +446,27 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
     if (e0 < -(1LL << 30)) e0 = -(1LL << 30);
     const int a = -dy, b = dx, e = (int)e0;
     E0[k] = e; A[k] = a; B[k] = b;
-    // extremes of A*x + B*y over one fine bin's sample span x in [8, 504], y in [8, 248]
-    const int hi = (a > 0 ? a * 504 : a * 8) + (b > 0 ? b * 248 : b * 8);
-    const int lo = (a > 0 ? a * 8 : a * 504) + (b > 0 ? b * 8 : b * 248);
+    if (fb) {
+#pragma unroll 1
+      for (int f = 0; f < 8; f++) {
+        const short4 q = fb[f];
+        if (q.z < q.x) { live &= ~(1u << f); continue; }   // no pixel of this fine bin has a source inside the image
+        const int X0 = q.x * kSub - ox + 8, X1 = q.z * kSub - ox + 56, Y0 = q.y * kSub - oy + 8, Y1 = q.w * kSub - oy + 56;
+        const int hi = (a > 0 ? a * X1 : a * X0) + (b > 0 ? b * Y1 : b * Y0);
+        const int lo = (a > 0 ? a * X0 : a * X1) + (b > 0 ? b * Y0 : b * Y1);
+        if (e + hi < 0) live &= ~(1u << f);
+        if (e + lo < 0) inside &= ~(1u << f);
+      }
+    } else {
+      // extremes of A*x + B*y over one fine bin's sample span x in [8, 504], y in [8, 248]
+      const int hi = (a > 0 ? a * 504 : a * 8) + (b > 0 ? b * 248 : b * 8);
+      const int lo = (a > 0 ? a * 8 : a * 504) + (b > 0 ? b * 8 : b * 248);
 #pragma unroll
-    for (int f = 0; f < 8; f++) {
-      const int ef = e + a * ((f & 3) * kBinW * kSub) + b * ((f >> 2) * kBinH * kSub);
-      if (ef + hi < 0) live &= ~(1u << f);
-      if (ef + lo < 0) inside &= ~(1u << f);
+      for (int f = 0; f < 8; f++) {
+        const int ef = e + a * ((f & 3) * kBinW * kSub) + b * ((f >> 2) * kBinH * kSub);
+        if (ef + hi < 0) live &= ~(1u << f);
+        if (ef + lo < 0) inside &= ~(1u << f);
+      }
     }
   }
   const int id = __float_as_int(w2.w);
@@ -609,10 +627,10 @@ int render_ctas_per_sm() { return DTS_RENDER_MIN_CTAS; }
 struct FrameMem {
   FrameCtx* ctx;        // [N]
   PrimRec* prims;       // [N][max_prims]
-  uint32_t* pairs;      // [N][max_pairs]  prim | coarse bin << 16, grouped by coarse bin (k_bin pass 1)
-  BinRec* recs;         // [N][max_pairs]  the pairs' visibility records, same order (k_bin pass 2)
+  uint32_t* pairs;      // [pool]  prim | coarse bin << 16, grouped by env and coarse bin (k_bin pass 1).  One pool for the
+  BinRec* recs;         // [pool]  batch: an env takes exactly the entries it needs (atomic cursor work[1]), densely packed
   int* bin_count;       // [N][cbins]
-  int* bin_start;       // [N][cbins]  offset of the bin's run inside the env's pairs / recs
+  int* bin_start;       // [N][cbins]  pool index of the bin's first pair / record
   float4* lat;          // [N][max_lat][64]
   uint8_t* undist;      // [N][H][W][3] (distortion only)
   int* work;            // [4] global work counters
@@ -629,8 +647,8 @@ __host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_
   f.bin_count = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
   f.bin_start = reinterpret_cast<int*>(p); p += align256((size_t)n * cbins * sizeof(int));
   f.prims = reinterpret_cast<PrimRec*>(p); p += align256((size_t)n * max_prims * sizeof(PrimRec));
-  f.pairs = reinterpret_cast<uint32_t*>(p); p += align256((size_t)n * max_pairs * sizeof(uint32_t));
-  f.recs = reinterpret_cast<BinRec*>(p); p += align256((size_t)n * max_pairs * sizeof(BinRec));
+  f.pairs = reinterpret_cast<uint32_t*>(p); p += align256((size_t)max_pairs * sizeof(uint32_t));   // max_pairs = pool entries
+  f.recs = reinterpret_cast<BinRec*>(p); p += align256((size_t)max_pairs * sizeof(BinRec));
   f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
   f.undist = undist_frame ? p : nullptr;
   f.status = nullptr;
@@ -639,8 +657,8 @@ __host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_
 
 size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
   return 256 + align256((size_t)n * sizeof(FrameCtx)) + 2 * align256((size_t)n * cbins * sizeof(int)) +
-         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)n * max_pairs * sizeof(uint32_t)) +
-         align256((size_t)n * max_pairs * sizeof(BinRec)) +
+         align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)max_pairs * sizeof(uint32_t)) +
+         align256((size_t)max_pairs * sizeof(BinRec)) +
          align256((size_t)n * max_lat * 64 * sizeof(float4)) + (size_t)n * undist_frame + 256;
 }
 
@@ -883,8 +901,9 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
 // a small bounding box are binned by it, larger ones test each bin of the box against their edges.  Pass 2, dense
 // over the pairs (one per lane, so a screen-filling prim costs no more lanes than a sliver): the pair's BinRec.
 constexpr int kBinWarps = 4;
+template <bool kFish>   // true: bins are the LUT's source boxes of the output bins (fused fisheye gather)
 __global__ void __launch_bounds__(kBinWarps * 32)
-k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restrict__ err) {
+k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32_t* __restrict__ err) {
   extern __shared__ int bin_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * kBinWarps + wib;
@@ -894,9 +913,9 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
   int* cnt = bin_smem + wib * 2 * cbins;
   int* start = cnt + cbins;
   const PrimRec* prims = fm.prims + (size_t)env * max_prims;
-  uint32_t* pairs = fm.pairs + (size_t)env * max_pairs;
+  uint32_t* pairs = fm.pairs;
   const int n = min(fm.ctx[env].n_prims, max_prims);
-  int total = 0;
+  int total = 0, pair0 = 0;
   for (int pass = 0; pass < 2; pass++) {
     for (int b = lane; b < cbins; b += 32) cnt[b] = 0;
     __syncwarp();
@@ -907,6 +926,24 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
       const int nv = ((__ldg(&prims[p].ltq) >> 24) & 1) ? 4 : 3;   // vertex 3 of a triangle repeats vertex 0
       const int minx = min(min(qx[0], qx[1]), min(qx[2], qx[3])), maxx = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
       const int miny = min(min(qy[0], qy[1]), min(qy[2], qy[3])), maxy = max(max(qy[0], qy[1]), max(qy[2], qy[3]));
+      if (kFish) {
+        // the output bins whose SOURCE box meets the prim: rows first, then the row's bins (the LUT is smooth, not
+        // monotone — no range arithmetic); the exact edge test weeds out the box-only overlaps of big prims
+        const int pminx = max(minx >> 6, 0), pmaxx = min(maxx >> 6, W - 1), pminy = max(miny >> 6, 0), pmaxy = min(maxy >> 6, H - 1);
+        const bool large = (pmaxx - pminx) > 2 * kCoarseW || (pmaxy - pminy) > 2 * kCoarseH;
+        for (int by = 0; by < cbins_y; by++) {
+          const short4 rb = ft.rbox[by];
+          if (rb.z < rb.x || pmaxy < rb.y || pminy > rb.w || pmaxx < rb.x || pminx > rb.z) continue;
+          for (int bx = 0; bx < cbins_x; bx++) {
+            const int b = by * cbins_x + bx;
+            const short4 cb = ft.cbox[b];
+            if (cb.z < cb.x || pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
+            if (large && !box_overlaps(qx, qy, nv, cb.x * kSub + 8, cb.z * kSub + 56, cb.y * kSub + 8, cb.w * kSub + 56)) continue;
+            const int pos = atomicAdd(&cnt[b], 1);
+            if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+          }
+        }
+      } else {
       const int bx0 = max(minx >> 6, 0) / kCoarseW, by0 = max(miny >> 6, 0) / kCoarseH;
       const int bx1 = min(maxx >> 6, W - 1) / kCoarseW, by1 = min(maxy >> 6, H - 1) / kCoarseH;
       const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
@@ -917,6 +954,7 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
           const int pos = atomicAdd(&cnt[b], 1);
           if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
         }
+      }
     }
     __syncwarp();
     if (pass == 0) {
@@ -931,11 +969,16 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
         carry += __shfl_sync(0xffffffffu, inc, 31);
       }
       total = carry;
-      const bool ok = total <= max_pairs;
+      unsigned base = 0;   // this env's run of the batch-wide pair pool
+      if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned*>(fm.work) + 1, (unsigned)total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const bool ok = (unsigned long long)base + (unsigned)total <= (unsigned long long)max_pairs;
       for (int b = lane; b < cbins; b += 32) {
+        start[b] += (int)base;
         fm.bin_count[(size_t)env * cbins + b] = ok ? cnt[b] : 0;   // lists that do not fit: the frame stays clear
         fm.bin_start[(size_t)env * cbins + b] = start[b];
       }
+      pair0 = (int)base;
       __syncwarp();
       if (!ok) {
         if (lane == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
@@ -945,30 +988,34 @@ k_bin(RenderCfg rc, FrameMem fm, int max_prims, int max_pairs, int32_t* __restri
   }
   // pass 2: one pair per lane -> its visibility record (the pairs were written by other lanes of this warp:
   // __syncwarp above orders those writes before these reads)
-  BinRec* recs = fm.recs + (size_t)env * max_pairs;
-  for (int i = lane; i < total; i += 32) {
+  BinRec* recs = fm.recs;
+  for (int i = pair0 + lane; i < pair0 + total; i += 32) {
     const uint32_t pair = pairs[i];
     const int p = (int)(pair & 0xffffu), b = (int)(pair >> 16);
-    const int cby = b / cbins_x, cbx = b - cby * cbins_x;
-    build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
+    if (kFish) {
+      const short4 cb = ft.cbox[b];
+      build_binrec(prims + p, p, cb.x * kSub, cb.y * kSub, recs + i, ft.fbox + (size_t)b * 8);
+    } else {
+      const int cby = b / cbins_x, cbx = b - cby * cbins_x;
+      build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
-template <bool kWrapFmt>   // true: a dts_output_format other than packed u8 HWC is written by the resolve
+template <bool kWrapFmt, bool kFish>   // kWrapFmt: a dts_output_format other than packed u8 HWC is written by the resolve;
+                                       // kFish: every lane renders the SOURCE pixel the fisheye LUT names for its output pixel
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
-k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, uint8_t* __restrict__ obs,
+k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, FishTab ft, uint8_t* __restrict__ obs,
          int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
   __shared__ __align__(128) BinRec stages[kWarps][2][kStage];   // per warp: two chunks of records in flight
   __shared__ __align__(8) uint64_t bars[kWarps][2];
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
   const size_t frame_bytes = (size_t)W * H * 3;
-  // wrapper output format (0 = packed u8 HWC); with the fisheye gather the raster writes the u8 HWC intermediate
-  const int out_fmt = (!kWrapFmt || fisheye) ? 0 : (rc.obs_layout | (rc.obs_dtype << 2));
-  const size_t out_elem = (kWrapFmt && !fisheye && rc.obs_dtype == DTS_OBS_F32_UNIT) ? 4 : 1;
+  const int out_fmt = !kWrapFmt ? 0 : (rc.obs_layout | (rc.obs_dtype << 2));   // wrapper output format (0 = packed u8 HWC)
+  const size_t out_elem = (kWrapFmt && rc.obs_dtype == DTS_OBS_F32_UNIT) ? 4 : 1;
   const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
   uint64_t* bar = bars[warp];
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
@@ -986,9 +1033,9 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     const DMap& m = maps[S.map_id[env]];
     const DTexture* textures = m.textures;
     const PrimRec* prims = fm.prims + (size_t)env * max_prims;
-    const BinRec* recs = fm.recs + (size_t)env * max_pairs;
+    const BinRec* recs = fm.recs;   // bin_start holds pool indices
     const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
-    uint8_t* out = fisheye ? fm.undist + (size_t)env * frame_bytes : obs + (size_t)env * frame_bytes * out_elem;
+    uint8_t* out = obs + (size_t)env * frame_bytes * out_elem;
     const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
     // lane l holds the list of coarse bin (cby, l)
@@ -1036,11 +1083,19 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       if (count == 0) {
 #pragma unroll 1
         for (int f = 0; f < kCFX * kCFY; f++)
-          if (fine_valid(cbx, f)) store_bin_any(out, out_fmt, clear_rgb, lane, cbx * kCFX + (f & 3), cby * kCFY + (f >> 2), W, H);
+          if (fine_valid(cbx, f)) {
+            unsigned rgb = clear_rgb;
+            if (kFish) {
+              const int gx = min((cbx * kCFX + (f & 3)) * kBinW + (lane & 7), W - 1), gy = min((cby * kCFY + (f >> 2)) * kBinH + (lane >> 3), H - 1);
+              if ((short)(__ldg(ft.src_xy + gy * W + gx) & 0xffff) == -32768) rgb = 0u;
+            }
+            store_bin_any(out, out_fmt, rgb, lane, cbx * kCFX + (f & 3), cby * kCFY + (f >> 2), W, H);
+          }
         continue;
       }
       const bool single = count <= kStage;
-      const int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
+      int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
+      if (kFish) { const short4 cb = ft.cbox[cby * cbins_x + cbx]; ox = cb.x * kSub; oy = cb.y * kSub; }   // ... of its source box
 #pragma unroll 1
       for (int g = 0; g < (single ? 1 : kCFX * kCFY); g++) {
         if (!single && !fine_valid(cbx, g)) continue;
@@ -1063,7 +1118,15 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           for (int f = (single ? 0 : g); f < (single ? kCFX * kCFY : g + 1); f++) {
             if (!fine_valid(cbx, f)) continue;
             const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
-            const int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
+            int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
+            bool px_valid = true;
+            if (kFish) {   // the source pixel of this lane's output pixel (lanes past the image edge read a clamped entry)
+              const int gx = min(bx * kBinW + (lane & 7), W - 1), gy = min(by * kBinH + (lane >> 3), H - 1);
+              const int sxy = __ldg(ft.src_xy + gy * W + gx);
+              const int sx = (int)(short)(sxy & 0xffff), sy = sxy >> 16;
+              px_valid = sx != -32768;
+              pxc = sx * kSub - ox; pyc = sy * kSub - oy;
+            }
             const bool live = (mine.x >> (16 + f)) & 1u;
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
             const unsigned ground_mask = __ballot_sync(0xffffffffu, live && (mine.y & 2u));
@@ -1189,6 +1252,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               }
             }
             if (!all_same) rgb = pack_rgb((s01[0] + s23[0]) * 0.25f, (s01[1] + s23[1]) * 0.25f, (s01[2] + s23[2]) * 0.25f);
+            if (kFish && !px_valid) rgb = 0u;   // cv2.remap BORDER_CONSTANT
             store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
           }
         }
@@ -1198,30 +1262,56 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   }
 }
 
-// ------------------------------------------------------------------------------------------------ k_fisheye
-__global__ void __launch_bounds__(256) k_fisheye(RenderCfg rc, const uint8_t* __restrict__ undist,
-                                                 const float* __restrict__ lut_x, const float* __restrict__ lut_y,
-                                                 uint8_t* __restrict__ obs) {
-  const int W = rc.width, H = rc.height;
-  const size_t npx = (size_t)W * H, total = npx * rc.n_envs;
-  const int fmt = rc.obs_layout | (rc.obs_dtype << 2);
+// ------------------------------------------------------------------------------------------------ k_resize
+// ResizeWrapper (wrappers.py:111-141): cv2.resize(..., interpolation=cv2.INTER_CUBIC) of the rendered frame, on the
+// device, so that a training stack's 84x84 payload (21 KB per env instead of 57.6 KB) is what crosses PCIe.  OpenCV's
+// 8-bit bicubic is fixed point: per output column / row four int16 taps = cvRound(2048 * w_k(frac)), w = the a = -0.75
+// cubic kernel evaluated in float32 at frac = (d + 0.5) * scale - 0.5 - floor(.), source indices clamped to the
+// image; horizontal pass in int32, then (sum_k beta_k * row_k + 2^21) >> 22, saturated.  The tap tables are built on
+// the host (dts_set_resize).  One thread per output pixel (3 channels); reads the full-size u8 HWC render.
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int W, int H, int ow, int oh, int n_envs,
+                                                const int16_t* __restrict__ xtab /*[ow][8]: 4 indices, 4 taps*/,
+                                                const int16_t* __restrict__ ytab /*[oh][8]*/, void* __restrict__ dst, int layout,
+                                                int dtype) {
+  const size_t total = (size_t)n_envs * ow * oh;
   for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-    const size_t env = g / npx, p = g - env * npx;
-    const int sx = (int)rintf(__ldg(lut_x + p)), sy = (int)rintf(__ldg(lut_y + p));
-    uint8_t r = 0, gg = 0, b = 0;
-    if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
-      const uint8_t* s = undist + (env * npx + (size_t)sy * W + sx) * 3;
-      r = s[0]; gg = s[1]; b = s[2];
+    const int x = (int)(g % ow), y = (int)((g / ow) % oh);
+    const size_t env = g / ((size_t)ow * oh);
+    const int4 xa = __ldg(reinterpret_cast<const int4*>(xtab + 8 * x)), ya = __ldg(reinterpret_cast<const int4*>(ytab + 8 * y));
+    const int xi[4] = {(short)(xa.x & 0xffff), xa.x >> 16, (short)(xa.y & 0xffff), xa.y >> 16};
+    const int xw[4] = {(short)(xa.z & 0xffff), xa.z >> 16, (short)(xa.w & 0xffff), xa.w >> 16};
+    const int yi[4] = {(short)(ya.x & 0xffff), ya.x >> 16, (short)(ya.y & 0xffff), ya.y >> 16};
+    const int yw[4] = {(short)(ya.z & 0xffff), ya.z >> 16, (short)(ya.w & 0xffff), ya.w >> 16};
+    const uint8_t* frame = src + env * (size_t)W * H * 3;
+    long long acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint8_t* row = frame + (size_t)yi[r] * W * 3;
+      int h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const uint8_t* px = row + xi[c] * 3;
+        h0 += (int)px[0] * xw[c]; h1 += (int)px[1] * xw[c]; h2 += (int)px[2] * xw[c];
+      }
+      acc[0] += (long long)h0 * yw[r]; acc[1] += (long long)h1 * yw[r]; acc[2] += (long long)h2 * yw[r];
     }
-    if (fmt == 0) {
-      uint8_t* d = obs + g * 3;
-      d[0] = r; d[1] = gg; d[2] = b;
-    } else {
-      const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-      store_px_fmt(obs + env * npx * 3 * (rc.obs_dtype == DTS_OBS_F32_UNIT ? 4 : 1), rc.obs_layout, rc.obs_dtype, x, y, W, H,
-                   (unsigned)r | ((unsigned)gg << 8) | ((unsigned)b << 16));
+    unsigned rgb = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      long long v = (acc[ch] + (1LL << 21)) >> 22;
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      rgb |= (unsigned)v << (8 * ch);
     }
+    void* out = reinterpret_cast<uint8_t*>(dst) + env * (size_t)ow * oh * 3 * (dtype == DTS_OBS_F32_UNIT ? 4 : 1);
+    store_px_fmt(out, layout, dtype, x, y, ow, oh, rgb);
   }
+}
+
+void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
+                   void* dst, int layout, int dtype, cudaStream_t st) {
+  const size_t total = (size_t)n_envs * ow * oh;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_resize<<<blocks, 256, 0, st>>>(src, W, H, ow, oh, n_envs, xtab, ytab, dst, layout, dtype);
 }
 
 // Test hook (dts_debug_frame): what k_frame_setup / k_geometry left in frame memory for one env of the last render —
@@ -1259,13 +1349,13 @@ int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pai
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs_any, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, int max_lat, int items_max, const float* lut_x, const float* lut_y,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish,
                   int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st) {
   const int W = rc.width, H = rc.height;
   uint8_t* obs = reinterpret_cast<uint8_t*>(obs_any);
   const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
-  FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, fisheye ? (size_t)W * H * 3 : 0);
+  FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, 0);
   fm.status = status_dev;
   int mk = 0;
   auto mark = [&]() { if (marks) cudaEventRecord(marks[mk++], st); };
@@ -1278,23 +1368,27 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   else k_geometry<false><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
   mark();
   const size_t bin_smem_bytes = (size_t)kBinWarps * 2 * cbins * sizeof(int);
-  if (bin_smem_bytes > 48 * 1024)   // cameras beyond ~640x480 (cbins > 1536): opt in to large dynamic shared memory
-    cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
-  k_bin<<<(rc.n_envs + kBinWarps - 1) / kBinWarps, kBinWarps * 32, bin_smem_bytes, st>>>(
-      rc, fm, max_prims, max_pairs, err_flag);
-  mark();
-  if (!fisheye && (rc.obs_layout | rc.obs_dtype) != 0)
-    k_raster<true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
-  else
-    k_raster<false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_pairs, max_lat, err_flag);
-  mark();
-  int launches = 4;
+  const int bin_grid = (rc.n_envs + kBinWarps - 1) / kBinWarps;
   if (fisheye) {
-    k_fisheye<<<148 * 8, 256, 0, st>>>(rc, fm.undist, lut_x, lut_y, obs);
-    launches++;
+    if (bin_smem_bytes > 48 * 1024) cudaFuncSetAttribute(k_bin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
+    k_bin<true><<<bin_grid, kBinWarps * 32, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
+  } else {
+    if (bin_smem_bytes > 48 * 1024)   // cameras beyond ~640x480 (cbins > 1536): opt in to large dynamic shared memory
+      cudaFuncSetAttribute(k_bin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
+    k_bin<false><<<bin_grid, kBinWarps * 32, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
   }
   mark();
-  return launches;
+  const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;
+  if (fisheye) {
+    if (wrap) k_raster<true, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+  } else {
+    if (wrap) k_raster<true, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+  }
+  mark();
+  mark();   // (post passes: none yet)
+  return 4;
 }
 
 }  // namespace dts

@@ -166,6 +166,8 @@ def load() -> C.CDLL:
     lib.dts_get_state.argtypes = [vp, C.POINTER(StateView)]
     lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp]
     lib.dts_assign_maps.argtypes = [vp, vp, vp, vp]
+    lib.dts_set_resize.argtypes = [vp, i, i]
+    lib.dts_resize_frames.argtypes = [vp, vp, vp, vp]
     lib.dts_status.argtypes = [vp]
     lib.dts_profile_enable.argtypes = [vp, i]
     lib.dts_profile_read.argtypes = [vp, vp, vp]
@@ -189,7 +191,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_debug_frame", "dts_last_error", "dts_destroy"]
 
 
@@ -372,6 +374,12 @@ class Sim:
         if ids.shape != (self.cfg.num_envs,):
             raise ValueError("map_ids must have one entry per env")
         self._check(self.lib.dts_assign_maps(self.h, mask_ptr, _ptr(ids), stream), "dts_assign_maps")
+
+    def set_resize(self, out_w: int, out_h: int):
+        self._check(self.lib.dts_set_resize(self.h, int(out_w), int(out_h)), "dts_set_resize")
+
+    def resize_frames(self, src_ptr: int, dst_ptr: int, stream: int = 0):
+        self._check(self.lib.dts_resize_frames(self.h, src_ptr, dst_ptr, stream), "dts_resize_frames")
 
     def status(self) -> int:
         """Sticky status bits, read without synchronising (bit 0: a frame overflowed its render frame memory)."""

@@ -11,8 +11,8 @@ same constructor arguments, same resulting observation_space as the reference cl
     env = DtRewardWrapper(ActionWrapper(ImgWrapper(NormalizeWrapper(env))))      # LW training stack
     obs, reward, done, info = env.step(actions)      # obs f32[N,3,H,W] in [0,1], written once by the GPU
 
-`ResizeWrapper` is not fused: render at the target size instead (`camera_width=84, camera_height=84` costs less
-than rendering large and filtering down); it raises with that hint.
+`ResizeWrapper` runs cv2.INTER_CUBIC's 8-bit arithmetic in a device pass right after the render
+(`dts_set_resize`), so the resized batch — not the full frames — is what a host-facing pipeline copies out.
 """
 from __future__ import annotations
 
@@ -40,7 +40,7 @@ class _FusedWrapper:
     def observation_space(self):
         b = self.unwrapped
         f = b.output_format
-        H, W = b.camera_height, b.camera_width
+        H, W = b.obs_size
         shape = {"hwc": (H, W, 3), "chw": (3, H, W), "cwh": (3, W, H)}[f["obs_layout"]]
         if f["obs_dtype"] == "float32":
             return spaces.Box(0.0, 1.0, shape, dtype=np.float32)
@@ -122,5 +122,12 @@ class SteeringToWheelVelWrapper(_FusedWrapper):
 
 
 class ResizeWrapper(_FusedWrapper):
-    def __init__(self, env=None, *a, **kw):
-        raise NotImplementedError("render at the target size instead: BatchedDuckietownEnv(camera_width=w, camera_height=h)")
+    """W:111-141 — `cv2.resize(obs.swapaxes(0, 2), dsize=(resize_w, resize_h), interpolation=cv2.INTER_CUBIC).swapaxes(0, 2)`
+    on reset and step.  The reference applies it on top of PyTorchObsWrapper ([C, W, H] observations, hence the
+    swapaxes); here it is a switch of the device path like the others: the env then emits resize_h x resize_w frames in
+    whatever layout / dtype the rest of the stack selected."""
+
+    def __init__(self, env=None, resize_w=80, resize_h=80):
+        super().__init__(env)
+        self.resize_w, self.resize_h = resize_w, resize_h
+        self.unwrapped.set_resize(resize_w, resize_h)

@@ -228,7 +228,11 @@ typedef struct {
 int dts_create(const dts_config* cfg, dts_sim** out);
 /* Simulator._load_map/_interpret_map/_load_objects (simulator.py:765-931) : device copy of one map. */
 int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* blob);
-/* Distortion.rmapx/rmapy (distortion.py:85-125): LUT of the fused fisheye gather, [H][W] each. */
+/* Distortion.rmapx/rmapy (distortion.py:85-125): LUT of the fused fisheye gather, [H][W] each (HOST pointers).  The
+ * rasteriser renders every output pixel AT the source position rint(rmap) names — obs[y,x] = undistorted[rint(rmapy),
+ * rint(rmapx)], 0 when that falls outside (distortion.py:118, cv2.remap INTER_NEAREST / BORDER_CONSTANT) — so no
+ * undistorted frame is materialised and no second pass runs.  Fails if the LUT scatters one 32x8 output bin over a
+ * source region too wide for the rasteriser's int32 edge functions. */
 int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, int width, int height);
 /* Simulator.reset() (simulator.py:528-763) with host-drawn episode parameters.
  * mask_dev: device u8[num_envs] (NULL = all). */
@@ -249,6 +253,13 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream);
 /* Select the fused wrapper behaviour for subsequent dts_step / dts_render calls (default: all zero, scale 1).
  * obs_dev then holds num_envs * 3 * H * W elements of uint8 or float32 in the chosen layout. */
 int dts_set_output_format(dts_sim* sim, const dts_output_format* fmt);
+/* ResizeWrapper (wrappers.py:111-141: cv2.resize(obs, (resize_w, resize_h), interpolation=cv2.INTER_CUBIC)) on the device:
+ * subsequent dts_step / dts_render calls render at the camera size into a library buffer and write obs_dev as
+ * num_envs x 3 x out_h x out_w elements in the selected layout / dtype (OpenCV's 8-bit fixed-point bicubic; matches cv2
+ * within 1 LSB).  out_w = out_h = 0 switches it off. */
+int dts_set_resize(dts_sim* sim, int out_w, int out_h);
+/* The resize pass alone, on caller-supplied frames: src u8[num_envs][cam_h][cam_w][3] -> dst in the selected layout / dtype. */
+int dts_resize_frames(dts_sim* sim, const uint8_t* src_dev, void* dst_dev, void* stream);
 int dts_get_state(dts_sim* sim, dts_state_view* out);
 /* Batched pose predicates for host callers — the de-facto public helpers of Simulator:
  * _valid_pose (S:1494), _collision(get_agent_corners()) (S:1473, run_tests.py:50), get_lane_pos2 (S:1371),

@@ -342,6 +342,74 @@ def gen_trafficlight(name="loop_trafficlights", steps=1300, seed=5):
     np.savez_compressed(os.path.join(OUT, f"trafficlight_{name}.npz"), **out)
 
 
+def gen_wrappers(seed=21):
+    """The reference's own wrapper classes (src/gym_duckietown/wrappers.py, learning/utils/wrappers.py) executed on
+    canned frames / rewards / actions -> tests/golden/wrappers.npz.  A stand-in env hands them the frames: what is
+    recorded is exactly what their observation() / reward() / action() / step() code returns."""
+    refstub.install()
+    sys.path.insert(0, "/root/reference")
+    import importlib
+    W = importlib.import_module("gym_duckietown.wrappers")
+    LW = importlib.import_module("learning.utils.wrappers")
+    spaces = sys.modules["gym.spaces"]
+    rng = np.random.default_rng(seed)
+    out = {}
+    for tag, (h, w_) in {"160x120": (120, 160), "640x480": (480, 640)}.items():
+        frames = rng.integers(0, 256, (3, h, w_, 3), dtype=np.uint8)
+        # smooth content too (renders are smooth; noise is the hard case for a fixed-point filter)
+        yy, xx = np.mgrid[0:h, 0:w_]
+        frames[2] = np.stack([(xx * 255 // w_), (yy * 255 // h), ((xx + yy) * 255 // (h + w_))], -1).astype(np.uint8)
+
+        class Env:   # what DuckietownEnv looks like to a wrapper
+            metadata, reward_range = {}, (-1000, 1000)
+            action_space = spaces.Box(low=-1, high=1, shape=(2,), dtype=np.float32)
+            observation_space = spaces.Box(low=np.zeros((h, w_, 3), np.uint8), high=np.full((h, w_, 3), 255, np.uint8),
+                                           shape=(h, w_, 3), dtype=np.uint8)
+            k = 0
+            actions = []
+
+            @property
+            def unwrapped(self):
+                return self
+
+            def reset(self):
+                return frames[0]
+
+            def step(self, a):
+                Env.actions.append(np.array(a, dtype=float))
+                Env.k += 1
+                return frames[Env.k % 3], -1000.0 if Env.k % 3 == 0 else float(Env.k) - 2.5, False, {}
+
+        # the test regenerates the frames from the seed (default_rng(seed), same draw order) and checks this digest
+        out[f"frames_sha_{tag}"] = hashlib.sha256(frames.tobytes()).hexdigest()
+        digest = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        pt = W.PyTorchObsWrapper(Env())
+        out[f"pytorch_sha_{tag}"] = digest(np.stack([pt.observation(f) for f in frames]))
+        assert tuple(pt.observation_space.shape) == (3, w_, h)
+        for rw, rh in ((80, 80), (84, 84), (64, 48)):
+            rz = W.ResizeWrapper(W.PyTorchObsWrapper(Env()), resize_w=rw, resize_h=rh)
+            got = [rz.reset()] + [rz.step([0.0, 0.0])[0] for _ in range(2)]
+            Env.k = 0
+            out[f"resize_{tag}_{rw}x{rh}"] = np.stack(got)        # [3][C][rw][rh] as the wrapper returns them
+        img = LW.ImgWrapper(Env())
+        out[f"img_sha_{tag}"] = digest(np.stack([img.observation(f) for f in frames]))
+        nm = LW.NormalizeWrapper(Env())
+        nf = np.stack([nm.observation(f) for f in frames[:1]])
+        out[f"norm_dtype_{tag}"] = str(nf.dtype)
+        out[f"norm_f32_sha_{tag}"] = digest(nf.astype(np.float32))
+    rewards = np.array([-1000.0, -999.0, -3.2, 0.0, 1e-9, 0.7, 12.5])
+    dt = LW.DtRewardWrapper(Env())
+    out["rewards"], out["dt_rewards"] = rewards, np.array([dt.reward(r) for r in rewards])
+    aw = LW.ActionWrapper(Env())
+    acts = rng.uniform(-1, 1, (16, 2))
+    out["actions"], out["scaled_actions"] = acts, np.array([aw.action(a) for a in acts])
+    dw = W.DiscreteWrapper(Env())
+    out["discrete_actions"] = np.array([dw.action(k) for k in range(3)])
+    out["seed"] = np.int64(seed)
+    np.savez_compressed(os.path.join(OUT, "wrappers.npz"), **out)
+    print("wrappers:", sorted(out))
+
+
 def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, height=120):
     """Run the reference's render path against the recording GL (oracle/gltrace.py): reset() + a short walk, twice per
     seed (the second episode captures GL_LIGHT0 under the previous frame's model-view, S:581), domain_rand off and on."""
@@ -429,6 +497,10 @@ def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, h
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wrappers":
+        os.makedirs(OUT, exist_ok=True)
+        gen_wrappers()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gltrace":
         os.makedirs(OUT, exist_ok=True)
         for m in MAPS:
@@ -446,5 +518,6 @@ if __name__ == "__main__":
     gen_trafficlight()
     gen_reset_start()
     gen_helpers()
+    gen_wrappers()
     for m in MAPS:
         gen_gltrace(m)

@@ -170,8 +170,11 @@ def install():
 
     class Box:
         def __init__(self, low, high, shape=None, dtype=np.float32):
-            self.low, self.high, self.dtype = low, high, dtype
+            # like gym.spaces.Box: scalar bounds are broadcast to `shape`
             self.shape = tuple(shape) if shape is not None else np.shape(low)
+            self.dtype = dtype
+            self.low = np.full(self.shape, low, dtype=dtype) if np.isscalar(low) or np.ndim(low) == 0 else np.asarray(low)
+            self.high = np.full(self.shape, high, dtype=dtype) if np.isscalar(high) or np.ndim(high) == 0 else np.asarray(high)
 
     class Discrete:
         def __init__(self, n):

@@ -64,8 +64,10 @@ def test_wrapper_classes_configure_the_fused_path(torch_cuda):
     obs, rew, done, info = w.step(torch.full((8, 2), 0.3, device=env.device))
     assert obs.shape == (8, 3, 120, 160) and obs.dtype == torch.float32 and 0.0 <= float(obs.min()) and float(obs.max()) <= 1.0
     assert tuple(Wr.PyTorchObsWrapper(make_env("small_loop", 2)).observation_space.shape) == (3, 160, 120)
-    with pytest.raises(NotImplementedError):
-        Wr.ResizeWrapper(env)
+    rz = Wr.ResizeWrapper(Wr.PyTorchObsWrapper(make_env("small_loop", 2)), resize_w=84, resize_h=84)
+    assert tuple(rz.observation_space.shape) == (3, 84, 84)
+    obs = rz.reset()
+    assert tuple(obs.shape) == (2, 3, 84, 84) and obs.dtype == torch.uint8 and float(obs.float().std()) > 5
     env.close()
 
 
