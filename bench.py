@@ -154,7 +154,7 @@ def workload_text(c):
             f"distortion={c['distortion']}, device-side auto-reset")
 
 
-def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sampler=None, gather=True):
+def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sampler=None, gather=True, gather_impl="fused"):
     """Device-resident arm of one workload: W warm-up steps, K timed steps (k_step_logic + render) bracketed by
     barrier + synchronize, + the end-of-rollout NCCL all-gather when world > 1.  Returns (result dict, env) —
     the env is left alive for the caller's end-to-end arm."""
@@ -175,11 +175,25 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     actions = torch.rand((K + Wm, E, 2), device=dev, generator=gen) * 2 - 1   # Box(-1,1,(2,)).sample() distribution
-    gathered = ag = None
+    gathered = ag = fg = None
+    gather_note = None
     if world > 1 and gather:
-        from gym_duckietown_b200.dist import ObsAllGather
-        ag = ObsAllGather(env, rank, world)
-        gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=env.obs.dtype, device=dev)
+        if gather_impl == "fused":
+            try:   # the exchange fused into the last step's rasteriser: peer-memory stores over NVLink (dts_gather_*)
+                from gym_duckietown_b200.dist import FusedObsGather
+                fg = FusedObsGather(env, rank, world)
+                gather_note = "fused: last step's k_raster stores every frame into all ranks' gather buffers (cudaIpc peer memory over NVLink)"
+            except Exception as ex:
+                gather_note = f"fused gather unavailable ({type(ex).__name__}: {ex}); NCCL all-gather"
+        ok = torch.tensor([1 if fg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank must have mapped every peer, else all fall back
+        if int(ok.item()) == 0:
+            fg = None
+        if fg is None:
+            from gym_duckietown_b200.dist import ObsAllGather
+            ag = ObsAllGather(env, rank, world)
+            gathered = torch.empty((world,) + tuple(env.obs.shape), dtype=env.obs.dtype, device=dev)
+            gather_note = gather_note or "NCCL all-gather after the last step (dts_allgather_obs)"
 
     def barrier():
         if world > 1:
@@ -187,7 +201,11 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
         torch.cuda.synchronize()
 
     for t in range(Wm):
+        if fg is not None and t == Wm - 1:
+            fg.arm()              # first peer stores map the pages: keep that out of the timed region
         env.step(actions[t])
+    if fg is not None:
+        fg.finish()
     if ag is not None:
         ag.all_gather(gathered)   # first collective on a communicator sets up channels: keep it out of the timed region
     barrier()
@@ -198,9 +216,11 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
     env.sim.profile(True)     # CUDA events around every render kernel, on the launching stream (roofline)
     ev0.record()
     for t in range(K):
+        if fg is not None and t == K - 1:
+            fg.arm()                              # the rollout's last step also fills every rank's gather buffer
         env.step(actions[Wm + t])                 # dts_step: k_step_logic (+ device auto-reset) + the render kernels
     if ag is not None:
-        ag.all_gather(gathered)                   # the single end-of-rollout NCCL all-gather
+        ag.all_gather(gathered)                   # baseline: the single end-of-rollout NCCL all-gather
     ev1.record()
     barrier()
     env.sim.profile(False)
@@ -220,7 +240,7 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
     render_ms = sum(per.values())
     res = {
         "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": Wm, "gpu_launches": int(launches),
-        "workload": workload_text(c),
+        "workload": workload_text(c), "gather": gather_note,
         "roofline": {"bound": "hbm", "kernel": "k_raster (dominant kernel of the step; CUDA events on the launching stream, mean over the timed steps)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": raster_ms,
@@ -261,6 +281,8 @@ def main():
                     help="extra BASELINE configs timed after the headline and attached as \"configs\": comma list of "
                          "c3,c4,c5, 'none', or 'auto' (N=1: c3,c4,c5; N>1: c5 with the NCCL all-gather)")
     ap.add_argument("--c4-envs", type=int, default=8192)
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: end-of-rollout observation exchange fused into the last step's rasteriser (peer memory), or NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -309,7 +331,8 @@ def main():
 
     # ---- device-resident arm: `value` -------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    res, env = run_config(head, K, Wm, rank, world, local_rank, args.obs_format, sampler)
+    res, env = run_config(head, K, Wm, rank, world, local_rank, args.obs_format, sampler, gather_impl=args.gather)
+    config["gather"] = res.get("gather")
     if args.obs_format != "hwc_uint8":
         config["obs_format"] = args.obs_format
 
@@ -382,7 +405,7 @@ def main():
         if name == "c4":
             c["envs"] = args.c4_envs
         try:
-            r, e_ = run_config(c, K, Wm, rank, world, local_rank, "hwc_uint8", None, gather=(name == "c5"))
+            r, e_ = run_config(c, K, Wm, rank, world, local_rank, "hwc_uint8", None, gather=(name == "c5"), gather_impl=args.gather)
             e_.close()
             del e_
             extra[name] = r

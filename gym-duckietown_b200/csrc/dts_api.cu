@@ -39,6 +39,12 @@ struct dts_sim {
   int32_t* d_err = nullptr;
   int32_t* h_status = nullptr;          // mapped pinned host word: bit 0 = a frame overflowed its frame memory
   int32_t* d_status = nullptr;          // its device address
+  // fused end-of-rollout gather over peer memory (dts_gather_*)
+  uint8_t* gather_buf = nullptr;        // [world][bytes_per_rank], this rank's copy of everybody's observations
+  uint64_t gather_bytes = 0;
+  int gather_world = 0, gather_rank = 0;
+  void* gather_peer[DTS_MAX_PEERS] = {};   // peers' buffers opened with cudaIpcOpenMemHandle (own entry = gather_buf)
+  bool gather_next = false;             // the next dts_render also stores into the gather buffers
   // fused ResizeWrapper (dts_set_resize): full-size render target + tap tables
   int resize_w = 0, resize_h = 0;
   uint8_t* resize_src = nullptr;
@@ -194,6 +200,9 @@ void dts_destroy(dts_sim* sim) {
   void* extra[] = {sim->render_scratch, (void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
                    sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
   for (void* p : extra) if (p) cudaFree(p);
+  for (int p = 0; p < sim->gather_world; p++)
+    if (sim->gather_peer[p] && sim->gather_peer[p] != sim->gather_buf) cudaIpcCloseMemHandle(sim->gather_peer[p]);
+  if (sim->gather_buf) cudaFree(sim->gather_buf);
   void* rz[] = {sim->resize_src, sim->resize_xtab, sim->resize_ytab};
   for (void* p : rz) if (p) cudaFree(p);
   if (sim->h_status) cudaFreeHost(sim->h_status);
@@ -551,8 +560,16 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
     rc.obs_layout = DTS_OBS_HWC; rc.obs_dtype = DTS_OBS_U8;
     target = sim->resize_src;
   }
+  GatherTab gt{};
+  if (sim->gather_next) {
+    if (sim->resize_w) return sim->fail("the fused gather writes the rasteriser's own output: not combined with dts_set_resize");
+    gt.n = sim->gather_world;
+    for (int p = 0; p < sim->gather_world; p++)
+      gt.base[p] = reinterpret_cast<uint8_t*>(sim->gather_peer[p]) + (uint64_t)sim->gather_rank * sim->gather_bytes;
+    sim->gather_next = false;
+  }
   int k = launch_render(sim->S, sim->d_maps, rc, target, sim->render_scratch, sim->render_ctas, sim->max_prims,
-                        sim->bin_cap, sim->max_lat, sim->items_max, sim->fish, sim->d_err,
+                        sim->bin_cap, sim->max_lat, sim->items_max, sim->fish, gt, sim->d_err,
                         sim->d_status, marks, (cudaStream_t)stream);
   if (sim->resize_w) {
     launch_resize(sim->resize_src, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
@@ -679,6 +696,46 @@ int dts_set_resize(dts_sim* sim, int out_w, int out_h) {
   DTS_CUDA(cudaMemcpy(sim->resize_xtab, xt.data(), xt.size() * 2, cudaMemcpyHostToDevice));
   DTS_CUDA(cudaMemcpy(sim->resize_ytab, yt.data(), yt.size() * 2, cudaMemcpyHostToDevice));
   sim->resize_w = out_w; sim->resize_h = out_h;
+  return 0;
+}
+
+// ---- fused end-of-rollout gather: peer buffers over cudaIpc, written by the rasteriser itself --------------------
+int dts_gather_alloc(dts_sim* sim, uint64_t bytes_per_rank, int rank, int world, uint8_t handle_out[64], void** buf_out) {
+  if (!sim) return 1;
+  if (world < 1 || world > DTS_MAX_PEERS || rank < 0 || rank >= world) return sim->fail("bad rank %d / world %d (max %d)", rank, world, DTS_MAX_PEERS);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  if (sim->gather_buf) return sim->fail("gather buffer already allocated");
+  DTS_CUDA(cudaMalloc(&sim->gather_buf, bytes_per_rank * (uint64_t)world));
+  DTS_CUDA(cudaMemset(sim->gather_buf, 0, bytes_per_rank * (uint64_t)world));
+  sim->gather_bytes = bytes_per_rank; sim->gather_rank = rank; sim->gather_world = world;
+  for (int p = 0; p < DTS_MAX_PEERS; p++) sim->gather_peer[p] = nullptr;
+  sim->gather_peer[rank] = sim->gather_buf;
+  cudaIpcMemHandle_t h;
+  DTS_CUDA(cudaIpcGetMemHandle(&h, sim->gather_buf));
+  memcpy(handle_out, &h, 64);
+  if (buf_out) *buf_out = sim->gather_buf;
+  return 0;
+}
+
+int dts_gather_open(dts_sim* sim, const uint8_t* handles /*[world][64]*/) {
+  if (!sim || !sim->gather_buf) return sim ? sim->fail("dts_gather_alloc first") : 1;
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  for (int p = 0; p < sim->gather_world; p++) {
+    if (p == sim->gather_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * p, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&sim->gather_peer[p], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return sim->fail("cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int dts_gather_next(dts_sim* sim) {
+  if (!sim || !sim->gather_buf) return sim ? sim->fail("dts_gather_alloc first") : 1;
+  for (int p = 0; p < sim->gather_world; p++)
+    if (!sim->gather_peer[p]) return sim->fail("dts_gather_open first (rank %d not mapped)", p);
+  sim->gather_next = true;
   return 0;
 }
 

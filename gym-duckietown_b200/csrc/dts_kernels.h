@@ -43,6 +43,16 @@ struct FishTab {
   const short4* rbox;      // [cbins_y]  and for each row of coarse bins
 };
 
+// Fused end-of-rollout observation gather: on the rollout's last step the rasteriser's resolve stores every
+// frame, besides the caller's tensor, straight into the gather buffers of all GPUs of the box — peer memory mapped with
+// cudaIpc, written over NVLink while the frame is being rasterised — instead of a separate all-gather pass afterwards.
+// base[p] = (rank p's gather buffer) + my_rank * bytes_per_rank.
+#define DTS_MAX_PEERS 8
+struct GatherTab {
+  int32_t n, pad;                 // 0: off
+  uint8_t* base[DTS_MAX_PEERS];
+};
+
 // render (dts_render.cu)
 int render_ctas_per_sm();
 // scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
@@ -52,7 +62,7 @@ size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int 
 // k_bin, k_raster and the post passes (dts_profile_*).  `status_dev`: device address of the mapped host status word.
 constexpr int kProfMarks = 6;
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish, const GatherTab& gather,
                   int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st);
 
 // ResizeWrapper on the device: src u8[N][H][W][3] -> dst [N] x (ow x oh) in `layout` / `dtype` (dts_set_resize)

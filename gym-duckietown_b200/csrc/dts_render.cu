@@ -1006,8 +1006,8 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
 template <bool kWrapFmt, bool kFish>   // kWrapFmt: a dts_output_format other than packed u8 HWC is written by the resolve;
                                        // kFish: every lane renders the SOURCE pixel the fisheye LUT names for its output pixel
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
-k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, FishTab ft, uint8_t* __restrict__ obs,
-         int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
+k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, FishTab ft, GatherTab gt,
+         uint8_t* __restrict__ obs, int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
   __shared__ __align__(128) BinRec stages[kWarps][2][kStage];   // per warp: two chunks of records in flight
   __shared__ __align__(8) uint64_t bars[kWarps][2];
   const int W = rc.width, H = rc.height;
@@ -1035,7 +1035,13 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     const PrimRec* prims = fm.prims + (size_t)env * max_prims;
     const BinRec* recs = fm.recs;   // bin_start holds pool indices
     const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
-    uint8_t* out = obs + (size_t)env * frame_bytes * out_elem;
+    const size_t env_off = (size_t)env * frame_bytes * out_elem;
+    uint8_t* out = obs + env_off;
+    // one fine bin -> the caller's tensor and, on a gathering step, every peer's gather buffer (NVLink stores)
+    auto emit = [&](unsigned rgb, int bx, int by) {
+      store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
+      for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+    };
     const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
     // lane l holds the list of coarse bin (cby, l)
@@ -1089,7 +1095,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               const int gx = min((cbx * kCFX + (f & 3)) * kBinW + (lane & 7), W - 1), gy = min((cby * kCFY + (f >> 2)) * kBinH + (lane >> 3), H - 1);
               if ((short)(__ldg(ft.src_xy + gy * W + gx) & 0xffff) == -32768) rgb = 0u;
             }
-            store_bin_any(out, out_fmt, rgb, lane, cbx * kCFX + (f & 3), cby * kCFY + (f >> 2), W, H);
+            emit(rgb, cbx * kCFX + (f & 3), cby * kCFY + (f >> 2));
           }
         continue;
       }
@@ -1253,7 +1259,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
             }
             if (!all_same) rgb = pack_rgb((s01[0] + s23[0]) * 0.25f, (s01[1] + s23[1]) * 0.25f, (s01[2] + s23[2]) * 0.25f);
             if (kFish && !px_valid) rgb = 0u;   // cv2.remap BORDER_CONSTANT
-            store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
+            emit(rgb, bx, by);
           }
         }
       }
@@ -1349,7 +1355,7 @@ int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pai
 }
 
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs_any, void* scratch, int n_ctas,
-                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish,
+                  int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish, const GatherTab& gather,
                   int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st) {
   const int W = rc.width, H = rc.height;
   uint8_t* obs = reinterpret_cast<uint8_t*>(obs_any);
@@ -1380,11 +1386,11 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   mark();
   const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;
   if (fisheye) {
-    if (wrap) k_raster<true, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
-    else k_raster<false, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+    if (wrap) k_raster<true, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
   } else {
-    if (wrap) k_raster<true, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
-    else k_raster<false, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_pairs, max_lat, err_flag);
+    if (wrap) k_raster<true, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
   }
   mark();
   mark();   // (post passes: none yet)

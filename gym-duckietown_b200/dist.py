@@ -81,3 +81,47 @@ class ObsAllGather:
                                              torch.cuda.current_stream(self.env.device).cuda_stream),
                    "dts_allgather_obs")
         return out
+
+
+class FusedObsGather:
+    """The end-of-rollout observation exchange FUSED into the last step's rasteriser (dts_gather_*): every rank maps the
+    other ranks' gather buffers as peer memory (cudaIpc over NVLink / NVSwitch) and its k_raster stores each finished
+    8x4 pixel block into all of them while it renders — no separate collective pass, the transfer rides under the
+    rasterisation.  Usage per rollout:
+
+        g.arm()                      # before the rollout's LAST env.step(): that step also fills the gather buffers
+        env.step(actions)
+        batch = g.finish()           # stream sync + barrier: u8[world, N, H, W, 3] (this rank's copy) is complete
+    """
+
+    def __init__(self, env, rank: int, world: int):
+        self.env, self.rank, self.world = env, rank, world
+        sim = env.sim
+        nbytes = env.obs.numel() * env.obs.element_size()
+        handle = (C.c_uint8 * 64)()
+        buf = C.c_void_p()
+        sim._check(sim.lib.dts_gather_alloc(sim.h, nbytes, rank, world, handle, C.byref(buf)), "dts_gather_alloc")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=env.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allh, mine)
+        else:
+            allh = [mine]
+        host = torch.stack(allh).cpu().numpy()
+        sim._check(sim.lib.dts_gather_open(sim.h, host.ctypes.data_as(C.c_void_p)), "dts_gather_open")
+        from .lib import _CudaArray
+        import numpy as np
+        flat = torch.as_tensor(_CudaArray(buf.value, world * nbytes, np.uint8), device=env.device)
+        self.gathered = flat.view(env.obs.dtype).view((world,) + tuple(env.obs.shape))
+        if world > 1:
+            dist.barrier()   # every rank has opened every buffer before anyone writes
+
+    def arm(self):
+        sim = self.env.sim
+        sim._check(sim.lib.dts_gather_next(sim.h), "dts_gather_next")
+
+    def finish(self) -> torch.Tensor:
+        torch.cuda.current_stream(self.env.device).synchronize()   # my stores to every peer have landed
+        if self.world > 1:
+            dist.barrier()                                         # ... and everybody else's into mine
+        return self.gathered

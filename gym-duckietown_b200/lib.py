@@ -173,6 +173,9 @@ def load() -> C.CDLL:
     lib.dts_profile_read.argtypes = [vp, vp, vp]
     lib.dts_set_output_format.argtypes = [vp, C.POINTER(OutputFormat)]
     lib.dts_get_dyn_state.argtypes = [vp, i, C.POINTER(vp), C.POINTER(C.c_int32)]
+    lib.dts_gather_alloc.argtypes = [vp, C.c_uint64, i, i, vp, C.POINTER(vp)]
+    lib.dts_gather_open.argtypes = [vp, vp]
+    lib.dts_gather_next.argtypes = [vp]
     lib.dts_comm_load.argtypes = [vp, C.c_char_p]
     lib.dts_comm_unique_id.argtypes = [vp, vp]
     lib.dts_comm_init.argtypes = [vp, vp, i, i]
@@ -191,7 +194,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_gather_alloc", "dts_gather_open", "dts_gather_next", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_debug_frame", "dts_last_error", "dts_destroy"]
 
 

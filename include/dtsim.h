@@ -296,6 +296,18 @@ int dts_status(dts_sim* sim);
  * they cover, and clears the accumulators. */
 int dts_profile_enable(dts_sim* sim, int on);
 int dts_profile_read(dts_sim* sim, double ms_out[8], int64_t* frames);
+/* FUSED end-of-rollout gather (the path's one exchange step) — instead of running an all-gather after the last
+ * step, the last step's rasteriser stores every frame straight into the gather buffers of all GPUs of the box:
+ *   dts_gather_alloc   this rank's buffer u8[world][bytes_per_rank] (returned in *buf_dev) and its 64-byte cudaIpc handle;
+ *   dts_gather_open    the other ranks' handles (the caller exchanges them, e.g. torch.distributed all_gather), mapped
+ *                      as peer memory (NVLink / NVSwitch);
+ *   dts_gather_next    the NEXT dts_step / dts_render also writes its observations, in the selected layout / dtype,
+ *                      to slot `rank` of every rank's buffer while it rasterises (one extra store per peer and word).
+ * A rank's buffer is complete once every rank's step has finished: the caller orders that (stream sync + barrier), exactly
+ * as it orders the use of an all-gather's output.  dts_allgather_obs remains as the NCCL baseline of the same exchange. */
+int dts_gather_alloc(dts_sim* sim, uint64_t bytes_per_rank, int rank, int world, uint8_t handle_out[64], void** buf_dev);
+int dts_gather_open(dts_sim* sim, const uint8_t* handles /* [world][64] */);
+int dts_gather_next(dts_sim* sim);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t dts_launch_count(dts_sim* sim);
 /* debug: the env's per-episode render record as 36 x 32-bit words (cam_height, cam_angle_deg, cam_fov_y_deg, -,
