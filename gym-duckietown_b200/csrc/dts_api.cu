@@ -304,12 +304,31 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   bad |= sim->upload(&m.tri_col, b->tri_col, (size_t)b->n_tris * 9, &own);
   bad |= sim->upload(&m.tri_tex, b->tri_tex, (size_t)b->n_tris, &own);
   std::vector<DTexture> tex(b->n_textures);
-  for (int t = 0; t < b->n_textures; t++) {
-    const dts_texture& s = b->textures[t];
-    if (s.width <= 0 || s.height <= 0 || (s.width & (s.width - 1)) || (s.height & (s.height - 1)))
-      return sim->fail("texture %d: %dx%d is not a power of two", t, s.width, s.height);
-    tex[t].w = s.width; tex[t].h = s.height;
-    bad |= sim->upload(&tex[t].rgba, s.rgba, (size_t)s.width * s.height * 4, &own);
+  {
+    size_t pool_bytes = 0;
+    std::vector<size_t> off(b->n_textures);
+    for (int t = 0; t < b->n_textures; t++) {
+      const dts_texture& s = b->textures[t];
+      off[t] = pool_bytes;
+      pool_bytes += ((size_t)s.width * s.height * 4 + 255) & ~size_t(255);
+    }
+    if (pool_bytes >= (size_t(1) << 32)) return sim->fail("textures exceed 4 GB");
+    std::vector<uint8_t> pool(pool_bytes ? pool_bytes : 256, 0);
+    for (int t = 0; t < b->n_textures; t++) {
+      const dts_texture& s = b->textures[t];
+      memcpy(pool.data() + off[t], s.rgba, (size_t)s.width * s.height * 4);
+    }
+    bad |= sim->upload(&m.tex_pool, pool.data(), pool.size(), &own);
+    for (int t = 0; t < b->n_textures && !bad; t++) {
+      const dts_texture& s = b->textures[t];
+      int lw = 0, lh = 0;
+      while ((1 << lw) < s.width) lw++;
+      while ((1 << lh) < s.height) lh++;
+      if (lw > 15 || lh > 15) return sim->fail("texture %d: %dx%d too large", t, s.width, s.height);
+      tex[t].w = s.width; tex[t].h = s.height; tex[t].rgba = m.tex_pool + off[t];
+      tex[t].info = (uint32_t)(off[t] >> 8) | ((uint32_t)lw << 24) | ((uint32_t)lh << 28);
+      tex[t].pad = 0;
+    }
   }
   m.n_textures = b->n_textures;
   bad |= sim->upload(&m.textures, tex.data(), tex.size(), &own);

@@ -38,7 +38,9 @@ struct DDyn {
   int32_t pad;
 };
 
-struct DTexture { const uint8_t* rgba; int32_t w, h; };
+// Textures of a map live in ONE pool allocation; `info` is what a prim carries to find its texels without a dependent
+// table lookup: (byte offset in the pool >> 8) | log2(w) << 24 | log2(h) << 28.
+struct DTexture { const uint8_t* rgba; int32_t w, h; uint32_t info, pad; };
 
 struct DMap {
   double tile_size;
@@ -71,6 +73,7 @@ struct DMap {
   const int16_t* tri_tex;
   int32_t n_textures;
   const DTexture* textures;
+  const uint8_t* tex_pool;      // all RGBA8 textures, each 256-byte aligned
   int32_t n_dyn;
   const DDyn* dyn;              // [n_dyn]
   double* dyn_state;            // [DTS_DYN_FIELDS][n_dyn][num_envs]: mutable, per env, survives resets

@@ -79,13 +79,13 @@ struct __align__(16) PrimRec {   // 128 B in the env's slab, words grouped for 1
   float ux, uy, v0, vx;          // w4
   float vy;                      // w5
   int32_t ltq;                   //     (lattice slot + 1) | (texture index + 1) << 16 | quad << 24
-  float r0, rx;
-  float ry, g0, gx, gy;          // w6
-  float b0, bx, by;              // w7
-  int32_t pad;
+  uint32_t tex;                  //     DTexture::info of the prim's texture (pool offset >> 8 | log2 w << 24 | log2 h << 28)
+  float r0;
+  float rx, ry, g0, gx;          // w6
+  float gy, b0, bx, by;          // w7
 };
 static_assert(sizeof(PrimRec) == 128, "PrimRec must be 128 bytes");
-static_assert(offsetof(PrimRec, q0) == 48 && offsetof(PrimRec, vy) == 80 && offsetof(PrimRec, ry) == 96, "PrimRec word groups");
+static_assert(offsetof(PrimRec, q0) == 48 && offsetof(PrimRec, vy) == 80 && offsetof(PrimRec, rx) == 96, "PrimRec word groups");
 
 struct __align__(16) BinRec {    // 80 B per (prim, coarse bin) pair: what visibility needs, re-based to the bin corner
   int32_t E0[4], A[4], B[4];     // E_k(x,y) = E0_k + A_k*x + B_k*y, x,y in 1/64 px from the bin corner (triangles: E_3 = 0)
@@ -214,6 +214,7 @@ __device__ __forceinline__ int classify(const Vtx& a, const Vtx& b, const Vtx& c
 }
 
 struct EmitCtx {
+  const DTexture* textures;
   GeoWarp* gw;
   FrameCtx* ctx;
   PrimRec* prims;          // this env's slab
@@ -293,7 +294,7 @@ __device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const
   r.b0 = f0[6]; r.bx = fx[6]; r.by = fy[6];
   r.id = id;
   r.ltq = (lat + 1) | ((tex + 1) << 16);
-  r.pad = 0;
+  r.tex = tex >= 0 ? ec.textures[tex].info : 0u;
   (void)px0; (void)py0; (void)px1; (void)py1;
   if (d) {   // vertices in cyclic order; planes stay those of triangle (a,b,c) anchored at a
     r.ltq |= 1 << 24;
@@ -481,13 +482,13 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
 // Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
 // 5-6 and 8): perspective-correct u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles,
 // bilinear REPEAT texel, MODULATE.  Deferred shading: each lane may shade a different prim.
-__device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, unsigned w, const DTexture* __restrict__ textures,
+__device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, unsigned w, const uint8_t* __restrict__ tex_pool,
                                            const float4* __restrict__ lat_tab, int pxa, int pya, float c3[3]) {
   const PrimRec* pr = prims + w;
   const int2 xy0 = __ldg(reinterpret_cast<const int2*>(pr));
   const float4 w3 = __ldg(reinterpret_cast<const float4*>(pr) + 3);   // q0 qx qy u0
   const float4 w4 = __ldg(reinterpret_cast<const float4*>(pr) + 4);   // ux uy v0 vx
-  const float2 w5 = __ldg(reinterpret_cast<const float2*>(pr) + 10);  // vy ltq
+  const float4 w5 = __ldg(reinterpret_cast<const float4*>(pr) + 5);   // vy ltq tex r0
   const int ltq = __float_as_int(w5.y);
   const float cdx = (float)(pxa + 32 - xy0.x) * 0.015625f, cdy = (float)(pya + 32 - xy0.y) * 0.015625f;
   float qq = fmaf(w3.z, cdy, fmaf(w3.y, cdx, w3.x));
@@ -495,11 +496,11 @@ __device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, un
   const float rq = 1.0f / qq;
   const float u = fmaf(w4.y, cdy, fmaf(w4.x, cdx, w3.w)) * rq;
   const float v = fmaf(w5.x, cdy, fmaf(w4.w, cdx, w4.z)) * rq;
-  const int lat = (ltq & 0xffff) - 1, tex = ((ltq >> 16) & 0xff) - 1;
+  const int lat = (ltq & 0xffff) - 1;
   if (lat >= 0) {
     // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
     const float fa_ = u * 7.0f, fb_ = (1.0f - v) * 7.0f;
-    int ia = (int)floorf(fa_), ib = (int)floorf(fb_);
+    int ia = __float2int_rd(fa_), ib = __float2int_rd(fb_);   // (int)floorf(.)
     ia = ia < 0 ? 0 : (ia > 6 ? 6 : ia);
     ib = ib < 0 ? 0 : (ib > 6 ? 6 : ib);
     const float fa = fa_ - (float)ia, fb = fb_ - (float)ib;
@@ -513,24 +514,25 @@ __device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, un
     c3[1] = fmaf(t2, c11.y - cm.y, fmaf(t1, cm.y - c00.y, c00.y));
     c3[2] = fmaf(t2, c11.z - cm.z, fmaf(t1, cm.z - c00.z, c00.z));
   } else {
-    const float2 w5b = __ldg(reinterpret_cast<const float2*>(pr) + 11);  // r0 rx
-    const float4 w6 = __ldg(reinterpret_cast<const float4*>(pr) + 6);    // ry g0 gx gy
-    const float4 w7 = __ldg(reinterpret_cast<const float4*>(pr) + 7);    // b0 bx by
-    c3[0] = fmaf(w6.x, cdy, fmaf(w5b.y, cdx, w5b.x)) * rq;
-    c3[1] = fmaf(w6.w, cdy, fmaf(w6.z, cdx, w6.y)) * rq;
-    c3[2] = fmaf(w7.z, cdy, fmaf(w7.y, cdx, w7.x)) * rq;
+    const float4 w6 = __ldg(reinterpret_cast<const float4*>(pr) + 6);    // rx ry g0 gx
+    const float4 w7 = __ldg(reinterpret_cast<const float4*>(pr) + 7);    // gy b0 bx by
+    c3[0] = fmaf(w6.y, cdy, fmaf(w6.x, cdx, w5.w)) * rq;
+    c3[1] = fmaf(w7.x, cdy, fmaf(w6.w, cdx, w6.z)) * rq;
+    c3[2] = fmaf(w7.w, cdy, fmaf(w7.z, cdx, w7.y)) * rq;
   }
-  if (tex >= 0) {
-    const DTexture t = textures[tex];
-    const int tw = t.w, th = t.h;
-    const float tx = u * (float)tw - 0.5f, ty = v * (float)th - 0.5f;
-    const float txf = floorf(tx), tyf = floorf(ty);
-    const float ffx = tx - txf, ffy = ty - tyf;
-    const int ti0 = ((int)txf) & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
-    const int tj0 = ((int)tyf) & (th - 1), tj1 = (tj0 + 1) & (th - 1);
-    const uchar4* tp = reinterpret_cast<const uchar4*>(t.rgba);
-    const uchar4 t00 = __ldg(tp + tj0 * tw + ti0), t10 = __ldg(tp + tj0 * tw + ti1);
-    const uchar4 t01 = __ldg(tp + tj1 * tw + ti0), t11 = __ldg(tp + tj1 * tw + ti1);
+  if (ltq & 0x00ff0000) {
+    const unsigned ti = __float_as_uint(w5.z);
+    const int lw = (ti >> 24) & 15, lh = ti >> 28;
+    const int tw = 1 << lw, th = 1 << lh;
+    const float twf = __int_as_float((127 + lw) << 23), thf = __int_as_float((127 + lh) << 23);   // (float)tw: a power of two
+    const float tx = u * twf - 0.5f, ty = v * thf - 0.5f;
+    const int txi = __float2int_rd(tx), tyi = __float2int_rd(ty);   // floorf(.) as the int the wrap needs; exact back in float
+    const float ffx = tx - (float)txi, ffy = ty - (float)tyi;
+    const int ti0 = txi & (tw - 1), ti1 = (ti0 + 1) & (tw - 1);
+    const int tj0 = tyi & (th - 1), tj1 = (tj0 + 1) & (th - 1);
+    const uchar4* tp = reinterpret_cast<const uchar4*>(tex_pool + ((size_t)(ti & 0xffffffu) << 8));
+    const uchar4 t00 = __ldg(tp + (tj0 << lw) + ti0), t10 = __ldg(tp + (tj0 << lw) + ti1);
+    const uchar4 t01 = __ldg(tp + (tj1 << lw) + ti0), t11 = __ldg(tp + (tj1 << lw) + ti1);
     const float a0[3] = {(float)t00.x, (float)t00.y, (float)t00.z}, a1[3] = {(float)t10.x, (float)t10.y, (float)t10.z};
     const float b0[3] = {(float)t01.x, (float)t01.y, (float)t01.z}, b1[3] = {(float)t11.x, (float)t11.y, (float)t11.z};
 #pragma unroll
@@ -753,7 +755,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   if (lane < 12) sh.V[lane] = ctx.V[lane];
   if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; }
   __syncwarp();
-  EmitCtx ec{&sh, &ctx, fm.prims + (size_t)env * max_prims, max_prims, W, H};
+  EmitCtx ec{m.textures, &sh, &ctx, fm.prims + (size_t)env * max_prims, max_prims, W, H};
   float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
   const int tris_per_tile = kTess ? 98 : 2;
   Xform& x = sh.x;
@@ -1031,7 +1033,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     if (lane == 0) next_work = atomicAdd(fm.work, 1);   // consumed after this row: latency hidden
     const int env = work / cbins_y, cby = work - env * cbins_y;
     const DMap& m = maps[S.map_id[env]];
-    const DTexture* textures = m.textures;
+    const uint8_t* tex_pool = m.tex_pool;
     const PrimRec* prims = fm.prims + (size_t)env * max_prims;
     const BinRec* recs = fm.recs;   // bin_start holds pool indices
     const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
@@ -1234,30 +1236,39 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
             // ---- deferred shading: once per distinct winner of this pixel, then the box resolve
             const int pxa = ox + pxc, pya = oy + pyc;
             const bool same = wn[1] == wn[0] && wn[2] == wn[0] && wn[3] == wn[0];
-            const bool all_same = __all_sync(0xffffffffu, same);
-            float s01[3] = {0.f, 0.f, 0.f}, s23[3] = {0.f, 0.f, 0.f};
-            unsigned rgb = 0;
-            unsigned pend = 0xfu;
-#pragma unroll 1
-            while (__any_sync(0xffffffffu, pend != 0u)) {
-              if (pend) {
-                const int s = __ffs(pend) - 1;
-                const unsigned w = s == 0 ? wn[0] : (s == 1 ? wn[1] : (s == 2 ? wn[2] : wn[3]));
-                float c3[3] = {clr[0], clr[1], clr[2]};
-                if (w != kNoPrim) shade_prim(prims, w, textures, lat_tab, pxa, pya, c3);
-                if (all_same) { rgb = pack_rgb(c3[0], c3[1], c3[2]); pend = 0u; }
-                else {
+            const bool all_same = simple || __all_sync(0xffffffffu, same);
+            unsigned rgb;
+            {
+              float c3[3] = {clr[0], clr[1], clr[2]};
+              if (wn[0] != kNoPrim) shade_prim(prims, wn[0], tex_pool, lat_tab, pxa, pya, c3);   // every lane: its first winner
+              if (all_same) rgb = pack_rgb(c3[0], c3[1], c3[2]);   // four equal samples: the mean is the value itself
+              else {
+                // edge pixels: the other winners of this pixel (at most three more), summed in the resolve's order
+                float s01[3] = {c3[0], c3[1], c3[2]}, s23[3] = {0.f, 0.f, 0.f};   // 0 + c == c
+                unsigned pend = 0xeu;
+                if (wn[1] == wn[0]) { pend &= ~2u; s01[0] = s01[0] + c3[0]; s01[1] = s01[1] + c3[1]; s01[2] = s01[2] + c3[2]; }
 #pragma unroll
-                  for (int t = 0; t < 4; t++)
-                    if ((pend >> t & 1u) && wn[t] == w) {
-                      pend &= ~(1u << t);
-                      if (t < 2) { s01[0] = s01[0] + c3[0]; s01[1] = s01[1] + c3[1]; s01[2] = s01[2] + c3[2]; }
-                      else { s23[0] = s23[0] + c3[0]; s23[1] = s23[1] + c3[1]; s23[2] = s23[2] + c3[2]; }
-                    }
+                for (int t = 2; t < 4; t++)
+                  if (wn[t] == wn[0]) { pend &= ~(1u << t); s23[0] = s23[0] + c3[0]; s23[1] = s23[1] + c3[1]; s23[2] = s23[2] + c3[2]; }
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, pend != 0u)) {
+                  if (pend) {
+                    const int s = __ffs(pend) - 1;
+                    const unsigned w = s == 1 ? wn[1] : (s == 2 ? wn[2] : wn[3]);
+                    float d3[3] = {clr[0], clr[1], clr[2]};
+                    if (w != kNoPrim) shade_prim(prims, w, tex_pool, lat_tab, pxa, pya, d3);
+#pragma unroll
+                    for (int t = 1; t < 4; t++)
+                      if ((pend >> t & 1u) && wn[t] == w) {
+                        pend &= ~(1u << t);
+                        if (t < 2) { s01[0] = s01[0] + d3[0]; s01[1] = s01[1] + d3[1]; s01[2] = s01[2] + d3[2]; }
+                        else { s23[0] = s23[0] + d3[0]; s23[1] = s23[1] + d3[1]; s23[2] = s23[2] + d3[2]; }
+                      }
+                  }
                 }
+                rgb = pack_rgb((s01[0] + s23[0]) * 0.25f, (s01[1] + s23[1]) * 0.25f, (s01[2] + s23[2]) * 0.25f);
               }
             }
-            if (!all_same) rgb = pack_rgb((s01[0] + s23[0]) * 0.25f, (s01[1] + s23[1]) * 0.25f, (s01[2] + s23[2]) * 0.25f);
             if (kFish && !px_valid) rgb = 0u;   // cv2.remap BORDER_CONSTANT
             emit(rgb, bx, by);
           }

@@ -209,6 +209,62 @@ def gen_reset(name: str, seeds=range(24)):
     print(f"reset_{name}: seeds={len(out['seeds'])} x 2 episodes x (dr off/on)")
 
 
+CUSTOM_DR = {   # a user's randomization_config_fp: other ranges, a shuffled-in unknown key before and after the known ones
+    "aa_first": {"type": "int", "low": 0, "high": 10, "size": 2},
+    "horz_mode": {"type": "int", "low": 1, "high": 3},
+    "light_pos": {"type": "uniform", "low": [-100, 150, -100], "high": [100, 250, 100], "size": 3},
+    "camera_noise": {"type": "uniform", "low": -0.01, "high": 0.01, "size": 3},
+    "trim": {"type": "normal", "loc": 0.01, "scale": 0.05},
+    "camera_height": {"type": "uniform", "low": 0.8, "high": 1.0},
+    "camera_angle": {"type": "uniform", "low": 0.9, "high": 1.1},
+    "camera_fov_y": {"type": "uniform", "low": 0.95, "high": 1.05},
+    "zz_extra": {"type": "uniform", "low": 0.0, "high": 1.0, "size": 5},
+}
+CUSTOM_SIM = dict(num_tris_distractors=5, color_sky=[0.2, 0.5, 0.7], color_ground=[0.3, 0.25, 0.2])
+
+
+def gen_reset_custom(name="loop_obstacles", seeds=range(40, 56)):
+    """reset() with Randomizer(randomization_config_fp=<custom table>) (randomizer.py:19-33) and non-default
+    num_tris_distractors / color_sky / color_ground (S:226-230), domain_rand and dynamics_rand on."""
+    raw = raw_map(name)
+    S, C, G, O = refstub.modules()
+    rows = {k: [] for k in RESET_KEYS + ["ambient", "diffuse"]}
+    for seed in seeds:
+        sim = refstub.build_reference_sim(raw, extents_for(raw), domain_rand=True, seed=int(seed), dynamics_rand=True)
+        sim.randomizer.randomization_config = dict(CUSTOM_DR)
+        sim.randomizer.keys = sorted(set(list(CUSTOM_DR.keys()) + list(sim.randomizer.default_config.keys())))
+        sim.num_tris_distractors = CUSTOM_SIM["num_tris_distractors"]
+        sim.color_sky, sim.color_ground = list(CUSTOM_SIM["color_sky"]), list(CUSTOM_SIM["color_ground"])
+        captured = []
+        S.gl.glLightfv = lambda light, pname, arr: captured.append(arr)
+
+        class _GLf:
+            def __mul__(self, n):
+                return lambda *v: np.array(v, dtype=np.float32)
+        S.gl.GLfloat = _GLf()
+        for episode in range(2):
+            captured.clear()
+            sim.reset()
+            rows["cur_pos"].append(np.array(sim.cur_pos, float)); rows["cur_angle"].append(float(sim.cur_angle))
+            rows["wheel_dist"].append(float(sim.wheel_dist)); rows["cam_height"].append(float(np.ravel(sim.cam_height)[0]))
+            rows["cam_angle"].append(float(np.ravel(sim.cam_angle[0])[0])); rows["cam_fov_y"].append(float(np.ravel(sim.cam_fov_y)[0]))
+            rows["camera_noise"].append(np.array(sim.randomization_settings["camera_noise"], float))
+            rows["horizon_color"].append(np.array(sim.horizon_color, float))
+            rows["ground_color"].append(np.array(sim.ground_color, float))
+            lp = np.zeros(4); lp[:len(captured[0])] = captured[0]
+            rows["light_pos"].append(lp)
+            rows["ambient"].append(np.array(captured[1], float)); rows["diffuse"].append(np.array(captured[2], float))
+            rows["trim"].append(float(sim.randomization_settings["trim"][0]))
+            rows["obj_visible"].append(np.array([o.visible for o in sim.objects], bool))
+    out = {f"dr_{k}": np.array(v) for k, v in rows.items()}
+    out["seeds"] = np.array(list(seeds))
+    import json
+    out["config_json"] = json.dumps(CUSTOM_DR)
+    out["sim_json"] = json.dumps(CUSTOM_SIM)
+    np.savez_compressed(os.path.join(OUT, f"reset_customdr_{name}.npz"), **out)
+    print(f"reset_customdr_{name}: {len(out['seeds'])} seeds x 2 episodes")
+
+
 def gen_reset_start(name="udem1", seeds=range(12)):
     """reset() with a fixed start: `user_tile_start` (S:659-666, beats the map's start_tile, no tile draw), the map's
     `start_tile` (S:668-669) and `start_pose` (S:679-686, no spawn loop at all) — as executed by the reference."""
@@ -497,6 +553,10 @@ def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, h
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "customdr":
+        os.makedirs(OUT, exist_ok=True)
+        gen_reset_custom()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "wrappers":
         os.makedirs(OUT, exist_ok=True)
         gen_wrappers()
@@ -517,6 +577,7 @@ if __name__ == "__main__":
         gen_dynamic(m)
     gen_trafficlight()
     gen_reset_start()
+    gen_reset_custom()
     gen_helpers()
     gen_wrappers()
     for m in MAPS:

@@ -191,6 +191,58 @@ def test_device_reset_reproduces_reference_reset_draw_for_draw(name, dr, golden_
     env.close()
 
 
+def test_device_reset_with_custom_randomizer_table_and_sim_colours(golden_dir, torch_cuda):
+    """dts_config.dr_ops / num_tris_distractors / color_sky / color_ground: the DEVICE reset replays the reference's
+    reset() under a custom Randomizer table draw for draw (golden produced by the reference's own Randomizer)."""
+    import json
+    torch = torch_cuda
+    g = np.load(os.path.join(golden_dir, "reset_customdr_loop_obstacles.npz"))
+    cfg, simkw = json.loads(str(g["config_json"])), json.loads(str(g["sim_json"]))
+    n = len(g["seeds"])
+    env = make_env("loop_obstacles", n, domain_rand=True, dynamics_rand=True, seed=int(g["seeds"][0]), device_reset=True,
+                   randomization_config=cfg, **simkw)
+    for ep in range(2):
+        env.reset(render=False)
+        torch.cuda.synchronize()
+        st = {k: v.cpu().numpy() for k, v in env.state.items()}
+        rows = np.arange(n) * 2 + ep
+        assert np.array_equal(st["pos_x"], g["dr_cur_pos"][rows, 0]) and np.array_equal(st["angle"], g["dr_cur_angle"][rows])
+        assert np.array_equal(st["wheel_dist"], g["dr_wheel_dist"][rows])
+        for k in range(n):
+            r, row = env.sim.debug_episode(k), rows[k]
+            assert r["cam_height"] == np.float32(g["dr_cam_height"][row]) and r["cam_angle_deg"] == np.float32(g["dr_cam_angle"][row])
+            assert r["cam_fov_y_deg"] == np.float32(g["dr_cam_fov_y"][row])
+            assert np.array_equal(r["horizon"], g["dr_horizon_color"][row].astype(np.float32))
+            assert np.array_equal(r["ground"], g["dr_ground_color"][row].astype(np.float32))
+            assert np.array_equal(r["cam_noise"], g["dr_camera_noise"][row].astype(np.float32))
+            assert np.array_equal(r["ambient"], g["dr_ambient"][row, :3].astype(np.float32))
+            if ep == 0:
+                assert np.array_equal(r["light_eye"], g["dr_light_pos"][row].astype(np.float32))
+    env.close()
+
+
+def test_randomize_maps_host_reset_keeps_the_stale_light_capture(torch_cuda):
+    """the host path of randomize_maps_on_reset must not disturb pose / camera before the reset proper, or the
+    stale model-view under which GL_LIGHT0 is captured (S:581) is wrong from the second episode on.  Host-drawn and
+    device-drawn resets must agree on light_eye."""
+    torch = torch_cuda
+    names = ["small_loop", "loop_obstacles", "udem1"]
+    envs = [make_env(names, 12, domain_rand=True, seed=300, randomize_maps_on_reset=True, device_reset=dev) for dev in (False, True)]
+    acts = torch.full((12, 2), 0.4, device=envs[0].device)
+    for ep in range(3):
+        for e in envs:
+            e.reset(render=False)
+            for _ in range(4):
+                e.step(acts, render=False)
+        torch.cuda.synchronize()
+        for k in range(12):
+            a, b = envs[0].sim.debug_episode(k), envs[1].sim.debug_episode(k)
+            assert np.array_equal(a["light_eye"], b["light_eye"]), (ep, k, a["light_eye"], b["light_eye"])
+            assert np.array_equal(a["horizon"], b["horizon"])
+    for e in envs:
+        e.close()
+
+
 def test_auto_reset_rollout_equals_reference_style_loop(torch_cuda):
     """Device auto-reset (step + respawn in one kernel, numpy-compatible streams) against the reference-style
     host loop `obs, r, done, _ = env.step(a); if done: env.reset()` built from the CPU oracle (step) and the host

@@ -105,3 +105,39 @@ def test_map_choice_draw_is_a_bounded_integer_draw():
         for _ in range(5):
             assert a.choice(names) == names[int(b.integers(0, len(names)))]
         assert a.bit_generator.state == b.bit_generator.state
+
+
+def test_custom_randomizer_table_and_sim_colours_match_reference(golden_dir):
+    """Randomizer(randomization_config_fp=custom) (randomizer.py:19-33: other ranges, extra keys drawn in sorted
+    position) + non-default num_tris_distractors / color_sky / color_ground: the host sampler replays the
+    reference's reset() draw for draw (golden from the reference's own Randomizer.randomize)."""
+    import json
+    g = np.load(os.path.join(golden_dir, "reset_customdr_loop_obstacles.npz"))
+    cfg, simkw = json.loads(str(g["config_json"])), json.loads(str(g["sim_json"]))
+    md = maps.load_map("loop_obstacles")
+    seeds = [int(v) for v in g["seeds"]]
+    s = EpisodeSampler(len(seeds), domain_rand=True, dynamics_rand=True, randomization_config=cfg, **simkw)
+    s.seed(seeds)
+    envs = list(range(len(seeds)))
+    for ep in range(2):
+        out = s.sample(envs, [md] * len(envs), oracle_query(md))
+        rows = np.arange(len(envs)) * 2 + ep
+        for ours, theirs in (("pos_x", None), ("angle", "cur_angle"), ("wheel_dist", "wheel_dist"), ("cam_height", "cam_height"),
+                             ("cam_angle_deg", "cam_angle"), ("cam_fov_y_deg", "cam_fov_y"), ("horizon_color", "horizon_color"),
+                             ("ground_color", "ground_color"), ("cam_noise", "camera_noise"), ("trim", "trim")):
+            want = g["dr_cur_pos"][rows, 0] if theirs is None else g[f"dr_{theirs}"][rows]
+            assert np.array_equal(out[ours], want), ours
+        assert np.array_equal(out["light_pos"].astype(np.float32), g["dr_light_pos"][rows].astype(np.float32))
+        assert np.array_equal(out["light_ambient"].astype(np.float32), g["dr_ambient"][rows, :3].astype(np.float32))
+
+
+def test_dr_ops_from_config_is_sorted_and_typed():
+    import json
+    from gym_duckietown_b200 import lib as L
+    g_cfg = {"trim": {"type": "normal", "loc": 0, "scale": 0.02}, "horz_mode": {"type": "int", "low": 0, "high": 4},
+             "zz": {"type": "uniform", "low": 0, "high": 1, "size": 5},
+             "light_pos": {"type": "uniform", "low": [-1, 2, -3], "high": [1, 3, 3], "size": 3}}
+    ops = L.dr_ops_from_config(g_cfg)
+    assert [o[2] for o in ops] == [L.DR_TARGETS["horz_mode"], L.DR_TARGETS["light_pos"], L.DR_TARGETS["trim"], 0]
+    assert [o[0] for o in ops] == [L.DR_INT, L.DR_UNIFORM, L.DR_NORMAL, L.DR_UNIFORM] and ops[3][1] == 5
+    assert list(ops[1][3]) == [-1, 2, -3] and list(ops[1][4]) == [1, 3, 3]
