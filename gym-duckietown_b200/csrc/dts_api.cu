@@ -758,6 +758,30 @@ int dts_gather_next(dts_sim* sim) {
   return 0;
 }
 
+int dts_blend4(dts_sim* sim, const uint8_t* const frames_dev[4], const double weights[4], double* out_dev, uint64_t n, void* stream) {
+  if (!sim) return 1;
+  if (!frames_dev || !weights || !out_dev) return sim->fail("NULL argument");
+  for (int k = 0; k < 4; k++) if (!frames_dev[k]) return sim->fail("frame %d is NULL", k);
+  DTS_CUDA(cudaSetDevice(sim->cfg.device));
+  launch_blend4(frames_dev, weights, out_dev, (size_t)n, (cudaStream_t)stream);
+  sim->launches++;
+  DTS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dts_set_timing(dts_sim* sim, double delta_time, int frame_skip, int action_mode) {
+  if (!sim) return 1;
+  if (!(delta_time > 0) || frame_skip < 1) return sim->fail("bad delta_time / frame_skip");
+  if (action_mode != DTS_ACTION_PWM && action_mode != DTS_ACTION_VEL_STEER) return sim->fail("bad action_mode");
+  int d = 0;
+  while (d * delta_time < sim->cfg.dyn_delay - 1e-12) d++;
+  if (d > DTS_MAX_DELAY) return sim->fail("dyn_delay / delta_time exceeds DTS_MAX_DELAY steps");
+  sim->step_cfg.dt = delta_time; sim->step_cfg.frame_skip = frame_skip; sim->step_cfg.action_mode = action_mode;
+  sim->step_cfg.dyn.delay_steps = d;
+  sim->cfg.frame_skip = frame_skip; sim->cfg.action_mode = action_mode; sim->cfg.frame_rate = 1.0 / delta_time;
+  return 0;
+}
+
 int dts_resize_frames(dts_sim* sim, const uint8_t* src_dev, void* dst_dev, void* stream) {
   if (!sim) return 1;
   if (!sim->resize_w) return sim->fail("dts_set_resize first");

@@ -1324,6 +1324,26 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ k_blend4
+// MotionBlurWrapper (learning/utils/wrappers.py:8-54): np.average(window, axis=0, weights=[0.8, 0.15, 0.04, 0.01]) of four
+// uint8 frames -> float64, in numpy's order: products in float64, summed frame by frame, divided by the weight sum.
+__global__ void __launch_bounds__(256) k_blend4(const uint8_t* __restrict__ f0, const uint8_t* __restrict__ f1,
+                                                const uint8_t* __restrict__ f2, const uint8_t* __restrict__ f3, double w0,
+                                                double w1, double w2, double w3, double scl, double* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double a = (double)f0[i] * w0;
+    a = a + (double)f1[i] * w1;
+    a = a + (double)f2[i] * w2;
+    a = a + (double)f3[i] * w3;
+    out[i] = a / scl;
+  }
+}
+void launch_blend4(const uint8_t* const f[4], const double w[4], double* out, size_t n, cudaStream_t st) {
+  const double scl = ((w[0] + w[1]) + w[2]) + w[3];   // numpy: wgt.sum() of four float64 (pairwise == sequential below 8 terms)
+  const size_t blocks = (n + 255) / 256;
+  k_blend4<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(f[0], f[1], f[2], f[3], w[0], w[1], w[2], w[3], scl, out, n);
+}
+
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
                    void* dst, int layout, int dtype, cudaStream_t st) {
   const size_t total = (size_t)n_envs * ow * oh;

@@ -168,6 +168,8 @@ def load() -> C.CDLL:
     lib.dts_assign_maps.argtypes = [vp, vp, vp, vp]
     lib.dts_set_resize.argtypes = [vp, i, i]
     lib.dts_resize_frames.argtypes = [vp, vp, vp, vp]
+    lib.dts_blend4.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
+    lib.dts_set_timing.argtypes = [vp, C.c_double, i, i]
     lib.dts_status.argtypes = [vp]
     lib.dts_profile_enable.argtypes = [vp, i]
     lib.dts_profile_read.argtypes = [vp, vp, vp]
@@ -194,7 +196,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_gather_alloc", "dts_gather_open", "dts_gather_next", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_blend4", "dts_set_timing", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_gather_alloc", "dts_gather_open", "dts_gather_next", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_debug_frame", "dts_last_error", "dts_destroy"]
 
 
@@ -383,6 +385,14 @@ class Sim:
 
     def resize_frames(self, src_ptr: int, dst_ptr: int, stream: int = 0):
         self._check(self.lib.dts_resize_frames(self.h, src_ptr, dst_ptr, stream), "dts_resize_frames")
+
+    def blend4(self, frame_ptrs, weights, out_ptr: int, n: int, stream: int = 0):
+        fp = (C.c_void_p * 4)(*frame_ptrs)
+        w = (C.c_double * 4)(*[float(x) for x in weights])
+        self._check(self.lib.dts_blend4(self.h, fp, w, out_ptr, n, stream), "dts_blend4")
+
+    def set_timing(self, delta_time: float, frame_skip: int, action_mode: int):
+        self._check(self.lib.dts_set_timing(self.h, float(delta_time), int(frame_skip), int(action_mode)), "dts_set_timing")
 
     def status(self) -> int:
         """Sticky status bits, read without synchronising (bit 0: a frame overflowed its render frame memory)."""

@@ -131,3 +131,43 @@ class ResizeWrapper(_FusedWrapper):
         super().__init__(env)
         self.resize_w, self.resize_h = resize_w, resize_h
         self.unwrapped.set_resize(resize_w, resize_h)
+
+
+class MotionBlurWrapper(_FusedWrapper):
+    """LW:8-54 — the reference class sets `frame_skip = 3`, divides the wrapped env's delta_time by it and, per step,
+    renders before each of three `update_physics(action)` calls and once after, returning
+    `np.average(window, axis=0, weights=[0.8, 0.15, 0.04, 0.01])` (float64, oldest frame heaviest) with the reward /
+    done of the final state.  `action` is what update_physics takes: wheel commands, clipped to [-1, 1].
+    Here: three physics-only device steps with a render in between, then one blend kernel (dts_blend4)."""
+
+    WEIGHTS = (0.8, 0.15, 0.04, 0.01)
+
+    def __init__(self, env=None):
+        super().__init__(env)
+        import torch
+        b = self.unwrapped
+        if b.auto_reset:
+            raise ValueError("MotionBlurWrapper steps the physics three times per step: build the env without auto_reset")
+        self.frame_skip = 3
+        b.delta_time = b.delta_time / self.frame_skip                       # LW:14
+        from . import lib as L
+        b.sim.set_timing(b.delta_time, 1, L.ACTION_PWM)                     # update_physics(action): one physics step per call
+        with torch.cuda.device(b.device):
+            self._window = [torch.empty_like(b.obs) for _ in range(4)]
+            self._blurred = torch.empty(tuple(b.obs.shape), dtype=torch.float64, device=b.device)
+
+    @property
+    def observation_space(self):
+        sp = super().observation_space
+        return spaces.Box(0.0, 255.0, sp.shape, dtype=np.float64)
+
+    def step(self, actions, **kw):
+        import torch
+        b = self.unwrapped
+        st = b._stream()
+        for k in range(self.frame_skip):
+            b.sim.render(self._window[k].data_ptr(), st)                    # obs = env.render_obs(); window.append(obs)
+            _, rew, done, info = b.step(actions, render=False)              # env.update_physics(action)
+        b.sim.render(self._window[3].data_ptr(), st)
+        b.sim.blend4([w.data_ptr() for w in self._window], self.WEIGHTS, self._blurred.data_ptr(), self._blurred.numel(), st)
+        return self._blurred, rew, done, info

@@ -258,6 +258,11 @@ int dts_set_output_format(dts_sim* sim, const dts_output_format* fmt);
  * num_envs x 3 x out_h x out_w elements in the selected layout / dtype (OpenCV's 8-bit fixed-point bicubic; matches cv2
  * within 1 LSB).  out_w = out_h = 0 switches it off. */
 int dts_set_resize(dts_sim* sim, int out_w, int out_h);
+/* MotionBlurWrapper (learning/utils/wrappers.py:8-54): out f64[n] = np.average of four u8 frame batches with `weights`
+ * (numpy's evaluation order), and the knobs that wrapper turns on the wrapped env: delta_time / frame_skip (it divides
+ * env.delta_time by 3 and drives update_physics itself, LW:13-14) and the action convention (wheel commands). */
+int dts_blend4(dts_sim* sim, const uint8_t* const frames_dev[4], const double weights[4], double* out_dev, uint64_t n, void* stream);
+int dts_set_timing(dts_sim* sim, double delta_time, int frame_skip, int action_mode);
 /* The resize pass alone, on caller-supplied frames: src u8[num_envs][cam_h][cam_w][3] -> dst in the selected layout / dtype. */
 int dts_resize_frames(dts_sim* sim, const uint8_t* src_dev, void* dst_dev, void* stream);
 int dts_get_state(dts_sim* sim, dts_state_view* out);

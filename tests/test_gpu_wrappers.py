@@ -110,3 +110,32 @@ def test_action_and_reward_wrappers_vs_oracle(mode, torch_cuda):
             assert abs(s["reward"][k] - o.reward) <= 1e-9 * max(1.0, abs(o.reward))     # the state keeps the raw reward
     assert seen == {0, 1, 2}
     env.close()
+
+
+def test_motion_blur_wrapper_equals_numpy_average_of_the_substep_frames(torch_cuda):
+    """MotionBlurWrapper LW:8-54: three update_physics(action) at delta_time / 3 with a render before each and one after,
+    np.average(window, axis=0, weights=[0.8, 0.15, 0.04, 0.01]) in float64; reward / done of the final state."""
+    torch = torch_cuda
+    from gym_duckietown_b200 import lib as L, wrappers as Wr
+    N = 6
+    a = make_env("loop_obstacles", N, action_mode="pwm")
+    b = make_env("loop_obstacles", N, action_mode="pwm")
+    a.reset(); b.reset()
+    w = Wr.MotionBlurWrapper(a)
+    b.sim.set_timing((1.0 / 30) / 3, 1, L.ACTION_PWM)
+    assert w.observation_space.dtype == np.float64
+    rng = np.random.default_rng(3)
+    for t in range(4):
+        act = torch.from_numpy(rng.uniform(-1, 1, (N, 2)).astype(np.float32)).to(a.device)
+        blurred, rew, done, info = w.step(act)
+        window = []
+        for k in range(3):
+            window.append(b.render_obs().cpu().numpy().copy())
+            _, rew_b, done_b, _ = b.step(act, render=False)
+        window.append(b.render_obs().cpu().numpy().copy())
+        want = np.average(window, axis=0, weights=[0.8, 0.15, 0.04, 0.01])
+        got = blurred.cpu().numpy()
+        assert got.dtype == np.float64 and np.array_equal(got, want), float(np.abs(got - want).max())
+        assert torch.equal(rew, rew_b) and torch.equal(done, done_b)
+        assert int(a.state["step_count"][0]) == 3 * (t + 1)
+    a.close(); b.close()
