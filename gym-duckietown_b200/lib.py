@@ -143,7 +143,9 @@ def load() -> C.CDLL:
         return _lib
     import shutil
     from . import build as _b
-    if shutil.which("nvcc"):
+    if os.environ.get("DTS_NO_REBUILD"):     # A/B runs of pre-built variants (tools/ab_all.sh): load what is there
+        pass
+    elif shutil.which("nvcc"):
         _b.build(force=False)
     elif not os.path.exists(LIB_PATH):
         raise DtsError(f"{LIB_PATH} is missing and nvcc is not available to build it")
