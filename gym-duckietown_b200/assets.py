@@ -278,6 +278,62 @@ def mesh_extents() -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
     return {k: (get_mesh(k).min_coords, get_mesh(k).max_coords) for k in _BUILDERS}
 
 
+# ----------------------------------------------------------------------------- segmentation assets (render_obs(segment=True))
+def gen_segmentation_color(name: str) -> List[int]:
+    """ObjMesh's per-class colour (objmesh.py:260-266): the decimal character codes of the mesh name concatenated,
+    cut into 3-digit groups, each `% 255`; the first three groups."""
+    hashed = "".join(str(ord(ch)) for ch in name)
+    col = [int(hashed[i:i + 3]) % 255 for i in range(0, len(hashed), 3)][:3]
+    assert len(col) == 3
+    return col
+
+
+def should_segment_out(tex_path: str) -> bool:
+    """graphics.py:59-67: which textures are replaced by one flat colour; the others keep their lane markings."""
+    for yes in ["sign", "trafficlight", "asphalt"]:
+        if yes in tex_path:
+            return True
+    for no in ["left", "right", "way", "curve", "straight"]:
+        if no in tex_path:
+            return False
+    return True
+
+
+def flat_texture(rgb) -> np.ndarray:
+    """load_texture(..., segment=True) of a segmented-out texture (graphics.py:92-98): every texel = `rgb`."""
+    t = np.zeros((1, 1, 4), np.uint8)
+    t[0, 0, :3] = [int(v) & 255 for v in rgb]
+    t[0, 0, 3] = 255
+    return t
+
+
+def segment_tile_texture(kind: str, rgba: np.ndarray, style: str = "photos") -> np.ndarray:
+    """Texture.bind(segment=True) for a road tile (graphics.py:52-56, 70-130): the texture path decides — grass, floor,
+    asphalt are flattened to black; tiles with lane markings keep what survives the reference's HSV filter (everything
+    outside H 0-179 / S 0-100 / V 0-160, i.e. bright or saturated paint, minus pixels that lose an 8-neighbour)."""
+    path = f"tiles-processed/{style}/{kind}/texture"
+    if should_segment_out(path):
+        return flat_texture([0, 0, 0])
+    try:
+        import cv2
+    except ImportError as e:   # the reference needs cv2 for this too
+        raise RuntimeError("segmentation textures need OpenCV (cv2), as in the reference (graphics.py:100-121)") from e
+    im = np.ascontiguousarray(rgba[:, :, 2::-1])             # cv2.imread gives BGR
+    hsv = cv2.cvtColor(im, cv2.COLOR_BGR2HSV)
+    mask = cv2.inRange(hsv, np.array([0, 0, 0], np.uint8), np.array([179, 100, 160], np.uint8))
+    mask = cv2.bitwise_not(mask)
+    k1 = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], np.uint8)
+    k2 = np.array([[1, 1, 1], [1, 0, 1], [1, 1, 1]], np.uint8)
+    h1 = cv2.morphologyEx(mask, cv2.MORPH_ERODE, k1)
+    h2 = cv2.morphologyEx(h1, cv2.MORPH_ERODE, k2)
+    mask = cv2.bitwise_and(h1, h2)
+    res = cv2.bitwise_and(hsv, hsv, mask=mask)
+    bgr = cv2.cvtColor(res, cv2.COLOR_HSV2BGR)
+    out = np.full(rgba.shape, 255, np.uint8)
+    out[:, :, :3] = bgr[:, :, ::-1]
+    return out
+
+
 # ----------------------------------------------------------------------------- OBJ / MTL reader
 def load_obj(path: str, name: str, texture_loader=None) -> Mesh:
     """Wavefront reader with the reference loader's semantics (objmesh.py:65-293): triangles only,

@@ -200,9 +200,18 @@ class BatchedDuckietownEnv:
                       self._stream())
         return obs, reward, done.view(torch.bool), self.state
 
-    def render_obs(self) -> torch.Tensor:
-        self.sim.render(self.obs.data_ptr(), self._stream())
-        return self.obs
+    def render_obs(self, segment: bool = False, top_down: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """render_obs(segment) (S:1953-1972) of the current state; `top_down` gives _render_img(top_down=True)'s camera."""
+        tgt = self.obs if out is None else out
+        if segment or top_down:
+            self.sim.set_render_mode(segment, top_down)
+            try:
+                self.sim.render(tgt.data_ptr(), self._stream())
+            finally:
+                self.sim.set_render_mode(False, False)
+        else:
+            self.sim.render(tgt.data_ptr(), self._stream())
+        return tgt
 
     # convenience views --------------------------------------------------------------------------
     @property

@@ -44,7 +44,8 @@ struct dts_sim {
   uint64_t gather_bytes = 0;
   int gather_world = 0, gather_rank = 0;
   void* gather_peer[DTS_MAX_PEERS] = {};   // peers' buffers opened with cudaIpcOpenMemHandle (own entry = gather_buf)
-  bool gather_next = false;             // the next dts_render also stores into the gather buffers
+  bool gather_next = false;
+  int render_mode = 0;                  // dts_set_render_mode             // the next dts_render also stores into the gather buffers
   // fused ResizeWrapper (dts_set_resize): full-size render target + tap tables
   int resize_w = 0, resize_h = 0;
   uint8_t* resize_src = nullptr;
@@ -281,6 +282,7 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
     if (s.dyn_slot >= b->n_dyn) return sim->fail("object %d: dyn_slot %d out of range", o, s.dyn_slot);
     d.scale = s.scale; d.y_rot_deg = s.y_rot_deg; d.mesh_id = s.mesh_id; d.optional = s.optional;
     d.tri_offset = me.tri_offset; d.tri_count = me.tri_count;
+    d.seg_tex = (me.seg_flat_tex >= 0 && me.seg_flat_tex < b->n_textures) ? me.seg_flat_tex : -1; d.pad_ = 0;
     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
     for (int t = 0; t < me.tri_count * 3; t++)
       for (int k = 0; k < 3; k++) {
@@ -332,6 +334,32 @@ int dts_upload_map(dts_sim* sim, int map_id, const dts_map_blob* b) {
   }
   m.n_textures = b->n_textures;
   bad |= sim->upload(&m.textures, tex.data(), tex.size(), &own);
+  {
+    std::vector<int16_t> seg(b->n_textures > 0 ? b->n_textures : 1);
+    for (int t = 0; t < b->n_textures; t++) {
+      const int v = b->tex_segment ? b->tex_segment[t] : -1;
+      seg[t] = (int16_t)((v >= 0 && v < b->n_textures) ? v : t);
+    }
+    bad |= sim->upload(&m.tex_segment, seg.data(), seg.size(), &own);
+    DObject ag{};
+    if (b->agent_mesh >= 0 && b->agent_mesh < b->n_meshes) {   // self.mesh, drawn by top-down views at cur_pos (S:1923-1929)
+      const dts_mesh& me = b->meshes[b->agent_mesh];
+      ag.scale = 1.0f; ag.mesh_id = b->agent_mesh; ag.tri_offset = me.tri_offset; ag.tri_count = me.tri_count;
+      ag.dyn_slot = -1; ag.alt_from = ag.alt_to = -1;
+      ag.seg_tex = (me.seg_flat_tex >= 0 && me.seg_flat_tex < b->n_textures) ? me.seg_flat_tex : -1;
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      for (int t = 0; t < me.tri_count * 3; t++)
+        for (int k = 0; k < 3; k++) {
+          const float v = b->tri_pos[((size_t)me.tri_offset * 3 + t) * 3 + k];
+          lo[k] = v < lo[k] ? v : lo[k];
+          hi[k] = v > hi[k] ? v : hi[k];
+        }
+      float r2 = 0.f;
+      for (int k = 0; k < 3; k++) { ag.centre[k] = 0.5f * (lo[k] + hi[k]); const float h = 0.5f * (hi[k] - lo[k]); r2 += h * h; }
+      ag.bound_rad = sqrtf(r2);
+    }
+    m.agent = ag;
+  }
   // dynamic obstacles: constants + every env's copy of the load-time state ([field][slot][env])
   m.n_dyn = b->n_dyn;
   {
@@ -519,13 +547,13 @@ static int ensure_render(dts_sim* sim) {
   int max_tris = 2, max_lat = 1, items_max = 1;
   for (const DMap& m : sim->h_maps) {
     if (!m.valid) continue;
-    int t = 2 + (tess ? 98 : 6) * m.n_tiles;   // a clipped tile quad fans into a few triangles
+    int t = 2 + (tess ? 98 : 6) * m.n_tiles + m.agent.tri_count;   // a clipped tile quad fans into a few triangles
     std::vector<DObject> objs(m.n_objects);
     if (m.n_objects) cudaMemcpy(objs.data(), m.objects, sizeof(DObject) * m.n_objects, cudaMemcpyDeviceToHost);
     for (const DObject& o : objs) t += o.tri_count;
     max_tris = t > max_tris ? t : max_tris;
     max_lat = m.n_tiles > max_lat ? m.n_tiles : max_lat;
-    const int items = 1 + m.n_tiles + m.n_objects;
+    const int items = 1 + m.n_tiles + m.n_objects + 1;   // + the agent's own mesh (top-down views)
     items_max = items > items_max ? items : items_max;
   }
   sim->render_ctas = sms * render_ctas_per_sm();
@@ -563,7 +591,7 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
   if (ensure_render(sim)) return 1;
   if ((sim->cfg.flags & DTS_FLAG_DISTORTION) && !sim->fish.src_xy) return sim->fail("distortion enabled but no fisheye LUT set");
   RenderCfg rc{sim->cfg.cam_width, sim->cfg.cam_height, sim->cfg.flags, sim->cfg.num_envs,
-               (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0, sim->fmt.obs_layout, sim->fmt.obs_dtype};
+               (sim->cfg.flags & DTS_FLAG_TESSELLATE) ? 1 : 0, sim->fmt.obs_layout, sim->fmt.obs_dtype, sim->render_mode};
   if (*(volatile int32_t*)sim->h_status & 1)
     return sim->fail("an earlier frame overflowed its render frame memory (prim slab / bin lists) and was left incomplete");
   cudaEvent_t* marks = nullptr;
@@ -779,6 +807,13 @@ int dts_set_timing(dts_sim* sim, double delta_time, int frame_skip, int action_m
   sim->step_cfg.dt = delta_time; sim->step_cfg.frame_skip = frame_skip; sim->step_cfg.action_mode = action_mode;
   sim->step_cfg.dyn.delay_steps = d;
   sim->cfg.frame_skip = frame_skip; sim->cfg.action_mode = action_mode; sim->cfg.frame_rate = 1.0 / delta_time;
+  return 0;
+}
+
+int dts_set_render_mode(dts_sim* sim, int mode) {
+  if (!sim) return 1;
+  if (mode & ~(DTS_RENDER_SEGMENT | DTS_RENDER_TOP_DOWN)) return sim->fail("bad render mode %d", mode);
+  sim->render_mode = mode;
   return 0;
 }
 

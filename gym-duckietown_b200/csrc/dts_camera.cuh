@@ -35,6 +35,25 @@ __host__ __device__ inline void camera_view(double px, double pz, double angle, 
   }
 }
 
+// top_down=True (S:1786-1798): gluLookAt from (a, H, b) to (a, 0, b - 0.01), up +y, a / b = half the map extents,
+// H = (max(a, b) + 0.1) / tan(fov_y / 2); no camera tilt / forward offset in this view.
+__host__ __device__ inline void top_down_view(double grid_w, double grid_h, double tile_size, double fov_y_deg, double V[12]) {
+  const double a = (grid_w * tile_size) / 2, b = (grid_h * tile_size) / 2;
+  const double H = ((a > b ? a : b) + 0.1) / tan(fov_y_deg * kDeg2Rad / 2);
+  const double ex = a, ey = H, ez = b;
+  double fx = 0.0, fy = 0.0 - H, fz = (b - 0.01) - b;
+  const double fn = sqrt(fx * fx + fy * fy + fz * fz);
+  fx /= fn; fy /= fn; fz /= fn;
+  double sx = fy * 0.0 - fz * 1.0, sy = fz * 0.0 - fx * 0.0, sz = fx * 1.0 - fy * 0.0;   // s = f x up
+  const double sn = sqrt(sx * sx + sy * sy + sz * sz);
+  sx /= sn; sy /= sn; sz /= sn;
+  const double ux = sy * fz - sz * fy, uy = sz * fx - sx * fz, uz = sx * fy - sy * fx;   // u = s x f
+  const double L[12] = {sx, sy, sz, -(sx * ex + sy * ey + sz * ez),
+                        ux, uy, uz, -(ux * ex + uy * ey + uz * ez),
+                        -fx, -fy, -fz, (fx * ex + fy * ey + fz * ez)};
+  for (int k = 0; k < 12; k++) V[k] = L[k];
+}
+
 // Eye-space GL_POSITION for a light given under modelview V: positional (w=1) or direction (w=0).
 __host__ __device__ inline void light_to_eye(const double V[12], const float lp[4], float out[4]) {
   const double x = lp[0], y = lp[1], z = lp[2], w = lp[3];

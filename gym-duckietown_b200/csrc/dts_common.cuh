@@ -22,6 +22,7 @@ struct DObject {
   float centre[3];   // object-space bounding-sphere centre
   int32_t dyn_slot;  // -1 static; else slot of the per-env dynamic state that supplies pos / y_rot / card
   int32_t alt_from, alt_to;   // traffic-light card swap (texture ids), -1 none
+  int32_t seg_tex, pad_;      // flat class-colour texture of the mesh under segment=True (-1 none)
   double dpos[3];    // float64 position (x.pos in _inconvenient_spawn S:1466)
 };
 
@@ -74,6 +75,8 @@ struct DMap {
   int32_t n_textures;
   const DTexture* textures;
   const uint8_t* tex_pool;      // all RGBA8 textures, each 256-byte aligned
+  const int16_t* tex_segment;   // [n_textures] segment=True replacement of each texture (or the same index)
+  DObject agent;                // top-down views: the agent's own mesh (tri_count 0 = none)
   int32_t n_dyn;
   const DDyn* dyn;              // [n_dyn]
   double* dyn_state;            // [DTS_DYN_FIELDS][n_dyn][num_envs]: mutable, per env, survives resets

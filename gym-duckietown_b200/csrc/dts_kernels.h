@@ -21,6 +21,7 @@ struct RenderCfg {
   int32_t n_envs;
   int32_t tessellate;         // 1: literal 98 triangles per road tile (spec tile mode 0)
   int32_t obs_layout, obs_dtype;   // DTS_OBS_* (dts_output_format)
+  int32_t mode;               // DTS_RENDER_SEGMENT | DTS_RENDER_TOP_DOWN (dts_set_render_mode)
 };
 
 void launch_step_logic(const DState& S, const DMap* maps, const StepCfg& c, int n_maps_cycle, const float* actions,

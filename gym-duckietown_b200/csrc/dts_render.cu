@@ -107,6 +107,7 @@ struct __align__(16) FrameCtx {   // per env, global memory
 };
 
 struct __align__(16) GeoWarp {    // per warp of k_geometry, shared memory
+  int32_t unlit, pad_[3];        // segment=True: GL_LIGHTING off, the vertex colour is the material colour (S:1730-1733)
   RenderEp ep;
   double V[12];
   float P00, P11, P22, P23;
@@ -172,7 +173,7 @@ __device__ DTS_GEO_FN Vtx shade_vertex(const Xform& x, const Shared& sh, float p
   for (int k = 0; k < 3; k++) {
     float s = 0.3f + sh.ep.ambient[k];
     s = s + ndl * sh.ep.diffuse[k];
-    const float c = col[k] * s;
+    const float c = sh.unlit ? col[k] : col[k] * s;
     lit[k] = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
   }
   o.r = lit[0]; o.g = lit[1]; o.b = lit[2];
@@ -665,13 +666,18 @@ size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int 
 }
 
 // ------------------------------------------------------------------------------------------------ k_frame_setup
-__global__ void __launch_bounds__(128) k_frame_setup(const DState S, RenderCfg rc, FrameMem fm) {
+__global__ void __launch_bounds__(128) k_frame_setup(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= rc.n_envs) return;
   FrameCtx& c = fm.ctx[env];
   const RenderEp ep = S.rep[env];
   double V[12];
-  camera_view(S.pos_x[env], S.pos_z[env], S.angle[env], ep, (rc.flags & DTS_FLAG_DOMAIN_RAND) != 0, V);
+  if (rc.mode & DTS_RENDER_TOP_DOWN) {
+    const DMap& m = maps[S.map_id[env]];
+    top_down_view((double)m.grid_w, (double)m.grid_h, m.tile_size, (double)ep.cam_fov_y_deg, V);
+  } else {
+    camera_view(S.pos_x[env], S.pos_z[env], S.angle[env], ep, (rc.flags & DTS_FLAG_DOMAIN_RAND) != 0, V);
+  }
 #pragma unroll
   for (int k = 0; k < 12; k++) c.V[k] = V[k];
   const double f = 1.0 / tan((double)ep.cam_fov_y_deg * kDeg2Rad / 2.0), aspect = (double)rc.width / (double)rc.height;
@@ -715,7 +721,10 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   if (env >= rc.n_envs) return;
   const DMap& m = maps[S.map_id[env]];
   const int n_tiles = m.grid_w * m.grid_h;
-  if (item >= 1 + n_tiles + m.n_objects) return;
+  const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;
+  const bool agent_item = item == 1 + n_tiles + m.n_objects;   // top-down views draw the agent's own mesh last (S:1923-1929)
+  if (item > 1 + n_tiles + m.n_objects) return;
+  if (agent_item && (!(rc.mode & DTS_RENDER_TOP_DOWN) || m.agent.tri_count == 0)) return;
   const int W = rc.width, H = rc.height;
   GeoWarp& sh = gws[wib];
   FrameCtx& ctx = fm.ctx[env];
@@ -731,9 +740,13 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, (float)(ts * 0.7071067811865476) * 1.001f + 1e-4f)) return;
   } else if (item > n_tiles) {
     const int o = item - 1 - n_tiles;
-    if (S.rep[env].hidden[o >> 5] >> (o & 31) & 1u) return;
-    const DObject& ob = m.objects[o];
+    if (!agent_item && (S.rep[env].hidden[o >> 5] >> (o & 31) & 1u)) return;
+    const DObject& ob = agent_item ? m.agent : m.objects[o];
     opx = ob.pos[0]; opz = ob.pos[2]; orot = ob.y_rot_deg;
+    if (agent_item) {   // glTranslatef(*cur_pos); glRotatef(cur_angle * 180 / pi, 0, 1, 0): GLfloat arguments
+      opx = (float)S.pos_x[env]; opz = (float)S.pos_z[env];
+      orot = (float)(S.angle[env] * 180.0 / 3.141592653589793);
+    }
     if (ob.dyn_slot >= 0) {
       dyn_kind = m.dyn[ob.dyn_slot].kind;
       if (dyn_kind != DTS_DYN_TRAFFICLIGHT) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
@@ -753,7 +766,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   for (int k = lane; k < (int)(sizeof(RenderEp) / 4); k += 32)
     reinterpret_cast<uint32_t*>(&sh.ep)[k] = reinterpret_cast<const uint32_t*>(&S.rep[env])[k];
   if (lane < 12) sh.V[lane] = ctx.V[lane];
-  if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; }
+  if (lane == 12) { sh.P00 = ctx.P00; sh.P11 = ctx.P11; sh.P22 = ctx.P22; sh.P23 = ctx.P23; sh.unlit = seg ? 1 : 0; }
   __syncwarp();
   EmitCtx ec{m.textures, &sh, &ctx, fm.prims + (size_t)env * max_prims, max_prims, W, H};
   float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
@@ -764,7 +777,8 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     model_view(sh.V, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, x, lane);
     const float gy = (float)(-0.8 * 0.01);
     const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
-    const float* g = sh.ep.ground;
+    const float magenta[3] = {255.f, 0.f, 255.f};   // glColor3f(255, 0, 255) S:1808: clamped to (1, 0, 1) as a vertex colour
+    const float* g = seg ? magenta : sh.ep.ground;
     const int pl_ = lane & 3;   // lanes 0..3 light the four corners, the two triangles (0,1,2)(0,2,3) are then warp-uniform
     const Vtx mine = shade_vertex(x, sh, P[pl_][0], P[pl_][1], P[pl_][2], 0.f, 1.f, 0.f, g[0], g[1], g[2], 0.f, 0.f);
     if (lane < 4) sh.corners[lane] = mine;
@@ -780,7 +794,8 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     const double ts = m.tile_size;
     // glTranslatef((i + 0.5) * TS, 0, (j + 0.5) * TS) S:1870 takes GLfloat arguments
     model_view(sh.V, (double)(float)((ti + 0.5) * ts), 0.0, (double)(float)((tj + 0.5) * ts), 1.0, cs, sn, x, lane);
-    const int tex = m.tile_tex[idx];
+    int tex = m.tile_tex[idx];
+    if (seg && tex >= 0) tex = m.tex_segment[tex];   // Texture.bind(segment=True) G:52-56
     const int base_id = 2 + tris_per_tile * t;
     if (!kTess) {
       // analytic tile: the prim is the quad of the 4 corners — cull on those before lighting the lattice
@@ -864,7 +879,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
   } else {
     // placed mesh S:1905-1907, O:123-148: T(pos) S(scale) Ry(y_rot)
     const int o = item - 1 - n_tiles;
-    const DObject& ob = m.objects[o];
+    const DObject& ob = agent_item ? m.agent : m.objects[o];
     int alt_from = -2;        // traffic-light card on pattern 1: swap this texture id for ob.alt_to
     if (dyn_kind == DTS_DYN_TRAFFICLIGHT) {
       const size_t nd = m.n_dyn, ne = rc.n_envs;
@@ -874,7 +889,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
     sincos((double)orot * kDeg2Rad, &sn, &cs);
     model_view(sh.V, (double)opx, (double)ob.pos[1], (double)opz, (double)ob.scale, cs, sn, x, lane);
     int base_id = 2 + tris_per_tile * n_tiles;
-    for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;
+    for (int q = 0; q < o; q++) base_id += m.objects[q].tri_count;   // (the agent item follows every object)
     for (int k0 = 0; k0 < ob.tri_count; k0 += 32) {
       const int k = k0 + lane;
       Vtx v[3];
@@ -891,6 +906,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
                               c[3 * j], c[3 * j + 1], c[3 * j + 2], uv[2 * j], uv[2 * j + 1]);
         ttex = m.tri_tex[ti];
         if (ttex == alt_from) ttex = ob.alt_to;
+        if (seg) ttex = ob.seg_tex;   // get_mesh(name, segment=True): every chunk shows the flat class colour (M:268-290)
       }
       process_triangle_lanes(ec, k < ob.tri_count, v[0], v[1], v[2], base_id + k, ttex, -1, lane);
       }
@@ -1044,7 +1060,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
       for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
     };
-    const float clr[3] = {S.rep[env].horizon[0], S.rep[env].horizon[1], S.rep[env].horizon[2]};
+    const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;   // glClearColor(255, 0, 255): clamped to magenta (S:1752)
+    const float clr[3] = {seg ? 1.0f : S.rep[env].horizon[0], seg ? 0.0f : S.rep[env].horizon[1], seg ? 1.0f : S.rep[env].horizon[2]};
     const unsigned clear_rgb = pack_rgb(clr[0], clr[1], clr[2]);
     // lane l holds the list of coarse bin (cby, l)
     int my_cnt = 0, my_start = 0;
@@ -1398,7 +1415,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   auto mark = [&]() { if (marks) cudaEventRecord(marks[mk++], st); };
   cudaMemsetAsync(fm.work, 0, 256, st);
   mark();
-  k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, rc, fm);
+  k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, maps, rc, fm);
   mark();
   const dim3 geo_grid((unsigned)((rc.n_envs + kGeoWarps - 1) / kGeoWarps), (unsigned)items_max);
   if (rc.tessellate) k_geometry<true><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);

@@ -88,7 +88,10 @@ class OutputFormat(C.Structure):
 
 
 class Mesh(C.Structure):
-    _fields_ = [("tri_offset", C.c_int32), ("tri_count", C.c_int32)]
+    _fields_ = [("tri_offset", C.c_int32), ("tri_count", C.c_int32), ("seg_flat_tex", C.c_int32), ("reserved", C.c_int32)]
+
+
+RENDER_SEGMENT, RENDER_TOP_DOWN = 1, 2
 
 
 class MapBlob(C.Structure):
@@ -102,6 +105,7 @@ class MapBlob(C.Structure):
         ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p), ("tri_tex", C.c_void_p), ("n_textures", C.c_int32),
         ("textures", C.c_void_p), ("start_tile", C.c_int32 * 2), ("n_dyn", C.c_int32), ("has_start_pose", C.c_int32),
         ("dyn", C.c_void_p), ("start_pose", C.c_double * 3),
+        ("tex_segment", C.c_void_p), ("agent_mesh", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -169,6 +173,7 @@ def load() -> C.CDLL:
     lib.dts_query_poses.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp]
     lib.dts_assign_maps.argtypes = [vp, vp, vp, vp]
     lib.dts_set_resize.argtypes = [vp, i, i]
+    lib.dts_set_render_mode.argtypes = [vp, i]
     lib.dts_resize_frames.argtypes = [vp, vp, vp, vp]
     lib.dts_blend4.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
     lib.dts_set_timing.argtypes = [vp, C.c_double, i, i]
@@ -198,7 +203,7 @@ def load() -> C.CDLL:
 
 
 EXPORTS = ["dts_create", "dts_upload_map", "dts_set_fisheye_lut", "dts_reset", "dts_seed_streams", "dts_reset_random", "dts_step",
-           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_resize_frames", "dts_blend4", "dts_set_timing", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_gather_alloc", "dts_gather_open", "dts_gather_next", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
+           "dts_render", "dts_get_state", "dts_query_poses", "dts_assign_maps", "dts_set_resize", "dts_set_render_mode", "dts_resize_frames", "dts_blend4", "dts_set_timing", "dts_status", "dts_profile_enable", "dts_profile_read", "dts_get_dyn_state", "dts_set_output_format", "dts_gather_alloc", "dts_gather_open", "dts_gather_next", "dts_comm_load", "dts_comm_unique_id", "dts_comm_init",
            "dts_allgather_obs", "dts_launch_count", "dts_debug_counters", "dts_debug_episode", "dts_debug_frame", "dts_last_error", "dts_destroy"]
 
 
@@ -221,6 +226,7 @@ class MapBlobHolder:
         for kid in sorted(set(int(x) for x in md.tile_kind if x >= 0)):
             kind_tex[kid] = len(tex_imgs)
             tex_imgs.append(np.ascontiguousarray(assets.tile_texture(TILE_KINDS[kid])))
+        n_tile_tex = len(tex_imgs)
         k["tex"] = np.array([kind_tex.get(int(x), -1) for x in md.tile_kind], np.int16)
         k["coff"] = np.ascontiguousarray(md.tile_curve_off, np.int32)
         k["ccnt"] = np.ascontiguousarray(md.tile_curve_cnt, np.int32)
@@ -229,20 +235,40 @@ class MapBlobHolder:
         k["cn"] = np.ascontiguousarray(md.coll_norms, np.float64)
         k["ce"] = np.ascontiguousarray(md.coll_centers, np.float64)
         k["cr"] = np.ascontiguousarray(md.coll_radii, np.float64)
-        meshes = (Mesh * max(1, len(md.meshes)))()
+        mesh_list = list(md.meshes)
+        agent_mesh = len(mesh_list)                       # self.mesh = get_duckiebot_mesh("red") S:864: top-down views draw it
+        mesh_list.append(assets.get_mesh("duckiebot"))
+        meshes = (Mesh * max(1, len(mesh_list)))()
         pos, nrm, uv, col, ttex = [], [], [], [], []
         off = 0
         alt_of_mesh = {}
-        for mi, m in enumerate(md.meshes):
+        mesh_tex_range = []
+        for mi, m in enumerate(mesh_list):
             base = len(tex_imgs)
             tex_imgs.extend(np.ascontiguousarray(t) for t in m.textures)
             for slot, img in getattr(m, "alt_textures", {}).items():   # traffic-light card for pattern 1
                 alt_of_mesh[mi] = (base + slot, len(tex_imgs))
                 tex_imgs.append(np.ascontiguousarray(img))
-            meshes[mi] = Mesh(off, len(m.tri_pos))
+            mesh_tex_range.append((base, len(tex_imgs)))
+            meshes[mi] = Mesh(off, len(m.tri_pos), -1, 0)
             off += len(m.tri_pos)
             pos.append(m.tri_pos); nrm.append(m.tri_nrm); uv.append(m.tri_uv); col.append(m.tri_col)
             ttex.append(np.where(m.tri_tex >= 0, m.tri_tex + base, -1).astype(np.int16))
+        # segment=True assets: tiles keep their lane markings or go black (graphics.py:70-130); every chunk of a mesh
+        # shows the flat class colour gen_segmentation_color(mesh_name) (objmesh.py:260-290)
+        seg_of = np.arange(len(tex_imgs), dtype=np.int64)
+        n_plain = len(tex_imgs)
+        for kid, ti in kind_tex.items():
+            seg_of[ti] = len(tex_imgs)
+            tex_imgs.append(np.ascontiguousarray(assets.segment_tile_texture(TILE_KINDS[kid], tex_imgs[ti])))
+        for mi, m in enumerate(mesh_list):
+            name = "sign_generic" if m.name.startswith("sign") else m.name
+            meshes[mi].seg_flat_tex = len(tex_imgs)
+            seg_of[mesh_tex_range[mi][0]:mesh_tex_range[mi][1]] = len(tex_imgs)
+            tex_imgs.append(assets.flat_texture(assets.gen_segmentation_color(name)))
+        seg_full = np.arange(len(tex_imgs), dtype=np.int16)
+        seg_full[:n_plain] = seg_of
+        k["seg"] = seg_full
         cat = lambda lst, shape, dt: (np.ascontiguousarray(np.concatenate(lst, 0), dt) if lst else np.zeros(shape, dt))
         k["tpos"] = cat(pos, (0, 3, 3), np.float32); k["tnrm"] = cat(nrm, (0, 3, 3), np.float32)
         k["tuv"] = cat(uv, (0, 3, 2), np.float32); k["tcol"] = cat(col, (0, 3, 3), np.float32)
@@ -274,14 +300,16 @@ class MapBlobHolder:
         self.blob = MapBlob(
             md.tile_size, md.grid_w, md.grid_h, _ptr(k["kind"]), _ptr(k["angle"]), _ptr(k["drv"]), _ptr(k["tex"]),
             _ptr(k["coff"]), _ptr(k["ccnt"]), len(md.curves), _ptr(k["curves"]), md.n_coll, _ptr(k["cc"]),
-            _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(md.meshes),
+            _ptr(k["cn"]), _ptr(k["ce"]), _ptr(k["cr"]), len(md.objects), C.cast(objs, C.c_void_p), len(mesh_list),
             C.cast(meshes, C.c_void_p), off, _ptr(k["tpos"]), _ptr(k["tnrm"]), _ptr(k["tuv"]), _ptr(k["tcol"]),
             _ptr(k["ttex"]), len(tex_imgs), C.cast(texs, C.c_void_p),
             (C.c_int32 * 2)(*(user_tile_start if user_tile_start else
                               (md.start_tile if md.start_tile is not None else (-1, -1)))),   # S:659-671
             len(md.dyn_objects), int(md.start_pose is not None), C.cast(dyn, C.c_void_p),
             (C.c_double * 3)(*((float(md.start_pose[0][0]), float(md.start_pose[0][2]), float(md.start_pose[1]))
-                               if md.start_pose is not None else (0.0, 0.0, 0.0))))
+                               if md.start_pose is not None else (0.0, 0.0, 0.0))),
+            _ptr(k["seg"]), agent_mesh, 0)
+        self.agent_mesh, self.n_tile_tex = agent_mesh, n_tile_tex
 
 
 class _CudaArray:
@@ -381,6 +409,10 @@ class Sim:
         if ids.shape != (self.cfg.num_envs,):
             raise ValueError("map_ids must have one entry per env")
         self._check(self.lib.dts_assign_maps(self.h, mask_ptr, _ptr(ids), stream), "dts_assign_maps")
+
+    def set_render_mode(self, segment: bool = False, top_down: bool = False):
+        self._check(self.lib.dts_set_render_mode(self.h, (RENDER_SEGMENT if segment else 0) | (RENDER_TOP_DOWN if top_down else 0)),
+                    "dts_set_render_mode")
 
     def set_resize(self, out_w: int, out_h: int):
         self._check(self.lib.dts_set_resize(self.h, int(out_w), int(out_h)), "dts_set_resize")

@@ -31,6 +31,7 @@ DEFAULT_MAP_NAME = "udem1"
 
 # module-level constants and helpers user scripts import from gym_duckietown.simulator (S:118-177, S:2056-2118)
 CAMERA_FORWARD_DIST, ROBOT_WIDTH, ROBOT_LENGTH, WHEEL_DIST = 0.066, 0.13 + 0.02, 0.18, 0.102
+WINDOW_WIDTH, WINDOW_HEIGHT = 800, 600   # S:100-101
 DEFAULT_ROBOT_SPEED, DEFAULT_FRAMERATE, DEFAULT_MAX_STEPS = 1.20, 30, 1500
 REWARD_INVALID_POSE = -1000
 
@@ -122,9 +123,9 @@ class Simulator(Env):
         return [seed]
 
     def reset(self, segment: bool = False):
-        if segment:
-            raise NotImplementedError("segmentation rendering is a debug mode (SURVEY 8f-4)")
-        obs = self._b.reset()
+        obs = self._b.reset(render=not segment)
+        if segment:   # S:760: the first observation is render_obs(segment=segment)
+            obs = self._b.render_obs(segment=True)
         self.timestamp = 0.0
         self._adopt_map()
         return self._obs_numpy(obs)
@@ -145,14 +146,49 @@ class Simulator(Env):
         return o, float(st["reward"]), bool(code != 0), misc
 
     def render_obs(self, segment: bool = False):
-        return self._obs_numpy(self._b.render_obs())
+        return self._obs_numpy(self._b.render_obs(segment=segment))
 
-    def render(self, mode: str = "rgb_array", close: bool = False, segment: bool = False):
-        if mode != "rgb_array":
-            raise NotImplementedError("window / top_down / free_cam rendering is interactive UI (out of scope)")
-        return self.render_obs()
+    def _human_view(self):
+        """A second 1-env handle at WINDOW_WIDTH x WINDOW_HEIGHT (S:100-101, 340) put into this env's state: what
+        `_render_img(WINDOW_WIDTH, WINDOW_HEIGHT, multi_fbo_human, ...)` draws (S:1988-1996)."""
+        import torch
+        from .batched_env import BatchedDuckietownEnv
+        if getattr(self, "_human", None) is None:
+            self._human = BatchedDuckietownEnv(1, list(self._b.maps), device=self._b.device_index, camera_width=WINDOW_WIDTH,
+                                               camera_height=WINDOW_HEIGHT, domain_rand=self.domain_rand, seed=0,
+                                               max_steps=self.max_steps)
+        h, b = self._human, self._b
+        ep, st = b.sim.debug_episode(0), self._scalars()
+        mid = self._map_index()
+        one = lambda v, dt: np.asarray([v], dtype=dt)
+        h.sim.reset(None, dict(
+            map_id=one(mid, np.int32), pos_x=one(st["pos_x"], np.float64), pos_z=one(st["pos_z"], np.float64),
+            angle=one(st["angle"], np.float64), wheel_dist=one(st["wheel_dist"], np.float64),
+            cam_height=one(ep["cam_height"], np.float32), cam_angle_deg=one(ep["cam_angle_deg"], np.float32),
+            cam_fov_y_deg=one(ep["cam_fov_y_deg"], np.float32), cam_noise=ep["cam_noise"][None].astype(np.float32),
+            horizon_color=ep["horizon"][None], light_ambient=ep["ambient"][None], light_diffuse=ep["diffuse"][None],
+            light_pos=ep["light_eye"][None], light_stale=one(0, np.int32), ground_color=ep["ground"][None],
+            obj_hidden=ep["hidden"][None].astype(np.uint32)), h._stream())
+        src, nd = b.sim.dyn_state(mid)
+        if nd:   # the obstacles where this env has them
+            dst, _ = h.sim.dyn_state(mid)
+            torch.as_tensor(dst, device=h.device).copy_(torch.as_tensor(src, device=b.device))
+        return h
+
+    def render(self, mode: str = "human", close: bool = False, segment: bool = False):
+        """S:1974-2054.  "rgb_array" / "top_down" return the WINDOW_WIDTH x WINDOW_HEIGHT image; "human" / "free_cam" open a
+        pyglet window in the reference (interactive UI: not provided).  The fisheye model is not applied to this view."""
+        assert mode in ["human", "top_down", "free_cam", "rgb_array"]
+        if close:
+            return None
+        if mode in ("human", "free_cam"):
+            raise NotImplementedError("window rendering (human / free_cam) is interactive UI; use rgb_array or top_down")
+        h = self._human_view()
+        return h.render_obs(segment=segment, top_down=(mode == "top_down"))[0].cpu().numpy()
 
     def close(self):
+        if getattr(self, "_human", None) is not None:
+            self._human.close()
         self._b.close()
 
     # ------------------------------------------------------------------ state the reference exposes as attributes

@@ -27,6 +27,15 @@ class _FusedWrapper:
     def __init__(self, env):
         self.env = env
 
+    @property
+    def batched(self):
+        """The BatchedDuckietownEnv whose device path the wrapper configures: the wrapped env itself, or the one inside
+        a single-env adapter (simulator.Simulator / DuckietownEnv keep it as `_b`)."""
+        e = self.env
+        while not hasattr(e, "set_output_format"):
+            e = e._b if hasattr(e, "_b") else e.env
+        return e
+
     def __getattr__(self, name):
         if name == "env":
             raise AttributeError(name)
@@ -38,7 +47,7 @@ class _FusedWrapper:
 
     @property
     def observation_space(self):
-        b = self.unwrapped
+        b = self.batched
         f = b.output_format
         H, W = b.obs_size
         shape = {"hwc": (H, W, 3), "chw": (3, H, W), "cwh": (3, W, H)}[f["obs_layout"]]
@@ -58,7 +67,7 @@ class ImgWrapper(_FusedWrapper):
 
     def __init__(self, env=None):
         super().__init__(env)
-        self.unwrapped.set_output_format(obs_layout="chw")
+        self.batched.set_output_format(obs_layout="chw")
 
 
 class PyTorchObsWrapper(_FusedWrapper):
@@ -66,7 +75,7 @@ class PyTorchObsWrapper(_FusedWrapper):
 
     def __init__(self, env=None):
         super().__init__(env)
-        self.unwrapped.set_output_format(obs_layout="cwh")
+        self.batched.set_output_format(obs_layout="cwh")
 
 
 class NormalizeWrapper(_FusedWrapper):
@@ -74,7 +83,7 @@ class NormalizeWrapper(_FusedWrapper):
 
     def __init__(self, env=None):
         super().__init__(env)
-        self.unwrapped.set_output_format(obs_dtype="float32")
+        self.batched.set_output_format(obs_dtype="float32")
 
 
 class DtRewardWrapper(_FusedWrapper):
@@ -82,7 +91,7 @@ class DtRewardWrapper(_FusedWrapper):
 
     def __init__(self, env):
         super().__init__(env)
-        self.unwrapped.set_output_format(reward="dt")
+        self.batched.set_output_format(reward="dt")
 
 
 class ActionWrapper(_FusedWrapper):
@@ -90,7 +99,7 @@ class ActionWrapper(_FusedWrapper):
 
     def __init__(self, env):
         super().__init__(env)
-        self.unwrapped.set_output_format(action_vel_scale=0.8)
+        self.batched.set_output_format(action_vel_scale=0.8)
 
 
 class DiscreteWrapper(_FusedWrapper):
@@ -98,12 +107,12 @@ class DiscreteWrapper(_FusedWrapper):
 
     def __init__(self, env):
         super().__init__(env)
-        self.unwrapped.set_output_format(discrete_actions=True)
+        self.batched.set_output_format(discrete_actions=True)
         self.action_space = spaces.Discrete(3)
 
     def step(self, actions, **kw):
         import torch
-        b = self.unwrapped
+        b = self.batched
         ids = actions.to(device=b.device, dtype=torch.float32).reshape(b.num_envs)
         return self.env.step(torch.stack([ids, torch.zeros_like(ids)], dim=1), **kw)
 
@@ -114,7 +123,7 @@ class SteeringToWheelVelWrapper(_FusedWrapper):
 
     def __init__(self, env, gain=1.0, trim=0.0, radius=0.0318, k=27.0, limit=1.0):
         super().__init__(env)
-        c = self.unwrapped.cfg
+        c = self.batched.cfg
         if c.action_mode != 1:
             raise ValueError("build the env with action_mode='vel_steer' and these gain/trim/radius/k/limit instead")
         if (c.gain, c.trim, c.radius, c.k, c.limit) != (gain, trim, radius, k, limit):
@@ -130,7 +139,7 @@ class ResizeWrapper(_FusedWrapper):
     def __init__(self, env=None, resize_w=80, resize_h=80):
         super().__init__(env)
         self.resize_w, self.resize_h = resize_w, resize_h
-        self.unwrapped.set_resize(resize_w, resize_h)
+        self.batched.set_resize(resize_w, resize_h)
 
 
 class MotionBlurWrapper(_FusedWrapper):
@@ -145,7 +154,7 @@ class MotionBlurWrapper(_FusedWrapper):
     def __init__(self, env=None):
         super().__init__(env)
         import torch
-        b = self.unwrapped
+        b = self.batched
         if b.auto_reset:
             raise ValueError("MotionBlurWrapper steps the physics three times per step: build the env without auto_reset")
         self.frame_skip = 3
@@ -163,7 +172,7 @@ class MotionBlurWrapper(_FusedWrapper):
 
     def step(self, actions, **kw):
         import torch
-        b = self.unwrapped
+        b = self.batched
         st = b._stream()
         for k in range(self.frame_skip):
             b.sim.render(self._window[k].data_ptr(), st)                    # obs = env.render_obs(); window.append(obs)

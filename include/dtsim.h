@@ -128,7 +128,12 @@ enum { DTS_DYN_PX = 0, DTS_DYN_PZ, DTS_DYN_ANGLE, DTS_DYN_YROT, DTS_DYN_CORNERS 
         * they all share currently shows (every flip assigns it; the last writer wins, like the reference) */
        DTS_DYN_PATTERN = DTS_DYN_ACTIVE, DTS_DYN_SHOWN = DTS_DYN_WAIT };
 
-typedef struct { int32_t tri_offset, tri_count; } dts_mesh;
+typedef struct {
+  int32_t tri_offset, tri_count;
+  int32_t seg_flat_tex;     /* texture every triangle of this mesh shows under segment=True: the flat class colour
+                               gen_segmentation_color(mesh_name) (objmesh.py:260-290); -1 = none */
+  int32_t reserved;
+} dts_mesh;
 
 /* What the reference's wrapper stacks do to actions, observations and rewards, fused into the step kernels
  * (SURVEY 8f-3).  W = src/gym_duckietown/wrappers.py, LW = learning/utils/wrappers.py. */
@@ -183,6 +188,10 @@ typedef struct {
   int32_t has_start_pose;         /* map `start_pose` (S:874-876): device resets then place the agent at start_pose */
   const dts_dyn_object* dyn;      /* [n_dyn] in the order of the map's object list (update order S:1570-1584) */
   double start_pose[3];           /* x offset, z offset inside the start tile, angle (S:679-686) */
+  const int16_t* tex_segment;     /* [n_textures] what Texture.bind(segment=True) / get_mesh(name, True) show instead of texture t
+                                     (graphics.py:52-56, 70-130; objmesh.py:268-290); NULL or -1 = unchanged */
+  int32_t agent_mesh;             /* mesh drawn at the agent's pose in top-down views (self.mesh, S:864, S:1923-1929); -1 = none */
+  int32_t reserved2;
 } dts_map_blob;
 
 /* Per-episode inputs produced by Simulator.reset() (simulator.py:528-763), one
@@ -250,6 +259,13 @@ int dts_step(dts_sim* sim, const float* actions_dev, void* obs_dev, float* rewar
              void* stream);
 /* Simulator.render_obs() (simulator.py:1953-1972) of the current state. */
 int dts_render(dts_sim* sim, void* obs_dev, void* stream);
+/* Render variants of _render_img (S:1707-1951) for subsequent dts_render / dts_step calls (0 = the agent camera):
+ *   DTS_RENDER_SEGMENT   segment=True: lighting off (S:1730-1733), magenta clear + ground (S:1752, 1808), no distractors
+ *                        (S:1814), segmentation textures / flat per-class mesh colours
+ *   DTS_RENDER_TOP_DOWN  top_down=True: camera above the map centre looking down (S:1786-1798), the agent's own mesh drawn
+ *                        at cur_pos (S:1923-1929) */
+enum { DTS_RENDER_SEGMENT = 1, DTS_RENDER_TOP_DOWN = 2 };
+int dts_set_render_mode(dts_sim* sim, int mode);
 /* Select the fused wrapper behaviour for subsequent dts_step / dts_render calls (default: all zero, scale 1).
  * obs_dev then holds num_envs * 3 * H * W elements of uint8 or float32 in the chosen layout. */
 int dts_set_output_format(dts_sim* sim, const dts_output_format* fmt);

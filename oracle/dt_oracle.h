@@ -44,6 +44,7 @@ typedef struct { int32_t w, h; const uint8_t* rgba; } orr_texture;
 typedef struct {
   float pos[3]; float scale; float y_rot_deg; int32_t tri_offset, tri_count;
   int32_t tex_from, tex_to; /* triangles textured tex_from draw tex_to instead (traffic-light card); -1 = off */
+  int32_t seg_tex;          /* segment=True: every triangle shows this flat class-colour texture (objmesh.py:260-290) */
 } orr_object;
 
 typedef struct {
@@ -61,6 +62,8 @@ typedef struct {
   const int16_t* tri_tex;
   int32_t n_textures;
   const orr_texture* textures;
+  const int16_t* tex_segment; /* [n_textures] Texture.bind(segment=True) replacement (graphics.py:52-56) */
+  orr_object agent;           /* top-down views: the agent's own mesh (tri_count 0 = none), S:1923-1929 */
 } orr_scene;
 
 typedef struct { /* mirrors the product's per-episode render record */
@@ -108,6 +111,7 @@ void orc_step(const orc_map* m, const orc_dyn_params* dp, orc_dyn_state* s, int*
               int frame_skip, double dt, int max_steps, double robot_speed, orc_step_out* o);
 void orr_render(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                 int domain_rand, const float* lut_x, const float* lut_y, uint8_t* out);
+void orr_set_render_mode(int mode); /* 1 = segment=True, 2 = top_down=True (simulator.py:1707-1951) */
 void orr_debug_frame(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                      int domain_rand, double* V_out, float* P_out, float* item_mv, float* item_n, float* lattice);
 #endif

@@ -48,6 +48,27 @@ typedef struct {
 static const int SX[4] = {24, 56, 8, 40}, SY[4] = {8, 24, 40, 56}; /* sample offsets in 1/64 px */
 static int g_tile_mode = 1;
 void orr_set_tile_mode(int mode) { g_tile_mode = mode; }
+static int g_render_mode = 0; /* 1 = segment (S:1730-1733, 1752, 1808, 1814), 2 = top_down (S:1786-1798, 1923-1929) */
+void orr_set_render_mode(int mode) { g_render_mode = mode; }
+#define SEGMENT (g_render_mode & 1)
+#define TOP_DOWN (g_render_mode & 2)
+
+/* top_down=True: gluLookAt from (a, H, b) to (a, 0, b - 0.01), up +y (S:1786-1798) */
+static void top_down_view(double grid_w, double grid_h, double tile_size, double fov_y_deg, double V[12]) {
+  const double a = (grid_w * tile_size) / 2, b = (grid_h * tile_size) / 2;
+  const double Hh = ((a > b ? a : b) + 0.1) / tan(fov_y_deg * 0.017453292519943295 / 2);
+  const double ex = a, ey = Hh, ez = b;
+  double fx = 0.0, fy = 0.0 - Hh, fz = (b - 0.01) - b;
+  const double fn = sqrt(fx * fx + fy * fy + fz * fz);
+  fx /= fn; fy /= fn; fz /= fn;
+  double sx = fy * 0.0 - fz * 1.0, sy = fz * 0.0 - fx * 0.0, sz = fx * 1.0 - fy * 0.0;
+  const double sn = sqrt(sx * sx + sy * sy + sz * sz);
+  sx /= sn; sy /= sn; sz /= sn;
+  const double ux = sy * fz - sz * fy, uy = sz * fx - sx * fz, uz = sx * fy - sy * fx;
+  const double L[12] = {sx, sy, sz, -(sx * ex + sy * ey + sz * ez), ux, uy, uz, -(ux * ex + uy * ey + uz * ez),
+                        -fx, -fy, -fz, (fx * ex + fy * ey + fz * ez)};
+  for (int k = 0; k < 12; k++) V[k] = L[k];
+}
 #define GUARD 4.0f
 
 /* ---- camera (simulator.py:1758-1803), float64 ------------------------------------------------ */
@@ -128,7 +149,7 @@ static vtx shade_vertex(const xform* x, const float p[3], const float n[3], cons
   for (int k = 0; k < 3; k++) {
     float s = 0.3f + x->ep->ambient[k];
     s = s + ndl * x->ep->diffuse[k];
-    float c = col[k] * s;
+    float c = SEGMENT ? col[k] : col[k] * s; /* segment=True: GL_LIGHTING off, the vertex colour is the material colour */
     lit[k] = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
   }
   o.r = lit[0]; o.g = lit[1]; o.b = lit[2];
@@ -388,12 +409,14 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
   fb.W = W; fb.H = H;
   fb.col = tl_col;
   fb.depth = tl_depth;
-  for (size_t k = 0; k < (size_t)W * H * 4; k++) {  /* glClear S:1753-1756 */
+  const float clear[3] = {SEGMENT ? 1.0f : ep->horizon[0], SEGMENT ? 0.0f : ep->horizon[1], SEGMENT ? 1.0f : ep->horizon[2]};
+  for (size_t k = 0; k < (size_t)W * H * 4; k++) {  /* glClear S:1753-1756; segment: glClearColor(255, 0, 255) clamps to magenta */
     fb.depth[k] = 1.0f;
-    fb.col[3 * k] = ep->horizon[0]; fb.col[3 * k + 1] = ep->horizon[1]; fb.col[3 * k + 2] = ep->horizon[2];
+    fb.col[3 * k] = clear[0]; fb.col[3 * k + 1] = clear[1]; fb.col[3 * k + 2] = clear[2];
   }
   double V[12];
-  camera_view(px, pz, angle, ep, domain_rand, V);
+  if (TOP_DOWN) top_down_view((double)sc->grid_w, (double)sc->grid_h, sc->tile_size, (double)ep->cam_fov_y_deg, V);
+  else camera_view(px, pz, angle, ep, domain_rand, V);
   xform x;
   x.ep = ep;
   {  /* gluPerspective(fovy, W/H, 0.04, 100) S:1761 */
@@ -411,7 +434,9 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
     const float P[4][3] = {{-50.f, gy, 50.f}, {-50.f, gy, -50.f}, {50.f, gy, -50.f}, {50.f, gy, 50.f}};
     const float nrm[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0}, uv[6] = {0, 0, 0, 0, 0, 0};
     float col[9];
-    for (int k = 0; k < 3; k++) { col[k] = ep->ground[k]; col[3 + k] = ep->ground[k]; col[6 + k] = ep->ground[k]; }
+    const float magenta[3] = {255.f, 0.f, 255.f}; /* glColor3f(255, 0, 255) S:1808 */
+    const float* gc = SEGMENT ? magenta : ep->ground;
+    for (int k = 0; k < 3; k++) { col[k] = gc[k]; col[3 + k] = gc[k]; col[6 + k] = gc[k]; }
     const int tri[2][3] = {{0, 1, 2}, {0, 2, 3}};
     for (int t = 0; t < 2; t++) {
       float p[9];
@@ -433,7 +458,9 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
       /* glTranslatef((i + 0.5) * TS, 0, (j + 0.5) * TS) S:1870: GLfloat arguments */
       const double t[3] = {(double)(float)((i + 0.5) * ts), 0.0, (double)(float)((j + 0.5) * ts)};
       model_view(V, t, 1.0, cs[quarter], sn[quarter], x.MV, x.N);
-      const orr_texture* tex = sc->tile_tex[idx] >= 0 ? &sc->textures[sc->tile_tex[idx]] : NULL;
+      int tile_tex = sc->tile_tex[idx];
+      if (SEGMENT && tile_tex >= 0 && sc->tex_segment) tile_tex = sc->tex_segment[tile_tex];
+      const orr_texture* tex = tile_tex >= 0 ? &sc->textures[tile_tex] : NULL;
       const float white[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1}, up[9] = {0, 1, 0, 0, 1, 0, 0, 1, 0};
       if (g_tile_mode == 1) {
         /* analytic: light the 8x8 lattice once, draw the tile as one quad (0,1,2)(0,2,3) */
@@ -472,10 +499,20 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
           }
         }
     }
-  /* 3. objects S:1905-1907, O:123-148, M:360-375 */
-  for (int o = 0; o < sc->n_objects; o++) {
-    if (ep->hidden[o >> 5] >> (o & 31) & 1u) continue;
-    const orr_object* ob = &sc->objects[o];
+  /* 3. objects S:1905-1907, O:123-148, M:360-375; top-down views then draw the agent's own mesh at cur_pos (S:1923-1929) */
+  for (int o = 0; o <= sc->n_objects; o++) {
+    orr_object agent = sc->agent;
+    const orr_object* ob;
+    if (o < sc->n_objects) {
+      if (ep->hidden[o >> 5] >> (o & 31) & 1u) continue;
+      ob = &sc->objects[o];
+    } else {
+      if (!TOP_DOWN || sc->agent.tri_count == 0) break;
+      agent.pos[0] = (float)px; agent.pos[1] = 0.0f; agent.pos[2] = (float)pz;   /* glTranslatef(*cur_pos) */
+      agent.scale = 1.0f;
+      agent.y_rot_deg = (float)(angle * 180.0 / 3.141592653589793);              /* glRotatef(cur_angle * 180 / pi, 0, 1, 0) */
+      ob = &agent;
+    }
     const double t[3] = {ob->pos[0], ob->pos[1], ob->pos[2]};
     const double th = (double)ob->y_rot_deg * 0.017453292519943295;
     model_view(V, t, (double)ob->scale, cos(th), sin(th), x.MV, x.N);
@@ -483,6 +520,7 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
       size_t ti = (size_t)ob->tri_offset + k;
       int tid = sc->tri_tex[ti];
       if (tid >= 0 && tid == ob->tex_from) tid = ob->tex_to;   /* TrafficLightObj card swap O:453,462 */
+      if (SEGMENT) tid = ob->seg_tex;                          /* get_mesh(name, segment=True): flat class colour M:268-290 */
       const orr_texture* tex = tid >= 0 ? &sc->textures[tid] : NULL;
       draw_triangle(&fb, &x, sc->tri_pos + ti * 9, sc->tri_nrm + ti * 9, sc->tri_uv + ti * 6, sc->tri_col + ti * 9, tex);
     }
@@ -515,7 +553,8 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
 void orr_debug_frame(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                      int domain_rand, double* V_out, float* P_out, float* item_mv, float* item_n, float* lattice) {
   double V[12];
-  camera_view(px, pz, angle, ep, domain_rand, V);
+  if (TOP_DOWN) top_down_view((double)sc->grid_w, (double)sc->grid_h, sc->tile_size, (double)ep->cam_fov_y_deg, V);
+  else camera_view(px, pz, angle, ep, domain_rand, V);
   memcpy(V_out, V, sizeof V);
   xform x;
   x.ep = ep;

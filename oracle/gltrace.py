@@ -268,6 +268,7 @@ def attach(rec: GLRecorder):
         rec.tex_names[t.id] = (str(path), bool(segment))
         return t
 
+    G.Texture.tex_cache.clear()   # class-level cache of Texture objects: ids of an earlier recorder must not survive
     rec._fake_load_texture = fake_load_texture
     S.load_texture = fake_load_texture
     G.load_texture = fake_load_texture

@@ -499,19 +499,29 @@ def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, h
                 rec.take()
                 sim.reset()
                 distractors.append(np.concatenate([sim.tri_vlist.attrs["v"], sim.tri_vlist.attrs["c"]], 1))
-                for k in range(poses_per_episode + 1):
-                    if k > 0:   # a short walk from the spawn pose: rendering does not need a valid pose
+                modes = [0] * (poses_per_episode + 1)
+                if episode == 1:
+                    modes += [2] + ([1] if not dr else [])   # one top_down frame; one segment frame (DR off: the DR texture
+                                                             # pick in get_texture calls rng.randint, absent from a Generator)
+                for k, mode in enumerate(modes):
+                    if k > 0 and mode == 0:   # a short walk from the spawn pose: rendering does not need a valid pose
                         d = S.get_dir_vec(sim.cur_angle)
                         sim.cur_pos = np.array(sim.cur_pos, float) + d * rng.uniform(0.02, 0.2)
                         sim.cur_angle = float(sim.cur_angle) + rng.uniform(-0.5, 0.5)
                         rec.take()
                         sim.render_obs()
+                    elif mode == 1:
+                        rec.take()
+                        sim.render_obs(segment=True)
+                    elif mode == 2:
+                        rec.take()
+                        sim._render_img(width, height, sim.multi_fbo, sim.final_fbo, sim.img_array, top_down=True, segment=False)
                     ev = rec.take()
                     lights = [e for e in ev if e["kind"] == "light"]
                     clear = [e for e in ev if e["kind"] == "clear"][-1]
                     look = [e for e in ev if e["kind"] == "lookat"][-1]
                     dl = [e for e in ev if e["kind"] == "draw"]
-                    f = dict(dr=dr, seed=seed, episode=episode, k=k, pos=np.array(sim.cur_pos, float), angle=float(sim.cur_angle),
+                    f = dict(dr=dr, seed=seed, episode=episode, k=k, mode=mode, pos=np.array(sim.cur_pos, float), angle=float(sim.cur_angle),
                              clear=clear["color"], persp=np.array(rec.perspective), eye=look["eye"], center=look["center"],
                              view=look["modelview"].reshape(-1), proj=dl[0]["projection"].reshape(-1),
                              light_eye=dl[0]["light_pos_eye"], light_ambient=dl[0]["light_ambient"],
@@ -535,8 +545,10 @@ def gen_gltrace(name: str, seeds=(11, 12, 13), poses_per_episode=8, width=160, h
                             if e["id"] not in mesh_kinds:
                                 mesh_kinds.append(e["id"])
                             sub = mesh_kinds.index(e["id"])
+                        tid = e["texture"]
                         draws.append(dict(frame=len(frames), kind=kind, sub=sub, mv=e["modelview"].reshape(-1), color=e["color"],
-                                          tex=tex_index(e["texture"]), lit=e["lighting"]))
+                                          tex=tex_index(tid), lit=e["lighting"],
+                                          tex_seg=bool(tid is not None and rec.tex_names[tid][1]), mesh_seg=bool(e.get("segment", False))))
                     f["ndraws"] = len(draws) - f["draw0"]
                     frames.append(f)
     out = {f"f_{k}": np.array([fr[k] for fr in frames]) for k in frames[0] if k != "visible"}

@@ -164,14 +164,15 @@ class OrrTexture(C.Structure):
 
 class OrrObject(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("scale", C.c_float), ("y_rot_deg", C.c_float), ("tri_offset", C.c_int32),
-                ("tri_count", C.c_int32), ("tex_from", C.c_int32), ("tex_to", C.c_int32)]
+                ("tri_count", C.c_int32), ("tex_from", C.c_int32), ("tex_to", C.c_int32), ("seg_tex", C.c_int32)]
 
 
 class OrrScene(C.Structure):
     _fields_ = [("tile_size", C.c_double), ("grid_w", C.c_int32), ("grid_h", C.c_int32), ("tile_kind", C.c_void_p),
                 ("tile_angle", C.c_void_p), ("tile_tex", C.c_void_p), ("n_objects", C.c_int32), ("objects", C.c_void_p),
                 ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("tri_uv", C.c_void_p), ("tri_col", C.c_void_p),
-                ("tri_tex", C.c_void_p), ("n_textures", C.c_int32), ("textures", C.c_void_p)]
+                ("tri_tex", C.c_void_p), ("n_textures", C.c_int32), ("textures", C.c_void_p),
+                ("tex_segment", C.c_void_p), ("agent", OrrObject)]
 
 
 class OrrEpisode(C.Structure):
@@ -207,13 +208,16 @@ class OracleScene:
         for i, o in enumerate(md.objects):
             src = k["objs"][i]
             me = k["meshes"][o.mesh_id]
-            self.objs[i] = OrrObject((C.c_float * 3)(*[float(v) for v in src.pos]), src.scale, src.y_rot_deg, me.tri_offset, me.tri_count, -1, -1)
+            self.objs[i] = OrrObject((C.c_float * 3)(*[float(v) for v in src.pos]), src.scale, src.y_rot_deg, me.tri_offset,
+                                     me.tri_count, -1, -1, me.seg_flat_tex)
         self.texs = (OrrTexture * max(1, len(k["tex_imgs"])))()
         for i, im in enumerate(k["tex_imgs"]):
             self.texs[i] = OrrTexture(im.shape[1], im.shape[0], im.ctypes.data)
         self.c = OrrScene(md.tile_size, md.grid_w, md.grid_h, _p(k["kind"]), _p(k["angle"]), _p(k["tex"]),
                           len(md.objects), C.cast(self.objs, C.c_void_p), _p(k["tpos"]), _p(k["tnrm"]), _p(k["tuv"]),
-                          _p(k["tcol"]), _p(k["ttex"]), len(k["tex_imgs"]), C.cast(self.texs, C.c_void_p))
+                          _p(k["tcol"]), _p(k["ttex"]), len(k["tex_imgs"]), C.cast(self.texs, C.c_void_p), _p(k["seg"]),
+                          OrrObject((C.c_float * 3)(0, 0, 0), 1.0, 0.0, k["meshes"][h.agent_mesh].tri_offset,
+                                    k["meshes"][h.agent_mesh].tri_count, -1, -1, k["meshes"][h.agent_mesh].seg_flat_tex))
 
     def set_trafficlight_card(self, pattern: int):
         """Which card the mesh shared by all traffic lights shows (TrafficLightObj O:453,462)."""
@@ -228,8 +232,15 @@ class OracleScene:
             self.objs[i].pos[k] = float(pos[k])
         self.objs[i].y_rot_deg = float(y_rot_deg)
 
-    def render(self, px, pz, angle, ep: OrrEpisode = None, W=160, H=120, domain_rand=False, lut=None) -> np.ndarray:
+    def render(self, px, pz, angle, ep: OrrEpisode = None, W=160, H=120, domain_rand=False, lut=None, segment=False,
+               top_down=False) -> np.ndarray:
         ep = ep or default_episode()
+        if segment or top_down:
+            lib().orr_set_render_mode((1 if segment else 0) | (2 if top_down else 0))
+            try:
+                return self.render(px, pz, angle, ep, W, H, domain_rand, lut)
+            finally:
+                lib().orr_set_render_mode(0)
         out = np.zeros((H, W, 3), np.uint8)
         lx = ly = None
         if lut is not None:

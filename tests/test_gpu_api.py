@@ -30,6 +30,16 @@ def test_run_tests_script_equivalent(torch_cuda):
     assert first_obs.shape == env.observation_space.shape == second_obs.shape
     assert first_obs.dtype == np.uint8 and isinstance(rew, float) and isinstance(done, bool)
     assert "Simulator" in info and "DuckietownEnv" in info and "action" in info["Simulator"]
+    assert first_render.shape == (600, 800, 3)                                       # WINDOW_HEIGHT x WINDOW_WIDTH S:100-101
+    top = env.render("top_down")
+    seg = env.render_obs(segment=True)
+    assert top.shape == (600, 800, 3) and top.std() > 5 and seg.shape == first_obs.shape and (seg[0, 0] == [255, 0, 255]).all()
+    assert env.reset(segment=True).shape == first_obs.shape
+    from gym_duckietown_b200.wrappers import PyTorchObsWrapper                       # :28-34
+    env = PyTorchObsWrapper(env)
+    first_obs = env.reset()
+    second_obs, _, _, _ = env.step([0, 0])
+    assert first_obs.shape == tuple(env.observation_space.shape) == second_obs.shape == (3, 160, 120)
     env.close()
     for map_name in ["loop_only_duckies", "small_loop_only_duckies"]:               # :37-39
         e = DuckietownEnv(map_name=map_name, camera_width=84, camera_height=84)

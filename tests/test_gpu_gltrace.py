@@ -59,7 +59,7 @@ def test_frame_setup_and_lattice_vs_gl_trace_and_oracle(name, torch_cuda):
     W, H = int(g["width"]), int(g["height"])
     cells = md.grid_w * md.grid_h
     for dr in (False, True):
-        idx = np.flatnonzero(g["f_dr"] == dr)
+        idx = np.flatnonzero((g["f_dr"] == dr) & (g["f_mode"] == 0))
         env = BatchedDuckietownEnv(len(idx), name, camera_width=W, camera_height=H, domain_rand=dr, seed=1)
         env.sim.reset(None, _params(g, idx), env._stream())
         env.render_obs()
@@ -89,7 +89,7 @@ def test_device_stale_light_capture_vs_gl_trace(name, torch_cuda):
 
     g = np.load(os.path.join(GOLD, f"gltrace_{name}.npz"))
     W, H = int(g["width"]), int(g["height"])
-    second = np.flatnonzero((g["f_k"] == 0) & (g["f_episode"] == 1))
+    second = np.flatnonzero((g["f_k"] == 0) & (g["f_episode"] == 1) & (g["f_mode"] == 0))
     for dr in (False, True):
         idx = second[g["f_dr"][second] == dr]
         prev = idx - 1            # last frame of episode 0 of the same simulator

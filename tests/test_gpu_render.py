@@ -218,3 +218,33 @@ def test_full_resolution_frame_vs_oracle(torch_cuda):
     cpu = np.stack([sc.render(st["pos_x"][k], st["pos_z"][k], st["angle"][k], None, W, H, False) for k in range(N)])
     compare(obs.cpu().numpy(), cpu, "full_res")
     env.close()
+
+
+@pytest.mark.parametrize("name,segment,top_down,W,H", [
+    ("loop_obstacles", True, False, 160, 120), ("udem1", True, False, 160, 120), ("small_loop", False, True, 160, 120),
+    ("udem1", False, True, 200, 150), ("loop_obstacles", True, True, 160, 120)])
+def test_segment_and_top_down_views_vs_oracle(name, segment, top_down, W, H, torch_cuda):
+    """render_obs(segment=True) / _render_img(top_down=True) (dts_set_render_mode): lighting off, magenta clear and ground,
+    segmentation textures and flat class colours; camera above the map with the agent's own mesh — bit-exact vs the oracle."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+    N = 24
+    env = BatchedDuckietownEnv(N, name, camera_width=W, camera_height=H, domain_rand=False, seed=77)
+    env.reset(render=False)
+    plain = env.render_obs().cpu().numpy().copy()
+    got = env.render_obs(segment=segment, top_down=top_down).cpu().numpy().copy()
+    again = env.render_obs().cpu().numpy()
+    assert np.array_equal(plain, again)                       # the mode does not stick
+    torch.cuda.synchronize()
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    sc = orc.OracleScene(maps.load_map(name))
+    ref = np.stack([sc.render(st["pos_x"][k], st["pos_z"][k], st["angle"][k], None, W, H, segment=segment, top_down=top_down)
+                    for k in range(N)])
+    compare(got, ref, f"modes_{name}_{int(segment)}{int(top_down)}")
+    assert (got != plain).mean() > 0.2
+    if segment and not top_down:
+        assert (got[:, 0, 0] == np.array([255, 0, 255])).all()
+    env.check()
+    env.close()
