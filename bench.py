@@ -226,6 +226,11 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
     env.sim.profile(False)
     launches = env.launch_count() - launches0
     env.check()   # no frame hit a capacity limit
+    try:
+        n_cells = env.maps[0].grid_w * env.maps[0].grid_h
+        pairs_per_env = env.sim.debug_frame(0, n_cells)["batch_pairs"] / E if not env.cfg.flags & 16 else None
+    except Exception:
+        pairs_per_env = None
     ms = ev0.elapsed_time(ev1)
     kms, frames = env.sim.profile_read()
     if world > 1:
@@ -246,7 +251,7 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": E * b_alg(W, H), "kernel_ms": raster_ms,
                      "compulsory_frac": (E * (W * H * 3 + 256) / (raster_ms / 1000.0) / 1e9) / peak,
                      "all_render_kernels_ms": render_ms, "frac_all_render_kernels": (E * b_alg(W, H) / (render_ms / 1000.0) / 1e9) / peak},
-        "kernel_ms": per,
+        "kernel_ms": per, "pairs_per_env": pairs_per_env,
     }
     return res, env
 

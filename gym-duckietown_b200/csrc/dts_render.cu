@@ -573,15 +573,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-// u8 = rint(255 * clamp(c)) packed r | g<<8 | b<<16 (resolve of 4 equal samples is the value itself)
+// u8 = rint(255 * clamp(c)) packed r | g<<8 | b<<16 (resolve of 4 equal samples is the value itself).  The
+// float->unsigned conversion rounds to nearest-even and saturates below at 0 (NaN -> 0), min() saturates above:
+// identical to clamping c to [0, 1] first.
 __device__ __forceinline__ unsigned pack_rgb(float r, float g, float b) {
-  r = r < 0.f ? 0.f : (r > 1.f ? 1.f : r);
-  g = g < 0.f ? 0.f : (g > 1.f ? 1.f : g);
-  b = b < 0.f ? 0.f : (b > 1.f ? 1.f : b);
-  return (unsigned)rintf(r * 255.0f) | ((unsigned)rintf(g * 255.0f) << 8) | ((unsigned)rintf(b * 255.0f) << 16);
+  const unsigned ur = min(__float2uint_rn(r * 255.0f), 255u);
+  const unsigned ug = min(__float2uint_rn(g * 255.0f), 255u);
+  const unsigned ub = min(__float2uint_rn(b * 255.0f), 255u);
+  return ur | (ug << 8) | (ub << 16);
 }
 
-// one 8x4 bin of packed pixels -> global memory: rows of 24 bytes as 6 aligned words built with shuffles
+// one 8x4 bin of packed pixels -> global memory: rows of 24 bytes as 6 aligned words built with shuffles.
+// The lane-constant parts (shuffle sources, shift, byte offset inside a bin) are computed once per kernel (StoreLane).
+struct StoreLane {
+  int src_lo, src_hi;   // lanes holding the two pixels this lane's output word straddles
+  int sh8;              // bit offset of the word inside lo | hi << 24
+  int off;              // byte offset of the word from the bin's first byte: (lane >> 3) * W * 3 + 4 * (lane & 7)
+  int j, row;           // word index in the row (only 0..5 store), row inside the bin
+};
+__device__ __forceinline__ StoreLane make_store_lane(int lane, int W) {
+  StoreLane sl;
+  const int j = lane & 7, rowbase = lane & ~7;
+  const int p0 = (4 * j) / 3;
+  sl.sh8 = (4 * j - 3 * p0) * 8;
+  sl.src_lo = rowbase + min(p0, 7);
+  sl.src_hi = rowbase + min(p0 + 1, 7);
+  sl.off = (lane >> 3) * W * 3 + 4 * j;
+  sl.j = j; sl.row = lane >> 3;
+  return sl;
+}
+// `bin0` = address of the bin's first byte (warp-uniform); rows_ok = how many of the bin's 4 rows are inside the image
+__device__ __forceinline__ void store_bin_fast(uint8_t* __restrict__ bin0, const StoreLane& sl, unsigned rgb, int rows_ok) {
+  const unsigned lo = __shfl_sync(0xffffffffu, rgb, sl.src_lo);
+  const unsigned hi = __shfl_sync(0xffffffffu, rgb, sl.src_hi);
+  const unsigned word = __funnelshift_r(lo | (hi << 24), hi >> 8, sl.sh8);   // (lo | hi << 24) >> sh8, low 32 bits
+  if (sl.j < 6 && sl.row < rows_ok) *reinterpret_cast<unsigned*>(bin0 + sl.off) = word;
+}
 __device__ __forceinline__ void store_bin(uint8_t* __restrict__ out, unsigned rgb, int lane, int bx, int by, int W, int H) {
   const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
   if ((W & 3) == 0 && bx * kBinW + kBinW <= W) {
@@ -937,40 +964,81 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
   for (int pass = 0; pass < 2; pass++) {
     for (int b = lane; b < cbins; b += 32) cnt[b] = 0;
     __syncwarp();
-    for (int p = lane; p < n; p += 32) {
-      const int4 w0 = __ldg(reinterpret_cast<const int4*>(prims + p));
-      const int4 w1 = __ldg(reinterpret_cast<const int4*>(prims + p) + 1);
-      const int qx[4] = {w0.x, w0.z, w1.x, w1.z}, qy[4] = {w0.y, w0.w, w1.y, w1.w};
-      const int nv = ((__ldg(&prims[p].ltq) >> 24) & 1) ? 4 : 3;   // vertex 3 of a triangle repeats vertex 0
+    for (int p0 = 0; p0 < n; p0 += 32) {
+      const int p = p0 + lane;
+      const bool have = p < n;
+      int qx[4] = {0, 0, 0, 0}, qy[4] = {0, 0, 0, 0}, nv = 3;
+      if (have) {
+        const int4 w0 = __ldg(reinterpret_cast<const int4*>(prims + p));
+        const int4 w1 = __ldg(reinterpret_cast<const int4*>(prims + p) + 1);
+        qx[0] = w0.x; qx[1] = w0.z; qx[2] = w1.x; qx[3] = w1.z;
+        qy[0] = w0.y; qy[1] = w0.w; qy[2] = w1.y; qy[3] = w1.w;
+        nv = ((__ldg(&prims[p].ltq) >> 24) & 1) ? 4 : 3;   // vertex 3 of a triangle repeats vertex 0
+      }
       const int minx = min(min(qx[0], qx[1]), min(qx[2], qx[3])), maxx = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
       const int miny = min(min(qy[0], qy[1]), min(qy[2], qy[3])), maxy = max(max(qy[0], qy[1]), max(qy[2], qy[3]));
-      if (kFish) {
-        // the output bins whose SOURCE box meets the prim: rows first, then the row's bins (the LUT is smooth, not
-        // monotone — no range arithmetic); the exact edge test weeds out the box-only overlaps of big prims
-        const int pminx = max(minx >> 6, 0), pmaxx = min(maxx >> 6, W - 1), pminy = max(miny >> 6, 0), pmaxy = min(maxy >> 6, H - 1);
-        const bool large = (pmaxx - pminx) > 2 * kCoarseW || (pmaxy - pminy) > 2 * kCoarseH;
-        for (int by = 0; by < cbins_y; by++) {
-          const short4 rb = ft.rbox[by];
-          if (rb.z < rb.x || pmaxy < rb.y || pminy > rb.w || pmaxx < rb.x || pminx > rb.z) continue;
-          for (int bx = 0; bx < cbins_x; bx++) {
-            const int b = by * cbins_x + bx;
-            const short4 cb = ft.cbox[b];
-            if (cb.z < cb.x || pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
-            if (large && !box_overlaps(qx, qy, nv, cb.x * kSub + 8, cb.z * kSub + 56, cb.y * kSub + 8, cb.w * kSub + 56)) continue;
-            const int pos = atomicAdd(&cnt[b], 1);
-            if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+      // pixel bounding box, and (identity bins) the range of coarse bins it meets
+      const int pminx = max(minx >> 6, 0), pmaxx = min(maxx >> 6, W - 1), pminy = max(miny >> 6, 0), pmaxy = min(maxy >> 6, H - 1);
+      const int bx0 = pminx / kCoarseW, by0 = pminy / kCoarseH, bx1 = pmaxx / kCoarseW, by1 = pmaxy / kCoarseH;
+      // A prim that may meet many bins is handed to the whole warp (one bin per lane and round) instead of one lane
+      // walking all of them while 31 wait: the ground quad and the near tiles span hundreds of bins.
+      const bool big = have && (kFish ? ((pmaxx - pminx) > 2 * kCoarseW || (pmaxy - pminy) > 2 * kCoarseH)
+                                      : (bx1 - bx0 + 1) * (by1 - by0 + 1) > 8);
+      if (have && !big) {
+        if (kFish) {
+          // the output bins whose SOURCE box meets the prim: rows first, then the row's bins (the LUT is smooth, not
+          // monotone — no range arithmetic)
+          for (int by = 0; by < cbins_y; by++) {
+            const short4 rb = ft.rbox[by];
+            if (rb.z < rb.x || pmaxy < rb.y || pminy > rb.w || pmaxx < rb.x || pminx > rb.z) continue;
+            for (int bx = 0; bx < cbins_x; bx++) {
+              const int b = by * cbins_x + bx;
+              const short4 cb = ft.cbox[b];
+              if (cb.z < cb.x || pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
+              const int pos = atomicAdd(&cnt[b], 1);
+              if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+            }
           }
+        } else {
+          const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
+          for (int by = by0; by <= by1; by++)
+            for (int bx = bx0; bx <= bx1; bx++) {
+              if (large && !bin_overlaps(qx, qy, nv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
+              const int b = by * cbins_x + bx;
+              const int pos = atomicAdd(&cnt[b], 1);
+              if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+            }
         }
-      } else {
-      const int bx0 = max(minx >> 6, 0) / kCoarseW, by0 = max(miny >> 6, 0) / kCoarseH;
-      const int bx1 = min(maxx >> 6, W - 1) / kCoarseW, by1 = min(maxy >> 6, H - 1) / kCoarseH;
-      const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
-      for (int by = by0; by <= by1; by++)
-        for (int bx = bx0; bx <= bx1; bx++) {
-          if (large && !bin_overlaps(qx, qy, nv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
-          const int b = by * cbins_x + bx;
-          const int pos = atomicAdd(&cnt[b], 1);
-          if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+      }
+      unsigned bigs = __ballot_sync(0xffffffffu, big);
+      while (bigs) {
+        const int src = __ffs(bigs) - 1;
+        bigs &= bigs - 1;
+        int vx[4], vy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { vx[k] = __shfl_sync(0xffffffffu, qx[k], src); vy[k] = __shfl_sync(0xffffffffu, qy[k], src); }
+        const int snv = __shfl_sync(0xffffffffu, nv, src), sp = p0 + src;
+        if (kFish) {
+          const int sminx = __shfl_sync(0xffffffffu, pminx, src), smaxx = __shfl_sync(0xffffffffu, pmaxx, src);
+          const int sminy = __shfl_sync(0xffffffffu, pminy, src), smaxy = __shfl_sync(0xffffffffu, pmaxy, src);
+          for (int b = lane; b < cbins; b += 32) {   // every output bin: source box overlap, then the exact edge test
+            const short4 cb = ft.cbox[b];
+            if (cb.z < cb.x || smaxx < cb.x || sminx > cb.z || smaxy < cb.y || sminy > cb.w) continue;
+            if (!box_overlaps(vx, vy, snv, cb.x * kSub + 8, cb.z * kSub + 56, cb.y * kSub + 8, cb.w * kSub + 56)) continue;
+            const int pos = atomicAdd(&cnt[b], 1);
+            if (pass == 1) pairs[start[b] + pos] = (uint32_t)sp | ((uint32_t)b << 16);
+          }
+        } else {
+          const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sbx1 = __shfl_sync(0xffffffffu, bx1, src);
+          const int sby0 = __shfl_sync(0xffffffffu, by0, src), sby1 = __shfl_sync(0xffffffffu, by1, src);
+          const int nbx = sbx1 - sbx0 + 1, nb = nbx * (sby1 - sby0 + 1);
+          for (int i = lane; i < nb; i += 32) {
+            const int by = sby0 + i / nbx, bx = sbx0 + i % nbx;
+            if (!bin_overlaps(vx, vy, snv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
+            const int b = by * cbins_x + bx;
+            const int pos = atomicAdd(&cnt[b], 1);
+            if (pass == 1) pairs[start[b] + pos] = (uint32_t)sp | ((uint32_t)b << 16);
+          }
         }
       }
     }
@@ -1035,6 +1103,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   const int out_fmt = !kWrapFmt ? 0 : (rc.obs_layout | (rc.obs_dtype << 2));   // wrapper output format (0 = packed u8 HWC)
   const size_t out_elem = (kWrapFmt && rc.obs_dtype == DTS_OBS_F32_UNIT) ? 4 : 1;
   const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
+  const StoreLane sl = make_store_lane(lane, W);
+  const bool fast_fmt = !kWrapFmt && (W & 3) == 0;   // packed u8 HWC rows of whole words
   uint64_t* bar = bars[warp];
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   __syncwarp();
@@ -1057,8 +1127,15 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     uint8_t* out = obs + env_off;
     // one fine bin -> the caller's tensor and, on a gathering step, every peer's gather buffer (NVLink stores)
     auto emit = [&](unsigned rgb, int bx, int by) {
-      store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
-      for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+      if (fast_fmt && bx * kBinW + kBinW <= W) {
+        const size_t bin_off = ((size_t)(by * kBinH) * W + bx * kBinW) * 3;   // warp-uniform
+        const int rows_ok = min(kBinH, H - by * kBinH);
+        store_bin_fast(out + bin_off, sl, rgb, rows_ok);
+        for (int p = 0; p < gt.n; p++) store_bin_fast(gt.base[p] + env_off + bin_off, sl, rgb, rows_ok);
+      } else {
+        store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
+        for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+      }
     };
     const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;   // glClearColor(255, 0, 255): clamped to magenta (S:1752)
     const float clr[3] = {seg ? 1.0f : S.rep[env].horizon[0], seg ? 0.0f : S.rep[env].horizon[1], seg ? 1.0f : S.rep[env].horizon[2]};
@@ -1075,9 +1152,13 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     // ONE chunk shared by the bin's 8 fine bins; a longer list is streamed chunk by chunk for each fine bin in turn
     // (the records are ready-made, re-reading them from L2 costs no arithmetic).
     int pcbx = nz ? __ffs(nz) - 1 : 32, pf = 0, pc = 0;
-    auto fine_valid = [&](int cbx, int f) -> bool {
-      return ((fvalid_y >> f) & 1u) && (cbx * kCFX + (f & 3)) * kBinW < W;
+    // fine bins of coarse bin `cbx` that lie inside the image, as a bit mask (all 8 except on the right / bottom border)
+    auto valid8 = [&](int cbx) -> unsigned {
+      const int nx = min(kCFX, (W - cbx * kCoarseW + kBinW - 1) / kBinW);   // fine-bin columns inside the image: 1..4
+      const unsigned cols = (1u << nx) - 1u;
+      return fvalid_y & (cols | (cols << 4));
     };
+    auto fine_valid = [&](int cbx, int f) -> bool { return (valid8(cbx) >> f) & 1u; };
     auto next_bin = [&]() {
       const unsigned rem = nz & ~((2u << pcbx) - 1u);
       pcbx = rem ? __ffs(rem) - 1 : 32;
@@ -1105,10 +1186,11 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     issue();
     for (int cbx = 0; cbx < cbins_x; cbx++) {
       const int count = __shfl_sync(0xffffffffu, my_cnt, cbx);
+      const unsigned fvalid = valid8(cbx);
       if (count == 0) {
 #pragma unroll 1
         for (int f = 0; f < kCFX * kCFY; f++)
-          if (fine_valid(cbx, f)) {
+          if ((fvalid >> f) & 1u) {
             unsigned rgb = clear_rgb;
             if (kFish) {
               const int gx = min((cbx * kCFX + (f & 3)) * kBinW + (lane & 7), W - 1), gy = min((cby * kCFY + (f >> 2)) * kBinH + (lane >> 3), H - 1);
@@ -1123,7 +1205,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       if (kFish) { const short4 cb = ft.cbox[cby * cbins_x + cbx]; ox = cb.x * kSub; oy = cb.y * kSub; }   // ... of its source box
 #pragma unroll 1
       for (int g = 0; g < (single ? 1 : kCFX * kCFY); g++) {
-        if (!single && !fine_valid(cbx, g)) continue;
+        if (!single && !((fvalid >> g) & 1u)) continue;
         float z[4];
         unsigned wn[4];   // per sample: depth and winning prim (index into the env's slab)
 #pragma unroll 1
@@ -1139,9 +1221,10 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           uint2 mine = make_uint2(0u, 0u);
           if (lane < nch) mine = *reinterpret_cast<const uint2*>(&stage[lane].prim_flags);
           const bool first = c0 == 0, last = c0 + kStage >= count;
+          const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
 #pragma unroll 1
           for (int f = (single ? 0 : g); f < (single ? kCFX * kCFY : g + 1); f++) {
-            if (!fine_valid(cbx, f)) continue;
+            if (!((fvalid >> f) & 1u)) continue;
             const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);   // fine bin
             int pxc = pxs + (f & 3) * kBinW * kSub, pyc = pys + (f >> 2) * kBinH * kSub;   // this lane's pixel, coarse-relative
             bool px_valid = true;
@@ -1154,7 +1237,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
             }
             const bool live = (mine.x >> (16 + f)) & 1u;
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-            const unsigned ground_mask = __ballot_sync(0xffffffffu, live && (mine.y & 2u));
+            const unsigned ground_mask = live_mask & ground_bits;
             bool simple = false;
             if (single) {
               // ---- simple bin: ONE prim (besides the ground quad) and it covers every sample of the bin.
@@ -1379,6 +1462,7 @@ int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pai
   for (int k = 0; k < 12; k++) V[k] = c.V[k];
   P[0] = c.P00; P[1] = c.P11; P[2] = c.P22; P[3] = c.P23;
   counts[0] = c.n_prims; counts[1] = c.n_lat; counts[2] = c.overflow; counts[3] = 0;
+  cudaMemcpy(&counts[3], fm.work + 1, sizeof(int32_t), cudaMemcpyDeviceToHost);   // (prim, coarse bin) pairs of the whole batch
   const int np = c.n_prims < max_prims ? c.n_prims : max_prims;
   PrimRec* prims = new PrimRec[np > 0 ? np : 1];
   float4* lat = new float4[(size_t)max_lat * 64];

@@ -466,7 +466,7 @@ class Sim:
         V, P, cnt = np.zeros(12), np.zeros(4, np.float32), np.zeros(4, np.int32)
         lat = np.zeros((n_cells, 64, 3), np.float32)
         self._check(self.lib.dts_debug_frame(self.h, env, _ptr(V), _ptr(P), _ptr(cnt), _ptr(lat), n_cells), "dts_debug_frame")
-        return dict(V=V, P=P, n_prims=int(cnt[0]), n_lat=int(cnt[1]), overflow=int(cnt[2]), lattice=lat)
+        return dict(V=V, P=P, n_prims=int(cnt[0]), n_lat=int(cnt[1]), overflow=int(cnt[2]), batch_pairs=int(cnt[3]), lattice=lat)
 
     def debug_counters(self) -> np.ndarray:
         out = np.zeros(32, np.int32)

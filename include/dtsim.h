@@ -18,7 +18,7 @@ extern "C" {
 #endif
 
 #define DTS_ABI_VERSION 3
-#define DTS_MAX_DELAY 8      /* command-delay line depth (steps) */
+#define DTS_MAX_DELAY 16     /* command-delay line depth (steps): 0.15 s at up to 100 Hz (MotionBlurWrapper steps at 90 Hz) */
 #define DTS_MAX_OBJECTS 256  /* per map; visibility bitmask is 8 x u32 */
 
 typedef struct dts_sim dts_sim; /* opaque, one per GPU, not thread-safe */
@@ -335,7 +335,7 @@ uint64_t dts_launch_count(dts_sim* sim);
  * cam_noise[3], -, horizon[3], -, ambient[3], -, diffuse[3], -, light_eye[4], ground[3], -, hidden u32[8]). */
 int dts_debug_episode(dts_sim* sim, int env, void* out144);
 /* debug (tests/test_gpu_gltrace.py): what k_frame_setup / k_geometry produced for `env` in the last dts_render — camera
- * model-view V (row-major 3x4, float64), projection P00 P11 P22 P23, counts = {prims, lattices, overflow, 0}, and the lit
+ * model-view V (row-major 3x4, float64), projection P00 P11 P22 P23, counts = {prims, lattices, overflow, (prim, bin) pairs of the whole batch}, and the lit
  * 8x8 lattice [n_cells][64][3] of every emitted road tile by grid cell i * grid_h + j (NaN where culled).  Synchronises. */
 int dts_debug_frame(dts_sim* sim, int env, double V[12], float P[4], int32_t counts[4], float* lattice_by_cell, int n_cells);
 /* 32 diagnostic counters: [0] != 0 -> a render scratch buffer overflowed (frame incomplete). */

@@ -28,7 +28,7 @@ def test_fused_gather_world1_equals_obs(fmt):
     g.arm()
     obs, *_ = env.step(acts[5])
     out = g.finish()
-    assert out.shape == (1,) + tuple(obs.shape) and torch.equal(out[0], obs) and float(obs.float().std()) > 1
+    assert out.shape == (1,) + tuple(obs.shape) and torch.equal(out[0], obs) and float(obs.float().std()) > (1 if fmt[1] == 'uint8' else 0.02)
     before = out.clone()
     env.step(acts[0])                                               # not armed: the gather buffer keeps the rollout's frames
     torch.cuda.synchronize()

@@ -65,6 +65,7 @@ def test_frame_setup_and_lattice_vs_gl_trace_and_oracle(name, torch_cuda):
         env.render_obs()
         torch.cuda.synchronize()
         worst_lat = 0.0
+        n_seen = 0
         for r, f in enumerate(idx):
             d = env.sim.debug_frame(r, cells)
             view = g["f_view"][f].reshape(4, 4)
@@ -73,10 +74,13 @@ def test_frame_setup_and_lattice_vs_gl_trace_and_oracle(name, torch_cuda):
             assert _close(d["P"], [proj[0, 0], proj[1, 1], proj[2, 2], proj[2, 3]]).all()
             o = sc.debug_frame(g["f_pos"][f][0], g["f_pos"][f][2], g["f_angle"][f], _episode(orc, g, f), W, H, dr)
             assert np.allclose(d["V"], o["V"], rtol=0, atol=1e-13) and np.array_equal(d["P"], o["P"])
-            seen = ~np.isnan(d["lattice"][:, 0, 0])
-            assert seen.any() and d["overflow"] == 0
+            seen = ~np.isnan(d["lattice"][:, 0, 0])   # tiles this frame emitted (a camera at the map's edge may see none)
+            assert d["overflow"] == 0
+            n_seen += int(seen.sum())
             assert np.array_equal(d["lattice"][seen], o["lattice"][seen]), f"frame {f}: lit lattice != raster oracle"
-            worst_lat = max(worst_lat, float(np.abs(d["lattice"][seen] - o["lattice"][seen]).max()))
+            if seen.any():
+                worst_lat = max(worst_lat, float(np.abs(d["lattice"][seen] - o["lattice"][seen]).max()))
+        assert n_seen > 4 * len(idx)
         env.close()
 
 
