@@ -576,7 +576,7 @@ static int ensure_render(dts_sim* sim) {
   if (pool > 2000000000LL) pool = 2000000000LL;
   if (pool < per_env) pool = per_env;
   sim->bin_cap = (int)pool;
-  const size_t frame = 0;   // the fisheye gather is fused: no undistorted intermediate
+  const size_t frame = (size_t)sim->items_max;   // (env, item) work-list entries per env
   const size_t bytes = render_scratch_bytes(sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame);
   cudaError_t e = cudaMalloc(&sim->render_scratch, bytes);
   if (e != cudaSuccess) return sim->fail("render scratch cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -899,7 +899,7 @@ int dts_debug_frame(dts_sim* sim, int env, double V[12], float P[4], int32_t cou
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   DTS_CUDA(cudaDeviceSynchronize());
   const int cbins = ((sim->cfg.cam_width + 31) / 32) * ((sim->cfg.cam_height + 7) / 8);
-  const size_t frame = 0;
+  const size_t frame = (size_t)sim->items_max;
   if (debug_frame_copy(sim->render_scratch, sim->cfg.num_envs, sim->max_prims, cbins, sim->bin_cap, sim->max_lat, frame, env, V, P,
                        counts, lattice_by_cell, n_cells, 2))
     return sim->fail("debug_frame_copy failed");

@@ -56,9 +56,9 @@ struct GatherTab {
 
 // render (dts_render.cu)
 int render_ctas_per_sm();
-// scratch for `n` envs: FrameCtx, PrimRec slabs, coarse-bin lists (cap entries each), lattice tables, and the
-// undistorted frames when the fisheye gather is on
-size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame);
+// scratch for `n` envs: FrameCtx, PrimRec slabs, the batch's pair / record pool (max_pairs entries), lattice tables and
+// the (env, item) work list of the geometry pass
+size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items);
 // `marks`: NULL or kProfMarks events recorded on `st` before k_frame_setup and after each of k_frame_setup, k_geometry,
 // k_bin, k_raster and the post passes (dts_profile_*).  `status_dev`: device address of the mapped host status word.
 constexpr int kProfMarks = 6;
@@ -70,7 +70,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
                    void* dst, int layout, int dtype, cudaStream_t st);
 void launch_blend4(const uint8_t* const f[4], const double w[4], double* out, size_t n, cudaStream_t st);
-int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame,
+int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items,
                      int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile);
 
 }  // namespace dts

@@ -662,14 +662,14 @@ struct FrameMem {
   int* bin_count;       // [N][cbins]
   int* bin_start;       // [N][cbins]  pool index of the bin's first pair / record
   float4* lat;          // [N][max_lat][64]
-  uint8_t* undist;      // [N][H][W][3] (distortion only)
-  int* work;            // [4] global work counters
+  uint2* geo_list;      // [N * items_max] (env, draw item) pairs that passed k_cull
+  int* work;            // global counters: [0] k_raster work items, [1] pair-pool cursor, [2] geo_list length
   int32_t* status;      // mapped host word (dts_status): bit 0 = a frame ran out of frame memory
 };
 
 __host__ __device__ inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 
-__host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
+__host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items) {
   uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
   FrameMem f;
   f.work = reinterpret_cast<int*>(p); p += 256;
@@ -680,16 +680,16 @@ __host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_
   f.pairs = reinterpret_cast<uint32_t*>(p); p += align256((size_t)max_pairs * sizeof(uint32_t));   // max_pairs = pool entries
   f.recs = reinterpret_cast<BinRec*>(p); p += align256((size_t)max_pairs * sizeof(BinRec));
   f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
-  f.undist = undist_frame ? p : nullptr;
+  f.geo_list = reinterpret_cast<uint2*>(p); p += align256((size_t)n * geo_items * sizeof(uint2));
   f.status = nullptr;
   return f;
 }
 
-size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame) {
+size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items) {
   return 256 + align256((size_t)n * sizeof(FrameCtx)) + 2 * align256((size_t)n * cbins * sizeof(int)) +
          align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)max_pairs * sizeof(uint32_t)) +
          align256((size_t)max_pairs * sizeof(BinRec)) +
-         align256((size_t)n * max_lat * 64 * sizeof(float4)) + (size_t)n * undist_frame + 256;
+         align256((size_t)n * max_lat * 64 * sizeof(float4)) + align256((size_t)n * geo_items * sizeof(uint2)) + 256;
 }
 
 // ------------------------------------------------------------------------------------------------ k_frame_setup
@@ -732,64 +732,91 @@ __device__ __forceinline__ void eye_point(const double* V, double wx, double wy,
   ez = (float)(V[8] * wx + V[9] * wy + V[10] * wz + V[11]);
 }
 
-// ------------------------------------------------------------------------------------------------ k_geometry
-// One warp per CTA, 64 registers, 32 CTAs per SM: the kernel is latency-bound (short dependent chains, most warps
-// exit at the pre-cull), so resident warps matter more than spills — measured 1 warp x 32 CTAs 178 us, 2 x 12 (80
-// registers) 207 us, 4 x 8 192 us on the bench workload.  A slot is never held by a finished sibling warp, and the
-// grid is item-major (blockIdx.y = draw item) so neighbouring CTAs run the same code path.
-constexpr int kGeoWarps = DTS_GEO_WARPS;
-template <bool kTess>   // true: spec tile mode 0 (DTS_FLAG_TESSELLATE), the literal 98 triangles per road tile
-__global__ void __launch_bounds__(kGeoWarps * 32, DTS_GEO_MIN_CTAS)
-k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max, int max_prims,
-           int max_lat, int32_t* __restrict__ err) {
-  __shared__ GeoWarp gws[kGeoWarps];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int item = blockIdx.y, env = blockIdx.x * kGeoWarps + wib;   // item-major: neighbouring CTAs run the same path
-  if (env >= rc.n_envs) return;
-  const DMap& m = maps[S.map_id[env]];
+// Does draw item `item` of env `env` need any work this frame?  Conservative bounding-sphere test against the view
+// frustum before anything is transformed (most (env, item) pairs end here), plus the values the mesh path needs later:
+// the obstacle's per-env pose.  Run once per pair by k_cull (one thread each) and again by the warp that draws the item.
+struct ItemPose { int dyn_kind; float opx, opz, orot; bool agent_item; };
+__device__ __forceinline__ bool item_visible(const DState& S, const DMap& m, const RenderCfg& rc, const FrameCtx& ctx, int env,
+                                             int item, ItemPose& ip) {
   const int n_tiles = m.grid_w * m.grid_h;
-  const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;
-  const bool agent_item = item == 1 + n_tiles + m.n_objects;   // top-down views draw the agent's own mesh last (S:1923-1929)
-  if (item > 1 + n_tiles + m.n_objects) return;
-  if (agent_item && (!(rc.mode & DTS_RENDER_TOP_DOWN) || m.agent.tri_count == 0)) return;
-  const int W = rc.width, H = rc.height;
-  GeoWarp& sh = gws[wib];
-  FrameCtx& ctx = fm.ctx[env];
-  // ---- pre-cull on a bounding sphere before anything else is loaded or transformed: most (env, item) pairs end here
-  int dyn_kind = 0;
-  float opx = 0.f, opz = 0.f, orot = 0.f;
+  ip.dyn_kind = 0; ip.opx = 0.f; ip.opz = 0.f; ip.orot = 0.f;
+  ip.agent_item = item == 1 + n_tiles + m.n_objects;   // top-down views draw the agent's own mesh last (S:1923-1929)
+  if (item > 1 + n_tiles + m.n_objects) return false;
+  if (ip.agent_item && (!(rc.mode & DTS_RENDER_TOP_DOWN) || m.agent.tri_count == 0)) return false;
   if (item >= 1 && item <= n_tiles) {
     const int t = item - 1, ti = t / m.grid_h, tj = t - ti * m.grid_h;
-    if (m.tile_kind[tj * m.grid_w + ti] < 0) return;
+    if (m.tile_kind[tj * m.grid_w + ti] < 0) return false;
     const double ts = m.tile_size;
     float ex, ey, ez;
     eye_point(ctx.V, (ti + 0.5) * ts, 0.0, (tj + 0.5) * ts, ex, ey, ez);
-    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, (float)(ts * 0.7071067811865476) * 1.001f + 1e-4f)) return;
+    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, (float)(ts * 0.7071067811865476) * 1.001f + 1e-4f)) return false;
   } else if (item > n_tiles) {
     const int o = item - 1 - n_tiles;
-    if (!agent_item && (S.rep[env].hidden[o >> 5] >> (o & 31) & 1u)) return;
-    const DObject& ob = agent_item ? m.agent : m.objects[o];
-    opx = ob.pos[0]; opz = ob.pos[2]; orot = ob.y_rot_deg;
-    if (agent_item) {   // glTranslatef(*cur_pos); glRotatef(cur_angle * 180 / pi, 0, 1, 0): GLfloat arguments
-      opx = (float)S.pos_x[env]; opz = (float)S.pos_z[env];
-      orot = (float)(S.angle[env] * 180.0 / 3.141592653589793);
+    if (!ip.agent_item && (S.rep[env].hidden[o >> 5] >> (o & 31) & 1u)) return false;
+    const DObject& ob = ip.agent_item ? m.agent : m.objects[o];
+    ip.opx = ob.pos[0]; ip.opz = ob.pos[2]; ip.orot = ob.y_rot_deg;
+    if (ip.agent_item) {   // glTranslatef(*cur_pos); glRotatef(cur_angle * 180 / pi, 0, 1, 0): GLfloat arguments
+      ip.opx = (float)S.pos_x[env]; ip.opz = (float)S.pos_z[env];
+      ip.orot = (float)(S.angle[env] * 180.0 / 3.141592653589793);
     }
     if (ob.dyn_slot >= 0) {
-      dyn_kind = m.dyn[ob.dyn_slot].kind;
-      if (dyn_kind != DTS_DYN_TRAFFICLIGHT) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
+      ip.dyn_kind = m.dyn[ob.dyn_slot].kind;
+      if (ip.dyn_kind != DTS_DYN_TRAFFICLIGHT) {   // a moving obstacle: this env's pos / y_rot, rounded to float like glTranslatef / glRotatef
         const size_t nd = m.n_dyn, ne = rc.n_envs;
-        opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
-        opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
-        orot = (float)m.dyn_state[((size_t)DTS_DYN_YROT * nd + ob.dyn_slot) * ne + env];
+        ip.opx = (float)m.dyn_state[((size_t)DTS_DYN_PX * nd + ob.dyn_slot) * ne + env];
+        ip.opz = (float)m.dyn_state[((size_t)DTS_DYN_PZ * nd + ob.dyn_slot) * ne + env];
+        ip.orot = (float)m.dyn_state[((size_t)DTS_DYN_YROT * nd + ob.dyn_slot) * ne + env];
       }
     }
     double sn, cs;
-    sincos((double)orot * kDeg2Rad, &sn, &cs);
+    sincos((double)ip.orot * kDeg2Rad, &sn, &cs);
     const double sc = (double)ob.scale, ccx = ob.centre[0], ccy = ob.centre[1], ccz = ob.centre[2];
     float ex, ey, ez;   // T(pos) S(scale) Ry(rot) applied to the bounding-sphere centre
-    eye_point(ctx.V, (double)opx + sc * (cs * ccx + sn * ccz), (double)ob.pos[1] + sc * ccy, (double)opz + sc * (-sn * ccx + cs * ccz), ex, ey, ez);
-    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, ob.bound_rad * ob.scale * 1.002f + 2e-4f)) return;
+    eye_point(ctx.V, (double)ip.opx + sc * (cs * ccx + sn * ccz), (double)ob.pos[1] + sc * ccy, (double)ip.opz + sc * (-sn * ccx + cs * ccz), ex, ey, ez);
+    if (sphere_outside(ctx.P00, ctx.P11, ex, ey, ez, ob.bound_rad * ob.scale * 1.002f + 2e-4f)) return false;
   }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ k_cull
+// thread per (env, draw item), item-major: the pairs that survive item_visible() go to a compact work list (warp-
+// aggregated atomic append), so that k_geometry spends warps only on items that will emit something.
+__global__ void __launch_bounds__(256) k_cull(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int items_max) {
+  const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int item = (int)(g / rc.n_envs), env = (int)(g - (size_t)item * rc.n_envs);
+  bool vis = false;
+  if (item < items_max) {
+    ItemPose ip;
+    vis = item_visible(S, maps[S.map_id[env]], rc, fm.ctx[env], env, item, ip);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, vis);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(fm.work + 2, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (vis) fm.geo_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)env, (unsigned)item);
+}
+
+// ------------------------------------------------------------------------------------------------ k_geometry
+// One warp per CTA, 64 registers, 32 CTAs per SM: the kernel is latency-bound (short dependent chains), so resident warps
+// matter more than spills.  Each warp draws the (env, item) pairs of k_cull's work list, grid-strided.
+constexpr int kGeoWarps = DTS_GEO_WARPS;
+template <bool kTess>   // true: spec tile mode 0 (DTS_FLAG_TESSELLATE), the literal 98 triangles per road tile
+__device__ __forceinline__ void geometry_item(const DState& S, const DMap* __restrict__ maps, const RenderCfg& rc, const FrameMem& fm,
+                                              int max_prims, int max_lat, int32_t* __restrict__ err, int env, int item, int lane,
+                                              GeoWarp& sh) {
+  const DMap& m = maps[S.map_id[env]];
+  const int n_tiles = m.grid_w * m.grid_h;
+  const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;
+  const int W = rc.width, H = rc.height;
+  FrameCtx& ctx = fm.ctx[env];
+  ItemPose ip;
+  if (!item_visible(S, m, rc, ctx, env, item, ip)) return;
+  const bool agent_item = ip.agent_item;
+  const int dyn_kind = ip.dyn_kind;
+  const float opx = ip.opx, opz = ip.opz, orot = ip.orot;
+  __syncwarp();   // the previous item of this warp is done with the shared GeoWarp
   for (int k = lane; k < (int)(sizeof(RenderEp) / 4); k += 32)
     reinterpret_cast<uint32_t*>(&sh.ep)[k] = reinterpret_cast<const uint32_t*>(&S.rep[env])[k];
   if (lane < 12) sh.V[lane] = ctx.V[lane];
@@ -939,6 +966,19 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
       }
   }
   if (lane == 0 && ctx.overflow) { atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
+}
+
+template <bool kTess>
+__global__ void __launch_bounds__(kGeoWarps * 32, DTS_GEO_MIN_CTAS)
+k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, int max_prims, int max_lat,
+           int32_t* __restrict__ err) {
+  __shared__ GeoWarp gws[kGeoWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_list = fm.work[2];   // written by k_cull
+  for (int wi = blockIdx.x * kGeoWarps + wib; wi < n_list; wi += gridDim.x * kGeoWarps) {
+    const uint2 e = fm.geo_list[wi];
+    geometry_item<kTess>(S, maps, rc, fm, max_prims, max_lat, err, (int)e.x, (int)e.y, lane, gws[wib]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ k_bin
@@ -1454,9 +1494,9 @@ void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs,
 // Test hook (dts_debug_frame): what k_frame_setup / k_geometry left in frame memory for one env of the last render —
 // the camera model-view and projection, the prim / lattice counts, and the lit 8x8 lattice of every road tile that
 // was emitted, re-ordered by grid cell (i * grid_h + j; cells that were culled stay NaN).
-int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t undist_frame,
+int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items,
                      int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile) {
-  const FrameMem fm = carve(scratch, n, max_prims, cbins, max_pairs, max_lat, undist_frame);
+  const FrameMem fm = carve(scratch, n, max_prims, cbins, max_pairs, max_lat, geo_items);
   FrameCtx c;
   if (cudaMemcpy(&c, fm.ctx + env, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   for (int k = 0; k < 12; k++) V[k] = c.V[k];
@@ -1493,7 +1533,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   uint8_t* obs = reinterpret_cast<uint8_t*>(obs_any);
   const int cbins = ((W + kCoarseW - 1) / kCoarseW) * ((H + kCoarseH - 1) / kCoarseH);
   const bool fisheye = (rc.flags & DTS_FLAG_DISTORTION) != 0;
-  FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, 0);
+  FrameMem fm = carve(scratch, rc.n_envs, max_prims, cbins, max_pairs, max_lat, (size_t)items_max);
   fm.status = status_dev;
   int mk = 0;
   auto mark = [&]() { if (marks) cudaEventRecord(marks[mk++], st); };
@@ -1501,9 +1541,11 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   mark();
   k_frame_setup<<<(rc.n_envs + 127) / 128, 128, 0, st>>>(S, maps, rc, fm);
   mark();
-  const dim3 geo_grid((unsigned)((rc.n_envs + kGeoWarps - 1) / kGeoWarps), (unsigned)items_max);
-  if (rc.tessellate) k_geometry<true><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
-  else k_geometry<false><<<geo_grid, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, items_max, max_prims, max_lat, err_flag);
+  const size_t pairs_total = (size_t)rc.n_envs * items_max;
+  k_cull<<<(unsigned)((pairs_total + 255) / 256), 256, 0, st>>>(S, maps, rc, fm, items_max);
+  const int geo_ctas = (n_ctas / DTS_RENDER_MIN_CTAS) * DTS_GEO_MIN_CTAS / kGeoWarps;   // SMs x resident geometry CTAs
+  if (rc.tessellate) k_geometry<true><<<geo_ctas, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, max_prims, max_lat, err_flag);
+  else k_geometry<false><<<geo_ctas, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, max_prims, max_lat, err_flag);
   mark();
   const size_t bin_smem_bytes = (size_t)kBinWarps * 2 * cbins * sizeof(int);
   const int bin_grid = (rc.n_envs + kBinWarps - 1) / kBinWarps;
@@ -1526,7 +1568,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   }
   mark();
   mark();   // (post passes: none yet)
-  return 4;
+  return 5;
 }
 
 }  // namespace dts

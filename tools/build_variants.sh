@@ -15,5 +15,8 @@ base
 r64 -DDTS_RENDER_MIN_CTAS=4
 t128x6 -DDTS_RENDER_THREADS=128 -DDTS_RENDER_MIN_CTAS=6
 t128x8 -DDTS_RENDER_THREADS=128 -DDTS_RENDER_MIN_CTAS=8
+g24 -DDTS_GEO_MIN_CTAS=24
+g16 -DDTS_GEO_MIN_CTAS=16
+r64g24 -DDTS_RENDER_MIN_CTAS=4 -DDTS_GEO_MIN_CTAS=24
 VARIANTS
 cp /tmp/libdtsim_base_keep.so libdtsim.so
