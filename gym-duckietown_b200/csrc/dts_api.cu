@@ -35,7 +35,7 @@ struct dts_sim {
   // render
   void* render_scratch = nullptr;
   int render_ctas = 0, max_prims = 0, bin_cap = 0, max_lat = 0, items_max = 0;
-  FishTab fish{nullptr, nullptr, nullptr, nullptr};   // fused fisheye tables (dts_set_fisheye_lut)
+  FishTab fish{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fused fisheye tables (dts_set_fisheye_lut)
   int32_t* d_err = nullptr;
   int32_t* h_status = nullptr;          // mapped pinned host word: bit 0 = a frame overflowed its frame memory
   int32_t* d_status = nullptr;          // its device address
@@ -199,6 +199,7 @@ void dts_destroy(dts_sim* sim) {
   for (void* p : sim->allocs) cudaFree(p);
   for (auto& v : sim->map_allocs) for (void* p : v) cudaFree(p);
   void* extra[] = {sim->render_scratch, (void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
+                   (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins,
                    sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
   for (void* p : extra) if (p) cudaFree(p);
   for (int p = 0; p < sim->gather_world; p++)
@@ -451,10 +452,28 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
     if ((long long)H * w + (long long)W * h >= (1LL << 30) / (5 * 64 * 64))
       return sim->fail("fisheye LUT sends output bin %d to a %lldx%lld px source region: too wide for the rasteriser's int32 edge functions", b, w, h);
   }
-  void* old[] = {(void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox};
+  // inverse index: source cell (same 32x8 grid, over the source image) -> output bins whose source box meets it
+  std::vector<int32_t> cell_start(cbins + 1, 0);
+  std::vector<uint16_t> cell_bins;
+  {
+    std::vector<std::vector<uint16_t>> lists(cbins);
+    for (int b = 0; b < cbins; b++) {
+      if (cbox[b].z < cbox[b].x) continue;
+      for (int cy = cbox[b].y / 8; cy <= cbox[b].w / 8; cy++)
+        for (int cx = cbox[b].x / 32; cx <= cbox[b].z / 32; cx++) lists[cy * cbx_n + cx].push_back((uint16_t)b);
+    }
+    for (int c = 0; c < cbins; c++) {
+      cell_start[c] = (int32_t)cell_bins.size();
+      cell_bins.insert(cell_bins.end(), lists[c].begin(), lists[c].end());
+    }
+    cell_start[cbins] = (int32_t)cell_bins.size();
+    if (cell_bins.empty()) cell_bins.push_back(0);
+  }
+  void* old[] = {(void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
+                 (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins};
   DTS_CUDA(cudaDeviceSynchronize());
   for (void* p : old) if (p) cudaFree(p);
-  sim->fish = FishTab{nullptr, nullptr, nullptr, nullptr};
+  sim->fish = FishTab{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int32_t* d_src = nullptr; short4 *d_c = nullptr, *d_f = nullptr, *d_r = nullptr;
   DTS_CUDA(cudaMalloc(&d_src, src.size() * sizeof(int32_t)));
   DTS_CUDA(cudaMalloc(&d_c, cbox.size() * sizeof(short4)));
@@ -464,7 +483,12 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
   DTS_CUDA(cudaMemcpy(d_c, cbox.data(), cbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
   DTS_CUDA(cudaMemcpy(d_f, fbox.data(), fbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
   DTS_CUDA(cudaMemcpy(d_r, rbox.data(), rbox.size() * sizeof(short4), cudaMemcpyHostToDevice));
-  sim->fish = FishTab{d_src, d_c, d_f, d_r};
+  int32_t* d_cs = nullptr; uint16_t* d_cb = nullptr;
+  DTS_CUDA(cudaMalloc(&d_cs, cell_start.size() * sizeof(int32_t)));
+  DTS_CUDA(cudaMalloc(&d_cb, cell_bins.size() * sizeof(uint16_t)));
+  DTS_CUDA(cudaMemcpy(d_cs, cell_start.data(), cell_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(d_cb, cell_bins.data(), cell_bins.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  sim->fish = FishTab{d_src, d_c, d_f, d_r, d_cs, d_cb};
   return 0;
 }
 

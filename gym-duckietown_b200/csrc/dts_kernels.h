@@ -42,6 +42,10 @@ struct FishTab {
   const short4* cbox;      // [cbins]    source bounding box (x0, y0, x1, y1) of a 32x8 coarse output bin; x1 < x0: empty
   const short4* fbox;      // [cbins][8] the same for each of its 8x4 fine bins
   const short4* rbox;      // [cbins_y]  and for each row of coarse bins
+  // inverse index for binning small prims: the output coarse bins whose source box meets cell c of a 32x8-px grid laid
+  // over the SOURCE image (CSR: cell_bins[cell_start[c] .. cell_start[c + 1]))
+  const int32_t* cell_start;   // [cbins + 1]
+  const uint16_t* cell_bins;
 };
 
 // Fused end-of-rollout observation gather: on the rollout's last step the rasteriser's resolve stores every

@@ -482,21 +482,37 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
 
 // Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
 // 5-6 and 8): perspective-correct u,v (+ rgb for meshes / ground), analytic lattice lighting for road tiles,
-// bilinear REPEAT texel, MODULATE.  Deferred shading: each lane may shade a different prim.
-__device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, unsigned w, const uint8_t* __restrict__ tex_pool,
-                                           const float4* __restrict__ lat_tab, int pxa, int pya, float c3[3]) {
+// bilinear REPEAT texel, MODULATE.  Deferred shading: each lane may shade a different prim.  Split in two so that a
+// coarse bin lying inside ONE prim fetches the prim's planes once for its 256 pixels.
+struct ShadeIn {
+  const PrimRec* pr;
+  int x0, y0;
+  float q0, qx, qy, u0, ux, uy, v0, vx, vy, r0;
+  int ltq;
+  unsigned tex;
+};
+__device__ __forceinline__ ShadeIn load_shade(const PrimRec* __restrict__ prims, unsigned w) {
   const PrimRec* pr = prims + w;
   const int2 xy0 = __ldg(reinterpret_cast<const int2*>(pr));
   const float4 w3 = __ldg(reinterpret_cast<const float4*>(pr) + 3);   // q0 qx qy u0
   const float4 w4 = __ldg(reinterpret_cast<const float4*>(pr) + 4);   // ux uy v0 vx
   const float4 w5 = __ldg(reinterpret_cast<const float4*>(pr) + 5);   // vy ltq tex r0
-  const int ltq = __float_as_int(w5.y);
-  const float cdx = (float)(pxa + 32 - xy0.x) * 0.015625f, cdy = (float)(pya + 32 - xy0.y) * 0.015625f;
-  float qq = fmaf(w3.z, cdy, fmaf(w3.y, cdx, w3.x));
+  ShadeIn si;
+  si.pr = pr; si.x0 = xy0.x; si.y0 = xy0.y;
+  si.q0 = w3.x; si.qx = w3.y; si.qy = w3.z; si.u0 = w3.w;
+  si.ux = w4.x; si.uy = w4.y; si.v0 = w4.z; si.vx = w4.w;
+  si.vy = w5.x; si.ltq = __float_as_int(w5.y); si.tex = __float_as_uint(w5.z); si.r0 = w5.w;
+  return si;
+}
+__device__ __forceinline__ void shade_eval(const ShadeIn& si, const uint8_t* __restrict__ tex_pool, const float4* __restrict__ lat_tab,
+                                           int pxa, int pya, float c3[3]) {
+  const float cdx = (float)(pxa + 32 - si.x0) * 0.015625f, cdy = (float)(pya + 32 - si.y0) * 0.015625f;
+  float qq = fmaf(si.qy, cdy, fmaf(si.qx, cdx, si.q0));
   if (!(qq > 1e-20f)) qq = 1e-20f;
   const float rq = 1.0f / qq;
-  const float u = fmaf(w4.y, cdy, fmaf(w4.x, cdx, w3.w)) * rq;
-  const float v = fmaf(w5.x, cdy, fmaf(w4.w, cdx, w4.z)) * rq;
+  const float u = fmaf(si.uy, cdy, fmaf(si.ux, cdx, si.u0)) * rq;
+  const float v = fmaf(si.vy, cdy, fmaf(si.vx, cdx, si.v0)) * rq;
+  const int ltq = si.ltq;
   const int lat = (ltq & 0xffff) - 1;
   if (lat >= 0) {
     // analytic road tile: Gouraud interpolant of the lit 8x8 lattice at (u,v)
@@ -515,14 +531,14 @@ __device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, un
     c3[1] = fmaf(t2, c11.y - cm.y, fmaf(t1, cm.y - c00.y, c00.y));
     c3[2] = fmaf(t2, c11.z - cm.z, fmaf(t1, cm.z - c00.z, c00.z));
   } else {
-    const float4 w6 = __ldg(reinterpret_cast<const float4*>(pr) + 6);    // rx ry g0 gx
-    const float4 w7 = __ldg(reinterpret_cast<const float4*>(pr) + 7);    // gy b0 bx by
-    c3[0] = fmaf(w6.y, cdy, fmaf(w6.x, cdx, w5.w)) * rq;
+    const float4 w6 = __ldg(reinterpret_cast<const float4*>(si.pr) + 6);    // rx ry g0 gx
+    const float4 w7 = __ldg(reinterpret_cast<const float4*>(si.pr) + 7);    // gy b0 bx by
+    c3[0] = fmaf(w6.y, cdy, fmaf(w6.x, cdx, si.r0)) * rq;
     c3[1] = fmaf(w7.x, cdy, fmaf(w6.w, cdx, w6.z)) * rq;
     c3[2] = fmaf(w7.w, cdy, fmaf(w7.z, cdx, w7.y)) * rq;
   }
   if (ltq & 0x00ff0000) {
-    const unsigned ti = __float_as_uint(w5.z);
+    const unsigned ti = si.tex;
     const int lw = (ti >> 24) & 15, lh = ti >> 28;
     const int tw = 1 << lw, th = 1 << lh;
     const float twf = __int_as_float((127 + lw) << 23), thf = __int_as_float((127 + lh) << 23);   // (float)tw: a power of two
@@ -544,6 +560,11 @@ __device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, un
       c3[ch] = tc * (c3[ch] * 0.00392156862745098f);
     }
   }
+}
+__device__ __forceinline__ void shade_prim(const PrimRec* __restrict__ prims, unsigned w, const uint8_t* __restrict__ tex_pool,
+                                           const float4* __restrict__ lat_tab, int pxa, int pya, float c3[3]) {
+  const ShadeIn si = load_shade(prims, w);
+  shade_eval(si, tex_pool, lat_tab, pxa, pya, c3);
 }
 
 // ---- bulk-async copy (TMA, 1-D) + mbarrier: global -> shared without register staging
@@ -609,6 +630,7 @@ __device__ __forceinline__ void store_bin_fast(uint8_t* __restrict__ bin0, const
   const unsigned word = __funnelshift_r(lo | (hi << 24), hi >> 8, sl.sh8);   // (lo | hi << 24) >> sh8, low 32 bits
   if (sl.j < 6 && sl.row < rows_ok) *reinterpret_cast<unsigned*>(bin0 + sl.off) = word;
 }
+// general form (any width, bins cut by the right border)
 __device__ __forceinline__ void store_bin(uint8_t* __restrict__ out, unsigned rgb, int lane, int bx, int by, int W, int H) {
   const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
   if ((W & 3) == 0 && bx * kBinW + kBinW <= W) {
@@ -1026,19 +1048,21 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
                                       : (bx1 - bx0 + 1) * (by1 - by0 + 1) > 8);
       if (have && !big) {
         if (kFish) {
-          // the output bins whose SOURCE box meets the prim: rows first, then the row's bins (the LUT is smooth, not
-          // monotone — no range arithmetic)
-          for (int by = 0; by < cbins_y; by++) {
-            const short4 rb = ft.rbox[by];
-            if (rb.z < rb.x || pmaxy < rb.y || pminy > rb.w || pmaxx < rb.x || pminx > rb.z) continue;
-            for (int bx = 0; bx < cbins_x; bx++) {
-              const int b = by * cbins_x + bx;
-              const short4 cb = ft.cbox[b];
-              if (cb.z < cb.x || pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
-              const int pos = atomicAdd(&cnt[b], 1);
-              if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+          // the output bins whose SOURCE box meets the prim, through the inverse index: the source cells under the prim's
+          // pixel box (the same 32x8 grid), each with its list of output bins.  A bin listed by several of those cells
+          // is taken from the first one only (the cell holding the top-left corner of box ∩ prim-cell-range).
+          for (int cy = by0; cy <= by1; cy++)
+            for (int cx = bx0; cx <= bx1; cx++) {
+              const int c = cy * cbins_x + cx;
+              for (int q = ft.cell_start[c]; q < ft.cell_start[c + 1]; q++) {
+                const int b = ft.cell_bins[q];
+                const short4 cb = ft.cbox[b];
+                if (pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
+                if (cx != max(bx0, cb.x / kCoarseW) || cy != max(by0, cb.y / kCoarseH)) continue;   // counted from another cell
+                const int pos = atomicAdd(&cnt[b], 1);
+                if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
+              }
             }
-          }
         } else {
           const bool large = (bx1 - bx0 + 1) * (by1 - by0 + 1) > 4;
           for (int by = by0; by <= by1; by++)
@@ -1128,6 +1152,14 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
   }
 }
 
+// Everything the inline store does not cover — wrapper layouts / dtypes, widths that are no multiple of 4, bins cut
+// by the right border, and the gathering step's extra stores into every peer's buffer — out of line.
+__device__ __noinline__ void emit_general(uint8_t* __restrict__ out, const GatherTab& gt, size_t env_off, int out_fmt, unsigned rgb,
+                                          int lane, int bx, int by, int W, int H) {
+  store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
+  for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+}
+
 // ------------------------------------------------------------------------------------------------ k_raster
 template <bool kWrapFmt, bool kFish>   // kWrapFmt: a dts_output_format other than packed u8 HWC is written by the resolve;
                                        // kFish: every lane renders the SOURCE pixel the fisheye LUT names for its output pixel
@@ -1167,14 +1199,13 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     uint8_t* out = obs + env_off;
     // one fine bin -> the caller's tensor and, on a gathering step, every peer's gather buffer (NVLink stores)
     auto emit = [&](unsigned rgb, int bx, int by) {
-      if (fast_fmt && bx * kBinW + kBinW <= W) {
-        const size_t bin_off = ((size_t)(by * kBinH) * W + bx * kBinW) * 3;   // warp-uniform
-        const int rows_ok = min(kBinH, H - by * kBinH);
-        store_bin_fast(out + bin_off, sl, rgb, rows_ok);
-        for (int p = 0; p < gt.n; p++) store_bin_fast(gt.base[p] + env_off + bin_off, sl, rgb, rows_ok);
+      if (fast_fmt && gt.n == 0 && bx * kBinW + kBinW <= W) {   // the common case inline: packed u8 HWC, whole bin inside
+        store_bin_fast(out + ((size_t)(by * kBinH) * W + bx * kBinW) * 3, sl, rgb, min(kBinH, H - by * kBinH));
+      } else if (kWrapFmt && gt.n == 0) {
+        const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
+        if (gx < W && gy < H) store_px_fmt(out, out_fmt & 3, out_fmt >> 2, gx, gy, W, H, rgb);   // wrapper layout / dtype, inline
       } else {
-        store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
-        for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+        emit_general(out, gt, env_off, out_fmt, rgb, lane, bx, by, W, H);
       }
     };
     const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;   // glClearColor(255, 0, 255): clamped to magenta (S:1752)
@@ -1262,6 +1293,23 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           if (lane < nch) mine = *reinterpret_cast<const uint2*>(&stage[lane].prim_flags);
           const bool first = c0 == 0, last = c0 + kStage >= count;
           const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
+          if (single && !kFish) {
+            // ---- the whole coarse bin lies inside ONE prim (besides the ground quad, hidden below it): no visibility
+            // work at all, the prim's planes are fetched once for the bin's 256 pixels
+            const unsigned ng = __ballot_sync(0xffffffffu, !(mine.y & 2u) && ((mine.x >> 16) & fvalid) != 0u);
+            const unsigned ngfull = __ballot_sync(0xffffffffu, !(mine.y & 2u) && ((mine.x >> 24) & fvalid) == fvalid);
+            if (ng && !(ng & (ng - 1)) && (ng & ngfull)) {
+              const ShadeIn si = load_shade(prims, stage[__ffs(ng) - 1].prim_flags & 0xffffu);
+#pragma unroll 1
+              for (int f = 0; f < kCFX * kCFY; f++) {
+                if (!((fvalid >> f) & 1u)) continue;
+                float c3[3];
+                shade_eval(si, tex_pool, lat_tab, ox + pxs + (f & 3) * kBinW * kSub, oy + pys + (f >> 2) * kBinH * kSub, c3);
+                emit(pack_rgb(c3[0], c3[1], c3[2]), cbx * kCFX + (f & 3), cby * kCFY + (f >> 2));
+              }
+              continue;
+            }
+          }
 #pragma unroll 1
           for (int f = (single ? 0 : g); f < (single ? kCFX * kCFY : g + 1); f++) {
             if (!((fvalid >> f) & 1u)) continue;
