@@ -40,6 +40,9 @@ namespace {
 #ifndef DTS_RENDER_MIN_CTAS
 #define DTS_RENDER_MIN_CTAS 3
 #endif
+#ifndef DTS_COARSE_FAST
+#define DTS_COARSE_FAST 1   // coarse bins lying inside one prim skip visibility and fetch the prim once (A/B switch)
+#endif
 constexpr int kThreads = DTS_RENDER_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kBinW = 8, kBinH = 4;   // fine bin = one warp's pixel block (one pixel per lane)
@@ -1293,7 +1296,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           if (lane < nch) mine = *reinterpret_cast<const uint2*>(&stage[lane].prim_flags);
           const bool first = c0 == 0, last = c0 + kStage >= count;
           const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
-          if (single && !kFish) {
+          if (DTS_COARSE_FAST && single) {
             // ---- the whole coarse bin lies inside ONE prim (besides the ground quad, hidden below it): no visibility
             // work at all, the prim's planes are fetched once for the bin's 256 pixels
             const unsigned ng = __ballot_sync(0xffffffffu, !(mine.y & 2u) && ((mine.x >> 16) & fvalid) != 0u);
@@ -1303,9 +1306,21 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
 #pragma unroll 1
               for (int f = 0; f < kCFX * kCFY; f++) {
                 if (!((fvalid >> f) & 1u)) continue;
+                const int bx = cbx * kCFX + (f & 3), by = cby * kCFY + (f >> 2);
+                int pxa = ox + pxs + (f & 3) * kBinW * kSub, pya = oy + pys + (f >> 2) * kBinH * kSub;
+                bool px_valid = true;
+                if (kFish) {
+                  const int gx = min(bx * kBinW + (lane & 7), W - 1), gy = min(by * kBinH + (lane >> 3), H - 1);
+                  const int sxy = __ldg(ft.src_xy + gy * W + gx);
+                  const int sx = (int)(short)(sxy & 0xffff), sy = sxy >> 16;
+                  px_valid = sx != -32768;
+                  pxa = sx * kSub; pya = sy * kSub;
+                }
                 float c3[3];
-                shade_eval(si, tex_pool, lat_tab, ox + pxs + (f & 3) * kBinW * kSub, oy + pys + (f >> 2) * kBinH * kSub, c3);
-                emit(pack_rgb(c3[0], c3[1], c3[2]), cbx * kCFX + (f & 3), cby * kCFY + (f >> 2));
+                shade_eval(si, tex_pool, lat_tab, pxa, pya, c3);
+                unsigned rgb = pack_rgb(c3[0], c3[1], c3[2]);
+                if (kFish && !px_valid) rgb = 0u;
+                emit(rgb, bx, by);
               }
               continue;
             }
