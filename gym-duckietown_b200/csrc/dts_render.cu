@@ -40,8 +40,13 @@ namespace {
 #ifndef DTS_RENDER_MIN_CTAS
 #define DTS_RENDER_MIN_CTAS 3
 #endif
+#ifndef DTS_TMA_STAGING
+#define DTS_TMA_STAGING 1   // 0: stage BinRec chunks with per-lane 128-bit loads + shared stores instead of cp.async.bulk (A/B switch)
+#endif
 #ifndef DTS_COARSE_FAST
-#define DTS_COARSE_FAST 1   // coarse bins lying inside one prim skip visibility and fetch the prim once (A/B switch)
+#define DTS_COARSE_FAST 0   // 1: coarse bins lying inside one prim skip visibility and fetch the prim once.  Measured
+                            // (profiles/README.md, r2d): +5 % k_raster time — the extra code and registers cost more
+                            // than the skipped flag tests save; kept as an A/B switch only
 #endif
 constexpr int kThreads = DTS_RENDER_THREADS;
 constexpr int kWarps = kThreads / 32;
@@ -1244,10 +1249,19 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       if (n > kStage) while (pf < kCFX * kCFY && !fine_valid(pcbx, pf)) pf++;   // fine bins outside the image are not visited
       if (n > kStage && pf >= kCFX * kCFY) { next_bin(); return; }               // (cannot happen: fine bin 0 is always inside)
       const int nch = min(kStage, n - pc);
+#if DTS_TMA_STAGING
       if (lane == 0) {
         mbar_expect_tx(&bar[ps], (uint32_t)(nch * sizeof(BinRec)));
         bulk_load(stages[warp][ps], recs + st + pc, (uint32_t)(nch * sizeof(BinRec)), &bar[ps]);
       }
+#else
+      if (lane < nch) {   // A/B baseline: one record per lane through registers
+        const int4* src = reinterpret_cast<const int4*>(recs + st + pc + lane);
+        int4* dst = reinterpret_cast<int4*>(&stages[warp][ps][lane]);
+#pragma unroll
+        for (int k = 0; k < 5; k++) dst[k] = __ldg(src + k);
+      }
+#endif
       ps ^= 1;
       if (n <= kStage) { next_bin(); return; }
       pc += kStage;
@@ -1287,8 +1301,12 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           // ---- acquire this chunk; the next one starts loading into the other slot meanwhile
           __syncwarp();   // every lane is done with the slot the producer is about to refill
           issue();
+#if DTS_TMA_STAGING
           mbar_wait(&bar[cs], (parity >> cs) & 1u);
           parity ^= 1u << cs;
+#else
+          __syncwarp();
+#endif
           const BinRec* stage = stages[warp][cs];
           cs ^= 1;
           const int nch = min(kStage, count - c0);

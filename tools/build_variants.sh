@@ -12,11 +12,7 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-nofast -DDTS_COARSE_FAST=0
-t256x2 -DDTS_RENDER_MIN_CTAS=2
-t224x3 -DDTS_RENDER_THREADS=224 -DDTS_RENDER_MIN_CTAS=3
-t192x3 -DDTS_RENDER_THREADS=192 -DDTS_RENDER_MIN_CTAS=3
-nofast224 -DDTS_COARSE_FAST=0 -DDTS_RENDER_THREADS=224 -DDTS_RENDER_MIN_CTAS=3
-g24 -DDTS_GEO_MIN_CTAS=24
+notma -DDTS_TMA_STAGING=0
+fast -DDTS_COARSE_FAST=1
 VARIANTS
 cp /tmp/libdtsim_base_keep.so libdtsim.so
