@@ -51,7 +51,7 @@ struct dts_sim {
   uint8_t* resize_src = nullptr;
   int16_t *resize_xtab = nullptr, *resize_ytab = nullptr;
   // per-kernel timing (dts_profile_*): event pairs recorded around the render launches
-  bool profiling = false;
+  int profiling = 0;                    // 0 off, 1 events around k_raster only, 2 around every render kernel
   std::vector<cudaEvent_t> prof_events; // kProfMarks events per profiled frame
   int64_t prof_frames = 0;
   // query scratch
@@ -626,6 +626,7 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
     marks = sim->prof_events.data() + base;
     sim->prof_frames++;
   }
+  const int mark_level = sim->profiling;
   void* target = obs_dev;
   if (sim->resize_w) {   // render full size, packed u8 HWC, into the library's buffer; k_resize writes the caller's tensor
     rc.obs_layout = DTS_OBS_HWC; rc.obs_dtype = DTS_OBS_U8;
@@ -641,13 +642,13 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
   }
   int k = launch_render(sim->S, sim->d_maps, rc, target, sim->render_scratch, sim->render_ctas, sim->max_prims,
                         sim->bin_cap, sim->max_lat, sim->items_max, sim->fish, gt, sim->d_err,
-                        sim->d_status, marks, (cudaStream_t)stream);
+                        sim->d_status, marks, mark_level, (cudaStream_t)stream);
   if (sim->resize_w) {
     launch_resize(sim->resize_src, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
                   sim->resize_xtab, sim->resize_ytab, obs_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, (cudaStream_t)stream);
     k++;
   }
-  if (marks) cudaEventRecord(marks[kProfMarks - 1], (cudaStream_t)stream);   // closes the "post" interval
+  if (marks && mark_level >= 2) cudaEventRecord(marks[kProfMarks - 1], (cudaStream_t)stream);   // closes the "post" interval
   sim->launches += k;
   DTS_CUDA(cudaGetLastError());
   return 0;
@@ -857,7 +858,7 @@ int dts_status(dts_sim* sim) { return (sim && sim->h_status) ? *(volatile int32_
 
 int dts_profile_enable(dts_sim* sim, int on) {
   if (!sim) return 1;
-  sim->profiling = on != 0;
+  sim->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
   return 0;
 }
 
@@ -866,14 +867,14 @@ int dts_profile_read(dts_sim* sim, double ms_out[8], int64_t* frames) {
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   for (int k = 0; k < 8; k++) ms_out[k] = 0.0;
   const size_t per = kProfMarks;
+  DTS_CUDA(cudaDeviceSynchronize());
   for (size_t f = 0; f + per <= sim->prof_events.size(); f += per) {
-    DTS_CUDA(cudaEventSynchronize(sim->prof_events[f + per - 1]));
     for (size_t k = 0; k + 1 < per; k++) {
-      float ms = 0.f;
-      DTS_CUDA(cudaEventElapsedTime(&ms, sim->prof_events[f + k], sim->prof_events[f + k + 1]));
-      ms_out[k] += ms;
+      float ms = 0.f;   // an interval whose events were not recorded (level 1 marks only k_raster) reports an error: skipped
+      if (cudaEventElapsedTime(&ms, sim->prof_events[f + k], sim->prof_events[f + k + 1]) == cudaSuccess) ms_out[k] += ms;
     }
   }
+  cudaGetLastError();
   if (frames) *frames = sim->prof_frames;
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   sim->prof_events.clear();

@@ -68,7 +68,7 @@ size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int 
 constexpr int kProfMarks = 6;
 int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* obs, void* scratch, int n_ctas,
                   int max_prims, int max_pairs, int max_lat, int items_max, const FishTab& fish, const GatherTab& gather,
-                  int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, cudaStream_t st);
+                  int32_t* err_flag, int32_t* status_dev, cudaEvent_t* marks, int mark_level, cudaStream_t st);
 
 // ResizeWrapper on the device: src u8[N][H][W][3] -> dst [N] x (ow x oh) in `layout` / `dtype` (dts_set_resize)
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,

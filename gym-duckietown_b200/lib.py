@@ -432,8 +432,9 @@ class Sim:
         """Sticky status bits, read without synchronising (bit 0: a frame overflowed its render frame memory)."""
         return int(self.lib.dts_status(self.h))
 
-    def profile(self, on: bool):
-        self._check(self.lib.dts_profile_enable(self.h, int(bool(on))), "dts_profile_enable")
+    def profile(self, level):
+        """0 / False off; 1 / True: CUDA events around k_raster only; 2: around every render kernel."""
+        self._check(self.lib.dts_profile_enable(self.h, int(level)), "dts_profile_enable")
 
     def profile_read(self):
         """(dict kernel -> summed ms, frames) since the last read; synchronises."""

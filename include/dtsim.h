@@ -315,7 +315,7 @@ int dts_status(dts_sim* sim);
  * kernels with CUDA events on the caller's stream.  dts_profile_read synchronises, returns the summed milliseconds of
  * [0] k_frame_setup, [1] k_geometry, [2] k_bin, [3] k_raster, [4] post passes (resize) and the number of frames
  * they cover, and clears the accumulators. */
-int dts_profile_enable(dts_sim* sim, int on);
+int dts_profile_enable(dts_sim* sim, int level);   /* 0 off; 1 events around k_raster only; 2 around every render kernel */
 int dts_profile_read(dts_sim* sim, double ms_out[8], int64_t* frames);
 /* FUSED end-of-rollout gather (the path's one exchange step) — instead of running an all-gather after the last
  * step, the last step's rasteriser stores every frame straight into the gather buffers of all GPUs of the box:
