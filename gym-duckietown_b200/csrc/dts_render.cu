@@ -43,6 +43,9 @@ namespace {
 #ifndef DTS_TMA_STAGING
 #define DTS_TMA_STAGING 1   // 0: stage BinRec chunks with per-lane 128-bit loads + shared stores instead of cp.async.bulk (A/B switch)
 #endif
+#ifndef DTS_TINY_PATH
+#define DTS_TINY_PATH 1     // triangles whose pixel box inside a coarse bin is <= 4x4 are rasterised one per lane (A/B switch)
+#endif
 #ifndef DTS_COARSE_FAST
 #define DTS_COARSE_FAST 0   // 1: coarse bins lying inside one prim skip visibility and fetch the prim once.  Measured
                             // (profiles/README.md, r2d): +5 % k_raster time — the extra code and registers cost more
@@ -101,7 +104,9 @@ struct __align__(16) BinRec {    // 80 B per (prim, coarse bin) pair: what visib
   int32_t id;                    // draw id
   int32_t x0, y0;                // anchor vertex relative to the bin corner (sub-pixels)
   uint32_t prim_flags;           // prim index | per fine bin f of the coarse bin: bit 16+f = may touch, bit 24+f = every sample inside
-  int32_t kind;                  // bit 0: quad (4 edges), bit 1: ground quad (draw id < 2)
+  int32_t kind;                  // bit 0: quad (4 edges), bit 1: ground quad (draw id < 2), bit 2: tiny triangle — its pixel box
+                                 // inside the coarse bin is at most 4x4 and sits in the unused 4th-edge slots:
+                                 // E0[3] = x0 | y0 << 16, A[3] = x1 | y1 << 16 (pixels from the bin corner, inclusive)
 };
 static_assert(sizeof(BinRec) == 80, "BinRec layout");
 constexpr unsigned kNoPrim = 0xffffu;   // sample not covered by any prim: clear colour
@@ -487,13 +492,25 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
       }
     }
   }
+  int tiny = 0;
+  if (DTS_TINY_PATH && !fb && !quad && live) {
+    // small triangles (a 6 cm duckie is 148 triangles in a dozen pixels) are rasterised one per LANE in k_raster instead
+    // of one per warp: they carry their pixel box
+    const int minx = min(qx[0], min(qx[1], qx[2])) - ox, maxx = max(qx[0], max(qx[1], qx[2])) - ox;
+    const int miny = min(qy[0], min(qy[1], qy[2])) - oy, maxy = max(qy[0], max(qy[1], qy[2])) - oy;
+    const int x0 = max(minx >> 6, 0), x1 = min(maxx >> 6, kCoarseW - 1), y0 = max(miny >> 6, 0), y1 = min(maxy >> 6, kCoarseH - 1);
+    if (x1 - x0 < 4 && y1 - y0 < 4 && x1 >= x0 && y1 >= y0) {
+      tiny = 4;
+      E0[3] = x0 | (y0 << 16); A[3] = x1 | (y1 << 16);
+    }
+  }
   const int id = __float_as_int(w2.w);
   int4* o = reinterpret_cast<int4*>(out);
   o[0] = make_int4(E0[0], E0[1], E0[2], E0[3]);
   o[1] = make_int4(A[0], A[1], A[2], A[3]);
   o[2] = make_int4(B[0], B[1], B[2], B[3]);
   o[3] = make_int4(__float_as_int(w2.x), __float_as_int(w2.y), __float_as_int(w2.z), id);
-  o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0));
+  o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0) | tiny);
 }
 
 // Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
@@ -1179,11 +1196,37 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
 
 // Everything the inline store does not cover — wrapper layouts / dtypes, widths that are no multiple of 4, bins cut
 // by the right border, and the gathering step's extra stores into every peer's buffer — out of line.
-__device__ __noinline__ void emit_general(uint8_t* __restrict__ out, const GatherTab& gt, size_t env_off, int out_fmt, unsigned rgb,
-                                          int lane, int bx, int by, int W, int H) {
+__device__ __noinline__ void emit_general(uint8_t* __restrict__ out, const GatherTab& gt, int n_peers, size_t env_off, int out_fmt,
+                                          unsigned rgb, int lane, int bx, int by, int W, int H) {
   store_bin_any(out, out_fmt, rgb, lane, bx, by, W, H);
-  for (int p = 0; p < gt.n; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
+  for (int p = 0; p < n_peers; p++) store_bin_any(gt.base[p] + env_off, out_fmt, rgb, lane, bx, by, W, H);
 }
+// A finished run of image rows -> every rank's gather buffer (peer memory over NVLink): 16-byte vectors, 512 contiguous
+// bytes per warp store.  The rows were written by this very warp (__syncwarp orders those stores before these loads).
+__device__ __noinline__ void gather_rows_out(const uint8_t* __restrict__ src, const GatherTab& gt, size_t off, size_t nbytes, int lane) {
+  __syncwarp();
+  const uint8_t* s = src + off;
+  if (((reinterpret_cast<size_t>(s) | nbytes) & 15) == 0) {
+    bool aligned = true;
+    for (int p = 0; p < gt.n; p++) aligned &= (reinterpret_cast<size_t>(gt.base[p] + off) & 15) == 0;
+    if (aligned) {
+      for (size_t i = (size_t)lane * 16; i < nbytes; i += 512) {
+        const int4 v = __ldcg(reinterpret_cast<const int4*>(s + i));   // from L2, where this warp's stores went
+        for (int p = 0; p < gt.n; p++) *reinterpret_cast<int4*>(gt.base[p] + off + i) = v;
+      }
+      return;
+    }
+  }
+  for (size_t i = lane; i < nbytes; i += 32) {
+    const uint8_t v = __ldcg(s + i);
+    for (int p = 0; p < gt.n; p++) gt.base[p][off + i] = v;
+  }
+}
+
+constexpr size_t kRasterSmem = (sizeof(BinRec) * 2 * kStage + 16 + 128 * sizeof(unsigned long long)) * kWarps;
+// order-preserving map of a float onto unsigned (and back): depth keys of the tiny-triangle buffer
+__device__ __forceinline__ unsigned float_key(float f) { const unsigned b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+__device__ __forceinline__ float key_float(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
 
 // ------------------------------------------------------------------------------------------------ k_raster
 template <bool kWrapFmt, bool kFish>   // kWrapFmt: a dts_output_format other than packed u8 HWC is written by the resolve;
@@ -1191,8 +1234,13 @@ template <bool kWrapFmt, bool kFish>   // kWrapFmt: a dts_output_format other th
 __global__ void __launch_bounds__(kThreads, DTS_RENDER_MIN_CTAS)
 k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm, FishTab ft, GatherTab gt,
          uint8_t* __restrict__ obs, int max_prims, int max_pairs, int max_lat, int32_t* __restrict__ err) {
-  __shared__ __align__(128) BinRec stages[kWarps][2][kStage];   // per warp: two chunks of records in flight
-  __shared__ __align__(8) uint64_t bars[kWarps][2];
+  // dynamic shared memory (kRasterSmem bytes): per warp two chunks of records in flight, their mbarriers, and a 128-sample
+  // depth / winner buffer for the tiny triangles of the fine bin being drawn
+  extern __shared__ __align__(128) unsigned char raster_smem[];
+  BinRec (*stages)[2][kStage] = reinterpret_cast<BinRec (*)[2][kStage]>(raster_smem);
+  uint64_t (*bars)[2] = reinterpret_cast<uint64_t (*)[2]>(raster_smem + sizeof(BinRec) * kWarps * 2 * kStage);
+  unsigned long long* zb = reinterpret_cast<unsigned long long*>(raster_smem + sizeof(BinRec) * kWarps * 2 * kStage + 16 * kWarps) +
+                           128 * (threadIdx.x >> 5);
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1223,14 +1271,18 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     const size_t env_off = (size_t)env * frame_bytes * out_elem;
     uint8_t* out = obs + env_off;
     // one fine bin -> the caller's tensor and, on a gathering step, every peer's gather buffer (NVLink stores)
+    // On a gathering step (gt.n > 0) the packed u8 HWC frame goes to the peers in BLOCKS: a work item is 8 whole image rows =
+    // one contiguous run of bytes, copied to every rank's gather buffer with 16-byte vector stores once the item is drawn
+    // (NVLink wants long writes: per-bin 4-byte stores reach a fifth of the link rate).  Other layouts store per bin.
+    const bool gather_rows = gt.n > 0 && !kWrapFmt;
     auto emit = [&](unsigned rgb, int bx, int by) {
-      if (fast_fmt && gt.n == 0 && bx * kBinW + kBinW <= W) {   // the common case inline: packed u8 HWC, whole bin inside
+      if (fast_fmt && (gt.n == 0 || gather_rows) && bx * kBinW + kBinW <= W) {   // the common case inline: packed u8 HWC, whole bin inside
         store_bin_fast(out + ((size_t)(by * kBinH) * W + bx * kBinW) * 3, sl, rgb, min(kBinH, H - by * kBinH));
       } else if (kWrapFmt && gt.n == 0) {
         const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
         if (gx < W && gy < H) store_px_fmt(out, out_fmt & 3, out_fmt >> 2, gx, gy, W, H, rgb);   // wrapper layout / dtype, inline
       } else {
-        emit_general(out, gt, env_off, out_fmt, rgb, lane, bx, by, W, H);
+        emit_general(out, gt, gather_rows ? 0 : gt.n, env_off, out_fmt, rgb, lane, bx, by, W, H);
       }
     };
     const bool seg = (rc.mode & DTS_RENDER_SEGMENT) != 0;   // glClearColor(255, 0, 255): clamped to magenta (S:1752)
@@ -1313,6 +1365,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
         if (!single && !((fvalid >> g) & 1u)) continue;
         float z[4];
         unsigned wn[4];   // per sample: depth and winning prim (index into the env's slab)
+        bool zb_used = false;   // tiny triangles of this fine bin went through the shared depth / winner buffer
 #pragma unroll 1
         for (int c0 = 0; c0 < count; c0 += kStage) {
           // ---- acquire this chunk; the next one starts loading into the other slot meanwhile
@@ -1331,6 +1384,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           if (lane < nch) mine = *reinterpret_cast<const uint2*>(&stage[lane].prim_flags);
           const bool first = c0 == 0, last = c0 + kStage >= count;
           const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
+          const unsigned tiny_bits = kFish ? 0u : __ballot_sync(0xffffffffu, (mine.y & 4u) != 0u);   // one-per-lane triangles
           if (DTS_COARSE_FAST && single) {
             // ---- the whole coarse bin lies inside ONE prim (besides the ground quad, hidden below it): no visibility
             // work at all, the prim's planes are fetched once for the bin's 256 pixels
@@ -1394,11 +1448,12 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               if (first) {
 #pragma unroll
                 for (int s = 0; s < 4; s++) { z[s] = 1.0f; wn[s] = kNoPrim; }
+                zb_used = false;
               }
               // ---- visibility: everything else first, the ground quad last (it is almost always hidden)
 #pragma unroll 1
               for (int phase = 0; phase < 2; phase++) {
-                unsigned todo = phase == 0 ? (live_mask & ~ground_mask) : ground_mask;
+                unsigned todo = phase == 0 ? (live_mask & ~ground_mask & ~tiny_bits) : ground_mask;
                 // every sample of the bin already belongs to a surface above the ground plane: the ground quad
                 // (y = -0.008, below everything else) cannot pass GL_LESS anywhere — same argument as the simple bin
                 if (phase == 1 && todo &&
@@ -1470,7 +1525,59 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 }
               }
             }
+            if (!kFish && !simple && (live_mask & tiny_bits)) {
+              // ---- tiny triangles, ONE PER LANE: each lane walks the few pixels of its triangle inside this fine bin and
+              // resolves GL_LESS (ties to the lower draw id) with a 64-bit atomicMin on depth | id | prim per sample —
+              // 32 triangles per pass instead of one warp-wide visit per triangle
+              if (!zb_used) {
+                zb_used = true;
+#pragma unroll
+                for (int s = 0; s < 4; s++) zb[lane * 4 + s] = ~0ull;
+                __syncwarp();
+              }
+              if ((live_mask & tiny_bits) >> lane & 1u) {
+                const BinRec& br = stage[lane];
+                const int4 E = *reinterpret_cast<const int4*>(br.E0);
+                const int4 A = *reinterpret_cast<const int4*>(br.A);
+                const int4 B = *reinterpret_cast<const int4*>(br.B);
+                const float4 zp = *reinterpret_cast<const float4*>(&br.z0);
+                const int2 xy0 = *reinterpret_cast<const int2*>(&br.x0);
+                const int fx0 = (f & 3) * kBinW, fy0 = (f >> 2) * kBinH;
+                const int x_lo = max(E.w & 0xffff, fx0), x_hi = min(A.w & 0xffff, fx0 + kBinW - 1);
+                const int y_lo = max(E.w >> 16, fy0), y_hi = min(A.w >> 16, fy0 + kBinH - 1);
+                const unsigned long long tail = ((unsigned long long)(unsigned)__float_as_int(zp.w) << 16) | (br.prim_flags & 0xffffu);
+                for (int py = y_lo; py <= y_hi; py++)
+                  for (int px = x_lo; px <= x_hi; px++) {
+                    const int X = px * kSub, Y = py * kSub;
+                    const int ec0 = E.x + A.x * X + B.x * Y, ec1 = E.y + A.y * X + B.y * Y, ec2 = E.z + A.z * X + B.z * Y;
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                      const int e0 = ec0 + A.x * sample_x(s) + B.x * sample_y(s);
+                      const int e1 = ec1 + A.y * sample_x(s) + B.y * sample_y(s);
+                      const int e2 = ec2 + A.z * sample_x(s) + B.z * sample_y(s);
+                      if ((e0 | e1 | e2) < 0) continue;
+                      const float sdx = (float)(X + sample_x(s) - xy0.x) * 0.015625f, sdy = (float)(Y + sample_y(s) - xy0.y) * 0.015625f;
+                      const float zs = fmaf(zp.z, sdy, fmaf(zp.y, sdx, zp.x));
+                      atomicMin(&zb[((py - fy0) * kBinW + (px - fx0)) * 4 + s], ((unsigned long long)float_key(zs) << 32) | tail);
+                    }
+                  }
+              }
+              __syncwarp();
+            }
             if (!(last || simple)) continue;
+            if (!kFish && !simple && zb_used) {
+              // merge the tiny triangles' winners into the per-sample state: GL_LESS, ties to the lower draw id
+#pragma unroll
+              for (int s = 0; s < 4; s++) {
+                const unsigned long long k = zb[lane * 4 + s];
+                if (k == ~0ull) continue;
+                const float zt = key_float((unsigned)(k >> 32));
+                bool win = zt < z[s];
+                if (zt == z[s] && wn[s] != kNoPrim) win = (int)((k >> 16) & 0xffffu) < __ldg(&prims[wn[s]].id);
+                if (win) { z[s] = zt; wn[s] = (unsigned)(k & 0xffffu); }
+              }
+              __syncwarp();   // the buffer is re-initialised by the next fine bin
+            }
             // ---- deferred shading: once per distinct winner of this pixel, then the box resolve
             const int pxa = ox + pxc, pya = oy + pyc;
             const bool same = wn[1] == wn[0] && wn[2] == wn[0] && wn[3] == wn[0];
@@ -1512,6 +1619,10 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           }
         }
       }
+    }
+    if (gather_rows) {   // the item's rows are complete: ship them to every rank
+      const int rows = min(kCoarseH, H - cby * kCoarseH);
+      gather_rows_out(obs, gt, env_off + (size_t)cby * kCoarseH * W * 3, (size_t)rows * W * 3, lane);
     }
     work = __shfl_sync(0xffffffffu, next_work, 0);
   }
@@ -1659,12 +1770,20 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   }
   mark();
   const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;
+  static bool smem_opt_in = false;
+  if (!smem_opt_in) {   // > 48 KB of dynamic shared memory per CTA needs the opt-in, once per kernel
+    cudaFuncSetAttribute(k_raster<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterSmem);
+    cudaFuncSetAttribute(k_raster<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterSmem);
+    cudaFuncSetAttribute(k_raster<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterSmem);
+    cudaFuncSetAttribute(k_raster<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterSmem);
+    smem_opt_in = true;
+  }
   if (fisheye) {
-    if (wrap) k_raster<true, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
-    else k_raster<false, true><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    if (wrap) k_raster<true, true><<<n_ctas, kThreads, kRasterSmem, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, true><<<n_ctas, kThreads, kRasterSmem, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
   } else {
-    if (wrap) k_raster<true, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
-    else k_raster<false, false><<<n_ctas, kThreads, 0, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    if (wrap) k_raster<true, false><<<n_ctas, kThreads, kRasterSmem, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
+    else k_raster<false, false><<<n_ctas, kThreads, kRasterSmem, st>>>(S, maps, rc, fm, fish, gather, obs, max_prims, max_pairs, max_lat, err_flag);
   }
   mark();
   mark();   // (post passes: none yet)

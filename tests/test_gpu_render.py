@@ -248,3 +248,34 @@ def test_segment_and_top_down_views_vs_oracle(name, segment, top_down, W, H, tor
         assert (got[:, 0, 0] == np.array([255, 0, 255])).all(axis=1).mean() > 0.6
     env.check()
     env.close()
+
+
+@pytest.mark.parametrize("name,W,H", [("loop_obstacles", 160, 120), ("loop_obstacles", 84, 84), ("udem1", 160, 120), ("udem1", 320, 240)])
+def test_small_triangle_path_vs_oracle(name, W, H, torch_cuda):
+    """Agents parked at 0.15 .. 2.5 m from the map's props, facing them: the props' triangles range from a few dozen pixels
+    down to sub-pixel size, so both raster paths (one warp per prim; one LANE per tiny triangle with the shared
+    depth / winner buffer) and the merge between them are exercised on the same frames — bit-exact vs the oracle."""
+    torch = torch_cuda
+    import oracle as orc
+    from gym_duckietown_b200 import maps
+    from gym_duckietown_b200.batched_env import BatchedDuckietownEnv
+    md = maps.load_map(name)
+    rng = np.random.default_rng(5)
+    poses = []
+    for o in md.objects:
+        for d in (0.15, 0.3, 0.5, 0.8, 1.2, 1.8, 2.5):
+            a = rng.uniform(-np.pi, np.pi)
+            x, z = o.pos[0] - d * np.cos(a), o.pos[2] + d * np.sin(a)      # get_dir_vec(a) = (cos a, 0, -sin a) points at the prop
+            poses.append((x, z, a + rng.uniform(-0.25, 0.25)))
+    poses = poses[:96]
+    N = len(poses)
+    env = BatchedDuckietownEnv(N, name, camera_width=W, camera_height=H, domain_rand=False, seed=3)
+    P = np.array(poses)
+    env.sim.reset(None, dict(pos_x=P[:, 0].copy(), pos_z=P[:, 1].copy(), angle=P[:, 2].copy(), map_id=np.zeros(N, np.int32)),
+                  env._stream())
+    got = env.render_obs().cpu().numpy()
+    sc = orc.OracleScene(md)
+    ref = np.stack([sc.render(x, z, a, None, W, H) for x, z, a in poses])
+    compare(got, ref, f"tiny_{name}_{W}")
+    env.check()
+    env.close()
