@@ -1,5 +1,6 @@
 // dts_api.cu — the C ABI of libdtsim.so (include/dtsim.h): handle management, host->device
 // staging of maps and episode parameters, and stream-ordered launches of the kernels.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -35,7 +36,7 @@ struct dts_sim {
   // render
   void* render_scratch = nullptr;
   int render_ctas = 0, max_prims = 0, bin_cap = 0, max_lat = 0, items_max = 0;
-  FishTab fish{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fused fisheye tables (dts_set_fisheye_lut)
+  FishTab fish{};   // fused fisheye tables (dts_set_fisheye_lut)
   int32_t* d_err = nullptr;
   int32_t* h_status = nullptr;          // mapped pinned host word: bit 0 = a frame overflowed its frame memory
   int32_t* d_status = nullptr;          // its device address
@@ -199,7 +200,7 @@ void dts_destroy(dts_sim* sim) {
   for (void* p : sim->allocs) cudaFree(p);
   for (auto& v : sim->map_allocs) for (void* p : v) cudaFree(p);
   void* extra[] = {sim->render_scratch, (void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
-                   (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins,
+                   (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins, (void*)sim->fish.home_start, (void*)sim->fish.home_ent,
                    sim->q_in, sim->q_outd, sim->q_outi, sim->q_hidden};
   for (void* p : extra) if (p) cudaFree(p);
   for (int p = 0; p < sim->gather_world; p++)
@@ -469,11 +470,32 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
     cell_start[cbins] = (int32_t)cell_bins.size();
     if (cell_bins.empty()) cell_bins.push_back(0);
   }
+  // ... and the index by HOME cell (the cell of the box's top-left corner): each bin once, with its box
+  std::vector<int32_t> home_start(cbins + 1, 0);
+  std::vector<int4> home_ent;
+  int ext_x = 0, ext_y = 0;
+  {
+    std::vector<std::vector<int>> lists(cbins);
+    for (int b = 0; b < cbins; b++) {
+      if (cbox[b].z < cbox[b].x) continue;
+      lists[(cbox[b].y / 8) * cbx_n + cbox[b].x / 32].push_back(b);
+      ext_x = std::max(ext_x, cbox[b].z / 32 - cbox[b].x / 32);
+      ext_y = std::max(ext_y, cbox[b].w / 8 - cbox[b].y / 8);
+    }
+    for (int c = 0; c < cbins; c++) {
+      home_start[c] = (int32_t)home_ent.size();
+      for (int b : lists[c])
+        home_ent.push_back(make_int4((int)((uint32_t)(uint16_t)cbox[b].x | ((uint32_t)(uint16_t)cbox[b].y << 16)),
+                                     (int)((uint32_t)(uint16_t)cbox[b].z | ((uint32_t)(uint16_t)cbox[b].w << 16)), b, 0));
+    }
+    home_start[cbins] = (int32_t)home_ent.size();
+    if (home_ent.empty()) home_ent.push_back(make_int4(0, 0, 0, 0));
+  }
   void* old[] = {(void*)sim->fish.src_xy, (void*)sim->fish.cbox, (void*)sim->fish.fbox, (void*)sim->fish.rbox,
-                 (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins};
+                 (void*)sim->fish.cell_start, (void*)sim->fish.cell_bins, (void*)sim->fish.home_start, (void*)sim->fish.home_ent};
   DTS_CUDA(cudaDeviceSynchronize());
   for (void* p : old) if (p) cudaFree(p);
-  sim->fish = FishTab{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  sim->fish = FishTab{};
   int32_t* d_src = nullptr; short4 *d_c = nullptr, *d_f = nullptr, *d_r = nullptr;
   DTS_CUDA(cudaMalloc(&d_src, src.size() * sizeof(int32_t)));
   DTS_CUDA(cudaMalloc(&d_c, cbox.size() * sizeof(short4)));
@@ -488,7 +510,12 @@ int dts_set_fisheye_lut(dts_sim* sim, const float* rmapx, const float* rmapy, in
   DTS_CUDA(cudaMalloc(&d_cb, cell_bins.size() * sizeof(uint16_t)));
   DTS_CUDA(cudaMemcpy(d_cs, cell_start.data(), cell_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   DTS_CUDA(cudaMemcpy(d_cb, cell_bins.data(), cell_bins.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  sim->fish = FishTab{d_src, d_c, d_f, d_r, d_cs, d_cb};
+  int32_t* d_hs = nullptr; int4* d_he = nullptr;
+  DTS_CUDA(cudaMalloc(&d_hs, home_start.size() * sizeof(int32_t)));
+  DTS_CUDA(cudaMalloc(&d_he, home_ent.size() * sizeof(int4)));
+  DTS_CUDA(cudaMemcpy(d_hs, home_start.data(), home_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  DTS_CUDA(cudaMemcpy(d_he, home_ent.data(), home_ent.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  sim->fish = FishTab{d_src, d_c, d_f, d_r, d_cs, d_cb, d_hs, d_he, ext_x, ext_y};
   return 0;
 }
 

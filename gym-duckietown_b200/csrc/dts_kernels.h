@@ -46,6 +46,12 @@ struct FishTab {
   // over the SOURCE image (CSR: cell_bins[cell_start[c] .. cell_start[c + 1]))
   const int32_t* cell_start;   // [cbins + 1]
   const uint16_t* cell_bins;
+  // second inverse index for prims spanning many cells: every output bin listed ONCE, under the source cell holding the
+  // top-left corner of its box (CSR); an entry is (x0 | y0 << 16, x1 | y1 << 16, bin, 0).  ext_x / ext_y: how many
+  // cells a box reaches to the right of / below its home cell at most
+  const int32_t* home_start;   // [cbins + 1]
+  const int4* home_ent;
+  int ext_x, ext_y;
 };
 
 // Fused end-of-rollout observation gather: on the rollout's last step the rasteriser's resolve stores every

@@ -25,6 +25,7 @@
 //
 // HBM traffic per env-frame: obs store W*H*3 B (compulsory) + PrimRec slab / BinRec lists / lattice table
 // (tens of KB per env, written by k_geometry / k_bin and read once by k_raster) + texels (shared, L2-resident).
+#include <cstdlib>
 #include <cstddef>
 
 #include "dts_camera.cuh"
@@ -45,6 +46,9 @@ namespace {
 #endif
 #ifndef DTS_TINY_PATH
 #define DTS_TINY_PATH 1     // triangles whose pixel box inside a coarse bin is <= 4x4 are rasterised one per lane (A/B switch)
+#endif
+#ifndef DTS_SAMPLE_CULL
+#define DTS_SAMPLE_CULL 1   // triangles of at most 3x3 pixels that cover no sample position are dropped at set-up (A/B switch)
 #endif
 #ifndef DTS_COARSE_FAST
 #define DTS_COARSE_FAST 0   // 1: coarse bins lying inside one prim skip visibility and fetch the prim once.  Measured
@@ -280,6 +284,32 @@ __device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const
   const int px0 = max(minx >> 6, 0), px1 = min(maxx >> 6, ec.W - 1);
   const int py0 = max(miny >> 6, 0), py1 = min(maxy >> 6, ec.H - 1);
   if (px0 > px1 || py0 > py1) return true;   // off screen: emitted nothing, and nothing is what it covers
+#if DTS_SAMPLE_CULL
+  if (!d && (maxx >> 6) - (minx >> 6) < 3 && (maxy >> 6) - (miny >> 6) < 3) {   // (the unclamped box: everything below stays small)
+    // A small triangle that covers NO sample position draws nothing — half the triangles of a distant mesh at
+    // 160x120 — so it needs no record, no bin pair and no visit by the rasteriser.  Same integer edge functions and
+    // fill rule as the coverage test proper (build_binrec / k_raster); coordinates relative to vertex 0 stay in int32.
+    const int ex[3] = {x1 - x0, x2 - x1, x0 - x2}, ey[3] = {y1 - y0, y2 - y1, y0 - y2};
+    const int ax[3] = {0, x1 - x0, x2 - x0}, ay[3] = {0, y1 - y0, y2 - y0};
+    int e00[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int bias = (ey[k] > 0 || (ey[k] == 0 && ex[k] < 0)) ? 0 : 1;
+      e00[k] = ex[k] * (py0 * kSub - y0 - ay[k]) - ey[k] * (px0 * kSub - x0 - ax[k]) - bias;
+    }
+    bool any = false;
+    for (int py = 0; py <= py1 - py0; py++)
+      for (int px = 0; px <= px1 - px0; px++) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int sx = px * kSub + sample_x(s), sy = py * kSub + sample_y(s);
+          const int e0 = e00[0] + ex[0] * sy - ey[0] * sx, e1 = e00[1] + ex[1] * sy - ey[1] * sx, e2 = e00[2] + ex[2] * sy - ey[2] * sx;
+          any |= (e0 | e1 | e2) >= 0;
+        }
+      }
+    if (!any) return true;
+  }
+#endif
   PrimRec r;
   r.X0 = x0; r.Y0 = y0; r.X1 = x1; r.Y1 = y1; r.X2 = x2; r.Y2 = y2; r.X3 = x0; r.Y3 = y0;
   const float dx1 = (float)(x1 - x0) * 0.015625f, dy1 = (float)(y1 - y0) * 0.015625f;
@@ -1037,29 +1067,29 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
 }
 
 // ------------------------------------------------------------------------------------------------ k_bin
-// warp per env.  Pass 1: exact-size lists of (prim, 32x8-px coarse bin) pairs — count, warp scan, scatter; prims with
-// a small bounding box are binned by it, larger ones test each bin of the box against their edges.  Pass 2, dense
-// over the pairs (one per lane, so a screen-filling prim costs no more lanes than a sliver): the pair's BinRec.
+// CTA (1 or 4 warps) per env, the env's prims striped over the warps.  Pass 1: exact-size lists of (prim, 32x8-px coarse bin)
+// pairs — count (shared-memory atomics), scan, scatter; prims with a small bounding box are binned by it, larger ones
+// test each bin of the box against their edges, one bin per lane.  Pass 2, dense over the pairs (one per thread, so a
+// screen-filling prim costs no more lanes than a sliver): the pair's BinRec.
 constexpr int kBinWarps = 4;
 template <bool kFish>   // true: bins are the LUT's source boxes of the output bins (fused fisheye gather)
 __global__ void __launch_bounds__(kBinWarps * 32)
 k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32_t* __restrict__ err) {
   extern __shared__ int bin_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * kBinWarps + wib;
-  if (env >= rc.n_envs) return;
+  __shared__ int s_total, s_base, s_ok;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
+  const int env = blockIdx.x, nthr = blockDim.x;   // 1 warp per env for small cameras, 4 for large ones (launch_render)
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW, cbins_y = (H + kCoarseH - 1) / kCoarseH, cbins = cbins_x * cbins_y;
-  int* cnt = bin_smem + wib * 2 * cbins;
+  int* cnt = bin_smem;
   int* start = cnt + cbins;
   const PrimRec* prims = fm.prims + (size_t)env * max_prims;
   uint32_t* pairs = fm.pairs;
   const int n = min(fm.ctx[env].n_prims, max_prims);
-  int total = 0, pair0 = 0;
   for (int pass = 0; pass < 2; pass++) {
-    for (int b = lane; b < cbins; b += 32) cnt[b] = 0;
-    __syncwarp();
-    for (int p0 = 0; p0 < n; p0 += 32) {
+    for (int b = tid; b < cbins; b += nthr) cnt[b] = 0;
+    __syncthreads();
+    for (int p0 = wib * 32; p0 < n; p0 += nthr) {
       const int p = p0 + lane;
       const bool have = p < n;
       int qx[4] = {0, 0, 0, 0}, qy[4] = {0, 0, 0, 0}, nv = 3;
@@ -1115,23 +1145,24 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
         for (int k = 0; k < 4; k++) { vx[k] = __shfl_sync(0xffffffffu, qx[k], src); vy[k] = __shfl_sync(0xffffffffu, qy[k], src); }
         const int snv = __shfl_sync(0xffffffffu, nv, src), sp = p0 + src;
         if (kFish) {
-          // one source cell per lane and round; each lane walks its cell's list of output bins (inverse index), takes a bin
-          // only from the first cell of the range that lists it, and applies the exact edge test to its source box
+          // one HOME cell per lane and round: every output bin is listed once, under the source cell holding the top-left
+          // corner of its source box (second inverse index), so a prim spanning many cells meets each candidate bin once;
+          // the range of home cells is the prim's cell range grown up / left by the largest box extent of the LUT
           const int sminx = __shfl_sync(0xffffffffu, pminx, src), smaxx = __shfl_sync(0xffffffffu, pmaxx, src);
           const int sminy = __shfl_sync(0xffffffffu, pminy, src), smaxy = __shfl_sync(0xffffffffu, pmaxy, src);
-          const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sbx1 = __shfl_sync(0xffffffffu, bx1, src);
-          const int sby0 = __shfl_sync(0xffffffffu, by0, src), sby1 = __shfl_sync(0xffffffffu, by1, src);
-          const int nbx = sbx1 - sbx0 + 1, nb = nbx * (sby1 - sby0 + 1);
+          const int hx0 = max(__shfl_sync(0xffffffffu, bx0, src) - ft.ext_x, 0), sbx1 = __shfl_sync(0xffffffffu, bx1, src);
+          const int hy0 = max(__shfl_sync(0xffffffffu, by0, src) - ft.ext_y, 0), sby1 = __shfl_sync(0xffffffffu, by1, src);
+          const int nbx = sbx1 - hx0 + 1, nb = nbx * (sby1 - hy0 + 1);
           for (int i = lane; i < nb; i += 32) {
-            const int cy = sby0 + i / nbx, cx = sbx0 + i % nbx, c = cy * cbins_x + cx;
-            for (int q = ft.cell_start[c]; q < ft.cell_start[c + 1]; q++) {
-              const int b = ft.cell_bins[q];
-              const short4 cb = ft.cbox[b];
-              if (smaxx < cb.x || sminx > cb.z || smaxy < cb.y || sminy > cb.w) continue;
-              if (cx != max(sbx0, cb.x / kCoarseW) || cy != max(sby0, cb.y / kCoarseH)) continue;   // counted from another cell
-              if (!box_overlaps(vx, vy, snv, cb.x * kSub + 8, cb.z * kSub + 56, cb.y * kSub + 8, cb.w * kSub + 56)) continue;
-              const int pos = atomicAdd(&cnt[b], 1);
-              if (pass == 1) pairs[start[b] + pos] = (uint32_t)sp | ((uint32_t)b << 16);
+            const int cy = hy0 + i / nbx, cx = hx0 + i % nbx, c = cy * cbins_x + cx;
+            const int q1 = __ldg(ft.home_start + c + 1);
+            for (int q = __ldg(ft.home_start + c); q < q1; q++) {
+              const int4 e = __ldg(ft.home_ent + q);   // x0 | y0 << 16, x1 | y1 << 16, bin
+              const int x0 = (int)(short)(e.x & 0xffff), y0 = e.x >> 16, x1 = (int)(short)(e.y & 0xffff), y1 = e.y >> 16;
+              if (smaxx < x0 || sminx > x1 || smaxy < y0 || sminy > y1) continue;
+              if (!box_overlaps(vx, vy, snv, x0 * kSub + 8, x1 * kSub + 56, y0 * kSub + 8, y1 * kSub + 56)) continue;
+              const int pos = atomicAdd(&cnt[e.z], 1);
+              if (pass == 1) pairs[start[e.z] + pos] = (uint32_t)sp | ((uint32_t)e.z << 16);
             }
           }
         } else {
@@ -1148,40 +1179,44 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
         }
       }
     }
-    __syncwarp();
+    __syncthreads();
     if (pass == 0) {
-      int carry = 0;
-      for (int b0 = 0; b0 < cbins; b0 += 32) {
-        const int b = b0 + lane;
-        const int v = b < cbins ? cnt[b] : 0;
-        int inc = v;
+      if (wib == 0) {
+        int carry = 0;
+        for (int b0 = 0; b0 < cbins; b0 += 32) {
+          const int b = b0 + lane;
+          const int v = b < cbins ? cnt[b] : 0;
+          int inc = v;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
-        if (b < cbins) start[b] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+          for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+          if (b < cbins) start[b] = carry + inc - v;
+          carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {   // this env's run of the batch-wide pair pool
+          const unsigned base = atomicAdd(reinterpret_cast<unsigned*>(fm.work) + 1, (unsigned)carry);
+          s_total = carry; s_base = (int)base;
+          s_ok = (unsigned long long)base + (unsigned)carry <= (unsigned long long)max_pairs;
+        }
       }
-      total = carry;
-      unsigned base = 0;   // this env's run of the batch-wide pair pool
-      if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned*>(fm.work) + 1, (unsigned)total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const bool ok = (unsigned long long)base + (unsigned)total <= (unsigned long long)max_pairs;
-      for (int b = lane; b < cbins; b += 32) {
-        start[b] += (int)base;
+      __syncthreads();
+      const int base = s_base;
+      const bool ok = s_ok != 0;
+      for (int b = tid; b < cbins; b += nthr) {
+        start[b] += base;
         fm.bin_count[(size_t)env * cbins + b] = ok ? cnt[b] : 0;   // lists that do not fit: the frame stays clear
         fm.bin_start[(size_t)env * cbins + b] = start[b];
       }
-      pair0 = (int)base;
-      __syncwarp();
       if (!ok) {
-        if (lane == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
+        if (tid == 0) { fm.ctx[env].overflow = 1; atomicOr(err, 1); *reinterpret_cast<volatile int32_t*>(fm.status) = 1; }
         return;
       }
     }
   }
-  // pass 2: one pair per lane -> its visibility record (the pairs were written by other lanes of this warp:
-  // __syncwarp above orders those writes before these reads)
+  // pass 2: one pair per thread -> its visibility record (the pairs were written by other threads of this CTA: the
+  // barrier above orders those writes before these reads)
+  const int pair0 = s_base, total = s_total;
   BinRec* recs = fm.recs;
-  for (int i = pair0 + lane; i < pair0 + total; i += 32) {
+  for (int i = pair0 + tid; i < pair0 + total; i += nthr) {
     const uint32_t pair = pairs[i];
     const int p = (int)(pair & 0xffffu), b = (int)(pair >> 16);
     if (kFish) {
@@ -1758,15 +1793,18 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   if (rc.tessellate) k_geometry<true><<<geo_ctas, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, max_prims, max_lat, err_flag);
   else k_geometry<false><<<geo_ctas, kGeoWarps * 32, 0, st>>>(S, maps, rc, fm, max_prims, max_lat, err_flag);
   mark();
-  const size_t bin_smem_bytes = (size_t)kBinWarps * 2 * cbins * sizeof(int);
-  const int bin_grid = (rc.n_envs + kBinWarps - 1) / kBinWarps;
+  const size_t bin_smem_bytes = (size_t)2 * cbins * sizeof(int);
+  const int bin_grid = rc.n_envs;   // CTA per env: one warp where a frame has few bins and prims (160x120: 75 bins — more warps
+  // only add barriers and CTA launches, measured 58 -> 88 us), four for large cameras (640x480: 9.0 -> 3.3 ms)
+  static const int bin_warps_env = getenv("DTS_BIN_WARPS") ? atoi(getenv("DTS_BIN_WARPS")) : 0;   // A/B override: 1..4
+  const int bin_threads = bin_warps_env >= 1 && bin_warps_env <= kBinWarps ? bin_warps_env * 32 : (cbins > 128 ? kBinWarps * 32 : 32);
   if (fisheye) {
     if (bin_smem_bytes > 48 * 1024) cudaFuncSetAttribute(k_bin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
-    k_bin<true><<<bin_grid, kBinWarps * 32, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
+    k_bin<true><<<bin_grid, bin_threads, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
   } else {
     if (bin_smem_bytes > 48 * 1024)   // cameras beyond ~640x480 (cbins > 1536): opt in to large dynamic shared memory
       cudaFuncSetAttribute(k_bin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes);
-    k_bin<false><<<bin_grid, kBinWarps * 32, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
+    k_bin<false><<<bin_grid, bin_threads, bin_smem_bytes, st>>>(rc, fm, fish, max_prims, max_pairs, err_flag);
   }
   mark();
   const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;

@@ -50,6 +50,11 @@ static int g_tile_mode = 1;
 void orr_set_tile_mode(int mode) { g_tile_mode = mode; }
 static int g_render_mode = 0; /* 1 = segment (S:1730-1733, 1752, 1808, 1814), 2 = top_down (S:1786-1798, 1923-1929) */
 void orr_set_render_mode(int mode) { g_render_mode = mode; }
+/* test-side statistics of the triangles handed to the rasteriser (single-threaded use): [0] set-up triangles on screen,
+ * [1] of those with no sample position inside their bounding box, [2] with no covered sample, [3] pixel box <= 2x2,
+ * [4] pixel box <= 4x4, [5] quads */
+static long long g_stats[8];
+void orr_stats_read(long long out[8], int reset) { for (int k = 0; k < 8; k++) { out[k] = g_stats[k]; if (reset) g_stats[k] = 0; } }
 #define SEGMENT (g_render_mode & 1)
 #define TOP_DOWN (g_render_mode & 2)
 
@@ -289,6 +294,25 @@ static int raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture*
   if (py0 < 0) py0 = 0;
   if (px1 >= fb->W) px1 = fb->W - 1;
   if (py1 >= fb->H) py1 = fb->H - 1;
+  int any_cov = 0;
+  if (px0 <= px1 && py0 <= py1) {
+    g_stats[0]++;
+    if (nv == 4) g_stats[5]++;
+    int has = 0;
+    for (int s = 0; s < 4; s++) {
+      /* pixels p with minx <= 64 p + SX <= maxx, and the same in y, for the SAME sample index */
+      int lo = minx - SX[s], hi = maxx - SX[s], lo2 = miny - SY[s], hi2 = maxy - SY[s];
+      int pxl = (lo + 63) >> 6, pxh = hi >> 6, pyl = (lo2 + 63) >> 6, pyh = hi2 >> 6;
+      if (pxl < 0) pxl = 0;
+      if (pyl < 0) pyl = 0;
+      if (pxh >= fb->W) pxh = fb->W - 1;
+      if (pyh >= fb->H) pyh = fb->H - 1;
+      if (pxl <= pxh && pyl <= pyh) has = 1;
+    }
+    if (!has) g_stats[1]++;
+    if (px1 - px0 < 2 && py1 - py0 < 2) g_stats[3]++;
+    if (px1 - px0 < 4 && py1 - py0 < 4) g_stats[4]++;
+  }
   for (int py = py0; py <= py1; py++)
     for (int px = px0; px <= px1; px++) {
       int mask = 0;
@@ -302,6 +326,7 @@ static int raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture*
         if (inside) mask |= 1 << s;
       }
       if (!mask) continue;
+      any_cov = 1;
       /* shade once at the pixel centre */
       const float cdx = (float)(px * 64 + 32 - x0) * 0.015625f, cdy = (float)(py * 64 + 32 - y0) * 0.015625f;
       float at[7];
@@ -353,6 +378,7 @@ static int raster_triangle(framebuf* fb, vtx a, vtx b, vtx c, const orr_texture*
         }
       }
     }
+  if (px0 <= px1 && py0 <= py1 && !any_cov) g_stats[2]++;
   return 1;
 }
 
