@@ -143,13 +143,18 @@ BASELINE_CONFIGS = {
     "c4": dict(map="udem1", envs=8192, width=640, height=480, domain_rand=True, distortion=True, cycle=False),
     "c5": dict(map="small_loop,loop_obstacles,udem1,loop_pedestrians,loop_dyn_duckiebots,loop_trafficlights",
                envs=4096, width=160, height=120, domain_rand=False, distortion=False, cycle=True),
+    # c2 with the LITERAL road tiles of simulator.py:386-507 (98 lit triangles per tile, DTS_FLAG_TESSELLATE = spec tile
+    # mode 0) instead of the analytic quad + lattice the headline uses (tile mode 1): the price of the literal reading
+    "c2_literal": dict(map="small_loop", envs=4096, width=160, height=120, domain_rand=False, distortion=False, cycle=False,
+                       tessellate=True),
 }
 PARITY_UNPINNED = ["dynamics (duckietown_world DB18 model restated, source absent)",
                    "pixels (no OpenGL here: raster spec of DESIGN.md 5; render INPUTS pinned by tests/golden/gltrace_*.npz)"]
 
 
 def workload_text(c):
-    return (f"Duckietown-{c['map']}-v0 (stand-in map{'s, cycled on reset (MultiMap)' if c['cycle'] else ''}), {c['envs']} envs/GPU, "
+    return (f"Duckietown-{c['map']}-v0 (stand-in map{'s, cycled on reset (MultiMap)' if c['cycle'] else ''}"
+            f"{'; road tiles as the literal 98 triangles (tile mode 0)' if c.get('tessellate') else ''}), {c['envs']} envs/GPU, "
             f"{c['width']}x{c['height']} RGB, random [vel,steer] actions, domain_rand={c['domain_rand']}, "
             f"distortion={c['distortion']}, device-side auto-reset")
 
@@ -167,7 +172,8 @@ def run_config(c, K, Wm, rank, world, local_rank, obs_format="hwc_uint8", sample
     names = c["map"].split(",")
     env = BatchedDuckietownEnv(E, names if len(names) > 1 else names[0], device=local_rank, camera_width=W, camera_height=H,
                                domain_rand=c["domain_rand"], distortion=c["distortion"], cycle_maps=c["cycle"],
-                               seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E)
+                               seed=1000, auto_reset=True, device_reset=True, env_id_offset=rank * E,
+                               tessellate_tiles=bool(c.get("tessellate", False)))
     if obs_format != "hwc_uint8":
         lay, dt = obs_format.split("_")
         env.set_output_format(obs_layout=lay, obs_dtype=dt)
@@ -410,7 +416,7 @@ def main():
     extra = {}
     want = args.configs
     if want == "auto":
-        want = "c3,c4,c5" if world == 1 else "c5"
+        want = "c3,c4,c5,c2_literal" if world == 1 else "c5"
     for name in [w for w in want.split(",") if w and w != "none"]:
         c = dict(BASELINE_CONFIGS[name])
         if name == "c4":

@@ -725,6 +725,31 @@ __device__ __forceinline__ void store_px_fmt(void* frame, int layout, int dtype,
     else reinterpret_cast<uint8_t*>(frame)[i] = (uint8_t)v;
   }
 }
+// One whole 8x4 bin in a PLANAR u8 layout (ImgWrapper's CHW, PyTorchObsWrapper's CWH) as 24 aligned 32-bit words, one per
+// lane: a word is four horizontally (CHW) or vertically (CWH) adjacent pixels of one channel plane, collected from the
+// four lanes holding them by shuffles and two byte permutes — instead of three scattered byte stores per lane.
+// Needs the bin inside the image and W % 4 == 0 (CHW) / H % 4 == 0 (CWH).
+__device__ __forceinline__ void store_bin_planar_u8(uint8_t* __restrict__ out, int layout, unsigned rgb, int lane, int bx, int by,
+                                                    int W, int H) {
+  const int j = lane < 24 ? lane : 0, c = j >> 3;
+  int s0, step;
+  size_t addr;
+  if (layout == DTS_OBS_CHW) {
+    const int r = (j & 7) >> 1, h = j & 1;
+    s0 = r * 8 + 4 * h; step = 1;
+    addr = ((size_t)c * H + by * kBinH + r) * W + bx * kBinW + 4 * h;
+  } else {
+    const int xi = j & 7;
+    s0 = xi; step = 8;
+    addr = ((size_t)c * W + bx * kBinW + xi) * H + by * kBinH;
+  }
+  const unsigned p0 = __shfl_sync(0xffffffffu, rgb, s0), p1 = __shfl_sync(0xffffffffu, rgb, s0 + step);
+  const unsigned p2 = __shfl_sync(0xffffffffu, rgb, s0 + 2 * step), p3 = __shfl_sync(0xffffffffu, rgb, s0 + 3 * step);
+  const unsigned sel = (unsigned)c | ((unsigned)(4 + c) << 4);   // byte c of the first operand, byte c of the second
+  const unsigned word = __byte_perm(__byte_perm(p0, p1, sel), __byte_perm(p2, p3, sel), 0x5410);
+  if (lane < 24) *reinterpret_cast<unsigned*>(out + addr) = word;
+}
+
 // Fine-bin store: the packed u8 HWC fast path, or the wrapper format straight from the resolve registers.
 __device__ __forceinline__ void store_bin_any(uint8_t* __restrict__ out, int fmt, unsigned rgb, int lane, int bx, int by,
                                               int W, int H) {
@@ -1285,6 +1310,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   const int pxs = (lane & 7) * kSub, pys = (lane >> 3) * kSub;   // this lane's pixel inside a fine bin (sub-pixels)
   const StoreLane sl = make_store_lane(lane, W);
   const bool fast_fmt = !kWrapFmt && (W & 3) == 0;   // packed u8 HWC rows of whole words
+  const bool planar_u8 = kWrapFmt && rc.obs_dtype == DTS_OBS_U8 &&
+                         ((rc.obs_layout == DTS_OBS_CHW && (W & 3) == 0) || (rc.obs_layout == DTS_OBS_CWH && (H & 3) == 0));
   uint64_t* bar = bars[warp];
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   __syncwarp();
@@ -1314,8 +1341,12 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
       if (fast_fmt && (gt.n == 0 || gather_rows) && bx * kBinW + kBinW <= W) {   // the common case inline: packed u8 HWC, whole bin inside
         store_bin_fast(out + ((size_t)(by * kBinH) * W + bx * kBinW) * 3, sl, rgb, min(kBinH, H - by * kBinH));
       } else if (kWrapFmt && gt.n == 0) {
-        const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
-        if (gx < W && gy < H) store_px_fmt(out, out_fmt & 3, out_fmt >> 2, gx, gy, W, H, rgb);   // wrapper layout / dtype, inline
+        if (planar_u8 && bx * kBinW + kBinW <= W && by * kBinH + kBinH <= H) {
+          store_bin_planar_u8(out, out_fmt & 3, rgb, lane, bx, by, W, H);   // CHW / CWH u8: 24 packed words per bin
+        } else {
+          const int gx = bx * kBinW + (lane & 7), gy = by * kBinH + (lane >> 3);
+          if (gx < W && gy < H) store_px_fmt(out, out_fmt & 3, out_fmt >> 2, gx, gy, W, H, rgb);   // wrapper layout / dtype, inline
+        }
       } else {
         emit_general(out, gt, gather_rows ? 0 : gt.n, env_off, out_fmt, rgb, lane, bx, by, W, H);
       }
