@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -49,6 +50,7 @@ struct dts_sim {
   int render_mode = 0;                  // dts_set_render_mode             // the next dts_render also stores into the gather buffers
   // fused ResizeWrapper (dts_set_resize): full-size render target + tap tables
   int resize_w = 0, resize_h = 0;
+  int resize_band = 0, resize_cap = 0;   // k_resize_band: output rows per CTA and the largest source-row span of a band (0: untiled kernel)
   uint8_t* resize_src = nullptr;
   int16_t *resize_xtab = nullptr, *resize_ytab = nullptr;
   // per-kernel timing (dts_profile_*): event pairs recorded around the render launches
@@ -672,7 +674,8 @@ int dts_render(dts_sim* sim, void* obs_dev, void* stream) {
                         sim->d_status, marks, mark_level, (cudaStream_t)stream);
   if (sim->resize_w) {
     launch_resize(sim->resize_src, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
-                  sim->resize_xtab, sim->resize_ytab, obs_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, (cudaStream_t)stream);
+                  sim->resize_xtab, sim->resize_ytab, obs_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, sim->resize_band, sim->resize_cap,
+                  (cudaStream_t)stream);
     k++;
   }
   if (marks && mark_level >= 2) cudaEventRecord(marks[kProfMarks - 1], (cudaStream_t)stream);   // closes the "post" interval
@@ -795,6 +798,19 @@ int dts_set_resize(dts_sim* sim, int out_w, int out_h) {
   DTS_CUDA(cudaMemcpy(sim->resize_xtab, xt.data(), xt.size() * 2, cudaMemcpyHostToDevice));
   DTS_CUDA(cudaMemcpy(sim->resize_ytab, yt.data(), yt.size() * 2, cudaMemcpyHostToDevice));
   sim->resize_w = out_w; sim->resize_h = out_h;
+  // band height of the tiled kernel: the tallest band (<= 16 output rows) whose source rows + horizontal sums fit in 40 KB
+  // of shared memory (several CTAs per SM); 0 = no band fits even in the opt-in maximum, use the untiled kernel
+  sim->resize_band = sim->resize_cap = 0;
+  const char* untiled = getenv("DTS_RESIZE_UNTILED");   // A/B switch
+  for (int R = 16; R >= 1 && !(untiled && untiled[0] == '1'); R--) {
+    int cap = 0;
+    for (int r0 = 0; r0 < out_h; r0 += R) {
+      const int r1 = std::min(r0 + R, out_h);
+      cap = std::max(cap, (int)yt[(size_t)8 * (r1 - 1) + 3] - (int)yt[(size_t)8 * r0] + 1);
+    }
+    const size_t smem = resize_band_smem(sim->cfg.cam_width, out_w, cap);
+    if (smem <= 40 * 1024 || (R == 1 && smem <= 200 * 1024)) { sim->resize_band = R; sim->resize_cap = cap; break; }
+  }
   return 0;
 }
 
@@ -875,7 +891,8 @@ int dts_resize_frames(dts_sim* sim, const uint8_t* src_dev, void* dst_dev, void*
   if (!src_dev || !dst_dev) return sim->fail("NULL frame pointer");
   DTS_CUDA(cudaSetDevice(sim->cfg.device));
   launch_resize(src_dev, sim->cfg.cam_width, sim->cfg.cam_height, sim->resize_w, sim->resize_h, sim->cfg.num_envs,
-                sim->resize_xtab, sim->resize_ytab, dst_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, (cudaStream_t)stream);
+                sim->resize_xtab, sim->resize_ytab, dst_dev, sim->fmt.obs_layout, sim->fmt.obs_dtype, sim->resize_band, sim->resize_cap,
+                (cudaStream_t)stream);
   sim->launches++;
   DTS_CUDA(cudaGetLastError());
   return 0;

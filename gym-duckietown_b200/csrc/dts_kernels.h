@@ -78,7 +78,8 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
 
 // ResizeWrapper on the device: src u8[N][H][W][3] -> dst [N] x (ow x oh) in `layout` / `dtype` (dts_set_resize)
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
-                   void* dst, int layout, int dtype, cudaStream_t st);
+                   void* dst, int layout, int dtype, int band_rows, int band_cap, cudaStream_t st);
+size_t resize_band_smem(int W, int ow, int cap);   // dynamic shared memory of k_resize_band for a band spanning `cap` source rows
 void launch_blend4(const uint8_t* const f[4], const double w[4], double* out, size_t n, cudaStream_t st);
 int debug_frame_copy(void* scratch, int n, int max_prims, int cbins, int max_pairs, int max_lat, size_t geo_items,
                      int env, double* V, float* P, int32_t* counts, float* lattice_by_cell, int n_cells, int tris_per_tile);

@@ -50,6 +50,14 @@ namespace {
 #ifndef DTS_SAMPLE_CULL
 #define DTS_SAMPLE_CULL 1   // triangles of at most 3x3 pixels that cover no sample position are dropped at set-up (A/B switch)
 #endif
+#ifndef DTS_STATS
+#define DTS_STATS 0         // 1: k_raster counts bins / prim visits / shading rounds into the diagnostic counters (tools/raster_stats.py)
+#endif
+#if DTS_STATS
+#define DTS_COUNT(slot, n) do { if (lane == 0) atomicAdd(err + (slot), (n)); } while (0)
+#else
+#define DTS_COUNT(slot, n) do { } while (0)
+#endif
 #ifndef DTS_COARSE_FAST
 #define DTS_COARSE_FAST 0   // 1: coarse bins lying inside one prim skip visibility and fetch the prim once.  Measured
                             // (profiles/README.md, r2d): +5 % k_raster time — the extra code and registers cost more
@@ -1410,7 +1418,9 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     for (int cbx = 0; cbx < cbins_x; cbx++) {
       const int count = __shfl_sync(0xffffffffu, my_cnt, cbx);
       const unsigned fvalid = valid8(cbx);
+      DTS_COUNT(8, 1);
       if (count == 0) {
+        DTS_COUNT(9, 1);
 #pragma unroll 1
         for (int f = 0; f < kCFX * kCFY; f++)
           if ((fvalid >> f) & 1u) {
@@ -1424,6 +1434,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
         continue;
       }
       const bool single = count <= kStage;
+      DTS_COUNT(10, count);
+      if (!single) { DTS_COUNT(14, 1); DTS_COUNT(15, count); }
       int ox = cbx * kCoarseW * kSub, oy = cby * kCoarseH * kSub;   // coarse bin corner, sub-pixels
       if (kFish) { const short4 cb = ft.cbox[cby * cbins_x + cbx]; ox = cb.x * kSub; oy = cb.y * kSub; }   // ... of its source box
 #pragma unroll 1
@@ -1506,6 +1518,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               const unsigned pick = others ? others : live_mask;
               if (pick && !(pick & (pick - 1)) && (pick & full_mask)) {
                 simple = true;
+                DTS_COUNT(13, 1);
                 const unsigned w = stage[__ffs(pick) - 1].prim_flags & 0xffffu;
                 wn[0] = w; wn[1] = w; wn[2] = w; wn[3] = w;
               }
@@ -1530,6 +1543,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                   todo &= todo - 1;
                   const BinRec& br = stage[k];
                   const uint32_t pflags = br.prim_flags;
+                  DTS_COUNT(16, 1);
+                  if ((pflags >> (24 + f)) & 1u) DTS_COUNT(17, 1);
                   int mask = 15;
                   if (!((pflags >> (24 + f)) & 1u)) {
                     const int4 E = *reinterpret_cast<const int4*>(br.E0);
@@ -1601,6 +1616,8 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 for (int s = 0; s < 4; s++) zb[lane * 4 + s] = ~0ull;
                 __syncwarp();
               }
+              DTS_COUNT(18, 1);
+              DTS_COUNT(19, __popc(live_mask & tiny_bits));
               if ((live_mask & tiny_bits) >> lane & 1u) {
                 const BinRec& br = stage[lane];
                 const int4 E = *reinterpret_cast<const int4*>(br.E0);
@@ -1645,6 +1662,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
               __syncwarp();   // the buffer is re-initialised by the next fine bin
             }
             // ---- deferred shading: once per distinct winner of this pixel, then the box resolve
+            DTS_COUNT(11, 1);
             const int pxa = ox + pxc, pya = oy + pyc;
             const bool same = wn[1] == wn[0] && wn[2] == wn[0] && wn[3] == wn[0];
             const bool all_same = simple || __all_sync(0xffffffffu, same);
@@ -1663,6 +1681,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                   if (wn[t] == wn[0]) { pend &= ~(1u << t); s23[0] = s23[0] + c3[0]; s23[1] = s23[1] + c3[1]; s23[2] = s23[2] + c3[2]; }
 #pragma unroll 1
                 while (__any_sync(0xffffffffu, pend != 0u)) {
+                  DTS_COUNT(12, 1);
                   if (pend) {
                     const int s = __ffs(pend) - 1;
                     const unsigned w = s == 1 ? wn[1] : (s == 2 ? wn[2] : wn[3]);
@@ -1759,8 +1778,107 @@ void launch_blend4(const uint8_t* const f[4], const double w[4], double* out, si
   k_blend4<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(f[0], f[1], f[2], f[3], w[0], w[1], w[2], w[3], scl, out, n);
 }
 
+// The same resize, tiled: a CTA per (band of `R` output rows, env).  The band's source rows (contiguous bytes of the
+// render) are copied to shared memory with 16-byte loads, the horizontal pass runs once per source row into an int32
+// buffer in shared memory, the vertical pass reads it and writes four output bytes per thread as one word — instead
+// of every output pixel fetching its own 48 source bytes from global memory (k_resize above: 0.49 ms at 4096 x
+// 160x120 -> 84x84).  Integer arithmetic identical to k_resize.  `cap` = the largest source-row span of any band
+// (computed on the host from the same tap table).
+__global__ void __launch_bounds__(256) k_resize_band(const uint8_t* __restrict__ src, int W, int H, int ow, int oh,
+                                                     const int16_t* __restrict__ xtab, const int16_t* __restrict__ ytab,
+                                                     void* __restrict__ dst, int layout, int dtype, int R, int cap) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const int bands = (oh + R - 1) / R;
+  const int env = blockIdx.x / bands, r0 = (blockIdx.x - env * bands) * R, r1 = min(r0 + R, oh);
+  const int s_lo = ytab[8 * r0], s_hi = ytab[8 * (r1 - 1) + 3], nrows = min(s_hi - s_lo + 1, cap);
+  const int rowb = W * 3, ow3 = ow * 3;
+  int4* xt = reinterpret_cast<int4*>(rs_smem);                                      // [ow] tap table
+  uint8_t* sb = rs_smem + (size_t)ow * 16;                                          // [cap][rowb] source bytes
+  int* hb = reinterpret_cast<int*>(sb + (((size_t)cap * rowb + 15) & ~(size_t)15));   // [cap][ow3] horizontal sums
+  const uint8_t* band = src + (size_t)env * W * H * 3 + (size_t)s_lo * rowb;
+  const int nbytes = nrows * rowb;
+  if ((reinterpret_cast<uintptr_t>(band) & 15) == 0 && (nbytes & 15) == 0) {
+    for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sb)[i] = __ldg(reinterpret_cast<const int4*>(band) + i);
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) sb[i] = __ldg(band + i);
+  }
+  for (int i = threadIdx.x; i < ow; i += blockDim.x) xt[i] = __ldg(reinterpret_cast<const int4*>(xtab) + i);
+  __syncthreads();
+  // horizontal pass: (source row, output column) per thread, three channels
+  for (int i = threadIdx.x; i < nrows * ow; i += blockDim.x) {
+    const int row = i / ow, x = i - row * ow;
+    const int4 xa = xt[x];
+    const int xi[4] = {(short)(xa.x & 0xffff), xa.x >> 16, (short)(xa.y & 0xffff), xa.y >> 16};
+    const int xw[4] = {(short)(xa.z & 0xffff), xa.z >> 16, (short)(xa.w & 0xffff), xa.w >> 16};
+    const uint8_t* rp = sb + row * rowb;
+    int h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint8_t* px = rp + xi[c] * 3;
+      h0 += (int)px[0] * xw[c]; h1 += (int)px[1] * xw[c]; h2 += (int)px[2] * xw[c];
+    }
+    int* hp = hb + row * ow3 + x * 3;
+    hp[0] = h0; hp[1] = h1; hp[2] = h2;
+  }
+  __syncthreads();
+  // vertical pass
+  const size_t out_elem = dtype == DTS_OBS_F32_UNIT ? 4 : 1;
+  uint8_t* out = reinterpret_cast<uint8_t*>(dst) + (size_t)env * ow3 * oh * out_elem;
+  const bool words = layout == DTS_OBS_HWC && dtype == DTS_OBS_U8 && (ow3 & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+  if (words) {
+    const int wpr = ow3 / 4;   // words per output row
+    for (int i = threadIdx.x; i < (r1 - r0) * wpr; i += blockDim.x) {
+      const int yy = i / wpr, e = (i - yy * wpr) * 4, y = r0 + yy;
+      const int4 ya = __ldg(reinterpret_cast<const int4*>(ytab) + y);
+      const int yi[4] = {(short)(ya.x & 0xffff), ya.x >> 16, (short)(ya.y & 0xffff), ya.y >> 16};
+      const int yw[4] = {(short)(ya.z & 0xffff), ya.z >> 16, (short)(ya.w & 0xffff), ya.w >> 16};
+      long long acc[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int4 hv = *reinterpret_cast<const int4*>(hb + (yi[r] - s_lo) * ow3 + e);
+        acc[0] += (long long)hv.x * yw[r]; acc[1] += (long long)hv.y * yw[r]; acc[2] += (long long)hv.z * yw[r]; acc[3] += (long long)hv.w * yw[r];
+      }
+      unsigned word = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        long long v = (acc[k] + (1LL << 21)) >> 22;
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        word |= (unsigned)v << (8 * k);
+      }
+      *reinterpret_cast<unsigned*>(out + (size_t)y * ow3 + e) = word;
+    }
+  } else {
+    for (int i = threadIdx.x; i < (r1 - r0) * ow3; i += blockDim.x) {
+      const int yy = i / ow3, e = i - yy * ow3, y = r0 + yy, x = e / 3, ch = e - 3 * x;
+      const int4 ya = __ldg(reinterpret_cast<const int4*>(ytab) + y);
+      const int yi[4] = {(short)(ya.x & 0xffff), ya.x >> 16, (short)(ya.y & 0xffff), ya.y >> 16};
+      const int yw[4] = {(short)(ya.z & 0xffff), ya.z >> 16, (short)(ya.w & 0xffff), ya.w >> 16};
+      long long acc = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) acc += (long long)hb[(yi[r] - s_lo) * ow3 + e] * yw[r];
+      long long v = (acc + (1LL << 21)) >> 22;
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      const size_t oi = fmt_index(layout, x, y, ch, ow, oh);
+      if (dtype == DTS_OBS_F32_UNIT) reinterpret_cast<float*>(out)[oi] = (float)(unsigned)v / 255.0f;
+      else out[oi] = (uint8_t)v;
+    }
+  }
+}
+
+size_t resize_band_smem(int W, int ow, int cap) {
+  return (size_t)ow * 16 + (((size_t)cap * W * 3 + 15) & ~(size_t)15) + (size_t)cap * ow * 3 * 4;
+}
+
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
-                   void* dst, int layout, int dtype, cudaStream_t st) {
+                   void* dst, int layout, int dtype, int band_rows, int band_cap, cudaStream_t st) {
+  if (band_rows > 0) {   // tiled form (dts_set_resize found a band height whose rows fit in shared memory)
+    const size_t smem = resize_band_smem(W, ow, band_cap);
+    static size_t opted = 0;
+    if (smem > 48 * 1024 && smem > opted) { cudaFuncSetAttribute(k_resize_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); opted = smem; }
+    k_resize_band<<<(unsigned)(((oh + band_rows - 1) / band_rows) * (size_t)n_envs), 256, smem, st>>>(src, W, H, ow, oh, xtab, ytab, dst, layout, dtype,
+                                                                                      band_rows, band_cap);
+    return;
+  }
   const size_t total = (size_t)n_envs * ow * oh;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   k_resize<<<blocks, 256, 0, st>>>(src, W, H, ow, oh, n_envs, xtab, ytab, dst, layout, dtype);

@@ -115,4 +115,16 @@ def test_device_resize_vs_reference_resize_wrapper(tag, rw, rh):
     env.set_output_format(obs_layout="hwc")
     hwc = env.sim_resize_only(src).cpu().numpy()
     assert np.array_equal(hwc.transpose(0, 3, 2, 1), got)
+    # the tiled kernel (bands of output rows staged in shared memory) against the one-thread-per-pixel kernel: same integers
+    import os
+    os.environ["DTS_RESIZE_UNTILED"] = "1"
+    try:
+        env.set_resize(rw, rh)
+        assert np.array_equal(env.sim_resize_only(src).cpu().numpy(), hwc)
+        env.set_output_format(obs_layout="chw", obs_dtype="float32")
+        untiled_f32 = env.sim_resize_only(src).cpu().numpy()
+    finally:
+        del os.environ["DTS_RESIZE_UNTILED"]
+    env.set_resize(rw, rh)
+    assert np.array_equal(env.sim_resize_only(src).cpu().numpy(), untiled_f32)
     env.close()

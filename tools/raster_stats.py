@@ -12,6 +12,8 @@ torch.cuda.synchronize()
 c0 = env.sim.debug_counters().astype(np.int64)
 env.render_obs(); torch.cuda.synchronize()
 c = env.sim.debug_counters().astype(np.int64) - c0
-names = {8: "coarse bins", 9: "empty coarse", 10: "sum list len", 11: "live prims (per fine bin chunks)", 12: "ground live", 13: "simple fine bins", 14: "coarse bins with > 32 prims", 15: "…their list lengths", 16: "general prim iterations", 17: "…of which fully inside"}
+names = {8: "coarse bins", 9: "  empty (cleared)", 10: "sum of list lengths (records)", 14: "coarse bins with > 32 records", 15: "  their records",
+         11: "fine bins shaded", 13: "  simple (one covering prim, no visibility pass)", 12: "extra shading rounds (2nd..4th winner of edge pixels)",
+         16: "warp-wide prim visits", 17: "  trivially accepted (no edge tests)", 18: "tiny-triangle passes (fine bins)", 19: "  tiny triangles in them"}
 for k, v in names.items():
-    print(f"{v:40s} {c[k]:12d}  per env {c[k]/4096:10.1f}")
+    print(f"{v:60s} {c[k]:12d}  per env {c[k]/4096:10.1f}")
