@@ -58,6 +58,9 @@ namespace {
 #else
 #define DTS_COUNT(slot, n) do { } while (0)
 #endif
+#ifndef DTS_COPLANAR
+#define DTS_COPLANAR 1      // fine bins whose prims are all road tiles (coplanar, disjoint) resolve visibility by coverage alone (A/B switch)
+#endif
 #ifndef DTS_COARSE_FAST
 #define DTS_COARSE_FAST 0   // 1: coarse bins lying inside one prim skip visibility and fetch the prim once.  Measured
                             // (profiles/README.md, r2d): +5 % k_raster time — the extra code and registers cost more
@@ -482,7 +485,9 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
   const int4 w0 = __ldg(reinterpret_cast<const int4*>(pr));
   const int4 w1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
   const float4 w2 = __ldg(reinterpret_cast<const float4*>(pr) + 2);
-  const int quad = (__ldg(&pr->ltq) >> 24) & 1;
+  const int ltq = __ldg(&pr->ltq);
+  const int quad = (ltq >> 24) & 1;
+  const int flat = (ltq & 0xffff) ? 8 : 0;   // a road tile of tile mode 1 (it carries a lattice): lies in the plane y = 0
   const int qx[4] = {w0.x, w0.z, w1.x, w1.z}, qy[4] = {w0.y, w0.w, w1.y, w1.w};
   const int nv = quad ? 4 : 3;
   unsigned live = 0xffu, inside = 0xffu;
@@ -548,7 +553,7 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
   o[1] = make_int4(A[0], A[1], A[2], A[3]);
   o[2] = make_int4(B[0], B[1], B[2], B[3]);
   o[3] = make_int4(__float_as_int(w2.x), __float_as_int(w2.y), __float_as_int(w2.z), id);
-  o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0) | tiny);
+  o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0) | tiny | flat);
 }
 
 // Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
@@ -1463,6 +1468,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           const bool first = c0 == 0, last = c0 + kStage >= count;
           const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
           const unsigned tiny_bits = kFish ? 0u : __ballot_sync(0xffffffffu, (mine.y & 4u) != 0u);   // one-per-lane triangles
+          const unsigned flat_bits = DTS_COPLANAR ? __ballot_sync(0xffffffffu, (mine.y & 8u) != 0u) : 0u;   // road tiles (plane y = 0)
           if (DTS_COARSE_FAST && single) {
             // ---- the whole coarse bin lies inside ONE prim (besides the ground quad, hidden below it): no visibility
             // work at all, the prim's planes are fetched once for the bin's 256 pixels
@@ -1523,6 +1529,9 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 wn[0] = w; wn[1] = w; wn[2] = w; wn[3] = w;
               }
             }
+            // every prim of the bin besides the ground quad is a road tile: the tiles are coplanar and disjoint, so a sample
+            // belongs to the one tile that covers it — no depth arithmetic (the ground lies below them and takes what is left)
+            const bool coplanar = DTS_COPLANAR && single && !(live_mask & ~ground_mask & ~flat_bits);
             if (!simple) {
               if (first) {
 #pragma unroll
@@ -1574,6 +1583,12 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                       }
                     }
                     if (!mask) continue;
+                  }
+                  if (coplanar && phase == 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+                      if (mask >> s & 1) { z[s] = -1.0f; wn[s] = pflags & 0xffffu; }   // (-1: nothing drawn later can pass or tie)
+                    continue;
                   }
                   // ---- depth of the covered samples, GL_LESS in draw order
                   const float4 zp = *reinterpret_cast<const float4*>(&br.z0);   // z0 zx zy id

@@ -12,7 +12,6 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-notiny -DDTS_TINY_PATH=0
-notma -DDTS_TMA_STAGING=0
+nocoplanar -DDTS_COPLANAR=0
 VARIANTS
 cp /tmp/libdtsim_base_keep.so libdtsim.so
