@@ -82,12 +82,26 @@ __host__ __device__ constexpr int sample_y(int s) { return s == 0 ? 8 : (s == 1 
 struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 
 #ifndef DTS_GEO_INLINE
-#define DTS_GEO_INLINE 1
+#define DTS_GEO_INLINE 5
 #endif
-#if DTS_GEO_INLINE
-#define DTS_GEO_FN __forceinline__
-#else
-#define DTS_GEO_FN __noinline__
+// which of the geometry pass's big device functions are inlined: bit 0 shade_vertex, bit 1 setup_and_emit, bit 2 the clipper.
+// The kernel is instruction-fetch bound (ncu: 6.9 stall_no_instruction cycles per issue, 174 KB of SASS against a 32 KB
+// L1.5 I-cache): with everything inlined setup_and_emit alone is 107 KB in a dozen copies.  Measured k_geometry at c2 / c3:
+// 7 (all inline) 198 / 466 us, 5 (one copy of setup_and_emit) 177 / 424 us, 1: 188 / 435, 3: 220 / 493, 0: 221 / 447.
+#define DTS_GEO_FN_SHADE __forceinline__
+#define DTS_GEO_FN_SETUP __forceinline__
+#define DTS_GEO_FN_CLIP __forceinline__
+#if !(DTS_GEO_INLINE & 1)
+#undef DTS_GEO_FN_SHADE
+#define DTS_GEO_FN_SHADE __noinline__
+#endif
+#if !(DTS_GEO_INLINE & 2)
+#undef DTS_GEO_FN_SETUP
+#define DTS_GEO_FN_SETUP __noinline__
+#endif
+#if !(DTS_GEO_INLINE & 4)
+#undef DTS_GEO_FN_CLIP
+#define DTS_GEO_FN_CLIP __noinline__
 #endif
 #ifndef DTS_GEO_WARPS
 #define DTS_GEO_WARPS 1
@@ -165,7 +179,7 @@ __device__ __forceinline__ void model_view(const double* V, double tx, double ty
 }
 
 // fixed-function transform & lighting of one vertex (float32, operation order = spec)
-__device__ DTS_GEO_FN Vtx shade_vertex(const Xform& x, const Shared& sh, float px, float py, float pz, float nx,
+__device__ DTS_GEO_FN_SHADE Vtx shade_vertex(const Xform& x, const Shared& sh, float px, float py, float pz, float nx,
                                             float ny, float nz, float cr, float cg, float cb, float u, float v) {
   float e[3], ne[3];
 #pragma unroll
@@ -254,7 +268,7 @@ struct EmitCtx {
 // With `d` the prim is the QUAD a,b,c,d (spec tile mode 1: an unclipped road tile): planes of triangle (a,b,c),
 // coverage by four edges.  Returns false — nothing emitted — if the snapped quad is not strictly convex; the
 // caller then draws the two triangles (a,b,c)(a,c,d) instead.
-__device__ DTS_GEO_FN bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+__device__ DTS_GEO_FN_SETUP bool setup_and_emit(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
                                                int tex, int lat, const Vtx* d = nullptr) {
   const Vtx* vs[3] = {&a, &b, &c};
   int X[3], Y[3];
@@ -379,7 +393,7 @@ __device__ __forceinline__ Vtx clip_lerp(const Vtx& in, const Vtx& out, float di
 // WHOLE warp for one triangle: lane k owns polygon vertex k, neighbours' plane distances come by shuffle, output
 // slots by ballot prefix sums, so a plane costs a few dozen instructions instead of a serial loop over vertices.
 // Same arithmetic, same vertex order (hence the same fan) as the serial formulation of the spec.
-__device__ DTS_GEO_FN void clip_and_emit_warp(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
+__device__ DTS_GEO_FN_CLIP void clip_and_emit_warp(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c, int id,
                                                    int tex, int lat, int lane) {
   for (int p2 = 0; p2 < 6; p2++) {   // the spec's trivial reject looks at the ORIGINAL triangle, guard planes
     const int cnt = !(plane_dist(a, p2) >= 0.0f) + !(plane_dist(b, p2) >= 0.0f) + !(plane_dist(c, p2) >= 0.0f);

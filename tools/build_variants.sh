@@ -12,6 +12,8 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-nocoplanar -DDTS_COPLANAR=0
+gi3 -DDTS_GEO_INLINE=3
+gi1 -DDTS_GEO_INLINE=1
+gi5 -DDTS_GEO_INLINE=5
 VARIANTS
 cp /tmp/libdtsim_base_keep.so libdtsim.so
