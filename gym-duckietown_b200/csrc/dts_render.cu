@@ -81,6 +81,9 @@ __host__ __device__ constexpr int sample_y(int s) { return s == 0 ? 8 : (s == 1 
 
 struct Vtx { float cx, cy, cz, cw, r, g, b, u, v; };
 
+#ifndef DTS_GEO_X
+#define DTS_GEO_X 0   // code-size experiments of the geometry pass: bit 0 process_triangle_uniform out of line, bit 1 lattice loop rolled, bit 2 mesh vertex loop rolled
+#endif
 #ifndef DTS_GEO_INLINE
 #define DTS_GEO_INLINE 5
 #endif
@@ -436,8 +439,13 @@ __device__ DTS_GEO_FN_CLIP void clip_and_emit_warp(const EmitCtx& ec, const Vtx&
 }
 
 // one warp-uniform triangle (ground, analytic tile): classify once, lane 0 emits or the warp clips
-__device__ __forceinline__ void process_triangle_uniform(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c,
-                                                         int id, int tex, int lat, int lane) {
+#if DTS_GEO_X & 1
+#define DTS_PTU_FN __noinline__
+#else
+#define DTS_PTU_FN __forceinline__
+#endif
+__device__ DTS_PTU_FN void process_triangle_uniform(const EmitCtx& ec, const Vtx& a, const Vtx& b, const Vtx& c,
+                                                    int id, int tex, int lat, int lane) {
   const int cls = classify(a, b, c);
   if (cls == 2) return;
   if (cls == 0) { if (lane == 0) setup_and_emit(ec, a, b, c, id, tex, lat); }
@@ -1007,7 +1015,11 @@ __device__ __forceinline__ void geometry_item(const DState& S, const DMap* __res
     // the tile's 8x8 lattice, two vertices per lane (tessellated mode: also frustum-culls the whole tile)
     Vtx lv[2];
     int outside[6] = {0, 0, 0, 0, 0, 0};
+#if DTS_GEO_X & 2
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int h = 0; h < 2; h++) {
       const int vi = lane + 32 * h, a = vi >> 3, b = vi & 7;             // a: u index (x), b: v index (z)
       const float lx = (float)(-ts / 2 + ((double)a / 7.0) * ts), lz = (float)(-ts / 2 + ((double)b / 7.0) * ts);

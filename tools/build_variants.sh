@@ -12,8 +12,9 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-gi3 -DDTS_GEO_INLINE=3
-gi1 -DDTS_GEO_INLINE=1
-gi5 -DDTS_GEO_INLINE=5
+gi4 -DDTS_GEO_INLINE=4
+gx1 -DDTS_GEO_X=1
+gx2 -DDTS_GEO_X=2
+gx3 -DDTS_GEO_X=3
 VARIANTS
 cp /tmp/libdtsim_base_keep.so libdtsim.so
