@@ -1555,9 +1555,12 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 wn[0] = w; wn[1] = w; wn[2] = w; wn[3] = w;
               }
             }
-            // every prim of the bin besides the ground quad is a road tile: the tiles are coplanar and disjoint, so a sample
-            // belongs to the one tile that covers it — no depth arithmetic (the ground lies below them and takes what is left)
-            const bool coplanar = DTS_COPLANAR && single && !(live_mask & ~ground_mask & ~flat_bits);
+            // every prim of the bin besides the ground quad is a road tile: the tiles are coplanar and (up to slivers where
+            // two neighbours snapped their shared border differently) disjoint, so a sample belongs to the one tile that
+            // covers it — no depth arithmetic; the ground lies below them and takes what is left.  A sample that turns
+            // out to be covered twice sends the whole bin through the depth-tested path (exactly the spec's answer).
+            bool coplanar = DTS_COPLANAR && single && !(live_mask & ~ground_mask & ~flat_bits);
+            if (coplanar && !simple) DTS_COUNT(20, 1);
             if (!simple) {
               if (first) {
 #pragma unroll
@@ -1573,6 +1576,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                 if (phase == 1 && todo &&
                     __all_sync(0xffffffffu, wn[0] != kNoPrim && wn[1] != kNoPrim && wn[2] != kNoPrim && wn[3] != kNoPrim))
                   todo = 0;
+                int seen = 0, twice = 0;   // (coverage-only mode) samples of this pixel covered so far / covered by two tiles
                 while (todo) {
                   const int k = __ffs(todo) - 1;
                   todo &= todo - 1;
@@ -1611,9 +1615,11 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
                     if (!mask) continue;
                   }
                   if (coplanar && phase == 0) {
+                    twice |= seen & mask;
+                    seen |= mask;
 #pragma unroll
                     for (int s = 0; s < 4; s++)
-                      if (mask >> s & 1) { z[s] = -1.0f; wn[s] = pflags & 0xffffu; }   // (-1: nothing drawn later can pass or tie)
+                      if (mask >> s & 1) wn[s] = pflags & 0xffffu;
                     continue;
                   }
                   // ---- depth of the covered samples, GL_LESS in draw order
@@ -1644,6 +1650,19 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
 #pragma unroll
                   for (int s = 0; s < 4; s++)
                     if (pass_mask >> s & 1) { z[s] = zs[s]; wn[s] = me; }
+                }
+                if (coplanar && phase == 0) {
+                  if (__any_sync(0xffffffffu, twice != 0)) {   // rare: start the bin over, depth-tested
+                    coplanar = false;
+                    DTS_COUNT(21, 1);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) wn[s] = kNoPrim;
+                    phase = -1;
+                  } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+                      if (seen >> s & 1) z[s] = -1.0f;   // the ground (phase 1) can neither pass nor tie there
+                  }
                 }
               }
             }

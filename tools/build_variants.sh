@@ -4,7 +4,6 @@
 set -e
 cd "$(dirname "$0")/../gym-duckietown_b200"
 mkdir -p variants
-cp libdtsim.so /tmp/libdtsim_base_keep.so
 while read -r tag flags; do
   [ -z "$tag" ] && continue
   DTS_NVCC_EXTRA="$flags" python build.py --force > /dev/null 2>&1
@@ -12,9 +11,6 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-gi4 -DDTS_GEO_INLINE=4
-gx1 -DDTS_GEO_X=1
-gx2 -DDTS_GEO_X=2
-gx3 -DDTS_GEO_X=3
+nocoplanar -DDTS_COPLANAR=0
 VARIANTS
-cp /tmp/libdtsim_base_keep.so libdtsim.so
+cp variants/libdtsim_base.so libdtsim.so   # the tree's library = the base variant, built from the current sources
