@@ -114,4 +114,7 @@ void orr_render(const orr_scene* sc, double px, double pz, double angle, const o
 void orr_set_render_mode(int mode); /* 1 = segment=True, 2 = top_down=True (simulator.py:1707-1951) */
 void orr_debug_frame(const orr_scene* sc, double px, double pz, double angle, const orr_episode* ep, int W, int H,
                      int domain_rand, double* V_out, float* P_out, float* item_mv, float* item_n, float* lattice);
+/* test-side statistics of the triangles handed to the rasteriser since the last reset (single-threaded use):
+ * [0] set-up triangles on screen, [1] no sample position in their box, [2] no covered sample, [3] box <= 2x2 px, [4] <= 4x4 px, [5] quads */
+void orr_stats_read(long long out[8], int reset);
 #endif
