@@ -1495,6 +1495,13 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
           const unsigned ground_bits = __ballot_sync(0xffffffffu, (mine.y & 2u) != 0u);   // the ground quad's records in this chunk
           const unsigned tiny_bits = kFish ? 0u : __ballot_sync(0xffffffffu, (mine.y & 4u) != 0u);   // one-per-lane triangles
           const unsigned flat_bits = DTS_COPLANAR ? __ballot_sync(0xffffffffu, (mine.y & 8u) != 0u) : 0u;   // road tiles (plane y = 0)
+#if DTS_STATS
+          if (single) {   // census: coarse bins lying inside ONE prim (besides the ground)
+            const unsigned ng_ = __ballot_sync(0xffffffffu, !(mine.y & 2u) && ((mine.x >> 16) & fvalid) != 0u);
+            const unsigned ngfull_ = __ballot_sync(0xffffffffu, !(mine.y & 2u) && ((mine.x >> 24) & fvalid) == fvalid);
+            if (ng_ && !(ng_ & (ng_ - 1)) && (ng_ & ngfull_)) { DTS_COUNT(22, 1); DTS_COUNT(23, __popc(fvalid)); }
+          }
+#endif
           if (DTS_COARSE_FAST && single) {
             // ---- the whole coarse bin lies inside ONE prim (besides the ground quad, hidden below it): no visibility
             // work at all, the prim's planes are fetched once for the bin's 256 pixels

@@ -14,6 +14,6 @@ env.render_obs(); torch.cuda.synchronize()
 c = env.sim.debug_counters().astype(np.int64) - c0
 names = {8: "coarse bins", 9: "  empty (cleared)", 10: "sum of list lengths (records)", 14: "coarse bins with > 32 records", 15: "  their records",
          11: "fine bins shaded", 13: "  simple (one covering prim, no visibility pass)", 12: "extra shading rounds (2nd..4th winner of edge pixels)",
-         16: "warp-wide prim visits", 17: "  trivially accepted (no edge tests)", 20: "general bins holding only road tiles (coverage-only visibility)", 21: "  of those redone with depth (a sample covered twice)", 18: "tiny-triangle passes (fine bins)", 19: "  tiny triangles in them"}
+         16: "warp-wide prim visits", 17: "  trivially accepted (no edge tests)", 20: "general bins holding only road tiles (coverage-only visibility)", 21: "  of those redone with depth (a sample covered twice)", 22: "coarse bins inside one prim (solo)", 23: "  their fine bins", 18: "tiny-triangle passes (fine bins)", 19: "  tiny triangles in them"}
 for k, v in names.items():
     print(f"{v:60s} {c[k]:12d}  per env {c[k]/4096:10.1f}")
