@@ -802,6 +802,7 @@ int dts_set_resize(dts_sim* sim, int out_w, int out_h) {
   // of shared memory (several CTAs per SM); 0 = no band fits even in the opt-in maximum, use the untiled kernel
   sim->resize_band = sim->resize_cap = 0;
   const char* untiled = getenv("DTS_RESIZE_UNTILED");   // A/B switch
+  const size_t budget = (size_t)(getenv("DTS_RESIZE_SMEM_KB") ? atoi(getenv("DTS_RESIZE_SMEM_KB")) : 40) * 1024;   // A/B: shared memory per band
   for (int R = 16; R >= 1 && !(untiled && untiled[0] == '1'); R--) {
     int cap = 0;
     for (int r0 = 0; r0 < out_h; r0 += R) {
@@ -809,7 +810,7 @@ int dts_set_resize(dts_sim* sim, int out_w, int out_h) {
       cap = std::max(cap, (int)yt[(size_t)8 * (r1 - 1) + 3] - (int)yt[(size_t)8 * r0] + 1);
     }
     const size_t smem = resize_band_smem(sim->cfg.cam_width, out_w, cap);
-    if (smem <= 40 * 1024 || (R == 1 && smem <= 200 * 1024)) { sim->resize_band = R; sim->resize_cap = cap; break; }
+    if (smem <= budget || (R == 1 && smem <= 200 * 1024)) { sim->resize_band = R; sim->resize_cap = cap; break; }
   }
   return 0;
 }

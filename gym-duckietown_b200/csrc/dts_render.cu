@@ -1871,21 +1871,23 @@ __global__ void __launch_bounds__(256) k_resize_band(const uint8_t* __restrict__
   }
   for (int i = threadIdx.x; i < ow; i += blockDim.x) xt[i] = __ldg(reinterpret_cast<const int4*>(xtab) + i);
   __syncthreads();
-  // horizontal pass: (source row, output column) per thread, three channels
-  for (int i = threadIdx.x; i < nrows * ow; i += blockDim.x) {
-    const int row = i / ow, x = i - row * ow;
+  // horizontal pass: a warp per source row, a lane per output column (no index divisions), three channels
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int x = lane; x < ow; x += 32) {
     const int4 xa = xt[x];
     const int xi[4] = {(short)(xa.x & 0xffff), xa.x >> 16, (short)(xa.y & 0xffff), xa.y >> 16};
     const int xw[4] = {(short)(xa.z & 0xffff), xa.z >> 16, (short)(xa.w & 0xffff), xa.w >> 16};
-    const uint8_t* rp = sb + row * rowb;
-    int h0 = 0, h1 = 0, h2 = 0;
+    for (int row = warp; row < nrows; row += nwarps) {
+      const uint8_t* rp = sb + row * rowb;
+      int h0 = 0, h1 = 0, h2 = 0;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const uint8_t* px = rp + xi[c] * 3;
-      h0 += (int)px[0] * xw[c]; h1 += (int)px[1] * xw[c]; h2 += (int)px[2] * xw[c];
+      for (int c = 0; c < 4; c++) {
+        const uint8_t* px = rp + xi[c] * 3;
+        h0 += (int)px[0] * xw[c]; h1 += (int)px[1] * xw[c]; h2 += (int)px[2] * xw[c];
+      }
+      int* hp = hb + row * ow3 + x * 3;
+      hp[0] = h0; hp[1] = h1; hp[2] = h2;
     }
-    int* hp = hb + row * ow3 + x * 3;
-    hp[0] = h0; hp[1] = h1; hp[2] = h2;
   }
   __syncthreads();
   // vertical pass
@@ -1894,25 +1896,27 @@ __global__ void __launch_bounds__(256) k_resize_band(const uint8_t* __restrict__
   const bool words = layout == DTS_OBS_HWC && dtype == DTS_OBS_U8 && (ow3 & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
   if (words) {
     const int wpr = ow3 / 4;   // words per output row
-    for (int i = threadIdx.x; i < (r1 - r0) * wpr; i += blockDim.x) {
-      const int yy = i / wpr, e = (i - yy * wpr) * 4, y = r0 + yy;
+    for (int y = r0 + warp; y < r1; y += nwarps) {   // a warp per output row, a lane per word of four bytes
       const int4 ya = __ldg(reinterpret_cast<const int4*>(ytab) + y);
       const int yi[4] = {(short)(ya.x & 0xffff), ya.x >> 16, (short)(ya.y & 0xffff), ya.y >> 16};
       const int yw[4] = {(short)(ya.z & 0xffff), ya.z >> 16, (short)(ya.w & 0xffff), ya.w >> 16};
-      long long acc[4] = {0, 0, 0, 0};
+      for (int j = lane; j < wpr; j += 32) {
+        const int e = 4 * j;
+        // int32 like OpenCV's own vertical pass (|sum| <= 255 * sum|xw| * sum|yw| < 2^31 for cubic taps: 255 * 2621^2 = 1.75e9)
+        int acc[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int4 hv = *reinterpret_cast<const int4*>(hb + (yi[r] - s_lo) * ow3 + e);
-        acc[0] += (long long)hv.x * yw[r]; acc[1] += (long long)hv.y * yw[r]; acc[2] += (long long)hv.z * yw[r]; acc[3] += (long long)hv.w * yw[r];
-      }
-      unsigned word = 0;
+        for (int r = 0; r < 4; r++) {
+          const int4 hv = *reinterpret_cast<const int4*>(hb + (yi[r] - s_lo) * ow3 + e);
+          acc[0] += hv.x * yw[r]; acc[1] += hv.y * yw[r]; acc[2] += hv.z * yw[r]; acc[3] += hv.w * yw[r];
+        }
+        unsigned word = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        long long v = (acc[k] + (1LL << 21)) >> 22;
-        v = v < 0 ? 0 : (v > 255 ? 255 : v);
-        word |= (unsigned)v << (8 * k);
+        for (int k = 0; k < 4; k++) {
+          const int v = min(max((acc[k] + (1 << 21)) >> 22, 0), 255);
+          word |= (unsigned)v << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(out + (size_t)y * ow3 + e) = word;
       }
-      *reinterpret_cast<unsigned*>(out + (size_t)y * ow3 + e) = word;
     }
   } else {
     for (int i = threadIdx.x; i < (r1 - r0) * ow3; i += blockDim.x) {
@@ -1933,7 +1937,7 @@ __global__ void __launch_bounds__(256) k_resize_band(const uint8_t* __restrict__
 }
 
 size_t resize_band_smem(int W, int ow, int cap) {
-  return (size_t)ow * 16 + (((size_t)cap * W * 3 + 15) & ~(size_t)15) + (size_t)cap * ow * 3 * 4;
+  return (size_t)ow * 16 + (((size_t)cap * W * 3 + 15) & ~(size_t)15) + (size_t)cap * ow * 3 * 4 + 16;   // (+16: word loads may run past the last row)
 }
 
 void launch_resize(const uint8_t* src, int W, int H, int ow, int oh, int n_envs, const int16_t* xtab, const int16_t* ytab,
