@@ -58,6 +58,9 @@ namespace {
 #else
 #define DTS_COUNT(slot, n) do { } while (0)
 #endif
+#ifndef DTS_SOLO
+#define DTS_SOLO 1          // coarse bins lying inside ONE prim (besides the ground) are drawn by the lean k_raster_solo (A/B switch)
+#endif
 #ifndef DTS_COPLANAR
 #define DTS_COPLANAR 1      // fine bins whose prims are all road tiles (coplanar, disjoint) resolve visibility by coverage alone (A/B switch)
 #endif
@@ -502,8 +505,9 @@ __device__ __forceinline__ bool bin_overlaps(const int qx[4], const int qy[4], i
 // trivial-accept bits for each of the bin's 8 fine bins, depth plane, draw id.
 // With `fb` (fused fisheye) the bin's pixels are wherever the LUT sends its output pixels: (ox, oy) is the corner of
 // their source bounding box and fb[f] the source box of fine bin f; the bits then speak about every pixel of that box.
-__device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int p, int ox, int oy, BinRec* __restrict__ out,
-                                             const short4* __restrict__ fb = nullptr) {
+// Returns the fine bins every sample of which the prim covers (bits 0-7) | ground quad << 8.
+__device__ __forceinline__ unsigned build_binrec(const PrimRec* __restrict__ pr, int p, int ox, int oy, BinRec* __restrict__ out,
+                                                 const short4* __restrict__ fb = nullptr) {
   const int4 w0 = __ldg(reinterpret_cast<const int4*>(pr));
   const int4 w1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
   const float4 w2 = __ldg(reinterpret_cast<const float4*>(pr) + 2);
@@ -576,6 +580,7 @@ __device__ __forceinline__ void build_binrec(const PrimRec* __restrict__ pr, int
   o[2] = make_int4(B[0], B[1], B[2], B[3]);
   o[3] = make_int4(__float_as_int(w2.x), __float_as_int(w2.y), __float_as_int(w2.z), id);
   o[4] = make_int4(qx[0] - ox, qy[0] - oy, (int)((unsigned)p | (live << 16) | ((inside & live) << 24)), quad | (id < 2 ? 2 : 0) | tiny | flat);
+  return (inside & live) | (id < 2 ? 0x100u : 0u);
 }
 
 // Fragment colour of prim `w` of the env's slab at the pixel whose centre is (pxa + 32, pya + 32) sub-pixels (spec steps
@@ -808,7 +813,8 @@ struct FrameMem {
   int* bin_start;       // [N][cbins]  pool index of the bin's first pair / record
   float4* lat;          // [N][max_lat][64]
   uint2* geo_list;      // [N * items_max] (env, draw item) pairs that passed k_cull
-  int* work;            // global counters: [0] k_raster work items, [1] pair-pool cursor, [2] geo_list length
+  uint2* solo;          // [N * cbins] (env, coarse bin | prim << 16): coarse bins lying inside one prim (k_bin -> k_raster_solo)
+  int* work;            // global counters: [0] k_raster work items, [1] pair-pool cursor, [2] geo_list length, [3] solo list length
   int32_t* status;      // mapped host word (dts_status): bit 0 = a frame ran out of frame memory
 };
 
@@ -826,6 +832,7 @@ __host__ FrameMem carve(void* scratch, int n, int max_prims, int cbins, int max_
   f.recs = reinterpret_cast<BinRec*>(p); p += align256((size_t)max_pairs * sizeof(BinRec));
   f.lat = reinterpret_cast<float4*>(p); p += align256((size_t)n * max_lat * 64 * sizeof(float4));
   f.geo_list = reinterpret_cast<uint2*>(p); p += align256((size_t)n * geo_items * sizeof(uint2));
+  f.solo = reinterpret_cast<uint2*>(p); p += align256((size_t)n * cbins * sizeof(uint2));
   f.status = nullptr;
   return f;
 }
@@ -834,7 +841,8 @@ size_t render_scratch_bytes(int n, int max_prims, int cbins, int max_pairs, int 
   return 256 + align256((size_t)n * sizeof(FrameCtx)) + 2 * align256((size_t)n * cbins * sizeof(int)) +
          align256((size_t)n * max_prims * sizeof(PrimRec)) + align256((size_t)max_pairs * sizeof(uint32_t)) +
          align256((size_t)max_pairs * sizeof(BinRec)) +
-         align256((size_t)n * max_lat * 64 * sizeof(float4)) + align256((size_t)n * geo_items * sizeof(uint2)) + 256;
+         align256((size_t)n * max_lat * 64 * sizeof(float4)) + align256((size_t)n * geo_items * sizeof(uint2)) +
+         align256((size_t)n * cbins * sizeof(uint2)) + 256;
 }
 
 // ------------------------------------------------------------------------------------------------ k_frame_setup
@@ -1136,6 +1144,7 @@ k_geometry(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem
 // test each bin of the box against their edges, one bin per lane.  Pass 2, dense over the pairs (one per thread, so a
 // screen-filling prim costs no more lanes than a sliver): the pair's BinRec.
 constexpr int kBinWarps = 4;
+constexpr int kCountMask = 0xfffff, kGroundInc = 1 << 20;   // a bin's counter: records | ground-quad records << 20
 template <bool kFish>   // true: bins are the LUT's source boxes of the output bins (fused fisheye gather)
 __global__ void __launch_bounds__(kBinWarps * 32)
 k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32_t* __restrict__ err) {
@@ -1156,13 +1165,14 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
     for (int p0 = wib * 32; p0 < n; p0 += nthr) {
       const int p = p0 + lane;
       const bool have = p < n;
-      int qx[4] = {0, 0, 0, 0}, qy[4] = {0, 0, 0, 0}, nv = 3;
+      int qx[4] = {0, 0, 0, 0}, qy[4] = {0, 0, 0, 0}, nv = 3, ginc = 1;
       if (have) {
         const int4 w0 = __ldg(reinterpret_cast<const int4*>(prims + p));
         const int4 w1 = __ldg(reinterpret_cast<const int4*>(prims + p) + 1);
         qx[0] = w0.x; qx[1] = w0.z; qx[2] = w1.x; qx[3] = w1.z;
         qy[0] = w0.y; qy[1] = w0.w; qy[2] = w1.y; qy[3] = w1.w;
         nv = ((__ldg(&prims[p].ltq) >> 24) & 1) ? 4 : 3;   // vertex 3 of a triangle repeats vertex 0
+        if (__ldg(&prims[p].id) < 2) ginc = 1 + kGroundInc;   // the ground quad's records are counted in the upper bits too
       }
       const int minx = min(min(qx[0], qx[1]), min(qx[2], qx[3])), maxx = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
       const int miny = min(min(qy[0], qy[1]), min(qy[2], qy[3])), maxy = max(max(qy[0], qy[1]), max(qy[2], qy[3]));
@@ -1185,7 +1195,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
                 const short4 cb = ft.cbox[b];
                 if (pmaxx < cb.x || pminx > cb.z || pmaxy < cb.y || pminy > cb.w) continue;
                 if (cx != max(bx0, cb.x / kCoarseW) || cy != max(by0, cb.y / kCoarseH)) continue;   // counted from another cell
-                const int pos = atomicAdd(&cnt[b], 1);
+                const int pos = atomicAdd(&cnt[b], ginc) & kCountMask;
                 if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
               }
             }
@@ -1195,7 +1205,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
             for (int bx = bx0; bx <= bx1; bx++) {
               if (large && !bin_overlaps(qx, qy, nv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
               const int b = by * cbins_x + bx;
-              const int pos = atomicAdd(&cnt[b], 1);
+              const int pos = atomicAdd(&cnt[b], ginc) & kCountMask;
               if (pass == 1) pairs[start[b] + pos] = (uint32_t)p | ((uint32_t)b << 16);
             }
         }
@@ -1207,7 +1217,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
         int vx[4], vy[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { vx[k] = __shfl_sync(0xffffffffu, qx[k], src); vy[k] = __shfl_sync(0xffffffffu, qy[k], src); }
-        const int snv = __shfl_sync(0xffffffffu, nv, src), sp = p0 + src;
+        const int snv = __shfl_sync(0xffffffffu, nv, src), sp = p0 + src, sginc = __shfl_sync(0xffffffffu, ginc, src);
         if (kFish) {
           // one HOME cell per lane and round: every output bin is listed once, under the source cell holding the top-left
           // corner of its source box (second inverse index), so a prim spanning many cells meets each candidate bin once;
@@ -1225,7 +1235,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
               const int x0 = (int)(short)(e.x & 0xffff), y0 = e.x >> 16, x1 = (int)(short)(e.y & 0xffff), y1 = e.y >> 16;
               if (smaxx < x0 || sminx > x1 || smaxy < y0 || sminy > y1) continue;
               if (!box_overlaps(vx, vy, snv, x0 * kSub + 8, x1 * kSub + 56, y0 * kSub + 8, y1 * kSub + 56)) continue;
-              const int pos = atomicAdd(&cnt[e.z], 1);
+              const int pos = atomicAdd(&cnt[e.z], sginc) & kCountMask;
               if (pass == 1) pairs[start[e.z] + pos] = (uint32_t)sp | ((uint32_t)e.z << 16);
             }
           }
@@ -1237,7 +1247,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
             const int by = sby0 + i / nbx, bx = sbx0 + i % nbx;
             if (!bin_overlaps(vx, vy, snv, bx * kCoarseW * kSub, by * kCoarseH * kSub)) continue;
             const int b = by * cbins_x + bx;
-            const int pos = atomicAdd(&cnt[b], 1);
+            const int pos = atomicAdd(&cnt[b], sginc) & kCountMask;
             if (pass == 1) pairs[start[b] + pos] = (uint32_t)sp | ((uint32_t)b << 16);
           }
         }
@@ -1249,7 +1259,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
         int carry = 0;
         for (int b0 = 0; b0 < cbins; b0 += 32) {
           const int b = b0 + lane;
-          const int v = b < cbins ? cnt[b] : 0;
+          const int v = b < cbins ? (cnt[b] & kCountMask) : 0;
           int inc = v;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
@@ -1267,7 +1277,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
       const bool ok = s_ok != 0;
       for (int b = tid; b < cbins; b += nthr) {
         start[b] += base;
-        fm.bin_count[(size_t)env * cbins + b] = ok ? cnt[b] : 0;   // lists that do not fit: the frame stays clear
+        fm.bin_count[(size_t)env * cbins + b] = ok ? (cnt[b] & kCountMask) : 0;   // lists that do not fit: the frame stays clear
         fm.bin_start[(size_t)env * cbins + b] = start[b];
       }
       if (!ok) {
@@ -1279,6 +1289,7 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
   // pass 2: one pair per thread -> its visibility record (the pairs were written by other threads of this CTA: the
   // barrier above orders those writes before these reads)
   const int pair0 = s_base, total = s_total;
+  const bool solo_on = DTS_SOLO && !kFish && rc.obs_layout == DTS_OBS_HWC && rc.obs_dtype == DTS_OBS_U8 && (W & 3) == 0;
   BinRec* recs = fm.recs;
   for (int i = pair0 + tid; i < pair0 + total; i += nthr) {
     const uint32_t pair = pairs[i];
@@ -1288,7 +1299,19 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
       build_binrec(prims + p, p, cb.x * kSub, cb.y * kSub, recs + i, ft.fbox + (size_t)b * 8);
     } else {
       const int cby = b / cbins_x, cbx = b - cby * cbins_x;
-      build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
+      const unsigned r = build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
+      if (solo_on && !(r & 0x100u)) {
+        // the coarse bin lies inside this prim and holds no other (besides the ground, hidden below it): no visibility
+        // work at all -> the bin goes to k_raster_solo, and k_raster skips it (negative count)
+        const int c = cnt[b];
+        const int nx = min(kCFX, (W - cbx * kCoarseW + kBinW - 1) / kBinW);
+        const unsigned cols = (1u << nx) - 1u, valid = (((cby * kCFY + 1) * kBinH < H) ? 0xffu : 0x0fu) & (cols | (cols << 4));
+        if ((c & kCountMask) - (c >> 20) == 1 && (r & valid) == valid) {
+          fm.bin_count[(size_t)env * cbins + b] = -(p + 1);
+          const int slot = atomicAdd(fm.work + 3, 1);
+          fm.solo[slot] = make_uint2((unsigned)env, (unsigned)b | ((unsigned)p << 16));
+        }
+      }
     }
   }
 }
@@ -1448,6 +1471,7 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
     issue();
     for (int cbx = 0; cbx < cbins_x; cbx++) {
       const int count = __shfl_sync(0xffffffffu, my_cnt, cbx);
+      if (count < 0) continue;   // drawn by k_raster_solo (a bin inside one prim)
       const unsigned fvalid = valid8(cbx);
       DTS_COUNT(8, 1);
       if (count == 0) {
@@ -1780,6 +1804,46 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
   }
 }
 
+// ------------------------------------------------------------------------------------------------ k_raster_solo
+// Coarse bins that lie inside ONE prim (k_bin found: one record besides the ground quad, covering every sample of every
+// fine bin — 22 of the 55 non-empty coarse bins of a c2 frame, 40 % of the shaded pixels) need no records, no staging, no
+// visibility state: a warp fetches the prim's planes once and shades the bin's 256 pixels.  A separate kernel so that the
+// lean loop gets its own register allocation (the same fast path inside k_raster cost more than it saved).
+// Packed u8 HWC output with whole-word rows only (k_bin marks no bin otherwise).  Runs before k_raster.
+__global__ void __launch_bounds__(256) k_raster_solo(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm,
+                                                     uint8_t* __restrict__ obs, int max_prims, int max_lat) {
+  const int W = rc.width, H = rc.height;
+  const int cbins_x = (W + kCoarseW - 1) / kCoarseW;
+  const int lane = threadIdx.x & 31;
+  const StoreLane sl = make_store_lane(lane, W);
+  const size_t frame_bytes = (size_t)W * H * 3;
+  const int n = fm.work[3];
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const uint2 e = fm.solo[i];
+    const int env = (int)e.x, b = (int)(e.y & 0xffffu);
+    const unsigned p = e.y >> 16;
+    const int cby = b / cbins_x, cbx = b - cby * cbins_x;
+    const uint8_t* tex_pool = maps[S.map_id[env]].tex_pool;
+    const float4* lat_tab = fm.lat + (size_t)env * max_lat * 64;
+    const ShadeIn si = load_shade(fm.prims + (size_t)env * max_prims, p);
+    uint8_t* out = obs + (size_t)env * frame_bytes;
+    const int nx = min(kCFX, (W - cbx * kCoarseW + kBinW - 1) / kBinW);
+    const int ny = ((cby * kCFY + 1) * kBinH < H) ? 2 : 1;
+#pragma unroll 1
+    for (int fy = 0; fy < ny; fy++)
+#pragma unroll 1
+      for (int fx = 0; fx < nx; fx++) {
+        const int bx = cbx * kCFX + fx, by = cby * kCFY + fy;
+        float c3[3];
+        shade_eval(si, tex_pool, lat_tab, (bx * kBinW + (lane & 7)) * kSub, (by * kBinH + (lane >> 3)) * kSub, c3);
+        const unsigned rgb = pack_rgb(c3[0], c3[1], c3[2]);
+        if (bx * kBinW + kBinW <= W) store_bin_fast(out + ((size_t)(by * kBinH) * W + bx * kBinW) * 3, sl, rgb, min(kBinH, H - by * kBinH));
+        else store_bin(out, rgb, lane, bx, by, W, H);
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ k_resize
 // ResizeWrapper (wrappers.py:111-141): cv2.resize(..., interpolation=cv2.INTER_CUBIC) of the rendered frame, on the
 // device, so that a training stack's 84x84 payload (21 KB per env instead of 57.6 KB) is what crosses PCIe.  OpenCV's
@@ -2028,6 +2092,11 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   }
   mark();
   const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;
+  int launches = 5;
+  if (DTS_SOLO && !fisheye && !wrap && (W & 3) == 0) {   // (inside the k_raster event bracket: it is rasterisation time)
+    k_raster_solo<<<n_ctas, 256, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_lat);
+    launches++;
+  }
   static bool smem_opt_in = false;
   if (!smem_opt_in) {   // > 48 KB of dynamic shared memory per CTA needs the opt-in, once per kernel
     cudaFuncSetAttribute(k_raster<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterSmem);
@@ -2045,7 +2114,7 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   }
   mark();
   mark();   // (post passes: none yet)
-  return 5;
+  return launches;
 }
 
 }  // namespace dts

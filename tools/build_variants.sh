@@ -11,6 +11,6 @@ while read -r tag flags; do
   grep -A2 "k_rasterILb0ELb0" build.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done <<'VARIANTS'
 base
-nocoplanar -DDTS_COPLANAR=0
+nosolo -DDTS_SOLO=0
 VARIANTS
 cp variants/libdtsim_base.so libdtsim.so   # the tree's library = the base variant, built from the current sources
