@@ -61,6 +61,9 @@ namespace {
 #ifndef DTS_SOLO
 #define DTS_SOLO 1          // coarse bins lying inside ONE prim (besides the ground) are drawn by the lean k_raster_solo (A/B switch)
 #endif
+#ifndef DTS_SOLO_MIN_CTAS
+#define DTS_SOLO_MIN_CTAS 3   // resident CTAs per SM of k_raster_solo (register budget 65536 / (256 * this))
+#endif
 #ifndef DTS_COPLANAR
 #define DTS_COPLANAR 1      // fine bins whose prims are all road tiles (coplanar, disjoint) resolve visibility by coverage alone (A/B switch)
 #endif
@@ -1289,24 +1292,29 @@ k_bin(RenderCfg rc, FrameMem fm, FishTab ft, int max_prims, int max_pairs, int32
   // pass 2: one pair per thread -> its visibility record (the pairs were written by other threads of this CTA: the
   // barrier above orders those writes before these reads)
   const int pair0 = s_base, total = s_total;
-  const bool solo_on = DTS_SOLO && !kFish && rc.obs_layout == DTS_OBS_HWC && rc.obs_dtype == DTS_OBS_U8 && (W & 3) == 0;
+  const bool solo_on = DTS_SOLO && rc.obs_layout == DTS_OBS_HWC && rc.obs_dtype == DTS_OBS_U8 && (W & 3) == 0;
   BinRec* recs = fm.recs;
   for (int i = pair0 + tid; i < pair0 + total; i += nthr) {
     const uint32_t pair = pairs[i];
     const int p = (int)(pair & 0xffffu), b = (int)(pair >> 16);
+    const int cby = b / cbins_x, cbx = b - cby * cbins_x;
+    unsigned r;
     if (kFish) {
       const short4 cb = ft.cbox[b];
-      build_binrec(prims + p, p, cb.x * kSub, cb.y * kSub, recs + i, ft.fbox + (size_t)b * 8);
+      r = build_binrec(prims + p, p, cb.x * kSub, cb.y * kSub, recs + i, ft.fbox + (size_t)b * 8);
     } else {
-      const int cby = b / cbins_x, cbx = b - cby * cbins_x;
-      const unsigned r = build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
-      if (solo_on && !(r & 0x100u)) {
+      r = build_binrec(prims + p, p, cbx * kCoarseW * kSub, cby * kCoarseH * kSub, recs + i);
+    }
+    {
+      if (solo_on) {
         // the coarse bin lies inside this prim and holds no other (besides the ground, hidden below it): no visibility
         // work at all -> the bin goes to k_raster_solo, and k_raster skips it (negative count)
         const int c = cnt[b];
         const int nx = min(kCFX, (W - cbx * kCoarseW + kBinW - 1) / kBinW);
         const unsigned cols = (1u << nx) - 1u, valid = (((cby * kCFY + 1) * kBinH < H) ? 0xffu : 0x0fu) & (cols | (cols << 4));
-        if ((c & kCountMask) - (c >> 20) == 1 && (r & valid) == valid) {
+        // (... or it is the bin's only record: a stretch of bare ground)
+        const bool alone = (r & 0x100u) ? (c & kCountMask) == 1 : (c & kCountMask) - (c >> 20) == 1;
+        if (alone && (r & valid) == valid) {
           fm.bin_count[(size_t)env * cbins + b] = -(p + 1);
           const int slot = atomicAdd(fm.work + 3, 1);
           fm.solo[slot] = make_uint2((unsigned)env, (unsigned)b | ((unsigned)p << 16));
@@ -1810,8 +1818,9 @@ k_raster(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem f
 // visibility state: a warp fetches the prim's planes once and shades the bin's 256 pixels.  A separate kernel so that the
 // lean loop gets its own register allocation (the same fast path inside k_raster cost more than it saved).
 // Packed u8 HWC output with whole-word rows only (k_bin marks no bin otherwise).  Runs before k_raster.
-__global__ void __launch_bounds__(256) k_raster_solo(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm,
-                                                     uint8_t* __restrict__ obs, int max_prims, int max_lat) {
+template <bool kFish>   // true: each lane shades the source pixel the fisheye LUT names for its output pixel
+__global__ void __launch_bounds__(256, DTS_SOLO_MIN_CTAS) k_raster_solo(const DState S, const DMap* __restrict__ maps, RenderCfg rc, FrameMem fm,
+                                                                        FishTab ft, uint8_t* __restrict__ obs, int max_prims, int max_lat) {
   const int W = rc.width, H = rc.height;
   const int cbins_x = (W + kCoarseW - 1) / kCoarseW;
   const int lane = threadIdx.x & 31;
@@ -1835,9 +1844,19 @@ __global__ void __launch_bounds__(256) k_raster_solo(const DState S, const DMap*
 #pragma unroll 1
       for (int fx = 0; fx < nx; fx++) {
         const int bx = cbx * kCFX + fx, by = cby * kCFY + fy;
+        int pxa = (bx * kBinW + (lane & 7)) * kSub, pya = (by * kBinH + (lane >> 3)) * kSub;
+        bool px_valid = true;
+        if (kFish) {   // (lanes past the image edge read a clamped entry; their pixels are not stored)
+          const int gx = min(bx * kBinW + (lane & 7), W - 1), gy = min(by * kBinH + (lane >> 3), H - 1);
+          const int sxy = __ldg(ft.src_xy + gy * W + gx);
+          const int sx = (int)(short)(sxy & 0xffff), sy = sxy >> 16;
+          px_valid = sx != -32768;
+          pxa = sx * kSub; pya = sy * kSub;
+        }
         float c3[3];
-        shade_eval(si, tex_pool, lat_tab, (bx * kBinW + (lane & 7)) * kSub, (by * kBinH + (lane >> 3)) * kSub, c3);
-        const unsigned rgb = pack_rgb(c3[0], c3[1], c3[2]);
+        shade_eval(si, tex_pool, lat_tab, pxa, pya, c3);
+        unsigned rgb = pack_rgb(c3[0], c3[1], c3[2]);
+        if (kFish && !px_valid) rgb = 0u;   // cv2.remap BORDER_CONSTANT
         if (bx * kBinW + kBinW <= W) store_bin_fast(out + ((size_t)(by * kBinH) * W + bx * kBinW) * 3, sl, rgb, min(kBinH, H - by * kBinH));
         else store_bin(out, rgb, lane, bx, by, W, H);
       }
@@ -2093,8 +2112,10 @@ int launch_render(const DState& S, const DMap* maps, const RenderCfg& rc, void* 
   mark();
   const bool wrap = (rc.obs_layout | rc.obs_dtype) != 0;
   int launches = 5;
-  if (DTS_SOLO && !fisheye && !wrap && (W & 3) == 0) {   // (inside the k_raster event bracket: it is rasterisation time)
-    k_raster_solo<<<n_ctas, 256, 0, st>>>(S, maps, rc, fm, obs, max_prims, max_lat);
+  if (DTS_SOLO && !wrap && (W & 3) == 0) {   // (inside the k_raster event bracket: it is rasterisation time)
+    const int solo_ctas = max(1, n_ctas * DTS_SOLO_MIN_CTAS / DTS_RENDER_MIN_CTAS);   // (n_ctas can be 1 for a handful of envs)
+    if (fisheye) k_raster_solo<true><<<solo_ctas, 256, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_lat);
+    else k_raster_solo<false><<<solo_ctas, 256, 0, st>>>(S, maps, rc, fm, fish, obs, max_prims, max_lat);
     launches++;
   }
   static bool smem_opt_in = false;

@@ -33,7 +33,10 @@ def test_run_tests_script_equivalent(torch_cuda):
     assert first_render.shape == (600, 800, 3)                                       # WINDOW_HEIGHT x WINDOW_WIDTH S:100-101
     top = env.render("top_down")
     seg = env.render_obs(segment=True)
-    assert top.shape == (600, 800, 3) and top.std() > 5 and seg.shape == first_obs.shape and (seg[0, 0] == [255, 0, 255]).all()
+    # (the env is unseeded like the reference's script: which class shows in a given pixel varies from run to run, so
+    # only ask that the clear / ground colour of segment mode, magenta, is on screen)
+    assert top.shape == (600, 800, 3) and top.std() > 5 and seg.shape == first_obs.shape
+    assert (seg == np.array([255, 0, 255], np.uint8)).all(-1).mean() > 0.05
     assert env.reset(segment=True).shape == first_obs.shape
     from gym_duckietown_b200.wrappers import PyTorchObsWrapper                       # :28-34
     env = PyTorchObsWrapper(env)
