@@ -1,7 +1,8 @@
 // dts_render.cu — batched software rasteriser for the agent camera (Simulator._render_img,
 // simulator.py:1707-1951) on sm_100a.  No tensor cores: there is no dense contraction here.
 //
-// Four stream-ordered kernels per frame batch, no CTA-wide barrier in any of them:
+// Stream-ordered kernels per frame batch (k_cull, a work-list pre-pass for k_geometry, and k_raster_solo, the lean
+// rasteriser of coarse bins lying inside one prim, are described at their definitions):
 //   k_frame_setup  thread per env: camera matrices (f64), gluPerspective, counters -> FrameCtx[env]
 //   k_geometry     warp per (env, draw item) over the whole GPU: ground / map tile / placed mesh.  Model-view
 //                  f64->f32, fixed-function per-vertex lighting, frustum cull, near + guard-band clip, snap to
