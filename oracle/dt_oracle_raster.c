@@ -53,7 +53,7 @@ void orr_set_render_mode(int mode) { g_render_mode = mode; }
 /* test-side statistics of the triangles handed to the rasteriser (single-threaded use): [0] set-up triangles on screen,
  * [1] of those with no sample position inside their bounding box, [2] with no covered sample, [3] pixel box <= 2x2,
  * [4] pixel box <= 4x4, [5] quads */
-static long long g_stats[8];
+static __thread long long g_stats[8]; /* per thread: the OpenMP batch paths neither share nor contend on them */
 void orr_stats_read(long long out[8], int reset) { for (int k = 0; k < 8; k++) { out[k] = g_stats[k]; if (reset) g_stats[k] = 0; } }
 #define SEGMENT (g_render_mode & 1)
 #define TOP_DOWN (g_render_mode & 2)
